@@ -1,0 +1,356 @@
+"""Host-side mirror of the reference's MATLAB interface for the eMagLS hot path.
+
+Same function names, positional argument order, argument meaning and error behaviour as the
+reference (lib/get*Filters*.m, dependencies/getSMAIRMatrix.m, dependencies/binauralDecode.m);
+every call goes through the C ABI of libemagls_cuda (include/emagls_cuda.h).  Arrays follow the
+MATLAB conventions: impulse responses ``[samples, dirs]`` (optionally ``[samples, dirs, sets]``),
+filters ``[taps, channels]`` (batched: ``[taps, channels, batch]``), grids in radians.
+
+Deviations from the reference interface, all explicit:
+* ``shFunction`` / ``chFunction`` handles other than the default ``getSH`` / ``getCH`` are not
+  accepted (a CUDA library cannot call back into host code).
+* keyword-only batch extensions: ``rotations`` ([B,3,3], world direction of grid direction u is
+  R u), ``handle``, ``config``, ``return_spectra``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import Config, EmaglsError, Handle, default_handle  # noqa: F401
+
+__all__ = ["getEMagLs2Filters", "getEMagLsFilters", "getMagLsFilters", "getLsFilters",
+           "getEMagLsFiltersFromAtf", "getEMagLsFiltersEMAinCH", "getEMagLsFiltersEMAinSH",
+           "getSMAIRMatrix", "binauralDecode", "getSH", "sphModalCoeffs", "regularizedApply",
+           "Handle", "EmaglsError"]
+
+
+def _f(x):
+    return np.asfortranarray(np.asarray(x, dtype=np.float64))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _vec(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.float64).ravel())
+
+
+def _basis(shDefinition):
+    if shDefinition is None or shDefinition == "real":
+        return 0
+    if shDefinition == "complex":
+        return 1
+    raise ValueError("shDefinition must be 'real' or 'complex'")
+
+
+def _check_sh_function(shFunction):
+    if shFunction is not None and shFunction is not getSH:
+        raise NotImplementedError("only the default shFunction (@getSH) is evaluated on the device")
+
+
+def _config(handle, config, shDefinition):
+    cfg = config if config is not None else handle.default_config()
+    cfg.basis = _basis(shDefinition)
+    return cfg
+
+
+def _prep_hrirs(hL, hR):
+    hL, hR = _f(hL), _f(hR)
+    if hL.shape != hR.shape:
+        raise ValueError("hL and hR must have the same size")
+    if hL.ndim == 2:
+        sets = 1
+    elif hL.ndim == 3:
+        sets = hL.shape[2]
+    else:
+        raise ValueError("hL/hR must be [samples, dirs] or [samples, dirs, sets]")
+    return hL, hR, hL.shape[0], hL.shape[1], sets
+
+
+def _design_sma(fn_name, channels_of, hL, hR, hrirGridAziRad, hrirGridZenRad, micRadius, micGridAziRad,
+                micGridZenRad, order, fs, length, shDefinition, shFunction, rotations, handle, config,
+                return_spectra):
+    _check_sh_function(shFunction)
+    h = handle or default_handle()
+    cfg = _config(h, config, shDefinition)
+    hL, hR, T, D, sets = _prep_hrirs(hL, hR)
+    az, ze = _vec(hrirGridAziRad), _vec(hrirGridZenRad)
+    maz, mze = _vec(micGridAziRad), _vec(micGridZenRad)
+    if az.size != D or ze.size != D:
+        raise ValueError("HRIR grid size does not match hL")
+    if maz.size != mze.size:
+        raise ValueError("microphone grid sizes differ")
+    if rotations is None:
+        rot, B = None, 1
+    else:
+        rot = np.ascontiguousarray(np.asarray(rotations, dtype=np.float64).reshape(-1, 9))
+        B = rot.shape[0]
+    M = maz.size
+    Mc = channels_of(M, int(order))
+    length = int(length)
+    P = sets * B
+    nfft = min(cfg.nfft_max_len, 2 * length)
+    K = nfft // 2 + 1
+    cplx_out = cfg.basis == 1 and fn_name != "emagls_design_emagls2"
+    odt = np.complex128 if cplx_out else np.float64
+    wL = np.zeros((length, Mc, P), dtype=odt, order="F")
+    wR = np.zeros((length, Mc, P), dtype=odt, order="F")
+    sp = np.zeros((K, Mc, P, 2), dtype=np.complex128, order="F") if return_spectra else None
+    rc = getattr(h.lib, fn_name)(h.ptr, C.byref(cfg), _p(hL), _p(hR), T, D, _p(az), _p(ze), float(micRadius),
+                                 _p(maz), _p(mze), M, int(order), float(fs), length, sets, B, _p(rot),
+                                 _p(wL), _p(wR), _p(sp))
+    h.check(rc)
+    if P == 1 and rotations is None and sets == 1:
+        wL, wR = wL[:, :, 0], wR[:, :, 0]
+        if sp is not None:
+            sp = sp[:, :, 0, :]
+    return (wL, wR, sp) if return_spectra else (wL, wR)
+
+
+def getEMagLs2Filters(hL, hR, hrirGridAziRad, hrirGridZenRad, micRadius, micGridAziRad, micGridZenRad,
+                      order, fs, len, shDefinition="real", shFunction=None, *, rotations=None,
+                      handle=None, config=None, return_spectra=False):
+    """[wMlsL, wMlsR] = getEMagLs2Filters(...)  -- lib/getEMagLs2Filters.m:1-2.
+
+    Returns filters ``[len, numMics]`` (``[len, numMics, batch]`` when batched).  With
+    ``return_spectra`` also the positive-frequency solutions ``[K, numMics, (batch,) 2]``.
+    """
+    return _design_sma("emagls_design_emagls2", lambda M, N: M, hL, hR, hrirGridAziRad, hrirGridZenRad,
+                       micRadius, micGridAziRad, micGridZenRad, order, fs, len, shDefinition, shFunction,
+                       rotations, handle, config, return_spectra)
+
+
+def getEMagLsFilters(hL, hR, hrirGridAziRad, hrirGridZenRad, micRadius, micGridAziRad, micGridZenRad,
+                     order, fs, len, shDefinition="real", shFunction=None, *, rotations=None,
+                     handle=None, config=None, return_spectra=False):
+    """[wMlsL, wMlsR] = getEMagLsFilters(...)  -- lib/getEMagLsFilters.m:1-2 ([len, (order+1)^2])."""
+    return _design_sma("emagls_design_emagls", lambda M, N: (N + 1) ** 2, hL, hR, hrirGridAziRad,
+                       hrirGridZenRad, micRadius, micGridAziRad, micGridZenRad, order, fs, len, shDefinition,
+                       shFunction, rotations, handle, config, return_spectra)
+
+
+def getMagLsFilters(hL, hR, hrirGridAziRad, hrirGridZenRad, order, fs, len, shDefinition="real",
+                    shFunction=None, *, handle=None, config=None, return_spectra=False):
+    """[wMlsL, wMlsR] = getMagLsFilters(...)  -- lib/getMagLsFilters.m:1-2."""
+    _check_sh_function(shFunction)
+    h = handle or default_handle()
+    cfg = _config(h, config, shDefinition)
+    hL, hR, T, D, sets = _prep_hrirs(hL, hR)
+    if sets != 1:
+        raise ValueError("getMagLsFilters is not batched")
+    az, ze = _vec(hrirGridAziRad), _vec(hrirGridZenRad)
+    H = (int(order) + 1) ** 2
+    nfft = min(cfg.nfft_max_len, 2 * int(len))
+    K = nfft // 2 + 1
+    odt = np.complex128 if cfg.basis == 1 else np.float64
+    wL = np.zeros((int(len), H), dtype=odt, order="F")
+    wR = np.zeros((int(len), H), dtype=odt, order="F")
+    sp = np.zeros((K, H, 2), dtype=np.complex128, order="F") if return_spectra else None
+    h.check(h.lib.emagls_design_magls(h.ptr, C.byref(cfg), _p(hL), _p(hR), T, D, _p(az), _p(ze), int(order),
+                                      float(fs), int(len), _p(wL), _p(wR), _p(sp)))
+    return (wL, wR, sp) if return_spectra else (wL, wR)
+
+
+def getLsFilters(hL, hR, hrirGridAziRad, hrirGridZenRad, order, shDefinition="real", shFunction=None, *,
+                 handle=None, config=None):
+    """[wLsL, wLsR] = getLsFilters(...)  -- lib/getLsFilters.m:1-2 ([numSamples, (order+1)^2])."""
+    _check_sh_function(shFunction)
+    h = handle or default_handle()
+    cfg = _config(h, config, shDefinition)
+    hL, hR, T, D, sets = _prep_hrirs(hL, hR)
+    az, ze = _vec(hrirGridAziRad), _vec(hrirGridZenRad)
+    H = (int(order) + 1) ** 2
+    odt = np.complex128 if cfg.basis == 1 else np.float64
+    wL = np.zeros((T, H), dtype=odt, order="F")
+    wR = np.zeros((T, H), dtype=odt, order="F")
+    h.check(h.lib.emagls_design_ls(h.ptr, C.byref(cfg), _p(hL), _p(hR), T, D, _p(az), _p(ze), int(order),
+                                   _p(wL), _p(wR)))
+    return wL, wR
+
+
+def getEMagLsFiltersFromAtf(hL, hR, hrirGridAziZenRad, atfIrs, atfGridAziZenRad, fs, filterLen, fTrans, *,
+                            handle=None, config=None, return_spectra=False, return_info=False):
+    """[wMlsL, wMlsR] = getEMagLsFiltersFromAtf(...)  -- lib/getEMagLsFiltersFromAtf.m:1."""
+    h = handle or default_handle()
+    cfg = _config(h, config, "real")
+    hL, hR, T, D, sets = _prep_hrirs(hL, hR)
+    if sets != 1:
+        raise ValueError("getEMagLsFiltersFromAtf is not batched")
+    hg = _f(np.asarray(hrirGridAziZenRad, dtype=np.float64).reshape(-1, 2))
+    atf = _f(atfIrs)
+    ag = _f(np.asarray(atfGridAziZenRad, dtype=np.float64).reshape(-1, 2))
+    Ta, M, Da = atf.shape
+    nfft = min(cfg.nfft_max_len, 2 * int(filterLen))
+    K = nfft // 2 + 1
+    wL = np.zeros((int(filterLen), M), order="F")
+    wR = np.zeros((int(filterLen), M), order="F")
+    sp = np.zeros((K, M, 2), dtype=np.complex128, order="F") if return_spectra else None
+    dev = C.c_double(0.0)
+    h.check(h.lib.emagls_design_from_atf(h.ptr, C.byref(cfg), _p(hL), _p(hR), T, D, _p(hg), _p(atf), Ta, M, Da,
+                                         _p(ag), float(fs), int(filterLen), float(fTrans), _p(wL), _p(wR),
+                                         _p(sp), C.cast(C.byref(dev), C.c_void_p)))
+    # the reference prints this line (lib/getEMagLsFiltersFromAtf.m:96)
+    print(f"Matching HRTF and ATF grids, average grid deviation: {dev.value:.5g} deg")
+    out = (wL, wR)
+    if return_spectra:
+        out += (sp,)
+    if return_info:
+        out += (dict(meanGridDevDeg=dev.value),)
+    return out
+
+
+def _design_ema(fn_name, channels, hL, hR, hrirGridAziRad, hrirGridZenRad, micRadius, micGridAziRad, order,
+                fs, length, shDefinition, shFunction, chFunction, handle, config, return_spectra):
+    _check_sh_function(shFunction)
+    if chFunction is not None:
+        raise NotImplementedError("only the default chFunction (@getCH) is evaluated on the device")
+    h = handle or default_handle()
+    cfg = _config(h, config, shDefinition)
+    hL, hR, T, D, sets = _prep_hrirs(hL, hR)
+    if sets != 1:
+        raise ValueError("EMA designs are not batched")
+    az, ze, maz = _vec(hrirGridAziRad), _vec(hrirGridZenRad), _vec(micGridAziRad)
+    Mc = channels(int(order))
+    nfft = min(cfg.nfft_max_len, 2 * int(length))
+    K = nfft // 2 + 1
+    odt = np.complex128 if cfg.basis == 1 else np.float64
+    wL = np.zeros((int(length), Mc), dtype=odt, order="F")
+    wR = np.zeros((int(length), Mc), dtype=odt, order="F")
+    sp = np.zeros((K, Mc, 2), dtype=np.complex128, order="F") if return_spectra else None
+    h.check(getattr(h.lib, fn_name)(h.ptr, C.byref(cfg), _p(hL), _p(hR), T, D, _p(az), _p(ze), float(micRadius),
+                                    _p(maz), maz.size, int(order), float(fs), int(length), _p(wL), _p(wR),
+                                    _p(sp)))
+    return (wL, wR, sp) if return_spectra else (wL, wR)
+
+
+def getEMagLsFiltersEMAinCH(hL, hR, hrirGridAziRad, hrirGridZenRad, micRadius, micGridAziRad, order, fs, len,
+                            shDefinition="real", shFunction=None, chFunction=None, *, handle=None, config=None,
+                            return_spectra=False):
+    """lib/getEMagLsFiltersEMAinCH.m:1-2 -> filters [len, 2*order+1]."""
+    return _design_ema("emagls_design_ema_ch", lambda N: 2 * N + 1, hL, hR, hrirGridAziRad, hrirGridZenRad,
+                       micRadius, micGridAziRad, order, fs, len, shDefinition, shFunction, chFunction, handle,
+                       config, return_spectra)
+
+
+def getEMagLsFiltersEMAinSH(hL, hR, hrirGridAziRad, hrirGridZenRad, micRadius, micGridAziRad, order, fs, len,
+                            shDefinition="real", shFunction=None, chFunction=None, *, handle=None, config=None,
+                            return_spectra=False):
+    """lib/getEMagLsFiltersEMAinSH.m:1-2 -> filters [len, (order+1)^2]."""
+    return _design_ema("emagls_design_ema_sh", lambda N: (N + 1) ** 2, hL, hR, hrirGridAziRad, hrirGridZenRad,
+                       micRadius, micGridAziRad, order, fs, len, shDefinition, shFunction, chFunction, handle,
+                       config, return_spectra)
+
+
+def getSMAIRMatrix(params: dict, *, handle=None):
+    """[smairMat, params] = getSMAIRMatrix(params)  -- dependencies/getSMAIRMatrix.m:1.
+
+    ``params`` is a dict with the reference's field names; defaults follow getSMAIRMatrix.m:30-84.
+    Returns ``(smairMat [rows, S, K] complex, params_with_defaults)``.
+    """
+    p = dict(params)
+    if "smaDesignAziZenRad" not in p:
+        raise ValueError("default mic layout needs des.3.32.7.txt, which the reference does not ship")
+    p.setdefault("order", 4)
+    p.setdefault("fs", 48000)
+    p.setdefault("smaRadius", 0.042)
+    p.setdefault("arrayType", "rigid")
+    p.setdefault("radialFilter", "regul")
+    p.setdefault("sourceDist", 2)
+    p.setdefault("dirCoeff", 0)
+    p.setdefault("waveModel", "planeWave")
+    p.setdefault("noiseGainDb", 20)
+    p.setdefault("zStyleMaxRe", 1)
+    p.setdefault("sourcePosCart", np.array([p["sourceDist"], 0.0, 0.0]))
+    p.setdefault("oversamplingFactor", 4)
+    p.setdefault("irLen", 2048)
+    p.setdefault("returnRawMicSigs", False)
+    p.setdefault("shDefinition", "real")
+    p["sourceDist"] = float(np.linalg.norm(p["sourcePosCart"]))
+    _check_sh_function(p.get("shFunction"))
+    if str(p["radialFilter"]).lower() != "none" and not p["returnRawMicSigs"]:
+        raise NotImplementedError("Unkown radialFilter on the device path: only 'none' is built "
+                                  "(getRadialFilter is a 'next' row, SURVEY.md 8(f))")
+    if p["arrayType"] not in ("rigid", "open"):
+        raise ValueError("Wrong array type")
+    h = handle or default_handle()
+    cfg = _config(h, None, p["shDefinition"])
+    cfg.array_type = 0 if p["arrayType"] == "rigid" else 1
+    nfft = int(p["oversamplingFactor"] * p["irLen"])
+    assert nfft % 2 == 0
+    mics = np.asarray(p["smaDesignAziZenRad"], dtype=np.float64).reshape(-1, 2)
+    maz, mze = _vec(mics[:, 0]), _vec(mics[:, 1])
+    simN = C.c_int(0)
+    raw = 1 if p["returnRawMicSigs"] else 0
+    h.check(h.lib.emagls_smair_matrix(h.ptr, C.byref(cfg), _p(maz), _p(mze), maz.size, int(p["order"]),
+                                      float(p["fs"]), float(p["smaRadius"]), nfft, raw, None, C.byref(simN)))
+    S = (simN.value + 1) ** 2
+    rows = maz.size if raw else (int(p["order"]) + 1) ** 2
+    K = nfft // 2 + 1
+    out = np.zeros((rows, S, K), dtype=np.complex128, order="F")
+    h.check(h.lib.emagls_smair_matrix(h.ptr, C.byref(cfg), _p(maz), _p(mze), maz.size, int(p["order"]),
+                                      float(p["fs"]), float(p["smaRadius"]), nfft, raw, _p(out), C.byref(simN)))
+    return out, p
+
+
+def binauralDecode(inp, inFs, decodingFilterLeft, decodingFilterRight, decodingFilterFs, compensateDelay=False,
+                   signal=None, signalFs=None, horRotAngleRad=None, *, handle=None):
+    """binauralOut = binauralDecode(in, inFs, decL, decR, decFs[, compensateDelay, ...])
+    -- dependencies/binauralDecode.m:1-2."""
+    if decodingFilterFs != inFs or (signal is not None and signalFs is not None and signalFs != inFs):
+        raise NotImplementedError("binauralDecode: resampling is outside the device path")
+    if horRotAngleRad is not None and horRotAngleRad != 0:
+        raise NotImplementedError("rotateHOA_N3D is not vendored by the reference (binauralDecode.m:26-30)")
+    if signal is not None:
+        raise NotImplementedError("mono-signal convolution (binauralDecode.m:45-48) is outside the device path")
+    h = handle or default_handle()
+    x = _f(inp)
+    wL, wR = _f(decodingFilterLeft), _f(decodingFilterRight)
+    if x.ndim != 2 or wL.shape != wR.shape or wL.shape[1] != x.shape[1]:
+        raise ValueError("size mismatch between input channels and decoding filters")
+    n, ch = x.shape
+    ln = wL.shape[0]
+    rows = n - (ln // 2 - 1) if compensateDelay else n
+    out = np.zeros((rows, 2), order="F")
+    h.check(h.lib.emagls_binaural_decode(h.ptr, _p(x), n, ch, _p(wL), _p(wR), ln, 1 if compensateDelay else 0,
+                                         _p(out)))
+    return out
+
+
+# ---- building blocks (each mirrors one reference function) -------------------------------------
+def getSH(N, dirs, basisType="real", *, handle=None):
+    """Y_N = getSH(N, [azi zen], basisType) -- dependencies/Spherical-Harmonic-Transform/getSH.m:1."""
+    h = handle or default_handle()
+    dirs = np.asarray(dirs, dtype=np.float64).reshape(-1, 2)
+    az, ze = _vec(dirs[:, 0]), _vec(dirs[:, 1])
+    S = (int(N) + 1) ** 2
+    b = _basis(basisType)
+    out = np.zeros((az.size, S), dtype=np.complex128 if b else np.float64, order="F")
+    h.check(h.lib.emagls_get_sh(h.ptr, int(N), _p(az), _p(ze), az.size, b, _p(out)))
+    return out
+
+
+def sphModalCoeffs(N, kr, arrayType="rigid", dirCoeff=0.0, *, handle=None):
+    """b_N = sphModalCoeffs(N, kr, arrayType) -- dependencies/Array-Response-Simulator/sphModalCoeffs.m:1."""
+    if arrayType not in ("rigid", "open"):
+        raise ValueError("Wrong array type")
+    h = handle or default_handle()
+    kr = _vec(kr)
+    out = np.zeros((kr.size, int(N) + 1), dtype=np.complex128, order="F")
+    h.check(h.lib.emagls_sph_modal_coeffs(h.ptr, int(N), _p(kr), kr.size, 0 if arrayType == "rigid" else 1,
+                                          _p(out)))
+    return out
+
+
+def regularizedApply(pwGrid, targets, svd_regul=0.01, *, handle=None):
+    """targets * Y_reg_inv with Y_reg_inv from lib/getEMagLs2Filters.m:87-89 (one bin)."""
+    h = handle or default_handle()
+    pw = np.asfortranarray(np.asarray(pwGrid, dtype=np.complex128))
+    t = np.asfortranarray(np.atleast_2d(np.asarray(targets, dtype=np.complex128)))
+    Mc, D = pw.shape
+    out = np.zeros((t.shape[0], Mc), dtype=np.complex128, order="F")
+    h.check(h.lib.emagls_regularized_apply(h.ptr, _p(pw), Mc, D, _p(t), t.shape[0], float(svd_regul), _p(out)))
+    return out

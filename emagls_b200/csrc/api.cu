@@ -1,0 +1,324 @@
+// C ABI of libemagls_cuda (see include/emagls_cuda.h).
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "engine.h"
+#include "special.cuh"
+
+using namespace emagls;
+
+extern "C" {
+
+int emagls_create(int device, emagls_handle* out) {
+  if (!out) return EMAGLS_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return EMAGLS_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return EMAGLS_ERR_CUDA;
+  emagls_ctx* h = new emagls_ctx();
+  h->device = device;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return EMAGLS_ERR_CUDA;
+  }
+  // keep freed scratch in the stream-ordered pool between calls
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  *out = h;
+  return EMAGLS_OK;
+}
+
+int emagls_destroy(emagls_handle h) {
+  if (!h) return EMAGLS_ERR_INVALID;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return EMAGLS_OK;
+}
+
+const char* emagls_last_error(emagls_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+void emagls_config_default(emagls_config* cfg) {
+  if (!cfg) return;
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->nfft_max_len = 2048;    // lib/getEMagLs2Filters.m:35
+  cfg->f_cut_min = 1e3;        // :36
+  cfg->svd_regul = 0.01;       // :39
+  cfg->speed_of_sound = 343.0; // getSMAIRMatrix.m:86
+  cfg->array_type = EMAGLS_ARRAY_RIGID;
+  cfg->basis = EMAGLS_BASIS_REAL;
+}
+
+long long emagls_launch_count(emagls_handle h) { return h ? h->launches : 0; }
+
+int emagls_profile_enable(emagls_handle h, int on) {
+  if (!h) return EMAGLS_ERR_INVALID;
+  h->profile = on != 0;
+  return EMAGLS_OK;
+}
+
+static void profile_collect(emagls_ctx* h) {
+  if (h->spans.empty()) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (auto& s : h->spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
+      h->prof_ms[s.cls] += ms;
+      h->prof_n[s.cls] += 1;
+    }
+  }
+  h->spans.clear();
+  h->ev_used = 0;
+}
+
+int emagls_profile_read(emagls_handle h, double* ms, long long* counts, int reset) {
+  if (!h || !ms || !counts) return EMAGLS_ERR_INVALID;
+  profile_collect(h);
+  for (int i = 0; i < EM_PROF_NUM; ++i) { ms[i] = h->prof_ms[i]; counts[i] = h->prof_n[i]; }
+  if (reset)
+    for (int i = 0; i < EM_PROF_NUM; ++i) { h->prof_ms[i] = 0; h->prof_n[i] = 0; }
+  return EM_PROF_NUM;
+}
+void* emagls_stream(emagls_handle h) { return h ? (void*)h->stream : nullptr; }
+
+// ------------------------------------------------------------------------------------------
+static void fill_args(DesignArgs& a, Variant v, const double* hL, const double* hR, int T, int D,
+                      const double* ga, const double* gz, double r, const double* ma, const double* mz,
+                      int M, int order, double fs, int len, int ns, int no, const double* rot,
+                      double* wL, double* wR, double* sp) {
+  a.variant = v; a.hL = hL; a.hR = hR; a.T = T; a.D = D; a.grid_azi = ga; a.grid_zen = gz;
+  a.mic_radius = r; a.mic_azi = ma; a.mic_zen = mz; a.M = M; a.order = order; a.fs = fs; a.len = len;
+  a.num_sets = ns; a.num_orient = no; a.rotations = rot; a.wL = wL; a.wR = wR; a.spectra = sp;
+}
+
+static int design_host(emagls_handle h, const emagls_config* cfg, Variant v, const double* hL,
+                       const double* hR, int T, int D, const double* ga, const double* gz, double r,
+                       const double* ma, const double* mz, int M, int order, double fs, int len,
+                       int ns, int no, const double* rot, double* wL, double* wR, double* sp) {
+  return guarded(h, [&] {
+    EM_REQUIRE(cfg && hL && hR && ga && gz && ma && mz && wL && wR, "null argument");
+    EM_REQUIRE(T > 0 && D > 0 && M > 0 && ns > 0 && no > 0 && len > 0, "empty input");
+    cudaStream_t st = h->stream;
+    Arena ar(st);
+    const int Mc = (v == Variant::EMAGLS2) ? M : (order + 1) * (order + 1);
+    const int nfft = std::min(cfg->nfft_max_len, 2 * len);
+    const int K = nfft / 2 + 1;
+    const size_t P = (size_t)ns * no;
+    DesignArgs a;
+    double* d_wL = ar.get<double>((size_t)len * Mc * P);
+    double* d_wR = ar.get<double>((size_t)len * Mc * P);
+    double* d_sp = sp ? ar.get<double>((size_t)2 * K * Mc * P * 2) : nullptr;
+    fill_args(a, v, ar.upload(hL, (size_t)T * D * ns), ar.upload(hR, (size_t)T * D * ns), T, D,
+              ar.upload(ga, D), ar.upload(gz, D), r, ar.upload(ma, M), ar.upload(mz, M), M, order, fs, len,
+              ns, no, rot ? ar.upload(rot, (size_t)no * 9) : nullptr, d_wL, d_wR, d_sp);
+    design_factored(h, *cfg, a);
+    EM_CUDA(cudaMemcpyAsync(wL, d_wL, (size_t)len * Mc * P * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaMemcpyAsync(wR, d_wR, (size_t)len * Mc * P * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (sp) EM_CUDA(cudaMemcpyAsync(sp, d_sp, (size_t)2 * K * Mc * P * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+int emagls_design_emagls2(emagls_handle h, const emagls_config* cfg, const double* hL, const double* hR,
+                          int num_samples, int num_dirs, const double* grid_azi, const double* grid_zen,
+                          double mic_radius, const double* mic_azi, const double* mic_zen, int num_mics,
+                          int order, double fs, int len, int num_sets, int num_orient,
+                          const double* rotations, double* wL, double* wR, double* spectra) {
+  return design_host(h, cfg, Variant::EMAGLS2, hL, hR, num_samples, num_dirs, grid_azi, grid_zen, mic_radius,
+                     mic_azi, mic_zen, num_mics, order, fs, len, num_sets, num_orient, rotations, wL, wR, spectra);
+}
+
+int emagls_design_emagls2_dev(emagls_handle h, const emagls_config* cfg, const double* hL, const double* hR,
+                              int num_samples, int num_dirs, const double* grid_azi, const double* grid_zen,
+                              double mic_radius, const double* mic_azi, const double* mic_zen, int num_mics,
+                              int order, double fs, int len, int num_sets, int num_orient,
+                              const double* rotations, double* wL, double* wR, double* spectra) {
+  return guarded(h, [&] {
+    EM_REQUIRE(cfg && hL && hR && grid_azi && grid_zen && mic_azi && mic_zen && wL && wR, "null argument");
+    DesignArgs a;
+    fill_args(a, Variant::EMAGLS2, hL, hR, num_samples, num_dirs, grid_azi, grid_zen, mic_radius, mic_azi,
+              mic_zen, num_mics, order, fs, len, num_sets, num_orient, rotations, wL, wR, spectra);
+    design_factored(h, *cfg, a);
+  });
+}
+
+int emagls_design_emagls(emagls_handle h, const emagls_config* cfg, const double* hL, const double* hR,
+                         int num_samples, int num_dirs, const double* grid_azi, const double* grid_zen,
+                         double mic_radius, const double* mic_azi, const double* mic_zen, int num_mics,
+                         int order, double fs, int len, int num_sets, int num_orient,
+                         const double* rotations, double* wL, double* wR, double* spectra) {
+  return design_host(h, cfg, Variant::EMAGLS_SH, hL, hR, num_samples, num_dirs, grid_azi, grid_zen, mic_radius,
+                     mic_azi, mic_zen, num_mics, order, fs, len, num_sets, num_orient, rotations, wL, wR, spectra);
+}
+
+static int unsupported(emagls_handle h, const char* what) {
+  if (!h) return EMAGLS_ERR_INVALID;
+  h->err = std::string(what) + " is not built yet in this round";
+  return EMAGLS_ERR_UNSUPPORTED;
+}
+
+int emagls_design_magls(emagls_handle h, const emagls_config*, const double*, const double*, int, int,
+                        const double*, const double*, int, double, int, double*, double*, double*) {
+  return unsupported(h, "getMagLsFilters");
+}
+int emagls_design_ls(emagls_handle h, const emagls_config*, const double*, const double*, int, int,
+                     const double*, const double*, int, double*, double*) {
+  return unsupported(h, "getLsFilters");
+}
+int emagls_design_from_atf(emagls_handle h, const emagls_config*, const double*, const double*, int, int,
+                           const double*, const double*, int, int, int, const double*, double, int, double,
+                           double*, double*, double*, double*) {
+  return unsupported(h, "getEMagLsFiltersFromAtf");
+}
+int emagls_design_ema_ch(emagls_handle h, const emagls_config*, const double*, const double*, int, int,
+                         const double*, const double*, double, const double*, int, int, double, int,
+                         double*, double*, double*) {
+  return unsupported(h, "getEMagLsFiltersEMAinCH");
+}
+int emagls_design_ema_sh(emagls_handle h, const emagls_config*, const double*, const double*, int, int,
+                         const double*, const double*, double, const double*, int, int, double, int,
+                         double*, double*, double*) {
+  return unsupported(h, "getEMagLsFiltersEMAinSH");
+}
+
+// ------------------------------------------------------------------------------------------
+// getSMAIRMatrix (dependencies/getSMAIRMatrix.m:86-127) for radialFilter = 'none'
+// ------------------------------------------------------------------------------------------
+__global__ void smair_raw_kernel(const double* __restrict__ Ym, const cplx* __restrict__ bn, int M, int S,
+                                 int N, int K, cplx* __restrict__ out) {
+  // out[(k*S + s)*M + m] = Ym[m][s] * bn[k][ord(s)]
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)K * S * M) return;
+  int m = (int)(idx % M);
+  int s = (int)((idx / M) % S);
+  int k = (int)(idx / ((long long)M * S));
+  int ord = (int)sqrt((double)s);
+  while ((ord + 1) * (ord + 1) <= s) ++ord;
+  while (ord * ord > s) --ord;
+  cplx b = bn[(long long)k * (N + 1) + ord];
+  double y = Ym[(long long)m * S + s];
+  out[idx] = mk(y * b.x, y * b.y);
+}
+
+int emagls_smair_matrix(emagls_handle h, const emagls_config* cfg, const double* mic_azi,
+                        const double* mic_zen, int num_mics, int order, double fs, double sma_radius,
+                        int nfft, int return_raw_mic_sigs, double* out, int* sim_order_out) {
+  return guarded(h, [&] {
+    EM_REQUIRE(cfg && mic_azi && mic_zen && num_mics > 0, "null argument");
+    EM_REQUIRE(nfft > 0 && nfft % 2 == 0, "nfft must be even");  // getSMAIRMatrix.m:89
+    const int simN = std::max(order, (int)std::ceil(fs * M_PI * sma_radius / cfg->speed_of_sound));
+    if (sim_order_out) *sim_order_out = simN;
+    if (!out) return;
+    EM_REQUIRE(simN <= MAX_SH_ORDER, "simulation order too high");
+    if (!return_raw_mic_sigs)
+      throw Fail{EMAGLS_ERR_UNSUPPORTED, "SH-domain getSMAIRMatrix output is wired in a later step"};
+    cudaStream_t st = h->stream;
+    Arena ar(st);
+    const int S = (simN + 1) * (simN + 1), K = nfft / 2 + 1, M = num_mics;
+    std::vector<double> kr(K);
+    const double df = (fs / 2.0) / (double)(K - 1);
+    for (int k = 0; k < K; ++k) kr[k] = 2.0 * M_PI * ((double)k * df) / cfg->speed_of_sound * sma_radius;
+    cplx* bn = ar.get<cplx>((size_t)K * (simN + 1));
+    EM_CUDA(launch_modal(st, simN, ar.upload(kr.data(), K), K, cfg->array_type, -1.0, 1, bn, simN + 1, 1));
+    double* Ym = ar.get<double>((size_t)M * S);
+    EM_CUDA(launch_sh_mics(st, simN, ar.upload(mic_azi, M), ar.upload(mic_zen, M), M, nullptr, 1, Ym));
+    cplx* d_out = ar.get<cplx>((size_t)K * S * M);
+    long long total = (long long)K * S * M;
+    smair_raw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Ym, bn, M, S, simN, K, d_out);
+    EM_CUDA(cudaGetLastError());
+    h->launches += 3;
+    EM_CUDA(cudaMemcpyAsync(out, d_out, (size_t)total * sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+// ------------------------------------------------------------------------------------------
+// building blocks for parity tests
+// ------------------------------------------------------------------------------------------
+int emagls_get_sh(emagls_handle h, int order, const double* azi, const double* zen, int num_dirs, int basis,
+                  double* out) {
+  return guarded(h, [&] {
+    EM_REQUIRE(azi && zen && out && num_dirs > 0, "null argument");
+    EM_REQUIRE(order >= 0 && order <= MAX_SH_ORDER, "order out of range");
+    cudaStream_t st = h->stream;
+    Arena ar(st);
+    const size_t S = (size_t)(order + 1) * (order + 1);
+    const size_t n = S * num_dirs * (basis == EMAGLS_BASIS_COMPLEX ? 2 : 1);
+    double* d_out = ar.get<double>(n);
+    EM_CUDA(launch_sh_angles(st, order, ar.upload(azi, num_dirs), ar.upload(zen, num_dirs), num_dirs,
+                             basis == EMAGLS_BASIS_COMPLEX, d_out));
+    h->launches += 1;
+    EM_CUDA(cudaMemcpyAsync(out, d_out, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+int emagls_sph_modal_coeffs(emagls_handle h, int order, const double* kr, int num_kr, int array_type,
+                            double* out) {
+  return guarded(h, [&] {
+    EM_REQUIRE(kr && out && num_kr > 0, "null argument");
+    EM_REQUIRE(order >= 0 && order <= MAX_SH_ORDER, "order out of range");
+    cudaStream_t st = h->stream;
+    Arena ar(st);
+    cplx* d_out = ar.get<cplx>((size_t)num_kr * (order + 1));
+    // column-major [num_kr x (order+1)]
+    EM_CUDA(launch_modal(st, order, ar.upload(kr, num_kr), num_kr, array_type, 1.0, 0, d_out, 1, num_kr));
+    h->launches += 1;
+    EM_CUDA(cudaMemcpyAsync(out, d_out, (size_t)num_kr * (order + 1) * sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+int emagls_regularized_apply(emagls_handle h, const double* pw, int num_ch, int num_dirs,
+                             const double* targets, int num_t, double svd_regul, double* out) {
+  return guarded(h, [&] {
+    EM_REQUIRE(pw && targets && out, "null argument");
+    EM_REQUIRE(num_ch > 0 && num_ch <= 64 && num_dirs >= num_ch && num_t > 0, "bad shape");
+    cudaStream_t st = h->stream;
+    Arena ar(st);
+    const int Mc = num_ch, D = num_dirs;
+    const BlockPlan bp = make_block_plan(D, Mc);
+    // pw is [Mc x D] column-major == rows of pwGrid.' with the channel index contiguous
+    cplx* At = reinterpret_cast<cplx*>(ar.upload(pw, (size_t)2 * Mc * D));
+    OperatorSet ops;
+    ops.v_stride = (long long)Mc * D; ops.tau_stride = (long long)bp.nblk * bp.MC;
+    ops.rc_stride = ops.pb_stride = (long long)Mc * Mc;
+    ops.V = ar.get<cplx>(ops.v_stride); ops.tau = ar.get<cplx>(ops.tau_stride);
+    ops.Rc = ar.get<cplx>(ops.rc_stride); ops.Pb = ar.get<cplx>(ops.pb_stride);
+    ops.info = ar.get<int>(1);
+    RowSource src{};
+    src.At = At; src.at_bin_stride = 0; src.at_prob_stride = 0;
+    EM_CUDA(launch_factor(st, bp, src, ops, 1, 0, 1, svd_regul));
+    h->launches += 1;
+    // targets [num_t x D] complex column-major -> pairs of rows (re | im) of length D
+    const int npair = (num_t + 1) / 2;
+    std::vector<double> rows((size_t)npair * 4 * D, 0.0);
+    for (int t = 0; t < num_t; ++t)
+      for (int d = 0; d < D; ++d) {
+        size_t base = ((size_t)(t / 2) * 2 + (t & 1)) * 2 * D;
+        rows[base + d] = targets[2 * ((size_t)d * num_t + t)];
+        rows[base + D + d] = targets[2 * ((size_t)d * num_t + t) + 1];
+      }
+    double* d_rows = ar.upload(rows.data(), rows.size());
+    cplx* W = ar.get<cplx>((size_t)2 * npair * Mc);  // [ear][pair][Mc][K=1]
+    EM_CUDA(launch_chain_bwd(st, bp, ops, 0, 1, d_rows, 0, 0, 0, 1, 1, W, (long long)npair * Mc, 1, 0, 0, npair));
+    h->launches += 1;
+    std::vector<cplx> Wh((size_t)2 * npair * Mc);
+    EM_CUDA(cudaMemcpyAsync(Wh.data(), W, Wh.size() * sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaStreamSynchronize(st));
+    for (int t = 0; t < num_t; ++t)
+      for (int m = 0; m < Mc; ++m) {
+        cplx v = Wh[((size_t)(t & 1) * npair + t / 2) * Mc + m];
+        out[2 * ((size_t)m * num_t + t)] = v.x;
+        out[2 * ((size_t)m * num_t + t) + 1] = v.y;
+      }
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,154 @@
+// Host-side engine state shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "../../include/emagls_cuda.h"
+#include "kernels.h"
+
+// kernel classes for the built-in event profiler (emagls_profile_*)
+enum EmProfClass {
+  EM_PROF_SETUP = 0,      // grid QR, SH, b_n, E rows, HRIR preparation
+  EM_PROF_FACTOR,         // per-(orientation, bin) TSQR + clipped inverse
+  EM_PROF_CHAIN_FWD,      // Q_C * R_C * W_prev
+  EM_PROF_GEMM_FWD,       // y = c Q^T + phase epilogue
+  EM_PROF_GEMM_BWD,       // t Q
+  EM_PROF_CHAIN_BWD,      // (Q_C^H tq) Pb
+  EM_PROF_TAIL,           // ifft/shift/crop/fade GEMM
+  EM_PROF_RENDER_MAC,     // spectral multiply-accumulate of the render
+  EM_PROF_RENDER_FFT,     // cuFFT transforms of the render
+  EM_PROF_RENDER_STAGE,   // staging copies of the render
+  EM_PROF_NUM
+};
+
+struct emagls_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  long long launches = 0;
+  // profiler
+  bool profile = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct Span { int cls; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  double prof_ms[EM_PROF_NUM] = {0};
+  long long prof_n[EM_PROF_NUM] = {0};
+};
+
+namespace emagls {
+
+struct Fail {
+  int code; std::string msg;
+};
+
+#define EM_CUDA(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      throw ::emagls::Fail{EMAGLS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)}; \
+  } while (0)
+
+#define EM_REQUIRE(cond, msg)                                                   \
+  do {                                                                          \
+    if (!(cond)) throw ::emagls::Fail{EMAGLS_ERR_INVALID, std::string(msg)};    \
+  } while (0)
+
+// Stream-ordered scratch arena: everything allocated through it is released when it dies.
+class Arena {
+ public:
+  explicit Arena(cudaStream_t st) : st_(st) {}
+  ~Arena() {
+    for (void* p : ptrs_) cudaFreeAsync(p, st_);
+  }
+  template <class T>
+  T* get(size_t n) {
+    void* p = nullptr;
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMallocAsync(&p, n * sizeof(T), st_);
+    if (e != cudaSuccess)
+      throw Fail{EMAGLS_ERR_CUDA, std::string("cudaMallocAsync(") + std::to_string(n * sizeof(T)) + " B): " +
+                                      cudaGetErrorString(e)};
+    ptrs_.push_back(p);
+    return static_cast<T*>(p);
+  }
+  template <class T>
+  T* upload(const T* host, size_t n) {
+    T* d = get<T>(n);
+    cudaError_t e = cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, st_);
+    if (e != cudaSuccess) throw Fail{EMAGLS_ERR_CUDA, std::string("H2D: ") + cudaGetErrorString(e)};
+    return d;
+  }
+
+ private:
+  cudaStream_t st_;
+  std::vector<void*> ptrs_;
+};
+
+template <class F>
+int guarded(emagls_ctx* h, F&& f) {
+  if (!h) return EMAGLS_ERR_INVALID;
+  try {
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) throw Fail{EMAGLS_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e)};
+    f();
+    return EMAGLS_OK;
+  } catch (const Fail& x) {
+    h->err = x.msg;
+    cudaGetLastError();
+    return x.code;
+  } catch (const std::exception& x) {
+    h->err = x.what();
+    return EMAGLS_ERR_INVALID;
+  }
+}
+
+// RAII span: records a CUDA-event pair around the launches issued while it is alive.
+class ProfSpan {
+ public:
+  ProfSpan(emagls_ctx* h, int cls) : h_(h), cls_(cls) {
+    if (!h_->profile) return;
+    a_ = next();
+    cudaEventRecord(a_, h_->stream);
+  }
+  ~ProfSpan() {
+    if (!h_->profile) return;
+    cudaEvent_t b = next();
+    cudaEventRecord(b, h_->stream);
+    h_->spans.push_back({cls_, a_, b});
+  }
+
+ private:
+  cudaEvent_t next() {
+    if (h_->ev_used == h_->ev_pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      h_->ev_pool.push_back(e);
+    }
+    return h_->ev_pool[h_->ev_used++];
+  }
+  emagls_ctx* h_;
+  int cls_;
+  cudaEvent_t a_ = nullptr;
+};
+
+// ---- design engine (engine.cu) ---------------------------------------------------------------
+enum class Variant { EMAGLS2, EMAGLS_SH };
+
+struct DesignArgs {
+  Variant variant;
+  const double *hL, *hR;  // device [T x D x sets]
+  int T, D;
+  const double *grid_azi, *grid_zen;  // device [D]
+  double mic_radius;
+  const double *mic_azi, *mic_zen;  // device [M]
+  int M, order;
+  double fs;
+  int len, num_sets, num_orient;
+  const double* rotations;  // device [B x 9] or nullptr
+  double *wL, *wR;          // device [len x Mc x P]
+  double* spectra;          // device or nullptr: complex [K x Mc x P x 2]
+};
+void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& a);
+
+}  // namespace emagls

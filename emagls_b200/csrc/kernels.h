@@ -1,0 +1,79 @@
+// Host-callable launchers of the hand-written kernels (one translation unit per group).
+#pragma once
+#include <cuda_runtime.h>
+#include "common.cuh"
+
+namespace emagls {
+
+// ---------------------------------------------------------------- setup_kernels.cu
+// getSH on a direction list given as angles.  out: [(N+1)^2][D] (D contiguous) real or complex.
+cudaError_t launch_sh_angles(cudaStream_t st, int N, const double* azi, const double* zen, int D,
+                             int complex_basis, double* out);
+// getSH('real') at rotated microphone positions: for orientation o and mic m the direction is
+// R_o^T * u_m.  out: [B][M][S] (S contiguous).  rot == nullptr -> identity, B = 1 and the
+// angles are used exactly as given (bit-compatible with launch_sh_angles).
+cudaError_t launch_sh_mics(cudaStream_t st, int N, const double* mic_azi, const double* mic_zen,
+                           int M, const double* rot, int B, double* out);
+// out[o][c][s] = sum_m L[c][m] * Y[o][m][s]   (L row-major [Mc][M])
+cudaError_t launch_left_mul(cudaStream_t st, const double* L, int Mc, int M, const double* Y,
+                            int B, int S, double* out);
+// b_n table: out[k*(N+1)+n] = sign * b_n(kr_k); nyquist_real: take real part of the last row.
+cudaError_t launch_modal(cudaStream_t st, int N, const double* kr, int nk, int array_type,
+                         double sign, int nyquist_real, cplx* out, long long stride_k,
+                         long long stride_n);
+// Householder QR of the column-major real matrix A [S cols][D rows]: after the call
+// Q [S][D] holds the thin orthonormal factor and R [S][S] (row-major, upper) the triangle.
+// work: D*S doubles (reflectors) + 2*S doubles.
+cudaError_t launch_householder_qr(cudaStream_t st, double* A, int D, int S, double* Q, double* R,
+                                  double* work, long long* launches);
+// E rows for the factored steering model:  E[o][rowoff[i] + (n-ord(i))*Mc + c] =
+//   sum_{j in order-n block} R[i][j] * Ym[o][c][j]
+cudaError_t launch_build_E(cudaStream_t st, const double* R, int S, int N, const double* Ym,
+                           int Mc, int B, const int* rowoff, const int* roword, long long Etot,
+                           double* E);
+// HRIR preparation
+cudaError_t launch_colsum(cudaStream_t st, const double* h, int T, int D, double* partial,
+                          int nchunk, double* out);
+cudaError_t launch_grpdelay(cudaStream_t st, const double* s, int T, int K, double fs, double* gd);
+// DFT twiddles [2K][T]: row (k,c) holds Re/Im of exp(-2 pi i k t / nfft)
+cudaError_t launch_dft_twiddle(cudaStream_t st, int K, int T, int nfft, double* tw);
+// absH[k][d] = | Hd[d][(k,*)] |
+cudaError_t launch_abs_transpose(cudaStream_t st, const double* Hd, int D, int K, double* absH);
+// tail twiddles [len][2K] for one ear: ifft + sub-sample delay + crop + fade folded into one matrix
+cudaError_t launch_tail_twiddle(cudaStream_t st, int K, int nfft, int len, double delay, double* tw);
+
+// ---------------------------------------------------------------- solver_kernels.cu
+struct RowSource {
+  // factored model: C[i][c] = sum_{n >= ord(i)} bn[k][n] * E[o][rowoff[i] + (n-ord(i))*Mc + c]
+  const double* E; long long Etot; const int* rowoff; const int* roword; const cplx* bn; int N;
+  // generic: rows read from At[(bin)][i][c] (interleaved complex, c contiguous);
+  // bin_shared != 0 -> the same matrix for every problem of a bin
+  const cplx* At; long long at_bin_stride; long long at_prob_stride;
+};
+struct OperatorSet {       // per-(problem, bin-slot) outputs of the factorisation kernel
+  cplx* V;    long long v_stride;    // [Mc][S] column-major (ld = S)
+  cplx* tau;  long long tau_stride;  // [nblk][MC]
+  cplx* Rc;   long long rc_stride;   // [Mc][Mc] column-major, upper triangular
+  cplx* Pb;   long long pb_stride;   // [Mc][Mc] row-major: W = g * Pb
+  int* info;                         // [problem*G + slot]: jacobi sweeps (0 = fast path)
+};
+struct BlockPlan { int S, Mc, MC, RB, R0, nblk; };
+BlockPlan make_block_plan(int S, int Mc);
+size_t factor_smem_bytes(const BlockPlan& bp);
+cudaError_t launch_factor(cudaStream_t st, const BlockPlan& bp, const RowSource& src,
+                          const OperatorSet& ops, int num_prob, int kbase, int G, double regul);
+// forward: Cv[(p*2+e)*2+c][s] = Q_C * (R_C * W_prev)   (rows S doubles apart)
+cudaError_t launch_chain_fwd(cudaStream_t st, const BlockPlan& bp, const OperatorSet& ops, int slot,
+                             int G, int ops_mod, const cplx* Wsp, long long w_ear_stride, int K,
+                             int kprev, int num_prob, double* Cv);
+// backward: W[k] = (Q_C^H tq) * Pb; tq rows (p*2+e)*2+c, or shared per set when tq_shared != 0
+cudaError_t launch_chain_bwd(cudaStream_t st, const BlockPlan& bp, const OperatorSet& ops, int slot,
+                             int G, const double* tq, long long tq_set_stride,
+                             long long tq_ear_stride, int tq_shared, int orient_per_set, int ops_mod,
+                             cplx* Wsp, long long w_ear_stride, int K, int k, int dc_fix, int num_prob);
+// generic-path phase step on rows: t = absH * y/|y|
+cudaError_t launch_phase_rows(cudaStream_t st, const double* Y, double* T, int num_prob, int D,
+                              const double* absH, long long abs_set_stride, long long abs_ear_stride,
+                              int orient_per_set, int nyquist);
+
+}  // namespace emagls

@@ -1,0 +1,402 @@
+// One-time (per grid / per HRTF set / per orientation) kernels of the design path.
+#include "kernels.h"
+#include "special.cuh"
+
+namespace emagls {
+
+// ---------------------------------------------------------------------------------------------
+// getSH on a list of directions (dependencies/Spherical-Harmonic-Transform/getSH.m:17-89)
+// ---------------------------------------------------------------------------------------------
+__global__ void sh_angles_kernel(int N, const double* __restrict__ azi, const double* __restrict__ zen,
+                                 int D, int complex_basis, double* __restrict__ out) {
+  int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  double cm[MAX_SH_ORDER + 1], sm[MAX_SH_ORDER + 1];
+  const double a = azi[d];
+  for (int m = 0; m <= N; ++m) sincos((double)m * a, &sm[m], &cm[m]);  // cos(m*azi) as in getSH.m:67-68
+  const double x = cos(zen[d]);
+  if (complex_basis) complex_sh_dir(N, x, cm, sm, reinterpret_cast<cplx*>(out) + d, D);
+  else real_sh_dir(N, x, cm, sm, out + d, D);
+}
+
+cudaError_t launch_sh_angles(cudaStream_t st, int N, const double* azi, const double* zen, int D,
+                             int complex_basis, double* out) {
+  sh_angles_kernel<<<(D + 63) / 64, 64, 0, st>>>(N, azi, zen, D, complex_basis, out);
+  return cudaGetLastError();
+}
+
+// Real SH at the microphone positions seen from a rotated head: direction R_o^T u_m.
+__global__ void sh_mics_kernel(int N, const double* __restrict__ mic_azi, const double* __restrict__ mic_zen,
+                               int M, const double* __restrict__ rot, int B, double* __restrict__ out) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * M) return;
+  int o = idx / M, m = idx % M;
+  const int S = (N + 1) * (N + 1);
+  double cm[MAX_SH_ORDER + 1], sm[MAX_SH_ORDER + 1];
+  double a = mic_azi[m], x;
+  if (rot == nullptr) {
+    x = cos(mic_zen[m]);
+  } else {
+    double sz, cz, sa, ca;
+    sincos(mic_zen[m], &sz, &cz);
+    sincos(a, &sa, &ca);
+    const double u[3] = {sz * ca, sz * sa, cz};
+    const double* R = rot + (long long)o * 9;
+    // v = R^T u
+    double v0 = R[0] * u[0] + R[3] * u[1] + R[6] * u[2];
+    double v1 = R[1] * u[0] + R[4] * u[1] + R[7] * u[2];
+    double v2 = R[2] * u[0] + R[5] * u[1] + R[8] * u[2];
+    double nrm = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+    x = v2 / nrm;
+    a = atan2(v1, v0);
+  }
+  for (int q = 0; q <= N; ++q) sincos((double)q * a, &sm[q], &cm[q]);
+  real_sh_dir(N, x, cm, sm, out + (long long)idx * S, 1);
+}
+
+cudaError_t launch_sh_mics(cudaStream_t st, int N, const double* mic_azi, const double* mic_zen,
+                           int M, const double* rot, int B, double* out) {
+  int total = B * M;
+  sh_mics_kernel<<<(total + 63) / 64, 64, 0, st>>>(N, mic_azi, mic_zen, M, rot, B, out);
+  return cudaGetLastError();
+}
+
+__global__ void left_mul_kernel(const double* __restrict__ L, int Mc, int M, const double* __restrict__ Y,
+                                int B, int S, double* __restrict__ out) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * Mc * S;
+  if (idx >= total) return;
+  int s = (int)(idx % S);
+  int c = (int)((idx / S) % Mc);
+  int o = (int)(idx / ((long long)S * Mc));
+  const double* y = Y + (long long)o * M * S + s;
+  double acc = 0.0;
+  for (int m = 0; m < M; ++m) acc = fma(L[c * M + m], y[(long long)m * S], acc);
+  out[idx] = acc;
+}
+
+cudaError_t launch_left_mul(cudaStream_t st, const double* L, int Mc, int M, const double* Y,
+                            int B, int S, double* out) {
+  long long total = (long long)B * Mc * S;
+  left_mul_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(L, Mc, M, Y, B, S, out);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// modal coefficients (sphModalCoeffs.m:25-59), bnAll = -sphModalCoeffs(...) (getSMAIRMatrix.m:107)
+// ---------------------------------------------------------------------------------------------
+__global__ void modal_kernel(int N, const double* __restrict__ kr, int nk, int array_type, double sign,
+                             int nyquist_real, cplx* __restrict__ out, long long stride_k,
+                             long long stride_n) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nk) return;
+  cplx b[MAX_SH_ORDER + 2];
+  modal_coeffs(N, kr[k], array_type, b);
+  for (int n = 0; n <= N; ++n) {
+    cplx v = mk(sign * b[n].x, sign * b[n].y);
+    if (nyquist_real && k == nk - 1) v.y = 0.0;
+    out[(long long)k * stride_k + (long long)n * stride_n] = v;
+  }
+}
+
+cudaError_t launch_modal(cudaStream_t st, int N, const double* kr, int nk, int array_type,
+                         double sign, int nyquist_real, cplx* out, long long stride_k,
+                         long long stride_n) {
+  modal_kernel<<<(nk + 63) / 64, 64, 0, st>>>(N, kr, nk, array_type, sign, nyquist_real, out, stride_k, stride_n);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Householder QR of the real D x S matrix of HRIR-grid harmonics (one-time per grid)
+// ---------------------------------------------------------------------------------------------
+constexpr int HQ_THREADS = 256, HQ_COLS = 8;
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
+}
+
+// step j of the factorisation: every CTA rebuilds reflector j from column j (read-only in this
+// launch), CTA 0 records it, and each warp updates one trailing column.
+__global__ void hh_factor_step(double* __restrict__ A, int D, int S, int j, double* __restrict__ Vst,
+                               double* __restrict__ tau, double* __restrict__ rdiag) {
+  extern __shared__ double vsh[];  // D doubles + 8
+  double* red = vsh + D;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* colj = A + (long long)j * D;
+  double xn = 0.0;
+  for (int i = j + 1 + tid; i < D; i += HQ_THREADS) { double v = colj[i]; vsh[i] = v; xn = fma(v, v, xn); }
+  xn = warp_sum_d(xn);
+  if (lane == 0) red[warp] = xn;
+  __syncthreads();
+  xn = 0.0;
+  for (int w = 0; w < HQ_THREADS / 32; ++w) xn += red[w];
+  const double alpha = colj[j];
+  double beta, t, scale;
+  if (xn == 0.0) { beta = alpha; t = 0.0; scale = 0.0; }
+  else {
+    beta = -copysign(sqrt(alpha * alpha + xn), alpha);
+    t = (beta - alpha) / beta;
+    scale = 1.0 / (alpha - beta);
+  }
+  for (int i = j + 1 + tid; i < D; i += HQ_THREADS) vsh[i] *= scale;
+  if (tid == 0) vsh[j] = 1.0;
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    for (int i = tid; i < D; i += HQ_THREADS) Vst[(long long)j * D + i] = (i >= j) ? vsh[i] : 0.0;
+    if (tid == 0) { tau[j] = t; rdiag[j] = beta; }
+  }
+  if (t == 0.0) return;
+  const int c = j + 1 + blockIdx.x * HQ_COLS + warp;
+  if (c >= S) return;
+  double* a = A + (long long)c * D;
+  double w = 0.0;
+  for (int i = j + lane; i < D; i += 32) w = fma(vsh[i], a[i], w);
+  w = warp_sum_d(w) * t;
+  for (int i = j + lane; i < D; i += 32) a[i] = fma(-w, vsh[i], a[i]);
+}
+
+// backward accumulation of the thin Q: Q = H_0 ... H_{S-1} [I; 0], step j touches columns >= j
+__global__ void hh_formq_step(double* __restrict__ Q, int D, int S, int j, const double* __restrict__ Vst,
+                              const double* __restrict__ tau) {
+  extern __shared__ double vsh[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double t = tau[j];
+  if (t == 0.0) return;
+  for (int i = j + tid; i < D; i += HQ_THREADS) vsh[i] = Vst[(long long)j * D + i];
+  __syncthreads();
+  const int c = j + blockIdx.x * HQ_COLS + warp;
+  if (c >= S) return;
+  double* q = Q + (long long)c * D;
+  double w = 0.0;
+  for (int i = j + lane; i < D; i += 32) w = fma(vsh[i], q[i], w);
+  w = warp_sum_d(w) * t;
+  for (int i = j + lane; i < D; i += 32) q[i] = fma(-w, vsh[i], q[i]);
+}
+
+__global__ void hh_init_q(double* __restrict__ Q, int D, int S) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)D * S) return;
+  int c = (int)(idx / D), i = (int)(idx % D);
+  Q[idx] = (i == c) ? 1.0 : 0.0;
+}
+
+__global__ void hh_extract_r(const double* __restrict__ A, int D, int S, const double* __restrict__ rdiag,
+                             double* __restrict__ R) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S * S) return;
+  int i = idx / S, jc = idx % S;
+  double v = 0.0;
+  if (i < jc) v = A[(long long)jc * D + i];
+  else if (i == jc) v = rdiag[i];
+  R[idx] = v;
+}
+
+cudaError_t launch_householder_qr(cudaStream_t st, double* A, int D, int S, double* Q, double* R,
+                                  double* work, long long* launches) {
+  double* Vst = work;
+  double* tau = work + (long long)D * S;
+  double* rdiag = tau + S;
+  size_t smem = (size_t)(D + 8) * sizeof(double);
+  static size_t set_to = 0;
+  if (smem > 48 * 1024 && smem > set_to) {
+    cudaError_t e = cudaFuncSetAttribute(hh_factor_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(hh_formq_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    set_to = smem;
+  }
+  long long n = 0;
+  for (int j = 0; j < S; ++j) {
+    int trailing = S - 1 - j;
+    int grid = (trailing + HQ_COLS - 1) / HQ_COLS;
+    if (grid < 1) grid = 1;
+    hh_factor_step<<<grid, HQ_THREADS, smem, st>>>(A, D, S, j, Vst, tau, rdiag);
+    ++n;
+  }
+  hh_extract_r<<<(S * S + 255) / 256, 256, 0, st>>>(A, D, S, rdiag, R);
+  hh_init_q<<<(unsigned)(((long long)D * S + 255) / 256), 256, 0, st>>>(Q, D, S);
+  n += 2;
+  for (int j = S - 1; j >= 0; --j) {
+    int cols = S - j;
+    int grid = (cols + HQ_COLS - 1) / HQ_COLS;
+    hh_formq_step<<<grid, HQ_THREADS, smem, st>>>(Q, D, S, j, Vst, tau);
+    ++n;
+  }
+  if (launches) *launches += n;
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// E rows:  E[o][rowoff[i] + (n-ord(i))*Mc + c] = sum_{j in block n, j >= i} R[i][j] Ym[o][c][j]
+// ---------------------------------------------------------------------------------------------
+__global__ void build_E_kernel(const double* __restrict__ R, int S, int N, const double* __restrict__ Ym,
+                               int Mc, int B, const int* __restrict__ rowoff, const int* __restrict__ roword,
+                               long long Etot, double* __restrict__ E) {
+  // grid: (row i, orientation o); threads over (n, c)
+  const int i = blockIdx.x, o = blockIdx.y;
+  const int ord = roword[i];
+  const int cnt = (N + 1 - ord) * Mc;
+  const double* Ri = R + (long long)i * S;
+  const double* Yo = Ym + (long long)o * Mc * S;
+  double* Eo = E + (long long)o * Etot + rowoff[i];
+  for (int idx = threadIdx.x; idx < cnt; idx += blockDim.x) {
+    int n = ord + idx / Mc, c = idx % Mc;
+    int j0 = n * n, j1 = (n + 1) * (n + 1);
+    if (j0 < i) j0 = i;  // R is upper triangular
+    const double* y = Yo + (long long)c * S;
+    double acc = 0.0;
+    for (int j = j0; j < j1; ++j) acc = fma(Ri[j], y[j], acc);
+    Eo[idx] = acc;
+  }
+}
+
+cudaError_t launch_build_E(cudaStream_t st, const double* R, int S, int N, const double* Ym,
+                           int Mc, int B, const int* rowoff, const int* roword, long long Etot,
+                           double* E) {
+  dim3 grid(S, B);
+  build_E_kernel<<<grid, 128, 0, st>>>(R, S, N, Ym, Mc, B, rowoff, roword, Etot, E);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// HRIR preparation (lib/getEMagLs2Filters.m:72-81)
+// ---------------------------------------------------------------------------------------------
+// sum(h, 2): h is [T x D] column-major.  Two deterministic passes.
+__global__ void colsum_partial(const double* __restrict__ h, int T, int D, int nchunk, double* __restrict__ partial) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int ch = blockIdx.y;
+  if (t >= T) return;
+  int per = (D + nchunk - 1) / nchunk;
+  int d0 = ch * per, d1 = min(D, d0 + per);
+  double acc = 0.0;
+  for (int d = d0; d < d1; ++d) acc += h[(long long)d * T + t];
+  partial[(long long)ch * T + t] = acc;
+}
+__global__ void colsum_final(const double* __restrict__ partial, int T, int nchunk, double* __restrict__ out) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  double acc = 0.0;
+  for (int c = 0; c < nchunk; ++c) acc += partial[(long long)c * T + t];
+  out[t] = acc;
+}
+cudaError_t launch_colsum(cudaStream_t st, const double* h, int T, int D, double* partial,
+                          int nchunk, double* out) {
+  dim3 grid((T + 127) / 128, nchunk);
+  colsum_partial<<<grid, 128, 0, st>>>(h, T, D, nchunk, partial);
+  colsum_final<<<(T + 127) / 128, 128, 0, st>>>(partial, T, nchunk, out);
+  return cudaGetLastError();
+}
+
+// grpdelay(b, 1, f, fs) at the K bin frequencies: Re(sum n b_n z^-n / sum b_n z^-n), |den| < 10 eps -> 0
+__global__ void grpdelay_kernel(const double* __restrict__ s, int T, int K, double fs, double* __restrict__ gd) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const double f = (double)k * ((fs / 2.0) / (double)(K - 1));
+  const double w = 2.0 * 3.141592653589793 * f / fs;
+  double nr = 0.0, ni = 0.0, dr = 0.0, di = 0.0;
+  for (int n = 0; n < T; ++n) {
+    double sn, cs;
+    sincos(w * (double)n, &sn, &cs);
+    double b = s[n];
+    dr = fma(b, cs, dr); di = fma(-b, sn, di);
+    double bn = b * (double)n;
+    nr = fma(bn, cs, nr); ni = fma(-bn, sn, ni);
+  }
+  double ad = sqrt(dr * dr + di * di);
+  double out = 0.0;
+  if (!(ad < 10.0 * 2.220446049250313e-16)) {
+    out = (nr * dr + ni * di) / (dr * dr + di * di);  // Re(num/den)
+  }
+  gd[k] = out;
+}
+cudaError_t launch_grpdelay(cudaStream_t st, const double* s, int T, int K, double fs, double* gd) {
+  grpdelay_kernel<<<(K + 63) / 64, 64, 0, st>>>(s, T, K, fs, gd);
+  return cudaGetLastError();
+}
+
+__global__ void dft_twiddle_kernel(int K, int T, int nfft, double* __restrict__ tw) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)K * T) return;
+  int k = (int)(idx / T), t = (int)(idx % T);
+  long long r = ((long long)k * t) % nfft;
+  double sn, cs;
+  sincospi(-2.0 * (double)r / (double)nfft, &sn, &cs);
+  tw[(long long)(2 * k) * T + t] = cs;
+  tw[(long long)(2 * k + 1) * T + t] = sn;
+}
+cudaError_t launch_dft_twiddle(cudaStream_t st, int K, int T, int nfft, double* tw) {
+  long long total = (long long)K * T;
+  dft_twiddle_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(K, T, nfft, tw);
+  return cudaGetLastError();
+}
+
+__global__ void abs_transpose_kernel(const double* __restrict__ Hd, int D, int K, double* __restrict__ absH) {
+  __shared__ double tile[32][33];
+  int k0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    int d = d0 + r, k = k0 + tx;
+    double v = 0.0;
+    if (d < D && k < K) {
+      const double* p = Hd + (long long)d * (2 * K) + 2 * k;
+      v = sqrt(fma(p[0], p[0], p[1] * p[1]));
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    int k = k0 + r, d = d0 + tx;
+    if (k < K && d < D) absH[(long long)k * D + d] = tile[tx][r];
+  }
+}
+cudaError_t launch_abs_transpose(cudaStream_t st, const double* Hd, int D, int K, double* absH) {
+  dim3 grid((K + 31) / 32, (D + 31) / 32), block(32, 8);
+  abs_transpose_kernel<<<grid, block, 0, st>>>(Hd, D, K, absH);
+  return cudaGetLastError();
+}
+
+// Tail (lib/getEMagLs2Filters.m:113-135) as one real matrix per ear:
+//   w[t'] = fade[t'] / nfft * sum_k c_k Re( W_k * ramp_k * exp(+2 pi i k (t'+lo)/nfft) )
+// ramp_k = exp(-2 pi i (k/nfft) delay), real part at Nyquist (applySubsampleDelay.m:10-13),
+// c_k = 1 for DC/Nyquist, 2 otherwise; fade = getFadeWindow(len) (getFadeWindow.m:9-16).
+__global__ void tail_twiddle_kernel(int K, int nfft, int len, double delay, double* __restrict__ tw) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)len * K) return;
+  int tp = (int)(idx / K), k = (int)(idx % K);
+  const int lo = nfft / 2 - len / 2;
+  // fade window
+  int nf = (int)floor(0.15 * (double)len + 0.5);
+  double win = 1.0;
+  if (nf > 0) {
+    double den = (double)(2 * nf - 1);
+    if (tp < nf) win = 0.5 * (1.0 - cos(2.0 * 3.141592653589793 * (double)tp / den));
+    else if (tp >= len - nf) {
+      int q = tp - (len - nf) + nf;  // index into hann(2*nf), second half
+      win = 0.5 * (1.0 - cos(2.0 * 3.141592653589793 * (double)q / den));
+    }
+  }
+  const double g = win / (double)nfft;
+  // ramp
+  const double omega = (double)k * (0.5 / (double)(K - 1));
+  double rs, rc;
+  sincos(-2.0 * 3.141592653589793 * omega * delay, &rs, &rc);
+  if (k == K - 1) rs = 0.0;
+  // exp(+2 pi i k (t'+lo) / nfft)
+  long long r = ((long long)k * (tp + lo)) % nfft;
+  double es, ec;
+  sincospi(2.0 * (double)r / (double)nfft, &es, &ec);
+  double pr = rc * ec - rs * es, pi_ = rc * es + rs * ec;
+  double ck = (k == 0 || k == K - 1) ? 1.0 : 2.0;
+  double* row = tw + (long long)tp * (2 * K);
+  row[2 * k] = g * ck * pr;
+  row[2 * k + 1] = (k == 0 || k == K - 1) ? 0.0 : -g * ck * pi_;
+}
+cudaError_t launch_tail_twiddle(cudaStream_t st, int K, int nfft, int len, double delay, double* tw) {
+  long long total = (long long)len * K;
+  tail_twiddle_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(K, nfft, len, delay, tw);
+  return cudaGetLastError();
+}
+
+}  // namespace emagls

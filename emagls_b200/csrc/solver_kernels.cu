@@ -1,0 +1,553 @@
+// Per-(problem, bin) factorisation kernel and the small chain kernels of the eMagLS hot loop.
+//
+// Reference step (lib/getEMagLs2Filters.m:86-89):
+//     pwGrid = smairMat(:,:,k) * Y_conj;  [U,s,V] = svd(pwGrid.','econ','vector');
+//     s = 1 ./ max(s, c*max(s));          Y_reg_inv = conj(U) * (s .* V.');
+// Here pwGrid.' = B * C with B orthonormal (the fixed Q of the HRIR-grid SH matrix, or the
+// identity for measured steering data) and C a tall [rows x Mc] complex matrix that never
+// leaves the SM:  C = Q_C R_C (flat-tree Householder TSQR in shared memory),
+// R_C^H J = X (one-sided Jacobi) so R_C = J diag(s) (X/s)^H, and
+//     Y_reg_inv = B * conj(Q_C) * Pb,     Pb = conj(J) diag(1/(s max(s, c s_max))) X^T.
+// When no singular value can be clipped (||R||_F ||R^-1||_F <= 1/c, a rigorous bound) the
+// Jacobi sweeps are skipped and Pb = R_C^-T (plain least squares).
+#include "kernels.h"
+
+namespace emagls {
+
+constexpr int FT = 256;  // threads of the factorisation kernel
+
+BlockPlan make_block_plan(int S, int Mc) {
+  BlockPlan bp;
+  bp.S = S; bp.Mc = Mc;
+  bp.MC = (Mc <= 32) ? 32 : 64;
+  bp.RB = (bp.MC == 32) ? 96 : 128;
+  bp.R0 = (S < Mc + bp.RB) ? S : Mc + bp.RB;
+  bp.nblk = 1 + (S - bp.R0 + bp.RB - 1) / bp.RB;
+  return bp;
+}
+
+size_t factor_smem_bytes(const BlockPlan& bp) {
+  return (size_t)bp.MC * (bp.MC + bp.RB) * sizeof(cplx) + (size_t)(bp.MC + 72) * sizeof(cplx) + 256;
+}
+
+__device__ __forceinline__ cplx gsum8(cplx v, unsigned mask) {
+#pragma unroll
+  for (int m = 4; m > 0; m >>= 1) {
+    v.x += __shfl_xor_sync(mask, v.x, m);
+    v.y += __shfl_xor_sync(mask, v.y, m);
+  }
+  return v;
+}
+__device__ __forceinline__ double gsum8(double v, unsigned mask) {
+#pragma unroll
+  for (int m = 4; m > 0; m >>= 1) v += __shfl_xor_sync(mask, v, m);
+  return v;
+}
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
+}
+
+// Householder reflector for column `col`, pivot row j, tail rows [lo, hi); executed by one
+// aligned group of 8 lanes (LAPACK zlarfg conventions: beta real, H = I - tau v v^H, v_j = 1).
+__device__ __forceinline__ void gen_reflector(cplx* col, int j, int lo, int hi, int rl,
+                                              unsigned mask, cplx* tau_out) {
+  double xn = 0.0;
+  for (int i = lo + rl; i < hi; i += 8) xn += cabs2(col[i]);
+  xn = gsum8(xn, mask);
+  cplx alpha = col[j];
+  cplx tau = mk(0.0, 0.0);
+  if (!(xn == 0.0 && alpha.y == 0.0)) {
+    double beta = -copysign(sqrt(cabs2(alpha) + xn), alpha.x);
+    tau = mk((beta - alpha.x) / beta, -alpha.y / beta);
+    cplx sc = cdiv(mk(1.0, 0.0), mk(alpha.x - beta, alpha.y));
+    for (int i = lo + rl; i < hi; i += 8) col[i] = cmul(col[i], sc);
+    __syncwarp(mask);
+    if (rl == 0) col[j] = mk(beta, 0.0);
+  }
+  if (rl == 0) *tau_out = tau;
+}
+
+// In-place QR of one block held in shared memory (column-major, leading dimension LD).
+// first: rows [0, nrows) dense;  otherwise: upper-triangular top (Mc rows) + dense rows [Mc, Mc+nb).
+__device__ void qr_block(cplx* Wk, int LD, int Mc, bool first, int hi, cplx* tau_s) {
+  const int tid = threadIdx.x, group = tid >> 3, rl = tid & 7;
+  const unsigned gmask = 0xffu << (threadIdx.x & 24);
+  if (group == 0) gen_reflector(Wk, 0, first ? 1 : Mc, hi, rl, gmask, &tau_s[0]);
+  __syncthreads();
+  for (int j = 0; j < Mc; ++j) {
+    const int lo = first ? j + 1 : Mc;
+    const cplx tau = tau_s[j];
+    const cplx* v = Wk + (size_t)j * LD;
+    if (tau.x != 0.0 || tau.y != 0.0) {
+      for (int c = j + 1 + group; c < Mc; c += FT / 8) {
+        cplx* a = Wk + (size_t)c * LD;
+        cplx w = (rl == 0) ? a[j] : mk(0.0, 0.0);
+        for (int i = lo + rl; i < hi; i += 8) cfmac(w, v[i], a[i]);
+        w = gsum8(w, gmask);
+        cplx f = cmul(cconj(tau), w);  // H^H = I - conj(tau) v v^H
+        if (rl == 0) a[j] = csub(a[j], f);
+        for (int i = lo + rl; i < hi; i += 8) cfms(a[i], f, v[i]);
+      }
+    }
+    if (group == 0 && j + 1 < Mc) {
+      __syncwarp(gmask);
+      gen_reflector(Wk + (size_t)(j + 1) * LD, j + 1, first ? j + 2 : Mc, hi, rl, gmask, &tau_s[j + 1]);
+    }
+    __syncthreads();
+  }
+}
+
+template <int MC, int RB>
+__global__ void __launch_bounds__(FT, (MC == 32) ? 3 : 1)
+factor_kernel(BlockPlan bp, RowSource src, OperatorSet ops, int kbase, int G, double regul) {
+  constexpr int LD = MC + RB;
+  extern __shared__ __align__(16) unsigned char fsm_raw[];
+  cplx* Wk = reinterpret_cast<cplx*>(fsm_raw);
+  cplx* tau_s = Wk + (size_t)MC * LD;
+  cplx* bn_s = tau_s + MC;  // up to 64 orders
+  double* red = reinterpret_cast<double*>(bn_s + 72);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int prob = blockIdx.x / G, slot = blockIdx.x % G, k = kbase + slot;
+  const long long oidx = (long long)prob * G + slot;
+  const int S = bp.S, Mc = bp.Mc;
+  cplx* Vg = ops.V + oidx * ops.v_stride;
+  cplx* taug = ops.tau + oidx * ops.tau_stride;
+
+  const bool factored = (src.E != nullptr);
+  if (factored) {
+    for (int n = tid; n <= src.N; n += FT) bn_s[n] = src.bn[(long long)k * (src.N + 1) + n];
+  }
+  __syncthreads();
+
+  // ---------------- flat-tree TSQR over row blocks
+  for (int t = 0; t < bp.nblk; ++t) {
+    const int r0 = (t == 0) ? 0 : bp.R0 + (t - 1) * RB;
+    const int r1 = (t == 0) ? bp.R0 : min(S, r0 + RB);
+    const int dst = (t == 0) ? 0 : Mc;
+    const int nb = r1 - r0;
+    if (factored) {
+      const double* Eo = src.E + (long long)prob * src.Etot;
+      for (int idx = tid; idx < nb * Mc; idx += FT) {
+        int i = r0 + idx / Mc, c = idx % Mc;
+        int ord = src.roword[i];
+        const double* e = Eo + src.rowoff[i] + c;
+        double ar = 0.0, ai = 0.0;
+        for (int n = ord; n <= src.N; ++n) {
+          double ev = e[(long long)(n - ord) * Mc];
+          ar = fma(bn_s[n].x, ev, ar);
+          ai = fma(bn_s[n].y, ev, ai);
+        }
+        Wk[(size_t)c * LD + dst + (i - r0)] = mk(ar, ai);
+      }
+    } else {
+      const cplx* At = src.At + (long long)k * src.at_bin_stride + (long long)prob * src.at_prob_stride;
+      for (int idx = tid; idx < nb * Mc; idx += FT) {
+        int i = r0 + idx / Mc, c = idx % Mc;
+        Wk[(size_t)c * LD + dst + (i - r0)] = At[(long long)i * Mc + c];
+      }
+    }
+    __syncthreads();
+    qr_block(Wk, LD, Mc, t == 0, dst + nb, tau_s);
+    // flush reflectors of this block (qr_block ends with a barrier)
+    for (int idx = tid; idx < nb * Mc; idx += FT) {
+      int c = idx / nb, q = idx % nb;
+      Vg[(long long)c * S + r0 + q] = Wk[(size_t)c * LD + dst + q];
+    }
+    for (int c = tid; c < Mc; c += FT) taug[t * MC + c] = tau_s[c];
+    __syncthreads();
+  }
+
+  // ---------------- compact R_C (upper triangular, column-major ld = MC) into region A0
+  cplx* Rs = Wk;
+  cplx* Xs = Wk + MC * MC;
+  cplx* Js = Wk + 2 * MC * MC;
+  {
+    constexpr int PER = MC * MC / FT;
+    cplx tmp[PER];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      int idx = tid + q * FT, c = idx / MC, r = idx % MC;
+      tmp[q] = (r <= c && c < Mc) ? Wk[(size_t)c * LD + r] : mk(0.0, 0.0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < PER; ++q) Rs[tid + q * FT] = tmp[q];
+    __syncthreads();
+  }
+  {
+    cplx* Rg = ops.Rc + oidx * ops.rc_stride;
+    for (int idx = tid; idx < Mc * Mc; idx += FT) {
+      int c = idx / Mc, r = idx % Mc;
+      Rg[idx] = Rs[c * MC + r];
+    }
+  }
+
+  // ---------------- R^-1 (upper triangular) into region A2, row by row from the bottom
+  cplx* Ri = Js;
+  for (int idx = tid; idx < MC * MC; idx += FT) Ri[idx] = mk(0.0, 0.0);
+  __syncthreads();
+  {
+    const int group = tid >> 3, rl = tid & 7;
+    const unsigned gmask = 0xffu << (threadIdx.x & 24);
+    for (int i = Mc - 1; i >= 0; --i) {
+      const cplx rii = Rs[i * MC + i];
+      for (int m = i + group; m < Mc; m += FT / 8) {
+        cplx sum = mk(0.0, 0.0);
+        for (int j = i + 1 + rl; j <= m; j += 8) cfma(sum, Rs[j * MC + i], Ri[m * MC + j]);
+        sum = gsum8(sum, gmask);
+        if (rl == 0) {
+          cplx num = mk((m == i ? 1.0 : 0.0) - sum.x, -sum.y);
+          Ri[m * MC + i] = cdiv(num, rii);   // Ri col-major: Ri[m*MC + i] = Rinv(i, m)
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // Frobenius norms
+  double fr = 0.0, fi = 0.0;
+  for (int idx = tid; idx < MC * MC; idx += FT) { fr += cabs2(Rs[idx]); fi += cabs2(Ri[idx]); }
+  fr = wsum(fr); fi = wsum(fi);
+  if (lane == 0) { red[warp] = fr; red[8 + warp] = fi; }
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < FT / 32; ++w) { a += red[w]; b += red[8 + w]; }
+    red[16] = sqrt(a) * sqrt(b);
+  }
+  __syncthreads();
+  const double condF = red[16];
+  const bool fast = (regul > 0.0) ? (condF <= 1.0 / regul) : (condF < 1e300);  // NaN -> false
+  cplx* Ps = Rs;  // region A0 is reused for Pb (row-major [i][m], ld = MC)
+  int sweeps = 0;
+  if (fast) {
+    __syncthreads();
+    for (int idx = tid; idx < MC * MC; idx += FT) {
+      int i = idx / MC, m = idx % MC;
+      Ps[idx] = Ri[i * MC + m];  // Pb(i,m) = Rinv(m,i) = Ri[i*MC + m]
+    }
+    __syncthreads();
+  } else {
+    // ---------------- one-sided Jacobi on X = R_C^H (columns graded like the rows of R_C)
+    for (int idx = tid; idx < MC * MC; idx += FT) {
+      int j = idx / MC, i = idx % MC;
+      cplx r = Rs[i * MC + j];  // R(j,i)
+      Xs[idx] = mk(r.x, -r.y);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < MC * MC; idx += FT) Js[idx] = mk((idx / MC == idx % MC) ? 1.0 : 0.0, 0.0);
+    __syncthreads();
+    const int ne = (Mc + 1) & ~1;  // even number of players (index Mc is a dummy when Mc is odd)
+    const double tol = 2.220446049250313e-16 * sqrt((double)Mc);
+    constexpr int RPL = MC / 32;   // rows per lane
+    for (sweeps = 1; sweeps <= 40; ++sweeps) {
+      int rotated = 0;
+      for (int r = 0; r < ne - 1; ++r) {
+        for (int pi = warp; pi < ne / 2; pi += FT / 32) {
+          int p, q;
+          if (pi == 0) { p = ne - 1; q = r; }
+          else { p = (r + pi) % (ne - 1); q = (r - pi + (ne - 1)) % (ne - 1); }
+          if (p >= Mc || q >= Mc) continue;
+          if (p > q) { int t_ = p; p = q; q = t_; }
+          cplx xp[RPL], xq[RPL];
+          double a = 0.0, b = 0.0; cplx g = mk(0.0, 0.0);
+#pragma unroll
+          for (int u = 0; u < RPL; ++u) {
+            int row = lane + 32 * u;
+            xp[u] = Xs[p * MC + row]; xq[u] = Xs[q * MC + row];
+            a += cabs2(xp[u]); b += cabs2(xq[u]);
+            cfmac(g, xp[u], xq[u]);
+          }
+          a = wsum(a); b = wsum(b); g.x = wsum(g.x); g.y = wsum(g.y);
+          double ag = sqrt(cabs2(g));
+          if (ag > tol * sqrt(a * b) && ag > 0.0) {
+            rotated = 1;
+            cplx ph = mk(g.x / ag, g.y / ag);
+            double zeta = (b - a) / (2.0 * ag);
+            double tt = ((zeta >= 0.0) ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            double cs = 1.0 / sqrt(1.0 + tt * tt), sn = cs * tt;
+            cplx sph = cscale(ph, sn);            // s * ph
+            cplx sphc = mk(sph.x, -sph.y);        // s * conj(ph)
+#pragma unroll
+            for (int u = 0; u < RPL; ++u) {
+              int row = lane + 32 * u;
+              cplx np_ = cscale(xp[u], cs); cfms(np_, sphc, xq[u]);
+              cplx nq_ = cscale(xq[u], cs); cfma(nq_, sph, xp[u]);
+              Xs[p * MC + row] = np_; Xs[q * MC + row] = nq_;
+              cplx jp = Js[p * MC + row], jq = Js[q * MC + row];
+              cplx njp = cscale(jp, cs); cfms(njp, sphc, jq);
+              cplx njq = cscale(jq, cs); cfma(njq, sph, jp);
+              Js[p * MC + row] = njp; Js[q * MC + row] = njq;
+            }
+          }
+        }
+        __syncthreads();
+      }
+      if (!__syncthreads_or(rotated)) break;
+    }
+    // singular values = column norms of X; gains 1/(s * max(s, c*smax))
+    double* sv = reinterpret_cast<double*>(bn_s);  // reuse (>= 64 doubles)
+    for (int j = warp; j < Mc; j += FT / 32) {
+      double a = 0.0;
+#pragma unroll
+      for (int u = 0; u < RPL; ++u) a += cabs2(Xs[j * MC + lane + 32 * u]);
+      a = wsum(a);
+      if (lane == 0) sv[j] = sqrt(a);
+    }
+    __syncthreads();
+    double smax = 0.0;
+    for (int j = 0; j < Mc; ++j) smax = fmax(smax, sv[j]);
+    __syncthreads();
+    if (tid < Mc) {
+      double s = sv[tid];
+      sv[tid] = (s > 0.0) ? 1.0 / (s * fmax(s, regul * smax)) : 0.0;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < MC * MC; idx += FT) {
+      int i = idx / MC, m = idx % MC;
+      cplx acc = mk(0.0, 0.0);
+      if (i < Mc && m < Mc) {
+        for (int j = 0; j < Mc; ++j) {
+          cplx jc = Js[j * MC + i];
+          cplx xg = cscale(Xs[j * MC + m], sv[j]);
+          cfmac(acc, jc, xg);  // conj(J(i,j)) * gain_j * X(m,j)
+        }
+      }
+      Ps[idx] = acc;
+    }
+    __syncthreads();
+  }
+  {
+    cplx* Pg = ops.Pb + oidx * ops.pb_stride;
+    for (int idx = tid; idx < Mc * Mc; idx += FT) {
+      int i = idx / Mc, m = idx % Mc;
+      Pg[idx] = Ps[i * MC + m];
+    }
+    if (tid == 0 && ops.info) ops.info[oidx] = fast ? 0 : sweeps;
+  }
+}
+
+cudaError_t launch_factor(cudaStream_t st, const BlockPlan& bp, const RowSource& src,
+                          const OperatorSet& ops, int num_prob, int kbase, int G, double regul) {
+  size_t smem = factor_smem_bytes(bp);
+  cudaError_t e;
+  if (bp.MC == 32) {
+    static bool set32 = false;
+    if (!set32) {
+      e = cudaFuncSetAttribute(factor_kernel<32, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      set32 = true;
+    }
+    factor_kernel<32, 96><<<num_prob * G, FT, smem, st>>>(bp, src, ops, kbase, G, regul);
+  } else {
+    static bool set64 = false;
+    if (!set64) {
+      e = cudaFuncSetAttribute(factor_kernel<64, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      set64 = true;
+    }
+    factor_kernel<64, 128><<<num_prob * G, FT, smem, st>>>(bp, src, ops, kbase, G, regul);
+  }
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// chain kernels: one warp per problem, both ears; x (rows x 2 ears) lives in shared memory.
+// =============================================================================================
+constexpr int CH_MAXW = 4;
+
+__device__ __forceinline__ cplx wsumc(cplx v) { v.x = wsum(v.x); v.y = wsum(v.y); return v; }
+
+// apply Q_C (forward = false: Q_C * x, blocks/reflectors in reverse order with tau) or
+// Q_C^H (forward = true: blocks/reflectors in order with conj(tau)) to x0, x1 (length S)
+__device__ void apply_qc(const BlockPlan& bp, const cplx* __restrict__ V, const cplx* __restrict__ tau,
+                         cplx* x0, cplx* x1, bool adjoint, int lane) {
+  const int S = bp.S, Mc = bp.Mc;
+  for (int tt = 0; tt < bp.nblk; ++tt) {
+    const int t = adjoint ? tt : bp.nblk - 1 - tt;
+    const int r0 = (t == 0) ? 0 : bp.R0 + (t - 1) * bp.RB;
+    const int r1 = (t == 0) ? bp.R0 : min(S, r0 + bp.RB);
+    for (int jj = 0; jj < Mc; ++jj) {
+      const int j = adjoint ? jj : Mc - 1 - jj;
+      cplx ta = tau[t * bp.MC + j];
+      if (ta.x == 0.0 && ta.y == 0.0) continue;
+      if (adjoint) ta.y = -ta.y;
+      const int lo = (t == 0) ? j + 1 : r0;
+      const cplx* v = V + (long long)j * S;
+      cplx w0 = mk(0.0, 0.0), w1 = mk(0.0, 0.0);
+      if (lane == 0) { w0 = x0[j]; w1 = x1[j]; }
+      for (int i = lo + lane; i < r1; i += 32) {
+        cplx vi = v[i];
+        cfmac(w0, vi, x0[i]);
+        cfmac(w1, vi, x1[i]);
+      }
+      w0 = wsumc(w0); w1 = wsumc(w1);
+      cplx f0 = cmul(ta, w0), f1 = cmul(ta, w1);
+      if (lane == 0) { x0[j] = csub(x0[j], f0); x1[j] = csub(x1[j], f1); }
+      for (int i = lo + lane; i < r1; i += 32) {
+        cplx vi = v[i];
+        cplx a0 = x0[i], a1 = x1[i];
+        cfms(a0, f0, vi); cfms(a1, f1, vi);
+        x0[i] = a0; x1[i] = a1;
+      }
+      __syncwarp();
+    }
+  }
+}
+
+__global__ void chain_fwd_kernel(BlockPlan bp, OperatorSet ops, int slot, int G, int ops_mod,
+                                 const cplx* Wsp, long long w_ear_stride, int K, int kprev,
+                                 int num_prob, double* Cv) {
+  extern __shared__ __align__(16) unsigned char csm_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const int p = blockIdx.x * wpc + warp;
+  if (p >= num_prob) return;
+  const int S = bp.S, Mc = bp.Mc;
+  cplx* x0 = reinterpret_cast<cplx*>(csm_raw) + (size_t)warp * 2 * S;
+  cplx* x1 = x0 + S;
+  const long long oidx = (long long)(p % ops_mod) * G + slot;
+  const cplx* V = ops.V + oidx * ops.v_stride;
+  const cplx* tau = ops.tau + oidx * ops.tau_stride;
+  const cplx* Rc = ops.Rc + oidx * ops.rc_stride;
+  for (int i = lane; i < S; i += 32) { x0[i] = mk(0.0, 0.0); x1[i] = mk(0.0, 0.0); }
+  __syncwarp();
+  // u = R_C * w   (R_C column-major [Mc][Mc], upper)
+  const cplx* w0p = Wsp + ((long long)p * Mc) * K + kprev;
+  const cplx* w1p = w0p + w_ear_stride;
+  for (int i = lane; i < Mc; i += 32) {
+    cplx u0 = mk(0.0, 0.0), u1 = mk(0.0, 0.0);
+    for (int m = i; m < Mc; ++m) {
+      cplx r = Rc[m * Mc + i];
+      cfma(u0, r, w0p[(long long)m * K]);
+      cfma(u1, r, w1p[(long long)m * K]);
+    }
+    x0[i] = u0; x1[i] = u1;
+  }
+  __syncwarp();
+  apply_qc(bp, V, tau, x0, x1, false, lane);
+  double* c0 = Cv + ((long long)(p * 2 + 0) * 2) * S;
+  double* c1 = Cv + ((long long)(p * 2 + 1) * 2) * S;
+  for (int i = lane; i < S; i += 32) {
+    cplx a = x0[i], b = x1[i];
+    c0[i] = a.x; c0[S + i] = a.y;
+    c1[i] = b.x; c1[S + i] = b.y;
+  }
+}
+
+__global__ void chain_bwd_kernel(BlockPlan bp, OperatorSet ops, int slot, int G, const double* tq,
+                                 long long tq_set_stride, long long tq_ear_stride, int tq_shared,
+                                 int orient_per_set, int ops_mod, cplx* Wsp, long long w_ear_stride,
+                                 int K, int k, int dc_fix, int num_prob) {
+  extern __shared__ __align__(16) unsigned char csm_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const int p = blockIdx.x * wpc + warp;
+  if (p >= num_prob) return;
+  const int S = bp.S, Mc = bp.Mc;
+  cplx* x0 = reinterpret_cast<cplx*>(csm_raw) + (size_t)warp * 2 * S;
+  cplx* x1 = x0 + S;
+  const long long oidx = (long long)(p % ops_mod) * G + slot;
+  const cplx* V = ops.V + oidx * ops.v_stride;
+  const cplx* tau = ops.tau + oidx * ops.tau_stride;
+  const cplx* Pb = ops.Pb + oidx * ops.pb_stride;
+  const double* t0 = tq_shared ? tq + (long long)(p / orient_per_set) * tq_set_stride
+                               : tq + ((long long)(p * 2 + 0) * 2) * S;
+  const double* t1 = t0 + (tq_shared ? tq_ear_stride : 2 * (long long)S);
+  for (int i = lane; i < S; i += 32) {
+    x0[i] = mk(t0[i], t0[S + i]);
+    x1[i] = mk(t1[i], t1[S + i]);
+  }
+  __syncwarp();
+  apply_qc(bp, V, tau, x0, x1, true, lane);
+  cplx* w0p = Wsp + ((long long)p * Mc) * K + k;
+  cplx* w1p = w0p + w_ear_stride;
+  for (int m = lane; m < Mc; m += 32) {
+    cplx a0 = mk(0.0, 0.0), a1 = mk(0.0, 0.0);
+    for (int i = 0; i < Mc; ++i) {
+      cplx pb = Pb[i * Mc + m];
+      cfma(a0, x0[i], pb);
+      cfma(a1, x1[i], pb);
+    }
+    w0p[(long long)m * K] = a0;
+    w1p[(long long)m * K] = a1;
+    if (dc_fix && k == 1) {  // W(1,:) = real(W(2,:)), lib/getEMagLs2Filters.m:109-110
+      w0p[(long long)m * K - 1] = mk(a0.x, 0.0);
+      w1p[(long long)m * K - 1] = mk(a1.x, 0.0);
+    }
+  }
+}
+
+static int chain_warps(int S) {
+  int w = (int)((200 * 1024) / ((size_t)2 * S * sizeof(cplx)));
+  if (w < 1) w = 1;
+  if (w > CH_MAXW) w = CH_MAXW;
+  return w;
+}
+
+cudaError_t launch_chain_fwd(cudaStream_t st, const BlockPlan& bp, const OperatorSet& ops, int slot,
+                             int G, int ops_mod, const cplx* Wsp, long long w_ear_stride, int K,
+                             int kprev, int num_prob, double* Cv) {
+  int w = chain_warps(bp.S);
+  size_t smem = (size_t)w * 2 * bp.S * sizeof(cplx);
+  static size_t set_to = 0;
+  if (smem > 48 * 1024 && smem > set_to) {
+    cudaError_t e = cudaFuncSetAttribute(chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    set_to = smem;
+  }
+  chain_fwd_kernel<<<(num_prob + w - 1) / w, w * 32, smem, st>>>(bp, ops, slot, G, ops_mod, Wsp, w_ear_stride, K, kprev,
+                                                                 num_prob, Cv);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_chain_bwd(cudaStream_t st, const BlockPlan& bp, const OperatorSet& ops, int slot,
+                             int G, const double* tq, long long tq_set_stride,
+                             long long tq_ear_stride, int tq_shared, int orient_per_set, int ops_mod,
+                             cplx* Wsp, long long w_ear_stride, int K, int k, int dc_fix, int num_prob) {
+  int w = chain_warps(bp.S);
+  size_t smem = (size_t)w * 2 * bp.S * sizeof(cplx);
+  static size_t set_to = 0;
+  if (smem > 48 * 1024 && smem > set_to) {
+    cudaError_t e = cudaFuncSetAttribute(chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    set_to = smem;
+  }
+  chain_bwd_kernel<<<(num_prob + w - 1) / w, w * 32, smem, st>>>(bp, ops, slot, G, tq, tq_set_stride, tq_ear_stride, tq_shared,
+                                                                 orient_per_set, ops_mod, Wsp, w_ear_stride, K, k, dc_fix,
+                                                                 num_prob);
+  return cudaGetLastError();
+}
+
+__global__ void phase_rows_kernel(const double* Y, double* T, int num_prob, int D, const double* absH,
+                                  long long abs_set_stride, long long abs_ear_stride,
+                                  int orient_per_set, int nyquist) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)num_prob * 2 * D;
+  if (idx >= total) return;
+  int d = (int)(idx % D);
+  long long pe = idx / D;
+  int ear = (int)(pe & 1);
+  int p = (int)(pe >> 1);
+  const double* yr = Y + (pe * 2) * D;
+  double re = yr[d], im = yr[D + d];
+  double mag = absH[(long long)(p / orient_per_set) * abs_set_stride + (long long)ear * abs_ear_stride + d];
+  double a2 = fma(re, re, im * im), tr, ti;
+  if (a2 > 0.0) { double inv = mag / sqrt(a2); tr = re * inv; ti = im * inv; }
+  else { tr = mag; ti = 0.0; }
+  if (nyquist) ti = 0.0;
+  double* tr_ = T + (pe * 2) * D;
+  tr_[d] = tr; tr_[D + d] = ti;
+}
+
+cudaError_t launch_phase_rows(cudaStream_t st, const double* Y, double* T, int num_prob, int D,
+                              const double* absH, long long abs_set_stride, long long abs_ear_stride,
+                              int orient_per_set, int nyquist) {
+  long long total = (long long)num_prob * 2 * D;
+  int bs = 256;
+  phase_rows_kernel<<<(unsigned)((total + bs - 1) / bs), bs, 0, st>>>(Y, T, num_prob, D, absH, abs_set_stride,
+                                                                      abs_ear_stride, orient_per_set, nyquist);
+  return cudaGetLastError();
+}
+
+}  // namespace emagls

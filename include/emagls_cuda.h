@@ -1,0 +1,176 @@
+/*
+ * libemagls_cuda -- C ABI of the B200-native eMagLS filter-design / binaural-render engine.
+ *
+ * The reference (thomasdeppisch/eMagLS @ d204b49) is pure MATLAB and has no FFI; its boundary
+ * is the set of MATLAB function signatures below.  Each entry point here is what a MEX drop-in
+ * of the same name binds (see INTEGRATION.md and mex/).  All matrices are column-major
+ * ("MATLAB layout"), all reals are IEEE double, all angles are radians (azimuth, zenith).
+ * Host pointers unless the function name ends in _dev.  Every function returns 0 on success or
+ * a negative emagls_status; emagls_last_error() gives the message (the MEX shim turns it into
+ * mexErrMsgIdAndTxt, mirroring the reference's assert()/error() behaviour).
+ *
+ * Batched extension (not in the reference API): `num_sets` HRTF sets (pages of hL/hR) times
+ * `num_orient` head orientations (3x3 rotations R_o, row-major; world direction of HRIR-grid
+ * direction u is R_o u, which equals one reference call with the rotated grid angles).
+ * Outputs are [len x channels x (num_sets*num_orient)], orientation fastest.
+ */
+#ifndef EMAGLS_CUDA_H
+#define EMAGLS_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct emagls_ctx* emagls_handle;
+
+typedef enum {
+  EMAGLS_OK = 0,
+  EMAGLS_ERR_INVALID = -1,      /* bad argument; reference: assert(len >= size(hL,1)) etc.   */
+  EMAGLS_ERR_CUDA = -2,         /* CUDA runtime / cuFFT failure                                */
+  EMAGLS_ERR_UNSUPPORTED = -3,  /* valid in the reference but outside this build's hot path    */
+  EMAGLS_ERR_NUMERIC = -4       /* e.g. HRIR grid too sparse for the simulation order          */
+} emagls_status;
+
+typedef enum { EMAGLS_BASIS_REAL = 0, EMAGLS_BASIS_COMPLEX = 1 } emagls_basis;
+typedef enum { EMAGLS_ARRAY_RIGID = 0, EMAGLS_ARRAY_OPEN = 1 } emagls_array_type;
+
+/* Constants that sit at the top of every reference function
+ * (lib/getEMagLs2Filters.m:35-39, dependencies/getSMAIRMatrix.m:86). */
+typedef struct {
+  int nfft_max_len;      /* NFFT_MAX_LEN    = 2048 */
+  double f_cut_min;      /* F_CUT_MIN_FREQ  = 1e3  */
+  double svd_regul;      /* SVD_REGUL_CONST = 0.01 */
+  double speed_of_sound; /* C               = 343  */
+  int array_type;        /* SIMULATION_ARRAY_TYPE = 'rigid' */
+  int basis;             /* shDefinition: 'real' (default) or 'complex' */
+  int reserved[6];
+} emagls_config;
+
+int emagls_create(int device, emagls_handle* out);
+int emagls_destroy(emagls_handle h);
+const char* emagls_last_error(emagls_handle h);
+void emagls_config_default(emagls_config* cfg);
+/* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
+long long emagls_launch_count(emagls_handle h);
+/* Built-in CUDA-event profiler: when enabled, every kernel class of the design / render paths is
+ * bracketed by an event pair on the handle's stream.  emagls_profile_read() synchronises, fills
+ * ms[i] / counts[i] (accumulated milliseconds and spans per class, i < EMAGLS_PROF_CLASSES) and
+ * returns the number of classes.  Class order: setup, factor, chain_fwd, gemm_fwd, gemm_bwd,
+ * chain_bwd, tail, render_mac, render_fft, render_stage.                                        */
+#define EMAGLS_PROF_CLASSES 10
+int emagls_profile_enable(emagls_handle h, int on);
+int emagls_profile_read(emagls_handle h, double* ms, long long* counts, int reset);
+/* Stream all work of this handle is enqueued on (cudaStream_t as void*), for event timing. */
+void* emagls_stream(emagls_handle h);
+
+/* ---- getEMagLs2Filters (lib/getEMagLs2Filters.m:1-2) ---------------------------------------
+ * [wMlsL, wMlsR] = getEMagLs2Filters(hL, hR, hrirGridAziRad, hrirGridZenRad, micRadius,
+ *                                    micGridAziRad, micGridZenRad, order, fs, len)
+ * hL,hR: [num_samples x num_dirs x num_sets]; wL,wR: [len x num_mics x (num_sets*num_orient)].
+ * rotations: [num_orient x 9] row-major 3x3, or NULL (num_orient must then be 1: identity,
+ * i.e. exactly the reference call).  spectra (optional, may be NULL) receives the
+ * positive-frequency solutions W_MLS as interleaved complex [K x num_mics x batch x 2 ears]
+ * (what the reference holds at lib/getEMagLs2Filters.m:110) for per-bin parity tests.          */
+int emagls_design_emagls2(emagls_handle h, const emagls_config* cfg,
+                          const double* hL, const double* hR, int num_samples, int num_dirs,
+                          const double* grid_azi, const double* grid_zen,
+                          double mic_radius, const double* mic_azi, const double* mic_zen,
+                          int num_mics, int order, double fs, int len,
+                          int num_sets, int num_orient, const double* rotations,
+                          double* wL, double* wR, double* spectra);
+
+/* Same, but every array argument is a device pointer on the handle's device and the call only
+ * enqueues work on emagls_stream(h) (bench.py's device-resident `value`).                      */
+int emagls_design_emagls2_dev(emagls_handle h, const emagls_config* cfg,
+                              const double* hL, const double* hR, int num_samples, int num_dirs,
+                              const double* grid_azi, const double* grid_zen,
+                              double mic_radius, const double* mic_azi, const double* mic_zen,
+                              int num_mics, int order, double fs, int len,
+                              int num_sets, int num_orient, const double* rotations,
+                              double* wL, double* wR, double* spectra);
+
+/* ---- getEMagLsFilters (lib/getEMagLsFilters.m:1-2): SH-domain output, (order+1)^2 channels.
+ * For cfg->basis == COMPLEX the outputs are interleaved complex [len x nsh x batch].           */
+int emagls_design_emagls(emagls_handle h, const emagls_config* cfg,
+                         const double* hL, const double* hR, int num_samples, int num_dirs,
+                         const double* grid_azi, const double* grid_zen,
+                         double mic_radius, const double* mic_azi, const double* mic_zen,
+                         int num_mics, int order, double fs, int len,
+                         int num_sets, int num_orient, const double* rotations,
+                         double* wL, double* wR, double* spectra);
+
+/* ---- getMagLsFilters (lib/getMagLsFilters.m:1-2) and getLsFilters (lib/getLsFilters.m:1-2) */
+int emagls_design_magls(emagls_handle h, const emagls_config* cfg,
+                        const double* hL, const double* hR, int num_samples, int num_dirs,
+                        const double* grid_azi, const double* grid_zen,
+                        int order, double fs, int len, double* wL, double* wR, double* spectra);
+int emagls_design_ls(emagls_handle h, const emagls_config* cfg,
+                     const double* hL, const double* hR, int num_samples, int num_dirs,
+                     const double* grid_azi, const double* grid_zen, int order,
+                     double* wL, double* wR);
+
+/* ---- getEMagLsFiltersFromAtf (lib/getEMagLsFiltersFromAtf.m:1) ------------------------------
+ * hrir_grid: [num_dirs x 2] (azi, zen) column-major; atf_irs: [atf_samples x num_mics x atf_dirs];
+ * atf_grid: [atf_dirs x 2].  mean_grid_dev_deg (optional) receives the value the reference
+ * prints at lib/getEMagLsFiltersFromAtf.m:96.                                                  */
+int emagls_design_from_atf(emagls_handle h, const emagls_config* cfg,
+                           const double* hL, const double* hR, int num_samples, int num_dirs,
+                           const double* hrir_grid, const double* atf_irs, int atf_samples,
+                           int num_mics, int atf_dirs, const double* atf_grid,
+                           double fs, int filter_len, double f_trans,
+                           double* wL, double* wR, double* spectra, double* mean_grid_dev_deg);
+
+/* ---- getEMagLsFiltersEMAinCH / EMAinSH (lib/getEMagLsFiltersEMAinCH.m:1-2, ...EMAinSH.m:1-2) */
+int emagls_design_ema_ch(emagls_handle h, const emagls_config* cfg,
+                         const double* hL, const double* hR, int num_samples, int num_dirs,
+                         const double* grid_azi, const double* grid_zen,
+                         double mic_radius, const double* mic_azi, int num_mics,
+                         int order, double fs, int len, double* wL, double* wR, double* spectra);
+int emagls_design_ema_sh(emagls_handle h, const emagls_config* cfg,
+                         const double* hL, const double* hR, int num_samples, int num_dirs,
+                         const double* grid_azi, const double* grid_zen,
+                         double mic_radius, const double* mic_azi, int num_mics,
+                         int order, double fs, int len, double* wL, double* wR, double* spectra);
+
+/* ---- getSMAIRMatrix (dependencies/getSMAIRMatrix.m:1) ---------------------------------------
+ * The `params` struct fields that are read on the hot path, flattened.  out: interleaved complex
+ * [rows x (simN+1)^2 x (nfft/2+1)], rows = num_mics if return_raw_mic_sigs else (order+1)^2.
+ * sim_order_out (optional) receives simulationOrder (getSMAIRMatrix.m:95).
+ * Call with out == NULL to query sim_order_out only.                                           */
+int emagls_smair_matrix(emagls_handle h, const emagls_config* cfg,
+                        const double* mic_azi, const double* mic_zen, int num_mics,
+                        int order, double fs, double sma_radius, int nfft,
+                        int return_raw_mic_sigs, double* out, int* sim_order_out);
+
+/* ---- binauralDecode (dependencies/binauralDecode.m:1-2) -------------------------------------
+ * in: [num_samples x num_ch]; wL,wR: [len x num_ch]; out: [out_rows x 2] with
+ * out_rows = num_samples (compensate_delay == 0) or num_samples - len/2 + 1.                   */
+int emagls_binaural_decode(emagls_handle h, const double* in, long long num_samples, int num_ch,
+                           const double* wL, const double* wR, int len, int compensate_delay,
+                           double* out);
+int emagls_binaural_decode_dev(emagls_handle h, const double* in, long long num_samples,
+                               int num_ch, const double* wL, const double* wR, int len,
+                               int compensate_delay, double* out);
+
+/* ---- building blocks exposed for parity tests (each mirrors one reference function) --------- */
+/* getSH(N, [azi zen], basis) (dependencies/Spherical-Harmonic-Transform/getSH.m:1):
+ * out [num_dirs x (N+1)^2] column-major; interleaved complex for COMPLEX.                      */
+int emagls_get_sh(emagls_handle h, int order, const double* azi, const double* zen, int num_dirs,
+                  int basis, double* out);
+/* sphModalCoeffs(N, kr, arrayType) (dependencies/Array-Response-Simulator/sphModalCoeffs.m:1):
+ * out interleaved complex [num_kr x (N+1)] column-major.                                       */
+int emagls_sph_modal_coeffs(emagls_handle h, int order, const double* kr, int num_kr,
+                            int array_type, double* out);
+/* Per-bin regularised inverse applied to targets (lib/getEMagLs2Filters.m:87-94):
+ * pw: interleaved complex [num_ch x num_dirs] column-major, targets: complex [num_t x num_dirs];
+ * out: complex [num_t x num_ch] = targets * Y_reg_inv.                                         */
+int emagls_regularized_apply(emagls_handle h, const double* pw, int num_ch, int num_dirs,
+                             const double* targets, int num_t, double svd_regul, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMAGLS_CUDA_H */
