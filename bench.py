@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Benchmark of the eMagLS hot path on B200: eMagLS2 filter sets / s (em32, N=4, 512 taps).
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...          # the reference algorithm on host cores
+
+A "step" designs one batch of head-orientation filter sets (BASELINE config 2: the 3600-orientation
+head-tracking grid, one HRTF set per rank -> weak scaling, no data-path collective).  Rank 0 prints
+ONE JSON line.  `value` is device-resident throughput (inputs already in HBM, CUDA events on the
+library's stream, max over ranks); `e2e` goes through the public host API (pinned host buffers,
+H2D + D2H inside the timed region, plus the NCCL gather of the banks onto rank 0 for N > 1).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "emagls2_filter_sets_per_sec"
+UNIT = "filter sets/s"
+ORDER, LEN = 4, 512
+# direct formulation, per filter set (512 bins): 22.3 GFLOP
+ALGO_GFLOP_PER_SET = 22.3
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--orient", type=int, default=3600, help="orientations per rank per step")
+    ap.add_argument("--render-seconds", type=float, default=60.0)
+    ap.add_argument("--no-render", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def problem(rank: int, n_orient: int):
+    from emagls_b200 import synth
+    g = synth.load_grids()
+    az, ze = g["hrirGridAziRad"], g["hrirGridZenRad"]
+    # one HRTF set per rank (seed = 20261017 + set index, randomised head)
+    rng = np.random.default_rng(20261017 + rank)
+    a = 0.0875 if rank == 0 else float(rng.uniform(0.075, 0.10))
+    ear = 90.0 if rank == 0 else float(rng.uniform(85.0, 100.0))
+    hL, hR = synth.synth_hrirs(az, ze, head_radius=a, ear_azi_deg=ear, seed=20261017 + rank)
+    R = synth.orientation_grid()
+    if n_orient <= R.shape[0]:
+        R = R[:: max(1, R.shape[0] // n_orient)][:n_orient]
+    else:
+        R = np.concatenate([R] * (n_orient // R.shape[0] + 1))[:n_orient]
+    return dict(g=g, az=az, ze=ze, hL=hL, hR=hR, R=np.ascontiguousarray(R), r=g["micRadius"],
+                maz=g["micGridAziRad"], mze=g["micGridZenRad"], fs=g["fs"])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def run_reference(args, rank, world):
+    """The reference's own algorithm on the box's host cores.  The reference is MATLAB, which this
+    image cannot run, so this is the NumPy restatement (oracle/), labelled kind = "port"."""
+    if rank != 0:
+        return
+    import oracle
+    pr = problem(0, args.orient)
+    ncores = os.cpu_count() or 1
+    sample = "1 filter set (orientation) of the 3600-orientation batch per step"
+
+    def one(i):
+        from emagls_b200 import synth
+        raz, rze = synth.rotate_grid(pr["az"], pr["ze"], pr["R"][i % len(pr["R"])])
+        oracle.getEMagLs2Filters(pr["hL"], pr["hR"], raz, rze, pr["r"], pr["maz"], pr["mze"], ORDER, pr["fs"], LEN)
+
+    for i in range(args.warmup):
+        one(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        one(args.warmup + i)
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "eMagLS2 em32 order 4, 512 taps, 2702-dir grid; bounded sample of the "
+                                   "3600-orientation batch", "sample_sets_per_step": 1},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import ctypes as C
+    import torch
+    import emagls_b200 as em
+    from emagls_b200 import dist as emdist
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    emdist.init("nccl")
+    dev = torch.device("cuda", local_rank)
+    h = em.Handle(local_rank)
+    cfg = h.default_config()
+    stream = torch.cuda.ExternalStream(h.stream, device=dev)
+    pr = problem(rank, args.orient)
+    B, M, D, T = args.orient, pr["maz"].size, pr["az"].size, pr["hL"].shape[0]
+
+    def dt64(x):
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float64))).to(dev)
+
+    # ---------------- device-resident inputs ([T, D] column-major == [D, T] row-major)
+    d_hL, d_hR = dt64(pr["hL"].T), dt64(pr["hR"].T)
+    d_az, d_ze, d_maz, d_mze, d_R = dt64(pr["az"]), dt64(pr["ze"]), dt64(pr["maz"]), dt64(pr["mze"]), dt64(pr["R"])
+    d_wL = torch.empty((B, M, LEN), dtype=torch.float64, device=dev)   # [len, M, B] column-major
+    d_wR = torch.empty_like(d_wL)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_dev():
+        rc = h.lib.emagls_design_emagls2_dev(
+            h.ptr, C.byref(cfg), d_hL.data_ptr(), d_hR.data_ptr(), T, D, d_az.data_ptr(), d_ze.data_ptr(),
+            float(pr["r"]), d_maz.data_ptr(), d_mze.data_ptr(), M, ORDER, float(pr["fs"]), LEN, 1, B,
+            d_R.data_ptr(), d_wL.data_ptr(), d_wR.data_ptr(), None)
+        h.check(rc)
+
+    def l2_flush():
+        with torch.cuda.stream(stream):
+            flush.fill_(1)
+
+    for _ in range(max(args.warmup, 3)):
+        l2_flush()
+        step_dev()
+    torch.cuda.synchronize()
+    h.profile(True)
+    h.profile_read()
+    launches0 = h.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    emdist.barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(local_rank) as clk:
+        for i in range(args.steps):
+            l2_flush()
+            ev[i][0].record(stream)
+            step_dev()
+            ev[i][1].record(stream)
+        torch.cuda.synchronize()
+    emdist.barrier()
+    ms_local = sum(a.elapsed_time(b) for a, b in ev)
+    ms = emdist.max_over_ranks(ms_local, dev)
+    prof = h.profile_read()
+    h.profile(False)
+    launches = h.launches - launches0
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---------------- end to end through the public API (pinned host buffers)
+    def pinned(shape):
+        t = torch.empty(shape[::-1], dtype=torch.float64, pin_memory=True)
+        return t, t.numpy().T  # Fortran-ordered view of the pinned block
+
+    p_hL, hLv = pinned((T, D))
+    p_hR, hRv = pinned((T, D))
+    hLv[...] = pr["hL"]
+    hRv[...] = pr["hR"]
+    p_wL, wLv = pinned((LEN, M, B))
+    p_wR, wRv = pinned((LEN, M, B))
+    h2d = 2 * T * D * 8 + 2 * D * 8 + 2 * M * 8 + B * 9 * 8
+    d2h = 2 * LEN * M * B * 8
+    bank_total = None
+
+    def step_e2e():
+        nonlocal bank_total
+        em.getEMagLs2Filters(hLv, hRv, pr["az"], pr["ze"], pr["r"], pr["maz"], pr["mze"], ORDER, pr["fs"], LEN,
+                             rotations=pr["R"], handle=h, out=(wLv, wRv))
+        if world > 1:  # NCCL gather of the finished banks onto rank 0 (the only collective)
+            bank = torch.stack([d_wL, d_wR], 1)          # device copy of the last device-resident banks
+            bank_total = emdist.gather_banks(bank, world * B, dst=0)
+            torch.cuda.synchronize()
+
+    step_e2e()
+    emdist.barrier()
+    torch.cuda.synchronize()
+    e2e_steps = max(1, min(args.steps, 2))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = emdist.max_over_ranks(time.perf_counter() - t0, dev)
+    e2e_value = world * B * e2e_steps / e2e_s
+
+    # ---------------- roofline of the dominant kernel class
+    S = (19 + 1) ** 2
+    peak = None
+    peak_src = "live cuBLAS DGEMM 8192^3, best of 5 (MEASURED_PEAKS.json has no FP64 entry)"
+    if rank == 0:
+        a = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+        b = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+        torch.matmul(a, b)
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        peak = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+        del a, b
+    flops_per_launch = {"gemm_fwd": 2.0 * D * 4 * B * S, "gemm_bwd": 2.0 * 4 * B * S * D}
+    tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    shares = {k: round(v["ms"] / tot_ms, 4) for k, v in prof.items() if v["n"]}
+    dom = max(("gemm_fwd", "gemm_bwd"), key=lambda k: prof[k]["ms"])
+    avg_ms = prof[dom]["ms"] / max(prof[dom]["n"], 1)
+    achieved = flops_per_launch[dom] / (avg_ms * 1e-3) / 1e12
+    roofline = {"kernel": f"gemm_f64_kernel ({dom})", "bound": "tensor", "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": (achieved / peak) if peak else None, "traffic": None,
+                "peak_source": peak_src, "flops_per_launch": flops_per_launch[dom],
+                "avg_launch_ms": avg_ms, "class_time_share": shares,
+                "algorithmic_tflops_whole_job": value / world * ALGO_GFLOP_PER_SET / 1e3}
+
+    # ---------------- render (secondary metric: Msamples/s of the 32 -> 2 channel, 512-tap FIR)
+    render = None
+    if not args.no_render and rank == 0:
+        n = int(args.render_seconds * 48000)
+        x = torch.randn((32, n), dtype=torch.float64, device=dev)           # [n, 32] column-major
+        y = torch.empty((2, n), dtype=torch.float64, device=dev)
+        wl, wr = d_wL[0].contiguous(), d_wR[0].contiguous()                 # [M, LEN] == [len, M] col-major
+
+        def rstep():
+            h.check(h.lib.emagls_binaural_decode_dev(h.ptr, x.data_ptr(), n, 32, wl.data_ptr(), wr.data_ptr(), LEN, 0,
+                                                     y.data_ptr()))
+        for _ in range(2):
+            rstep()
+        torch.cuda.synchronize()
+        h.profile(True)
+        h.profile_read()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record(stream)
+        for _ in range(3):
+            rstep()
+        r1.record(stream)
+        torch.cuda.synchronize()
+        rp = h.profile_read()
+        h.profile(False)
+        rms = r0.elapsed_time(r1) / 3
+        hbm = None
+        try:
+            hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+        except Exception:
+            pass
+        hbm = hbm or 6650.0
+        algo_bytes = n * 272.0                                              # 272 B / frame
+        render = {"metric": "render_msamples_per_sec", "value": n / (rms * 1e-3) / 1e6, "unit": "Msamples/s",
+                  "frames": n, "channels": 32, "taps": LEN, "ms": rms,
+                  "roofline": {"bound": "hbm", "achieved": algo_bytes / (rms * 1e-3) / 1e9, "peak": hbm,
+                               "unit": "GB/s", "frac": algo_bytes / (rms * 1e-3) / 1e9 / hbm,
+                               "class_ms": {k: v["ms"] / 3 for k, v in rp.items() if v["n"]}}}
+        del x, y
+
+    # ---------------- CPU baseline (the reference algorithm restated, on this box's host cores)
+    cpu = None
+    if not args.no_cpu_baseline and rank == 0 and world == 1:
+        import oracle
+        from emagls_b200 import synth
+        t0 = time.perf_counter()
+        nset = 0
+        while nset < 2 or (time.perf_counter() - t0 < 10.0 and nset < 6):
+            raz, rze = synth.rotate_grid(pr["az"], pr["ze"], pr["R"][nset])
+            oracle.getEMagLs2Filters(pr["hL"], pr["hR"], raz, rze, pr["r"], pr["maz"], pr["mze"], ORDER,
+                                     pr["fs"], LEN)
+            nset += 1
+        dtc = time.perf_counter() - t0
+        cpu = {"value": nset / dtc, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"{nset} of the {B} filter sets of one step (NumPy restatement of the MATLAB reference)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "BASELINE config 2: eMagLS2, em32 (32 mics, r=4.2 cm), SH order 4, 512 taps, "
+                                       "2702-direction HRIR grid @48 kHz, head-orientation batch",
+                           "orientations_per_gpu_per_step": B, "hrtf_sets_per_gpu": 1, "parallelism": f"shard{world}",
+                           "l2": "flushed between steps (256 MiB write); per-step working set is several GB"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": e2e_steps, "includes_nccl_gather": world > 1},
+                "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline,
+                "cpu_baseline": cpu, "render": render}
+        print(json.dumps(line), flush=True)
+    emdist.barrier()
+
+
+if __name__ == "__main__":
+    main()

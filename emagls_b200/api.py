@@ -73,7 +73,7 @@ def _prep_hrirs(hL, hR):
 
 def _design_sma(fn_name, channels_of, hL, hR, hrirGridAziRad, hrirGridZenRad, micRadius, micGridAziRad,
                 micGridZenRad, order, fs, length, shDefinition, shFunction, rotations, handle, config,
-                return_spectra):
+                return_spectra, out=None):
     _check_sh_function(shFunction)
     h = handle or default_handle()
     cfg = _config(h, config, shDefinition)
@@ -97,14 +97,20 @@ def _design_sma(fn_name, channels_of, hL, hR, hrirGridAziRad, hrirGridZenRad, mi
     K = nfft // 2 + 1
     cplx_out = cfg.basis == 1 and fn_name != "emagls_design_emagls2"
     odt = np.complex128 if cplx_out else np.float64
-    wL = np.zeros((length, Mc, P), dtype=odt, order="F")
-    wR = np.zeros((length, Mc, P), dtype=odt, order="F")
+    if out is not None:  # caller-provided (e.g. pinned) Fortran-ordered [len, Mc, P] buffers
+        wL, wR = out
+        for w in (wL, wR):
+            if w.shape != (length, Mc, P) or w.dtype != odt or not w.flags.f_contiguous:
+                raise ValueError("out buffers must be Fortran-ordered [len, channels, batch]")
+    else:
+        wL = np.zeros((length, Mc, P), dtype=odt, order="F")
+        wR = np.zeros((length, Mc, P), dtype=odt, order="F")
     sp = np.zeros((K, Mc, P, 2), dtype=np.complex128, order="F") if return_spectra else None
     rc = getattr(h.lib, fn_name)(h.ptr, C.byref(cfg), _p(hL), _p(hR), T, D, _p(az), _p(ze), float(micRadius),
                                  _p(maz), _p(mze), M, int(order), float(fs), length, sets, B, _p(rot),
                                  _p(wL), _p(wR), _p(sp))
     h.check(rc)
-    if P == 1 and rotations is None and sets == 1:
+    if P == 1 and rotations is None and sets == 1 and out is None:
         wL, wR = wL[:, :, 0], wR[:, :, 0]
         if sp is not None:
             sp = sp[:, :, 0, :]
@@ -113,7 +119,7 @@ def _design_sma(fn_name, channels_of, hL, hR, hrirGridAziRad, hrirGridZenRad, mi
 
 def getEMagLs2Filters(hL, hR, hrirGridAziRad, hrirGridZenRad, micRadius, micGridAziRad, micGridZenRad,
                       order, fs, len, shDefinition="real", shFunction=None, *, rotations=None,
-                      handle=None, config=None, return_spectra=False):
+                      handle=None, config=None, return_spectra=False, out=None):
     """[wMlsL, wMlsR] = getEMagLs2Filters(...)  -- lib/getEMagLs2Filters.m:1-2.
 
     Returns filters ``[len, numMics]`` (``[len, numMics, batch]`` when batched).  With
@@ -121,7 +127,7 @@ def getEMagLs2Filters(hL, hR, hrirGridAziRad, hrirGridZenRad, micRadius, micGrid
     """
     return _design_sma("emagls_design_emagls2", lambda M, N: M, hL, hR, hrirGridAziRad, hrirGridZenRad,
                        micRadius, micGridAziRad, micGridZenRad, order, fs, len, shDefinition, shFunction,
-                       rotations, handle, config, return_spectra)
+                       rotations, handle, config, return_spectra, out)
 
 
 def getEMagLsFilters(hL, hR, hrirGridAziRad, hrirGridZenRad, micRadius, micGridAziRad, micGridZenRad,

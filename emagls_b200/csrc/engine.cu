@@ -12,6 +12,8 @@
 //   tail               : DC fix, ifft, sub-sample shift, crop, fade folded into one GEMM per ear
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include "engine.h"
 #include "gemm.cuh"
@@ -215,6 +217,16 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
       EM_CUDA(launch_factor(st, bp, src, ops, PF, g0, Gn, cfg.svd_regul));
     }
     h->launches += 1;
+    if (getenv("EMAGLS_DEBUG_INFO")) {
+      std::vector<int> info((size_t)PF * Gn);
+      EM_CUDA(cudaMemcpyAsync(info.data(), ops.info, info.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+      EM_CUDA(cudaStreamSynchronize(st));
+      for (int slot = 0; slot < Gn; ++slot) {
+        int nfast = 0, smax = 0; long long ssum = 0;
+        for (int p = 0; p < PF; ++p) { int v = info[(size_t)p * Gn + slot]; nfast += (v == 0); smax = std::max(smax, v); ssum += v; }
+        fprintf(stderr, "bin %d: fast %d/%d, sweeps max %d mean %.2f\n", g0 + slot, nfast, PF, smax, (double)ssum / PF);
+      }
+    }
     for (int slot = 0; slot < Gn; ++slot) {
       const int kb = g0 + slot;
       if (kb < kls1) {

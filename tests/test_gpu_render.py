@@ -1,0 +1,86 @@
+"""Parity of the binaural render (dependencies/binauralDecode.m) through the C ABI (B200 only).
+Tolerance: 1e-9 relative max-norm (north_star); measured ~1e-15."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def em():
+    import emagls_b200
+    return emagls_b200
+
+
+@pytest.fixture(scope="module")
+def h(em):
+    return em.Handle(0)
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+@pytest.mark.parametrize("n,ch,ln,comp", [(5000, 32, 512, False), (70000, 32, 512, True), (1000, 25, 512, False),
+                                            (300, 4, 64, True), (513, 3, 512, False), (100, 2, 512, False),
+                                            (1, 1, 2, False), (360290, 32, 512, False), (40000, 8, 256, True),
+                                            (3000, 5, 100, False)])
+def test_binaural_decode_matches_oracle(em, h, n, ch, ln, comp):
+    rng = np.random.default_rng(n + ch)
+    x = rng.standard_normal((n, ch))
+    wl, wr = rng.standard_normal((ln, ch)), rng.standard_normal((ln, ch))
+    y = em.binauralDecode(x, 48000, wl, wr, 48000, comp, handle=h)
+    yo = oracle.binauralDecode(x, 48000, wl, wr, 48000, comp)
+    assert y.shape == yo.shape
+    assert rel(y, yo) < 1e-9
+
+
+def test_chunk_boundaries(em, h, monkeypatch):
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((512 * 70 + 17, 6))
+    wl, wr = rng.standard_normal((512, 6)), rng.standard_normal((512, 6))
+    yo = oracle.binauralDecode(x, 48000, wl, wr, 48000)
+    for chunk in ("1", "7", "64"):
+        monkeypatch.setenv("EMAGLS_RENDER_CHUNK", chunk)
+        assert rel(em.binauralDecode(x, 48000, wl, wr, 48000, handle=h), yo) < 1e-9
+
+
+def test_linearity_and_impulse_properties_at_full_size(em, h):
+    """Size-independent properties on a 10 s, 32-channel signal: linearity and the impulse response."""
+    rng = np.random.default_rng(12)
+    n, ch, ln = 480000, 32, 512
+    wl, wr = rng.standard_normal((ln, ch)), rng.standard_normal((ln, ch))
+    a, b = rng.standard_normal((n, ch)), rng.standard_normal((n, ch))
+    ya = em.binauralDecode(a, 48000, wl, wr, 48000, handle=h)
+    yb = em.binauralDecode(b, 48000, wl, wr, 48000, handle=h)
+    yab = em.binauralDecode(2.0 * a - 3.0 * b, 48000, wl, wr, 48000, handle=h)
+    assert rel(yab, 2.0 * ya - 3.0 * yb) < 1e-11
+    imp = np.zeros((n, ch))
+    imp[1000, 5] = 1.0
+    yi = em.binauralDecode(imp, 48000, wl, wr, 48000, handle=h)
+    assert np.abs(yi[1000:1000 + ln, 0] - wl[:, 5]).max() < 1e-12
+    assert np.abs(yi[1000:1000 + ln, 1] - wr[:, 5]).max() < 1e-12
+    assert np.abs(yi[:1000]).max() < 1e-12 and np.abs(yi[1000 + ln:]).max() < 1e-12
+
+
+def test_render_with_designed_filters_end_to_end(em, h, grids):
+    """The consumer path: design eMagLS2 filters on the device, render a 32-channel signal with them."""
+    from emagls_b200 import synth
+    az, ze = grids["hrirGridAziRad"], grids["hrirGridZenRad"]
+    hL, hR = synth.synth_hrirs(az, ze)
+    wL, wR = em.getEMagLs2Filters(hL, hR, az, ze, grids["micRadius"], grids["micGridAziRad"],
+                                  grids["micGridZenRad"], 4, grids["fs"], 512, handle=h)
+    x = np.random.default_rng(13).standard_normal((20000, 32))
+    y = em.binauralDecode(x, 48000, wL, wR, 48000, True, handle=h)
+    yo = oracle.binauralDecode(x, 48000, wL, wR, 48000, True)
+    assert y.shape == (20000 - 255, 2) and rel(y, yo) < 1e-9
+
+
+def test_errors(em, h):
+    x = np.zeros((10, 3))
+    with pytest.raises(ValueError):
+        em.binauralDecode(x, 48000, np.zeros((4, 2)), np.zeros((4, 2)), 48000, handle=h)
+    with pytest.raises(NotImplementedError):
+        em.binauralDecode(x, 48000, np.zeros((4, 3)), np.zeros((4, 3)), 44100, handle=h)
