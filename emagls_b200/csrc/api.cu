@@ -111,15 +111,17 @@ static int design_host(emagls_handle h, const emagls_config* cfg, Variant v, con
     const int K = nfft / 2 + 1;
     const size_t P = (size_t)ns * no;
     DesignArgs a;
-    double* d_wL = ar.get<double>((size_t)len * Mc * P);
-    double* d_wR = ar.get<double>((size_t)len * Mc * P);
+    // complex SH-domain output is interleaved complex (lib/getEMagLsFilters.m:117-120)
+    const size_t wn = (size_t)len * Mc * P * ((v == Variant::EMAGLS_SH && cfg->basis == EMAGLS_BASIS_COMPLEX) ? 2 : 1);
+    double* d_wL = ar.get<double>(wn);
+    double* d_wR = ar.get<double>(wn);
     double* d_sp = sp ? ar.get<double>((size_t)2 * K * Mc * P * 2) : nullptr;
     fill_args(a, v, ar.upload(hL, (size_t)T * D * ns), ar.upload(hR, (size_t)T * D * ns), T, D,
               ar.upload(ga, D), ar.upload(gz, D), r, ar.upload(ma, M), ar.upload(mz, M), M, order, fs, len,
               ns, no, rot ? ar.upload(rot, (size_t)no * 9) : nullptr, d_wL, d_wR, d_sp);
     design_factored(h, *cfg, a);
-    EM_CUDA(cudaMemcpyAsync(wL, d_wL, (size_t)len * Mc * P * sizeof(double), cudaMemcpyDeviceToHost, st));
-    EM_CUDA(cudaMemcpyAsync(wR, d_wR, (size_t)len * Mc * P * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaMemcpyAsync(wL, d_wL, wn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaMemcpyAsync(wR, d_wR, wn * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (sp) EM_CUDA(cudaMemcpyAsync(sp, d_sp, (size_t)2 * K * Mc * P * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     EM_CUDA(cudaStreamSynchronize(st));
   });
@@ -283,19 +285,8 @@ int emagls_regularized_apply(emagls_handle h, const double* pw, int num_ch, int 
     cudaStream_t st = h->stream;
     Arena ar(st);
     const int Mc = num_ch, D = num_dirs;
-    const BlockPlan bp = make_block_plan(D, Mc);
     // pw is [Mc x D] column-major == rows of pwGrid.' with the channel index contiguous
     cplx* At = reinterpret_cast<cplx*>(ar.upload(pw, (size_t)2 * Mc * D));
-    OperatorSet ops;
-    ops.v_stride = (long long)Mc * D; ops.tau_stride = (long long)bp.nblk * bp.MC;
-    ops.rc_stride = ops.pb_stride = (long long)Mc * Mc;
-    ops.V = ar.get<cplx>(ops.v_stride); ops.tau = ar.get<cplx>(ops.tau_stride);
-    ops.Rc = ar.get<cplx>(ops.rc_stride); ops.Pb = ar.get<cplx>(ops.pb_stride);
-    ops.info = ar.get<int>(1);
-    RowSource src{};
-    src.At = At; src.at_bin_stride = 0; src.at_prob_stride = 0;
-    EM_CUDA(launch_factor(st, bp, src, ops, 1, 0, 1, svd_regul));
-    h->launches += 1;
     // targets [num_t x D] complex column-major -> pairs of rows (re | im) of length D
     const int npair = (num_t + 1) / 2;
     std::vector<double> rows((size_t)npair * 4 * D, 0.0);
@@ -306,9 +297,8 @@ int emagls_regularized_apply(emagls_handle h, const double* pw, int num_ch, int 
         rows[base + D + d] = targets[2 * ((size_t)d * num_t + t) + 1];
       }
     double* d_rows = ar.upload(rows.data(), rows.size());
-    cplx* W = ar.get<cplx>((size_t)2 * npair * Mc);  // [ear][pair][Mc][K=1]
-    EM_CUDA(launch_chain_bwd(st, bp, ops, 0, 1, d_rows, 0, 0, 0, 1, 1, W, (long long)npair * Mc, 1, 0, 0, npair));
-    h->launches += 1;
+    cplx* W = ar.get<cplx>((size_t)2 * npair * Mc);  // [ear][pair][Mc]
+    regularized_apply_dev(h, ar, At, D, Mc, d_rows, npair, svd_regul, W);
     std::vector<cplx> Wh((size_t)2 * npair * Mc);
     EM_CUDA(cudaMemcpyAsync(Wh.data(), W, Wh.size() * sizeof(cplx), cudaMemcpyDeviceToHost, st));
     EM_CUDA(cudaStreamSynchronize(st));

@@ -48,6 +48,20 @@ __device__ __forceinline__ cplx cdiv(cplx a, cplx b) {  // Smith's algorithm
   }
 }
 
+// getFadeWindow(len) (dependencies/getFadeWindow.m:9-16): half-Hann fade over round(0.15 len) taps
+// at both ends, hann(2n) symmetric with zero end points.
+__host__ __device__ inline double fade_window(int tp, int len) {
+  const int nf = (int)floor(0.15 * (double)len + 0.5);
+  if (nf <= 0) return 1.0;
+  const double den = (double)(2 * nf - 1);
+  if (tp < nf) return 0.5 * (1.0 - cos(2.0 * 3.141592653589793 * (double)tp / den));
+  if (tp >= len - nf) {
+    const int q = tp - (len - nf) + nf;  // index into hann(2*nf), second half
+    return 0.5 * (1.0 - cos(2.0 * 3.141592653589793 * (double)q / den));
+  }
+  return 1.0;
+}
+
 // ---------------------------------------------------------------- warp helpers
 __device__ __forceinline__ double shfl_xor_d(double v, int m, unsigned mask = 0xffffffffu) {
   return __shfl_xor_sync(mask, v, m);

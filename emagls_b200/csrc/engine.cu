@@ -1,15 +1,19 @@
-// Host orchestration of the factored eMagLS design path (getEMagLs2Filters / getEMagLsFilters).
+// Host orchestration of the model-based eMagLS design path (getEMagLs2Filters / getEMagLsFilters).
 //
 // Reference flow being reproduced (lib/getEMagLs2Filters.m:44-135), restructured for a batch of
-// P = num_sets * num_orient problems:
-//   once per grid      : Y_h = getSH(simN, grid) = Q R                       (Householder, on device)
-//   once per array     : b_n(kr_k) for all bins                              (getSMAIRMatrix.m:107)
-//   once per orientation: Ym_o = L * getSH(simN, R_o^T mics);  E_o = R-blocks * Ym_o^T
-//   once per HRTF set  : group delays, H = fft(h) .* ramp, |H|, H*Q for the LS bins
-//   per bin k          : C = sum_n b_n(k) E_n -> TSQR -> clipped inverse   (factor kernel, SM-local)
-//                        LS bins:    W_k = (H_k Q) conj(Q_C) Pb
-//                        MagLS bins: y = W_{k-1} C^T Q^T;  t = |H_k| y/|y|;  W_k = (t Q) conj(Q_C) Pb
-//   tail               : DC fix, ifft, sub-sample shift, crop, fade folded into one GEMM per ear
+// P = num_sets * num_orient problems.  With A_k = pwGrid_k.' = Y_h diag(b_k) Y_o^T (Y_o = real SH at
+// the microphones seen from head orientation o, times pinv(Y_lo) for SH-domain output):
+//   once per grid       : Y_h = getSH(simN, grid) = Q R (Householder), Gh = Y_h^T Y_h
+//   once per array      : b_n(kr_k) for all bins                              (getSMAIRMatrix.m:107)
+//   once per HRTF set   : group delays, H = fft(h) .* ramp, |H|, H*Q and H*Y_h for the LS bins
+//   once per orientation: Y_o, E_o = R-blocks * Y_o^T (TSQR route), F_o = Y_o Gh-blocks Y_o^T (Gram route)
+//   per bin k           : Gram route (no singular value clipped, decided by a rigorous bound on
+//                         cond(A_k^H A_k)):  G_k = sum conj(b_n) b_n' F_nn' (DMMA GEMM), Cholesky,
+//                             W_k = ((t Y_h) .* conj(b_k)) Y_o^T G_k^-T
+//                         TSQR route (clipping possible):  C = R diag(b_k) Y_o^T -> TSQR -> Jacobi ->
+//                             W_k = (t Q) conj(Q_C) Pb
+//                         with t = H_k (LS bins) or |H_k| .* exp(i angle(Y_h (b_k .* (Y_o^T W_{k-1}))))
+//   tail                : DC fix, ifft, sub-sample shift, crop, fade folded into one GEMM per ear
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -39,7 +43,120 @@ double median_of(std::vector<double> v) {
   return (n & 1) ? v[n / 2] : 0.5 * (v[n / 2 - 1] + v[n / 2]);
 }
 
+__global__ void identity_rows_kernel(double* rows, int npair, int D, int n) {
+  // rows [(pair*2 + ear)*2 + c][D]: target t = pair*2 + ear is the unit vector e_t (t < n)
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)npair * 4 * D) return;
+  int d = (int)(idx % D);
+  int row = (int)(idx / D);
+  int c = row & 1, t = row >> 1;
+  rows[idx] = (c == 0 && t == d && t < n) ? 1.0 : 0.0;
+}
+
+__global__ void real_to_cplx_kernel(const double* in, long long n, cplx* out) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) out[idx] = mk(in[idx], 0.0);
+}
+
+// L[c][m] = Re(W[(m&1)*npair + m/2][c])
+__global__ void extract_pinv_kernel(const cplx* W, int npair, int Mc, int M, double* L) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Mc * M) return;
+  int c = idx / M, m = idx % M;
+  L[idx] = W[((long long)(m & 1) * npair + m / 2) * Mc + c].x;
+}
+
+// ---- complex SH basis (shDefinition = 'complex', lib/getEMagLsFilters.m:117-120) ---------------
+// pwGrid_complex = conj(T) pwGrid_real with the unitary real->complex map Y_c = Y_r T^T
+// (getSH.m:25-49), so every bin but DC obeys W_c = W_r T^T; the DC fix W(1,:) = real(W(2,:)) acts on
+// the complex-basis coefficients (lib/getEMagLsFilters.m:110-111) and getShFreqDomainConjugate makes
+// the remaining spectrum the image of a real-basis Hermitian one.  Hence
+//   w_c = tail(W_r with DC := 0) T^T + fade/nfft * real(W_r(2,:) T^T).
+// T rows: m = 0: e_0;  m > 0: (-1)^m (e_m + i e_-m)/sqrt2;  m < 0: (e_|m| - i e_-|m|)/sqrt2.
+__device__ __forceinline__ cplx to_complex_basis(double ap, double am, int m) {
+  // ap, am: real-basis coefficients of (n, +|m|) and (n, -|m|); returns the complex-basis (n, m) one
+  const double r = 0.7071067811865476;
+  if (m == 0) return mk(ap, 0.0);
+  if (m > 0) { const double s = (m & 1) ? -r : r; return mk(s * ap, s * am); }
+  return mk(r * ap, -r * am);
+}
+__device__ __forceinline__ cplx to_complex_basis(cplx ap, cplx am, int m) {
+  const double r = 0.7071067811865476;
+  if (m == 0) return ap;
+  if (m > 0) { const double s = (m & 1) ? -r : r; return mk(s * (ap.x - am.y), s * (ap.y + am.x)); }
+  return mk(r * (ap.x + am.y), r * (ap.y - am.x));
+}
+
+// out (interleaved complex) [len x nsh x P]; wr [len x nsh x P] real tail of W_r with DC = 0;
+// Wsp_e: this ear's real-basis spectra [P][nsh][K]
+__global__ void complex_basis_filters_kernel(const double* __restrict__ wr, const cplx* __restrict__ Wsp_e,
+                                             int order, int len, int K, int nfft, long long P,
+                                             cplx* __restrict__ out) {
+  const int nsh = (order + 1) * (order + 1);
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P * nsh * len) return;
+  const int t = (int)(idx % len);
+  const int j = (int)((idx / len) % nsh);
+  const long long p = idx / ((long long)len * nsh);
+  int n = (int)sqrt((double)j);
+  while ((n + 1) * (n + 1) <= j) ++n;
+  while (n * n > j) --n;
+  const int m = j - n * n - n, am = m < 0 ? -m : m;
+  const long long ip = p * nsh + n * n + n + am, im = p * nsh + n * n + n - am;
+  cplx v = to_complex_basis(wr[ip * len + t], wr[im * len + t], m);
+  const cplx dc = to_complex_basis(Wsp_e[ip * K + 1], Wsp_e[im * K + 1], m);
+  v.x += fade_window(t, len) / (double)nfft * dc.x;
+  out[idx] = v;
+}
+
+// in place: spectra of one (ear, problem, order n, |m|) pair -> complex basis, DC := real(bin 1)
+__global__ void complex_basis_spectra_kernel(cplx* __restrict__ Wsp, int order, int K, long long EP) {
+  const int nsh = (order + 1) * (order + 1);
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= EP * nsh * K) return;
+  const int k = (int)(idx % K);
+  const int j = (int)((idx / K) % nsh);
+  const long long ep = idx / ((long long)K * nsh);
+  int n = (int)sqrt((double)j);
+  while ((n + 1) * (n + 1) <= j) ++n;
+  while (n * n > j) --n;
+  const int m = j - n * n - n;
+  if (m < 0 || k == 0) return;  // the thread of +m converts both rows; the thread of bin 1 also writes DC
+  cplx* rp = Wsp + (ep * nsh + n * n + n + m) * K;
+  cplx* rm = Wsp + (ep * nsh + n * n + n - m) * K;
+  const cplx ap = rp[k], am = rm[k];
+  const cplx cp = to_complex_basis(ap, am, m), cm = to_complex_basis(ap, am, -m);
+  rp[k] = cp;
+  if (m > 0) rm[k] = cm;
+  if (k == 1) {
+    rp[0] = mk(cp.x, 0.0);
+    if (m > 0) rm[0] = mk(cm.x, 0.0);
+  }
+}
+
 }  // namespace
+
+// targets * Y_reg_inv for one steering matrix held as rows At [D][Mc] (lib/getEMagLs2Filters.m:87-94).
+// rows: [(pair*2 + ear)*2 + {re,im}][D];  W: [ear][pair][Mc].
+void regularized_apply_dev(emagls_ctx* h, Arena& ar, const cplx* At, int D, int Mc, const double* rows,
+                           int npair, double regul, cplx* W) {
+  cudaStream_t st = h->stream;
+  const BlockPlan bp = make_block_plan(D, Mc);
+  OperatorSet ops;
+  ops.v_stride = (long long)Mc * D; ops.tau_stride = (long long)bp.nblk * bp.MC;
+  ops.pb_stride = (long long)Mc * Mc;
+  ops.V = ar.get<cplx>(ops.v_stride); ops.tau = ar.get<cplx>(ops.tau_stride);
+  ops.Pb = ar.get<cplx>(ops.pb_stride);
+  ops.info = ar.get<int>(1);
+  RowSource src{};
+  src.At = At; src.at_bin_stride = 0; src.at_prob_stride = 0;
+  EM_CUDA(launch_factor(st, bp, src, ops, 1, 0, 1, regul));
+  // every pair of targets shares the one operator set: chain_bwd indexes operators by j % oc and
+  // solutions by global(j), so oc = 1 addresses the pairs through the set index
+  ProbMap pm1{1, 0, 1};
+  EM_CUDA(launch_chain_bwd(st, bp, ops, 0, 1, rows, 0, 0, 0, pm1, W, (long long)npair * Mc, 1, 0, 0, npair));
+  h->launches += 2;
+}
 
 void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& a) {
   cudaStream_t st = h->stream;
@@ -49,8 +166,6 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
   EM_REQUIRE(a.len % 2 == 0, "len must be even");
   EM_REQUIRE(a.num_sets >= 1 && a.num_orient >= 1, "empty batch");
   EM_REQUIRE(a.rotations != nullptr || a.num_orient == 1, "num_orient > 1 needs rotations");
-  EM_REQUIRE(cfg.basis == EMAGLS_BASIS_REAL || a.variant == Variant::EMAGLS2,
-             "complex basis for SH-domain output is not built yet");
   const int nfft = std::min(cfg.nfft_max_len, 2 * a.len);
   EM_REQUIRE(nfft % 2 == 0, "nfft must be even");  // getSMAIRMatrix.m:89
   EM_REQUIRE(nfft / 2 >= a.len / 2, "len exceeds NFFT_MAX_LEN (reference indexes out of range here)");
@@ -61,13 +176,18 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
   const int simN = std::max(a.order, (int)std::ceil(a.fs * M_PI * a.mic_radius / cfg.speed_of_sound));
   EM_REQUIRE(simN <= MAX_SH_ORDER, "simulation order too high");
   const int S = (simN + 1) * (simN + 1);
-  const int Mc = (a.variant == Variant::EMAGLS2) ? a.M : (a.order + 1) * (a.order + 1);
-  EM_REQUIRE(Mc <= 64, "more than 64 output channels are not supported");
+  const int nsh = (a.order + 1) * (a.order + 1);
+  const int Mc = (a.variant == Variant::EMAGLS2) ? a.M : nsh;
+  EM_REQUIRE(Mc <= 64 && a.M <= 64, "more than 64 channels are not supported");
+  if (a.variant == Variant::EMAGLS_SH) EM_REQUIRE(a.M >= nsh, "fewer microphones than SH channels");
   if (a.D < S)
     throw Fail{EMAGLS_ERR_UNSUPPORTED, "HRIR grid has fewer directions than simulation harmonics"};
   EM_REQUIRE(S >= Mc, "fewer simulation harmonics than channels");
   const int P = a.num_sets * a.num_orient;
   const int D = a.D, T = a.T;
+  // complex SH-domain output: solved in the real basis, converted at the tail (see above)
+  const bool cplx_out = (a.variant == Variant::EMAGLS_SH && cfg.basis == EMAGLS_BASIS_COMPLEX);
+  const int dc_fix = cplx_out ? 0 : 1;
   // bins (0-based): LS 1 .. kls1-1, MagLS kls1 .. K-1, with kls1 = k_cut - 1
   const int kls1 = std::min(std::max(k_cut - 1, 1), K);
   const int nLS = kls1 - 1;
@@ -75,15 +195,21 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
   Arena ar(st);
   ProfSpan* setup_span = new ProfSpan(h, EM_PROF_SETUP);
   struct SpanGuard { ProfSpan*& p; ~SpanGuard() { delete p; p = nullptr; } } setup_guard{setup_span};
-  // ---------------- grid: Y_h = Q R
+  // ---------------- grid: Y_h = Q R, Gh = Y_h^T Y_h
   double* Yh = ar.get<double>((size_t)S * D);
   double* Q = ar.get<double>((size_t)S * D);
   double* R = ar.get<double>((size_t)S * S);
+  double* Gh = ar.get<double>((size_t)S * S);
   {
     double* work = ar.get<double>((size_t)S * D + 2 * S);
+    double* Ytmp = ar.get<double>((size_t)S * D);
     EM_CUDA(launch_sh_angles(st, simN, a.grid_azi, a.grid_zen, D, 0, Yh));
+    EM_CUDA(cudaMemcpyAsync(Ytmp, Yh, (size_t)S * D * sizeof(double), cudaMemcpyDeviceToDevice, st));
     h->launches += 1;
-    EM_CUDA(launch_householder_qr(st, Yh, D, S, Q, R, work, &h->launches));
+    EM_CUDA(launch_householder_qr(st, Ytmp, D, S, Q, R, work, &h->launches));  // destroys its input
+    GemmOperand A0{Yh, D, 1}, B0{Yh, D, 1};
+    EM_CUDA(launch_gemm(st, A0, B0, GemmShape{S, S, D}, EpiStore{Gh, S, 1.0}));
+    h->launches += 1;
   }
   // ---------------- array: b_n table (minus sign, Nyquist real: getSMAIRMatrix.m:107,115-117)
   std::vector<double> kr(K);
@@ -94,9 +220,13 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
   double* d_kr = ar.upload(kr.data(), K);
   cplx* bn = ar.get<cplx>((size_t)K * (simN + 1));
   EM_CUDA(launch_modal(st, simN, d_kr, K, cfg.array_type, -1.0, 1, bn, simN + 1, 1));
-  h->launches += 1;
+  const int nqs = (simN + 1) * (simN + 2) / 2, nqa = std::max(1, simN * (simN + 1) / 2);
+  double* bre = ar.get<double>((size_t)K * nqs);
+  double* bim = ar.get<double>((size_t)K * nqa);
+  EM_CUDA(launch_gram_beta(st, bn, simN, K, bre, bim));
+  h->launches += 2;
 
-  // ---------------- orientations: Ym_o (and L * Ym_o for SH-domain output), E rows
+  // ---------------- orientations: Y_o = getSH at the rotated microphones (times pinv(Y_lo))
   std::vector<int> rowoff(S), roword(S);
   long long Etot = 0;
   {
@@ -110,24 +240,45 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
   }
   int* d_rowoff = ar.upload(rowoff.data(), S);
   int* d_roword = ar.upload(roword.data(), S);
-  double* E = ar.get<double>((size_t)a.num_orient * Etot);
+  double* Yo = nullptr;  // [num_orient][Mc][S]
   {
     double* Ym = ar.get<double>((size_t)a.num_orient * a.M * S);
     EM_CUDA(launch_sh_mics(st, simN, a.mic_azi, a.mic_zen, a.M, a.rotations, a.num_orient, Ym));
     h->launches += 1;
-    const double* Yeff = Ym;
+    Yo = Ym;
     if (a.variant == Variant::EMAGLS_SH) {
-      throw Fail{EMAGLS_ERR_UNSUPPORTED, "SH-domain eMagLS is wired in a later step"};
-    }
-    for (int o0 = 0; o0 < a.num_orient; o0 += 32768) {
-      int nb = std::min(32768, a.num_orient - o0);
-      EM_CUDA(launch_build_E(st, R, S, simN, Yeff + (size_t)o0 * Mc * S, Mc, nb, d_rowoff, d_roword, Etot,
-                             E + (size_t)o0 * Etot));
-      h->launches += 1;
+      // L = pinv(Y_Hi(:, 1:(order+1)^2)) at the microphones as given (getSMAIRMatrix.m:102),
+      // obtained from the same factorisation kernel with the clip disabled.
+      double* Ym0 = ar.get<double>((size_t)a.M * S);
+      EM_CUDA(launch_sh_mics(st, simN, a.mic_azi, a.mic_zen, a.M, nullptr, 1, Ym0));
+      cplx* At = ar.get<cplx>((size_t)a.M * nsh);
+      {
+        // At[m][c] = Y_lo[m][c]
+        double* tmp = ar.get<double>((size_t)a.M * nsh);
+        EM_CUDA(cudaMemcpy2DAsync(tmp, (size_t)nsh * sizeof(double), Ym0, (size_t)S * sizeof(double),
+                                  (size_t)nsh * sizeof(double), a.M, cudaMemcpyDeviceToDevice, st));
+        long long n = (long long)a.M * nsh;
+        real_to_cplx_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tmp, n, At);
+      }
+      const int npair = (a.M + 1) / 2;
+      double* rows = ar.get<double>((size_t)npair * 4 * a.M);
+      {
+        long long n = (long long)npair * 4 * a.M;
+        identity_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rows, npair, a.M, a.M);
+      }
+      cplx* Wp = ar.get<cplx>((size_t)2 * npair * nsh);
+      regularized_apply_dev(h, ar, At, a.M, nsh, rows, npair, 0.0, Wp);
+      double* L = ar.get<double>((size_t)nsh * a.M);
+      extract_pinv_kernel<<<(nsh * a.M + 255) / 256, 256, 0, st>>>(Wp, npair, nsh, a.M, L);
+      double* Yeff = ar.get<double>((size_t)a.num_orient * nsh * S);
+      EM_CUDA(launch_left_mul(st, L, nsh, a.M, Ym, a.num_orient, S, Yeff));
+      EM_CUDA(cudaGetLastError());
+      h->launches += 6;
+      Yo = Yeff;
     }
   }
 
-  // ---------------- HRTF sets: group delay, H, |H|, H*Q
+  // ---------------- HRTF sets: group delay, H, |H|, H*Q, H*Y_h
   std::vector<double> grpD((size_t)a.num_sets * 2);
   {
     const int nchunk = 32;
@@ -147,8 +298,10 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
     for (int i = 0; i < a.num_sets * 2; ++i)
       grpD[i] = median_of(std::vector<double>(gdh.begin() + (size_t)i * K, gdh.begin() + (size_t)(i + 1) * K));
   }
-  double* absH = ar.get<double>((size_t)a.num_sets * 2 * K * D);           // [set][ear][K][D]
-  double* Tls = ar.get<double>((size_t)a.num_sets * 2 * std::max(nLS, 1) * 2 * S);  // [set][ear][kls][c][S]
+  double* absH = ar.get<double>((size_t)a.num_sets * 2 * K * D);                     // [set][ear][K][D]
+  const size_t ls_elems = (size_t)a.num_sets * 2 * std::max(nLS, 1) * 2 * S;         // [set][ear][kls][c][S]
+  double* Tls = ar.get<double>(ls_elems);   // H * Q
+  double* Zls = ar.get<double>(ls_elems);   // H * Y_h
   {
     double* tw = ar.get<double>((size_t)2 * K * T);
     EM_CUDA(launch_dft_twiddle(st, K, T, nfft, tw));
@@ -173,90 +326,181 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
         EM_CUDA(launch_abs_transpose(st, Hd, D, K, absH + ((size_t)s * 2 + e) * K * D));
         h->launches += 2;
         if (nLS > 0) {
-          GemmOperand A2{Hd + 2, 2LL * K, 0}, B2{Q, D, 1};
-          EpiStore st2{Tls + ((size_t)s * 2 + e) * nLS * 2 * S, S, 1.0};
-          EM_CUDA(launch_gemm(st, A2, B2, GemmShape{2 * nLS, S, D}, st2));
-          h->launches += 1;
+          GemmOperand A2{Hd + 2, 2LL * K, 0}, B2{Q, D, 1}, B3{Yh, D, 1};
+          const size_t off = ((size_t)s * 2 + e) * nLS * 2 * S;
+          EM_CUDA(launch_gemm(st, A2, B2, GemmShape{2 * nLS, S, D}, EpiStore{Tls + off, S, 1.0}));
+          EM_CUDA(launch_gemm(st, A2, B3, GemmShape{2 * nLS, S, D}, EpiStore{Zls + off, S, 1.0}));
+          h->launches += 2;
         }
       }
   }
-
   delete setup_span; setup_span = nullptr;
-  // ---------------- the hot loop over bins
+
+  // ---------------- memory plan: orientation chunks of OC, Gram bin groups of NB, TSQR slots of G
+  const int ne = Mc * (Mc + 1) / 2, ne_ld = (ne + 1) & ~1;
   const BlockPlan bp = make_block_plan(S, Mc);
-  int G = std::max(4, (1776 + P - 1) / P);
-  G = std::min(G, 32);
-  G = std::min(G, K - 1);
-  OperatorSet ops;
-  ops.v_stride = (long long)Mc * S;
-  ops.tau_stride = (long long)bp.nblk * bp.MC;
-  ops.rc_stride = (long long)Mc * Mc;
-  ops.pb_stride = (long long)Mc * Mc;
-  ops.V = ar.get<cplx>((size_t)P * G * ops.v_stride);
-  ops.tau = ar.get<cplx>((size_t)P * G * ops.tau_stride);
-  ops.Rc = ar.get<cplx>((size_t)P * G * ops.rc_stride);
-  ops.Pb = ar.get<cplx>((size_t)P * G * ops.pb_stride);
-  ops.info = ar.get<int>((size_t)P * G);
-  RowSource src{};
-  src.E = E; src.Etot = Etot; src.rowoff = d_rowoff; src.roword = d_roword; src.bn = bn; src.N = simN;
-  // E is per orientation; problems of different HRTF sets share it: problem p -> orientation p % num_orient.
-  // The factor kernel indexes E by problem, so factor per set when num_sets > 1 (operators are
-  // identical across sets; only computed once and reused).
-  const int PF = a.num_orient;  // problems factorised
+  const int NB = std::min(128, K - 1);
+  const int G = std::min(4, K - 1);
+  const long long v_stride = (long long)Mc * S, tau_stride = (long long)bp.nblk * bp.MC, pb_stride = (long long)Mc * Mc;
+  const size_t per_orient =
+      (size_t)Etot * 8 + (size_t)(nqs + nqa) * ne_ld * 8 + (size_t)2 * NB * ne_ld * 8 + (size_t)NB * pb_stride * 16 +
+      (size_t)G * (v_stride + tau_stride + pb_stride) * 16 +
+      (size_t)a.num_sets * ((size_t)2 * 4 * S * 8 + (size_t)4 * D * 8);
+  size_t free_b = 0, total_b = 0;
+  EM_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  // memory still cached in the stream-ordered pool is reusable: plan against the larger figure
+  {
+    cudaMemPool_t pool;
+    unsigned long long reserved = 0, used = 0;
+    if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+      free_b += (size_t)(reserved - used);
+  }
+  const size_t wsp_bytes = a.spectra ? 0 : (size_t)2 * P * Mc * K * sizeof(cplx);
+  EM_REQUIRE(free_b > wsp_bytes + (size_t)(1u << 28), "not enough device memory for the solution array");
+  long long oc_fit = (long long)((double)(free_b - wsp_bytes) * 0.7 / (double)per_orient);
+  if (const char* e = getenv("EMAGLS_ORIENT_CHUNK")) oc_fit = std::max(1, atoi(e));
+  EM_REQUIRE(oc_fit >= 1, "not enough device memory for one orientation");
+  const int OC = (int)std::min<long long>({(long long)a.num_orient, oc_fit, 8192LL});
+  const int PJ = a.num_sets * OC;
+
   cplx* Wsp = a.spectra ? reinterpret_cast<cplx*>(a.spectra) : ar.get<cplx>((size_t)2 * P * Mc * K);
   const long long w_ear = (long long)P * Mc * K;
-  double* Cv = ar.get<double>((size_t)4 * P * S);
-  double* Tt = ar.get<double>((size_t)D * 4 * P);
-  double* tq = ar.get<double>((size_t)4 * P * S);
   EM_CUDA(cudaMemsetAsync(Wsp, 0, (size_t)2 * P * Mc * K * sizeof(cplx), st));
+  double* E = ar.get<double>((size_t)OC * Etot);
+  double* Fs = ar.get<double>((size_t)nqs * OC * ne_ld);
+  double* Fa = ar.get<double>((size_t)nqa * OC * ne_ld);
+  double* Gre = ar.get<double>((size_t)NB * OC * ne_ld);
+  double* Gim = ar.get<double>((size_t)NB * OC * ne_ld);
+  cplx* PbG = ar.get<cplx>((size_t)NB * OC * pb_stride);
+  int* d_fail = ar.get<int>(NB + 1);
+  OperatorSet ops;
+  ops.v_stride = v_stride; ops.tau_stride = tau_stride; ops.pb_stride = pb_stride;
+  ops.V = ar.get<cplx>((size_t)OC * G * v_stride);
+  ops.tau = ar.get<cplx>((size_t)OC * G * tau_stride);
+  ops.Pb = ar.get<cplx>((size_t)OC * G * pb_stride);
+  ops.info = ar.get<int>((size_t)OC * G);
+  double* Cv = ar.get<double>((size_t)4 * PJ * S);
+  double* Tt = ar.get<double>((size_t)D * 4 * PJ);
+  double* tq = ar.get<double>((size_t)4 * PJ * S);
+  // Gram route admissible iff cond_2(G) <= 1/c^2 (no singular value below c*s_max); the Frobenius
+  // bound is tested with a factor-2 margin, and normal equations are never used beyond cond(G) = 1e4.
+  double gram_thr = (cfg.svd_regul > 0.0) ? std::min(1e4, 0.5 / (cfg.svd_regul * cfg.svd_regul)) : 1e4;
+  if (getenv("EMAGLS_NO_GRAM")) gram_thr = -1.0;
+  const bool debug = getenv("EMAGLS_DEBUG_INFO") != nullptr;
+  std::vector<int> fail_h(NB + 1);
 
-  for (int g0 = 1; g0 < K; g0 += G) {
-    const int Gn = std::min(G, K - g0);
+  for (int o0 = 0; o0 < a.num_orient; o0 += OC) {
+    const int oc = std::min(OC, a.num_orient - o0);
+    const int pj = a.num_sets * oc;
+    const ProbMap pm{oc, o0, a.num_orient};
+    const double* Yc = Yo + (size_t)o0 * Mc * S;
     {
-      ProfSpan ps(h, EM_PROF_FACTOR);
-      EM_CUDA(launch_factor(st, bp, src, ops, PF, g0, Gn, cfg.svd_regul));
-    }
-    h->launches += 1;
-    if (getenv("EMAGLS_DEBUG_INFO")) {
-      std::vector<int> info((size_t)PF * Gn);
-      EM_CUDA(cudaMemcpyAsync(info.data(), ops.info, info.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
-      EM_CUDA(cudaStreamSynchronize(st));
-      for (int slot = 0; slot < Gn; ++slot) {
-        int nfast = 0, smax = 0; long long ssum = 0;
-        for (int p = 0; p < PF; ++p) { int v = info[(size_t)p * Gn + slot]; nfast += (v == 0); smax = std::max(smax, v); ssum += v; }
-        fprintf(stderr, "bin %d: fast %d/%d, sweeps max %d mean %.2f\n", g0 + slot, nfast, PF, smax, (double)ssum / PF);
+      ProfSpan ps(h, EM_PROF_SETUP);
+      for (int b0 = 0; b0 < oc; b0 += 32768) {
+        int nb = std::min(32768, oc - b0);
+        EM_CUDA(launch_build_E(st, R, S, simN, Yc + (size_t)b0 * Mc * S, Mc, nb, d_rowoff, d_roword, Etot,
+                               E + (size_t)b0 * Etot));
+        h->launches += 1;
       }
     }
-    for (int slot = 0; slot < Gn; ++slot) {
-      const int kb = g0 + slot;
-      if (kb < kls1) {
-        ProfSpan ps(h, EM_PROF_CHAIN_BWD);
-        EM_CUDA(launch_chain_bwd(st, bp, ops, slot, Gn, Tls + (size_t)(kb - 1) * 2 * S, (long long)2 * nLS * 2 * S,
-                                 (long long)nLS * 2 * S, 1, a.num_orient, PF, Wsp, w_ear, K, kb, 1, P));
-        h->launches += 1;
-      } else {
-        {
-          ProfSpan ps(h, EM_PROF_CHAIN_FWD);
-          EM_CUDA(launch_chain_fwd(st, bp, ops, slot, Gn, PF, Wsp, w_ear, K, kb - 1, P, Cv));
+    if (gram_thr > 0.0) {
+      ProfSpan ps(h, EM_PROF_GRAM);
+      // build_F addresses (q*P + o) with P = oc: one launch per <= 32768 orientations is not possible
+      // with that layout, so the grid's y dimension limits a chunk to 65535 orientations (OC <= 8192).
+      EM_CUDA(launch_build_F(st, Gh, S, simN, Yc, Mc, oc, ne_ld, Fs, Fa));
+      h->launches += 1;
+    }
+    RowSource src{};
+    src.E = E; src.Etot = Etot; src.rowoff = d_rowoff; src.roword = d_roword; src.bn = bn; src.N = simN;
+
+    for (int gb0 = 1; gb0 < K; gb0 += NB) {
+      const int nb = std::min(NB, K - gb0);
+      std::fill(fail_h.begin(), fail_h.end(), 1);
+      if (gram_thr > 0.0) {
+        ProfSpan ps(h, EM_PROF_GRAM);
+        const int ncol = oc * ne_ld;
+        EM_CUDA(cudaMemsetAsync(d_fail, 0, (size_t)(NB + 1) * sizeof(int), st));
+        GemmOperand A1{bre + (size_t)gb0 * nqs, nqs, 1}, B1{Fs, (long long)ncol, 0};
+        EM_CUDA(launch_gemm(st, A1, B1, GemmShape{nb, ncol, nqs}, EpiStore{Gre, (long long)ncol, 1.0}));
+        if (simN > 0) {
+          GemmOperand A2{bim + (size_t)gb0 * nqa, nqa, 1}, B2{Fa, (long long)ncol, 0};
+          EM_CUDA(launch_gemm(st, A2, B2, GemmShape{nb, ncol, simN * (simN + 1) / 2}, EpiStore{Gim, (long long)ncol, 1.0}));
+        } else {
+          EM_CUDA(cudaMemsetAsync(Gim, 0, (size_t)nb * ncol * sizeof(double), st));
         }
-        {
-          ProfSpan ps(h, EM_PROF_GEMM_FWD);
-          GemmOperand A3{Q, D, 0}, B3{Cv, S, 1};
-          EpiPhase ep{Tt, 4LL * P, absH + (size_t)kb * D, 2LL * K * D, (long long)K * D, a.num_orient,
-                      kb == K - 1 ? 1 : 0};
-          EM_CUDA(launch_gemm(st, A3, B3, GemmShape{D, 4 * P, S}, ep));
+        EM_CUDA(launch_gram_chol(st, Gre, Gim, Mc, oc, ne_ld, nb, gram_thr, PbG, d_fail));
+        h->launches += 3;
+        EM_CUDA(cudaMemcpyAsync(fail_h.data(), d_fail, (size_t)(nb + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+        EM_CUDA(cudaStreamSynchronize(st));
+      }
+      if (debug) {
+        int ng = 0;
+        for (int i = 0; i < nb; ++i) ng += (fail_h[1 + i] == 0);
+        fprintf(stderr, "orient chunk %d: bins %d..%d: %d Gram bins, %d TSQR bins\n", o0, gb0, gb0 + nb - 1, ng, nb - ng);
+      }
+      int slot_base = -1, slot_n = 0;  // bins [slot_base, slot_base + slot_n) hold valid TSQR operators
+      for (int kb = gb0; kb < gb0 + nb; ++kb) {
+        const bool gram = fail_h[1 + kb - gb0] == 0;
+        const cplx* bk = bn + (size_t)kb * (simN + 1);
+        if (!gram && !(kb >= slot_base && kb < slot_base + slot_n)) {
+          int Gn = 0;
+          while (Gn < G && kb + Gn < gb0 + nb && fail_h[1 + kb + Gn - gb0] != 0) ++Gn;
+          {
+            ProfSpan ps(h, EM_PROF_FACTOR);
+            EM_CUDA(launch_factor(st, bp, src, ops, oc, kb, Gn, cfg.svd_regul));
+          }
+          h->launches += 1;
+          slot_base = kb; slot_n = Gn;
+          if (debug) {
+            std::vector<int> info((size_t)oc * Gn);
+            EM_CUDA(cudaMemcpyAsync(info.data(), ops.info, info.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+            EM_CUDA(cudaStreamSynchronize(st));
+            for (int slot = 0; slot < Gn; ++slot) {
+              int nfast = 0, smax = 0; long long ssum = 0;
+              for (int p = 0; p < oc; ++p) { int v = info[(size_t)p * Gn + slot]; nfast += (v == 0); smax = std::max(smax, v); ssum += v; }
+              fprintf(stderr, "bin %d: fast %d/%d, sweeps max %d mean %.2f\n", kb + slot, nfast, oc, smax, (double)ssum / oc);
+            }
+          }
         }
-        {
-          ProfSpan ps(h, EM_PROF_GEMM_BWD);
-          GemmOperand A4{Tt, 4LL * P, 0}, B4{Q, D, 1};
-          EpiStore es{tq, S, 1.0};
-          EM_CUDA(launch_gemm(st, A4, B4, GemmShape{4 * P, S, D}, es));
-        }
-        {
+        const int slot = kb - slot_base;
+        const cplx* pbg = PbG + (size_t)(kb - gb0) * oc * pb_stride;
+        if (kb < kls1) {
           ProfSpan ps(h, EM_PROF_CHAIN_BWD);
-          EM_CUDA(launch_chain_bwd(st, bp, ops, slot, Gn, tq, 0, 0, 0, a.num_orient, PF, Wsp, w_ear, K, kb, 1, P));
+          const size_t off = (size_t)(kb - 1) * 2 * S;
+          if (gram)
+            EM_CUDA(launch_bwd_small(st, Yc, Mc, S, d_roword, bk, pbg, pm, pj, Zls + off, (long long)2 * nLS * 2 * S,
+                                     (long long)nLS * 2 * S, 1, Wsp, w_ear, K, kb, dc_fix));
+          else
+            EM_CUDA(launch_chain_bwd(st, bp, ops, slot, slot_n, Tls + off, (long long)2 * nLS * 2 * S,
+                                     (long long)nLS * 2 * S, 1, pm, Wsp, w_ear, K, kb, dc_fix, pj));
+          h->launches += 1;
+        } else {
+          {
+            ProfSpan ps(h, EM_PROF_CHAIN_FWD);
+            EM_CUDA(launch_fwd_small(st, Yc, Mc, S, d_roword, bk, pm, pj, Wsp, w_ear, K, kb - 1, Cv));
+          }
+          {
+            ProfSpan ps(h, EM_PROF_GEMM_FWD);
+            GemmOperand A3{Yh, D, 0}, B3{Cv, S, 1};
+            EpiPhase ep{Tt, 4LL * pj, absH + (size_t)kb * D, 2LL * K * D, (long long)K * D, oc, kb == K - 1 ? 1 : 0};
+            EM_CUDA(launch_gemm(st, A3, B3, GemmShape{D, 4 * pj, S}, ep));
+          }
+          {
+            ProfSpan ps(h, EM_PROF_GEMM_BWD);
+            GemmOperand A4{Tt, 4LL * pj, 0}, B4{gram ? Yh : Q, D, 1};
+            EM_CUDA(launch_gemm(st, A4, B4, GemmShape{4 * pj, S, D}, EpiStore{tq, S, 1.0}));
+          }
+          {
+            ProfSpan ps(h, EM_PROF_CHAIN_BWD);
+            if (gram)
+              EM_CUDA(launch_bwd_small(st, Yc, Mc, S, d_roword, bk, pbg, pm, pj, tq, 0, 0, 0, Wsp, w_ear, K, kb, dc_fix));
+            else
+              EM_CUDA(launch_chain_bwd(st, bp, ops, slot, slot_n, tq, 0, 0, 0, pm, Wsp, w_ear, K, kb, dc_fix, pj));
+          }
+          h->launches += 4;
         }
-        h->launches += 4;
       }
     }
   }
@@ -265,17 +509,34 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
   {
     ProfSpan ps(h, EM_PROF_TAIL);
     double* twT = ar.get<double>((size_t)a.len * 2 * K);
+    double* wtmp = cplx_out ? ar.get<double>((size_t)a.num_orient * Mc * a.len) : nullptr;
     for (int s = 0; s < a.num_sets; ++s)
       for (int e = 0; e < 2; ++e) {
         double delay = (double)(nfft / 2) + (e == 1 ? (grpD[(size_t)s * 2 + 1] - grpD[(size_t)s * 2]) : 0.0);
         EM_CUDA(launch_tail_twiddle(st, K, nfft, a.len, delay, twT));
-        const double* Wse = reinterpret_cast<const double*>(Wsp + ((size_t)e * P + (size_t)s * a.num_orient) * Mc * K);
+        const cplx* Wse_c = Wsp + ((size_t)e * P + (size_t)s * a.num_orient) * Mc * K;
+        const double* Wse = reinterpret_cast<const double*>(Wse_c);
         GemmOperand A5{Wse, 2LL * K, 1}, B5{twT, 2LL * K, 1};
-        double* out = (e == 0 ? a.wL : a.wR) + (size_t)s * a.num_orient * Mc * a.len;
+        const size_t out_off = (size_t)s * a.num_orient * Mc * a.len;
+        double* out = cplx_out ? wtmp : (e == 0 ? a.wL : a.wR) + out_off;
         EpiStore es{out, a.len, 1.0};
         EM_CUDA(launch_gemm(st, A5, B5, GemmShape{a.num_orient * Mc, a.len, 2 * K}, es));
         h->launches += 2;
+        if (cplx_out) {
+          cplx* outc = reinterpret_cast<cplx*>(e == 0 ? a.wL : a.wR) + out_off;
+          long long n = (long long)a.num_orient * Mc * a.len;
+          complex_basis_filters_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(wtmp, Wse_c, a.order, a.len, K, nfft,
+                                                                                   a.num_orient, outc);
+          EM_CUDA(cudaGetLastError());
+          h->launches += 1;
+        }
       }
+    if (cplx_out && a.spectra) {
+      long long n = (long long)2 * P * Mc * K;
+      complex_basis_spectra_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Wsp, a.order, K, 2LL * P);
+      EM_CUDA(cudaGetLastError());
+      h->launches += 1;
+    }
   }
 }
 

@@ -18,6 +18,7 @@ enum EmProfClass {
   EM_PROF_RENDER_MAC,     // spectral multiply-accumulate of the render
   EM_PROF_RENDER_FFT,     // cuFFT transforms of the render
   EM_PROF_RENDER_STAGE,   // staging copies of the render
+  EM_PROF_GRAM,           // Gram route: F blocks, DMMA assembly of G_k, warp-per-matrix Cholesky
   EM_PROF_NUM
 };
 
@@ -150,5 +151,9 @@ struct DesignArgs {
   double* spectra;          // device or nullptr: complex [K x Mc x P x 2]
 };
 void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& a);
+// targets * Y_reg_inv for one steering matrix given as rows At [D][Mc]; rows [(pair*2+ear)*2+{re,im}][D],
+// W [ear][pair][Mc]
+void regularized_apply_dev(emagls_ctx* h, Arena& ar, const cplx* At, int D, int Mc, const double* rows,
+                           int npair, double regul, cplx* W);
 
 }  // namespace emagls

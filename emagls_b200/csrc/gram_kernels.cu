@@ -1,0 +1,347 @@
+// Gram route of the eMagLS hot loop for the bins where no singular value can be clipped.
+//
+// Reference step (lib/getEMagLs2Filters.m:86-89): Y_reg_inv = conj(U) diag(1/max(s, c s_max)) V.'.
+// With A = pwGrid.' = Y_h diag(b_k) Ym^T and G = A^H A, the clip is inactive iff
+// cond_2(G) <= 1/c^2; then Y_reg_inv = pinv(A).' = conj(A) G^-T exactly, i.e.
+//     W_k = ((t Y_h) .* conj(b_k)) Ym^T G^-T.
+// G is assembled on the FP64 tensor cores from k-independent per-orientation blocks,
+//     G_k = sum_{n,n'} conj(b_n) b_n' F_nn',   F_nn' = Ym_n (Y_h^T Y_h)_{nn'} Ym_n'^T,
+// folded by the symmetries F_n'n = F_nn'^T into a symmetric (Fs) and an antisymmetric (Fa) part:
+//     Re G = sum_{n<=n'} Re(conj(b_n) b_n') Fs_nn',    Im G = sum_{n<n'} Im(conj(b_n) b_n') Fa_nn'
+// (one real GEMM each, [bins x pairs] x [pairs x (orientation, packed lower triangle)]).
+// A warp-per-matrix Cholesky in shared memory then yields G^-1 and the rigorous bound
+// cond_2(G) <= ||G||_F ||G^-1||_F that decides whether the bin may use this route; bins that fail
+// it go through the TSQR + Jacobi kernel (solver_kernels.cu).
+#include "kernels.h"
+
+namespace emagls {
+
+// ---------------------------------------------------------------------------------------------
+// F blocks.  grid (pairs n<=n', orientation), pair index q = n'(n'+1)/2 + n.
+// Fs[(q*P + o)*ne + e], Fa[(qa*P + o)*ne + e] with qa = n'(n'-1)/2 + n (n < n'),
+// e = m(m+1)/2 + m' (m >= m').
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+build_F_kernel(const double* __restrict__ Gh, int S, const double* __restrict__ Y, int Mc, int P,
+               int ne_ld, double* __restrict__ Fs, double* __restrict__ Fa) {
+  extern __shared__ double fsm[];
+  const int q = blockIdx.x, o = blockIdx.y, tid = threadIdx.x;
+  int np = (int)((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);
+  while ((np + 1) * (np + 2) / 2 <= q) ++np;
+  while (np * (np + 1) / 2 > q) --np;
+  const int n = q - np * (np + 1) / 2;
+  const int wn = 2 * n + 1, wnp = 2 * np + 1, s0 = n * n, sp0 = np * np;
+  double* Yn = fsm;                 // [Mc][wn]
+  double* Ynp = Yn + Mc * wn;       // [Mc][wnp]
+  double* Z = Ynp + Mc * wnp;       // [wn][Mc]
+  double* Fm = Z + wn * Mc;         // [Mc][Mc+1]
+  const double* Yo = Y + (long long)o * Mc * S;
+  for (int idx = tid; idx < Mc * wn; idx += blockDim.x) Yn[idx] = Yo[(long long)(idx / wn) * S + s0 + idx % wn];
+  for (int idx = tid; idx < Mc * wnp; idx += blockDim.x) Ynp[idx] = Yo[(long long)(idx / wnp) * S + sp0 + idx % wnp];
+  __syncthreads();
+  for (int idx = tid; idx < wn * Mc; idx += blockDim.x) {
+    const int s = idx / Mc, mp = idx % Mc;
+    const double* g = Gh + (long long)(s0 + s) * S + sp0;
+    const double* y = Ynp + mp * wnp;
+    double acc = 0.0;
+    for (int t = 0; t < wnp; ++t) acc = fma(g[t], y[t], acc);
+    Z[idx] = acc;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < Mc * Mc; idx += blockDim.x) {
+    const int m = idx / Mc, mp = idx % Mc;
+    const double* y = Yn + m * wn;
+    double acc = 0.0;
+    for (int s = 0; s < wn; ++s) acc = fma(y[s], Z[s * Mc + mp], acc);
+    Fm[m * (Mc + 1) + mp] = acc;
+  }
+  __syncthreads();
+  const int ne = Mc * (Mc + 1) / 2;
+  double* fs = Fs + ((long long)q * P + o) * ne_ld;
+  double* fa = (n < np) ? Fa + ((long long)(np * (np - 1) / 2 + n) * P + o) * ne_ld : nullptr;
+  if (tid == 0 && ne_ld > ne) { fs[ne] = 0.0; if (fa) fa[ne] = 0.0; }  // alignment pad column
+  for (int e = tid; e < ne; e += blockDim.x) {
+    int m = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+    while ((m + 1) * (m + 2) / 2 <= e) ++m;
+    while (m * (m + 1) / 2 > e) --m;
+    const int mp = e - m * (m + 1) / 2;
+    const double a = Fm[m * (Mc + 1) + mp], b = Fm[mp * (Mc + 1) + m];
+    if (n == np) fs[e] = 0.5 * (a + b);
+    else { fs[e] = a + b; fa[e] = a - b; }
+  }
+}
+
+cudaError_t launch_build_F(cudaStream_t st, const double* Gh, int S, int N, const double* Y, int Mc,
+                           int P, int ne_ld, double* Fs, double* Fa) {
+  const int wmax = 2 * N + 1;
+  size_t smem = ((size_t)2 * Mc * wmax + (size_t)wmax * Mc + (size_t)Mc * (Mc + 1)) * sizeof(double);
+  static size_t set_to = 0;
+  if (smem > 48 * 1024 && smem > set_to) {
+    cudaError_t e = cudaFuncSetAttribute(build_F_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    set_to = smem;
+  }
+  dim3 grid((N + 1) * (N + 2) / 2, P);
+  build_F_kernel<<<grid, 256, smem, st>>>(Gh, S, Y, Mc, P, ne_ld, Fs, Fa);
+  return cudaGetLastError();
+}
+
+// beta tables: bre[k][q] = Re(conj(b_n) b_n') (n <= n'), bim[k][qa] = Im(conj(b_n) b_n') (n < n')
+__global__ void gram_beta_kernel(const cplx* __restrict__ bn, int N, int K, double* __restrict__ bre,
+                                 double* __restrict__ bim) {
+  const int nqs = (N + 1) * (N + 2) / 2, nqa = N * (N + 1) / 2;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)K * nqs) return;
+  const int k = (int)(idx / nqs), q = (int)(idx % nqs);
+  int np = (int)((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);
+  while ((np + 1) * (np + 2) / 2 <= q) ++np;
+  while (np * (np + 1) / 2 > q) --np;
+  const int n = q - np * (np + 1) / 2;
+  const cplx a = bn[(long long)k * (N + 1) + n], b = bn[(long long)k * (N + 1) + np];
+  bre[(long long)k * nqs + q] = fma(a.x, b.x, a.y * b.y);
+  if (n < np) bim[(long long)k * nqa + np * (np - 1) / 2 + n] = fma(a.x, b.y, -a.y * b.x);
+}
+
+cudaError_t launch_gram_beta(cudaStream_t st, const cplx* bn, int N, int K, double* bre, double* bim) {
+  long long total = (long long)K * ((N + 1) * (N + 2) / 2);
+  gram_beta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(bn, N, K, bre, bim);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-per-matrix Cholesky, inverse and condition bound.  Matrix id = bin * P + o.
+// Output Pb[id][i][m] = Ginv[m][i] (so that W = v * Pb), fail[bin] += 1 when the route is refused.
+// ---------------------------------------------------------------------------------------------
+constexpr int GC_WPC = 4;
+
+__global__ void __launch_bounds__(GC_WPC * 32)
+gram_chol_kernel(const double* __restrict__ Gre, const double* __restrict__ Gim, int Mc, int P, int ne_ld,
+                 long long nmat, double thr, cplx* __restrict__ Pb, int* __restrict__ fail) {
+  extern __shared__ __align__(16) unsigned char gsm_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long id = (long long)blockIdx.x * GC_WPC + warp;
+  if (id >= nmat) return;
+  const int LD = Mc + 1;
+  const int ne = Mc * (Mc + 1) / 2;
+  cplx* L = reinterpret_cast<cplx*>(gsm_raw) + (size_t)warp * ((size_t)Mc * LD + (Mc + 1) / 2);
+  double* dinv = reinterpret_cast<double*>(L + (size_t)Mc * LD);  // 1 / L[j][j]
+  const double* gr = Gre + id * ne_ld;
+  const double* gi = Gim + id * ne_ld;
+
+  // load the packed lower triangle; ||G||_F^2
+  double fro = 0.0;
+  for (int e = lane; e < ne; e += 32) {
+    int m = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+    while ((m + 1) * (m + 2) / 2 <= e) ++m;
+    while (m * (m + 1) / 2 > e) --m;
+    const int mp = e - m * (m + 1) / 2;
+    const double re = gr[e], im = (m == mp) ? 0.0 : gi[e];
+    L[m * LD + mp] = mk(re, im);
+    fro += (m == mp) ? re * re : 2.0 * fma(re, re, im * im);
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) fro += __shfl_xor_sync(0xffffffffu, fro, s);
+  __syncwarp();
+
+  // right-looking Cholesky, lane = row
+  bool ok = true;
+  for (int j = 0; j < Mc; ++j) {
+    const double d = L[j * LD + j].x;
+    if (!(d > 0.0) || !(d < 1e300)) { ok = false; break; }
+    const double ljj = sqrt(d), inv = 1.0 / ljj;
+    __syncwarp();
+    for (int r = lane; r < Mc; r += 32) {
+      if (r > j) { cplx v = L[r * LD + j]; L[r * LD + j] = mk(v.x * inv, v.y * inv); }
+      else if (r == j) { L[j * LD + j] = mk(ljj, 0.0); dinv[j] = inv; }
+    }
+    __syncwarp();
+    for (int r = lane; r < Mc; r += 32) {
+      if (r > j) {
+        const cplx lrj = L[r * LD + j];
+        for (int c = j + 1; c <= r; ++c) {
+          const cplx lcj = L[c * LD + j];
+          cplx a = L[r * LD + c];
+          // a -= lrj * conj(lcj)
+          a.x = fma(-lrj.x, lcj.x, a.x); a.x = fma(-lrj.y, lcj.y, a.x);
+          a.y = fma(-lrj.y, lcj.x, a.y); a.y = fma(lrj.x, lcj.y, a.y);
+          L[r * LD + c] = a;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (!ok) {
+    if (lane == 0) atomicAdd(fail, 1), atomicAdd(fail + 1 + (int)(id / P), 1);
+    return;
+  }
+  // Li = L^-1 (lower), stored transposed in the strict upper triangle: Li[r][c] -> L[c*LD + r]
+  // lane = column c;  Li[r][c] = -(sum_{l=c}^{r-1} L[r][l] Li[l][c]) / L[r][r],  Li[c][c] = dinv[c]
+  for (int r = 1; r < Mc; ++r) {
+    for (int c0 = 0; c0 < r; c0 += 32) {
+      const int c = c0 + lane;
+      cplx sum = mk(0.0, 0.0);
+      if (c < r) {
+        for (int l = c; l < r; ++l) {
+          const cplx lrl = L[r * LD + l];
+          const cplx lic = (l == c) ? mk(dinv[c], 0.0) : L[c * LD + l];
+          cfma(sum, lrl, lic);
+        }
+        const double di = -dinv[r];
+        L[c * LD + r] = mk(sum.x * di, sum.y * di);
+      }
+    }
+    __syncwarp();
+  }
+  // Ginv[m][i] = sum_{l >= max(m,i)} conj(Li[l][m]) Li[l][i];  lane = i, loop over m
+  double froi = 0.0;
+  cplx* out = Pb + id * (long long)Mc * Mc;
+  for (int m = 0; m < Mc; ++m) {
+    for (int i = lane; i < Mc; i += 32) {
+      cplx g = mk(0.0, 0.0);
+      const int l0 = (m > i) ? m : i;
+      for (int l = l0; l < Mc; ++l) {
+        const cplx a = (l == m) ? mk(dinv[m], 0.0) : L[m * LD + l];   // Li[l][m]
+        const cplx b = (l == i) ? mk(dinv[i], 0.0) : L[i * LD + l];   // Li[l][i]
+        cfmac(g, a, b);
+      }
+      froi += cabs2(g);
+      out[(long long)m * Mc + i] = mk(g.x, -g.y);   // Pb[m][i] = Ginv[i][m] = conj(Ginv[m][i])
+    }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) froi += __shfl_xor_sync(0xffffffffu, froi, s);
+  const double condF = sqrt(fro) * sqrt(froi);
+  if (!(condF <= thr)) {
+    if (lane == 0) atomicAdd(fail, 1), atomicAdd(fail + 1 + (int)(id / P), 1);
+  }
+}
+
+cudaError_t launch_gram_chol(cudaStream_t st, const double* Gre, const double* Gim, int Mc, int P,
+                             int ne_ld, int nbins, double thr, cplx* Pb, int* fail) {
+  const long long nmat = (long long)nbins * P;
+  size_t per_warp = ((size_t)Mc * (Mc + 1) + (Mc + 1) / 2) * sizeof(cplx);
+  size_t smem = per_warp * GC_WPC;
+  static size_t set_to = 0;
+  if (smem > 48 * 1024 && smem > set_to) {
+    cudaError_t e = cudaFuncSetAttribute(gram_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    set_to = smem;
+  }
+  gram_chol_kernel<<<(unsigned)((nmat + GC_WPC - 1) / GC_WPC), GC_WPC * 32, smem, st>>>(Gre, Gim, Mc, P, ne_ld, nmat, thr,
+                                                                                    Pb, fail);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward: u = b_k .* (Y_o^T w_{k-1})  ->  Cv rows (j*2+ear)*2 + {re, im}, S doubles each.
+// One CTA per chunk-local problem j (set = j / oc, orientation o0 + j % oc), both ears.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+fwd_small_kernel(const double* __restrict__ Y, int Mc, int S, const int* __restrict__ roword,
+                 const cplx* __restrict__ bk, ProbMap pm, const cplx* __restrict__ Wsp,
+                 long long w_ear_stride, int K, int kprev, double* __restrict__ Cv) {
+  __shared__ cplx w_s[2][64];
+  const int j = blockIdx.x, tid = threadIdx.x;
+  const int ol = j % pm.oc;
+  const long long p = pm.global(j);
+  for (int idx = tid; idx < 2 * Mc; idx += blockDim.x) {
+    const int e = idx / Mc, m = idx % Mc;
+    w_s[e][m] = Wsp[(long long)e * w_ear_stride + (p * Mc + m) * K + kprev];
+  }
+  __syncthreads();
+  const double* Yo = Y + (long long)ol * Mc * S;
+  double* c0 = Cv + ((long long)(j * 2 + 0) * 2) * S;
+  double* c1 = Cv + ((long long)(j * 2 + 1) * 2) * S;
+  for (int s = tid; s < S; s += blockDim.x) {
+    double a0r = 0.0, a0i = 0.0, a1r = 0.0, a1i = 0.0;
+#pragma unroll 8
+    for (int m = 0; m < Mc; ++m) {
+      const double y = Yo[(long long)m * S + s];
+      a0r = fma(y, w_s[0][m].x, a0r); a0i = fma(y, w_s[0][m].y, a0i);
+      a1r = fma(y, w_s[1][m].x, a1r); a1i = fma(y, w_s[1][m].y, a1i);
+    }
+    const cplx b = bk[roword[s]];
+    c0[s] = fma(b.x, a0r, -b.y * a0i); c0[S + s] = fma(b.x, a0i, b.y * a0r);
+    c1[s] = fma(b.x, a1r, -b.y * a1i); c1[S + s] = fma(b.x, a1i, b.y * a1r);
+  }
+}
+
+cudaError_t launch_fwd_small(cudaStream_t st, const double* Y, int Mc, int S, const int* roword,
+                             const cplx* bk, ProbMap pm, int num_prob, const cplx* Wsp,
+                             long long w_ear_stride, int K, int kprev, double* Cv) {
+  if (Mc > 64) return cudaErrorInvalidValue;
+  fwd_small_kernel<<<num_prob, 128, 0, st>>>(Y, Mc, S, roword, bk, pm, Wsp, w_ear_stride, K, kprev, Cv);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward (Gram bins): v = Y_o (conj(b_k) .* z),  W_k = v * Pb.   z rows like Cv, or shared per
+// (set, ear) for the LS bins (z_shared != 0: z + set*z_set_stride + ear*z_ear_stride, [re | im]).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bwd_small_kernel(const double* __restrict__ Y, int Mc, int S, const int* __restrict__ roword,
+                 const cplx* __restrict__ bk, const cplx* __restrict__ Pb, ProbMap pm,
+                 const double* __restrict__ z, long long z_set_stride, long long z_ear_stride,
+                 int z_shared, cplx* __restrict__ Wsp, long long w_ear_stride, int K, int k, int dc_fix) {
+  extern __shared__ __align__(16) unsigned char bsm_raw[];
+  cplx* zb = reinterpret_cast<cplx*>(bsm_raw);   // [2][S]
+  cplx* v = zb + 2 * (size_t)S;                  // [2][Mc]
+  const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int ol = j % pm.oc;
+  const long long p = pm.global(j);
+  const double* z0 = z_shared ? z + (long long)(j / pm.oc) * z_set_stride : z + ((long long)(j * 2) * 2) * S;
+  const double* z1 = z0 + (z_shared ? z_ear_stride : 2LL * S);
+  for (int s = tid; s < S; s += blockDim.x) {
+    const cplx b = bk[roword[s]];
+    const double r0 = z0[s], i0 = z0[S + s], r1 = z1[s], i1 = z1[S + s];
+    // conj(b) * z
+    zb[s] = mk(fma(b.x, r0, b.y * i0), fma(b.x, i0, -b.y * r0));
+    zb[S + s] = mk(fma(b.x, r1, b.y * i1), fma(b.x, i1, -b.y * r1));
+  }
+  __syncthreads();
+  const double* Yo = Y + (long long)ol * Mc * S;
+  for (int i = warp; i < Mc; i += nw) {
+    const double* y = Yo + (long long)i * S;
+    double a0r = 0.0, a0i = 0.0, a1r = 0.0, a1i = 0.0;
+    for (int s = lane; s < S; s += 32) {
+      const double yv = y[s];
+      const cplx q0 = zb[s], q1 = zb[S + s];
+      a0r = fma(yv, q0.x, a0r); a0i = fma(yv, q0.y, a0i);
+      a1r = fma(yv, q1.x, a1r); a1i = fma(yv, q1.y, a1i);
+    }
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) {
+      a0r += __shfl_xor_sync(0xffffffffu, a0r, sh); a0i += __shfl_xor_sync(0xffffffffu, a0i, sh);
+      a1r += __shfl_xor_sync(0xffffffffu, a1r, sh); a1i += __shfl_xor_sync(0xffffffffu, a1i, sh);
+    }
+    if (lane == 0) { v[i] = mk(a0r, a0i); v[Mc + i] = mk(a1r, a1i); }
+  }
+  __syncthreads();
+  const cplx* pb = Pb + (long long)ol * Mc * Mc;
+  for (int idx = tid; idx < 2 * Mc; idx += blockDim.x) {
+    const int e = idx / Mc, m = idx % Mc;
+    cplx acc = mk(0.0, 0.0);
+    for (int i = 0; i < Mc; ++i) cfma(acc, v[e * Mc + i], pb[i * Mc + m]);
+    cplx* wp = Wsp + (long long)e * w_ear_stride + (p * Mc + m) * K + k;
+    *wp = acc;
+    if (dc_fix && k == 1) wp[-1] = mk(acc.x, 0.0);  // W(1,:) = real(W(2,:)), lib/getEMagLs2Filters.m:109-110
+  }
+}
+
+cudaError_t launch_bwd_small(cudaStream_t st, const double* Y, int Mc, int S, const int* roword,
+                             const cplx* bk, const cplx* Pb, ProbMap pm, int num_prob, const double* z,
+                             long long z_set_stride, long long z_ear_stride, int z_shared, cplx* Wsp,
+                             long long w_ear_stride, int K, int k, int dc_fix) {
+  size_t smem = ((size_t)2 * S + 2 * Mc) * sizeof(cplx);
+  static size_t set_to = 0;
+  if (smem > 48 * 1024 && smem > set_to) {
+    cudaError_t e = cudaFuncSetAttribute(bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    set_to = smem;
+  }
+  bwd_small_kernel<<<num_prob, 256, smem, st>>>(Y, Mc, S, roword, bk, Pb, pm, z, z_set_stride, z_ear_stride, z_shared,
+                                               Wsp, w_ear_stride, K, k, dc_fix);
+  return cudaGetLastError();
+}
+
+}  // namespace emagls

@@ -42,6 +42,15 @@ cudaError_t launch_abs_transpose(cudaStream_t st, const double* Hd, int D, int K
 // tail twiddles [len][2K] for one ear: ifft + sub-sample delay + crop + fade folded into one matrix
 cudaError_t launch_tail_twiddle(cudaStream_t st, int K, int nfft, int len, double delay, double* tw);
 
+// Chunk-local problem index j -> (set = j / oc, orientation o0 + j % oc); global problem index
+// p = set * num_orient + orientation addresses the solution array Wsp.
+struct ProbMap {
+  int oc, o0, num_orient;
+  __host__ __device__ __forceinline__ long long global(int j) const {
+    return (long long)(j / oc) * num_orient + o0 + (j % oc);
+  }
+};
+
 // ---------------------------------------------------------------- solver_kernels.cu
 struct RowSource {
   // factored model: C[i][c] = sum_{n >= ord(i)} bn[k][n] * E[o][rowoff[i] + (n-ord(i))*Mc + c]
@@ -53,7 +62,6 @@ struct RowSource {
 struct OperatorSet {       // per-(problem, bin-slot) outputs of the factorisation kernel
   cplx* V;    long long v_stride;    // [Mc][S] column-major (ld = S)
   cplx* tau;  long long tau_stride;  // [nblk][MC]
-  cplx* Rc;   long long rc_stride;   // [Mc][Mc] column-major, upper triangular
   cplx* Pb;   long long pb_stride;   // [Mc][Mc] row-major: W = g * Pb
   int* info;                         // [problem*G + slot]: jacobi sweeps (0 = fast path)
 };
@@ -62,18 +70,33 @@ BlockPlan make_block_plan(int S, int Mc);
 size_t factor_smem_bytes(const BlockPlan& bp);
 cudaError_t launch_factor(cudaStream_t st, const BlockPlan& bp, const RowSource& src,
                           const OperatorSet& ops, int num_prob, int kbase, int G, double regul);
-// forward: Cv[(p*2+e)*2+c][s] = Q_C * (R_C * W_prev)   (rows S doubles apart)
-cudaError_t launch_chain_fwd(cudaStream_t st, const BlockPlan& bp, const OperatorSet& ops, int slot,
-                             int G, int ops_mod, const cplx* Wsp, long long w_ear_stride, int K,
-                             int kprev, int num_prob, double* Cv);
-// backward: W[k] = (Q_C^H tq) * Pb; tq rows (p*2+e)*2+c, or shared per set when tq_shared != 0
+// backward: W[k] = (Q_C^H tq) * Pb; tq rows (j*2+e)*2+c, or shared per set when tq_shared != 0
 cudaError_t launch_chain_bwd(cudaStream_t st, const BlockPlan& bp, const OperatorSet& ops, int slot,
                              int G, const double* tq, long long tq_set_stride,
-                             long long tq_ear_stride, int tq_shared, int orient_per_set, int ops_mod,
+                             long long tq_ear_stride, int tq_shared, ProbMap pm,
                              cplx* Wsp, long long w_ear_stride, int K, int k, int dc_fix, int num_prob);
 // generic-path phase step on rows: t = absH * y/|y|
 cudaError_t launch_phase_rows(cudaStream_t st, const double* Y, double* T, int num_prob, int D,
                               const double* absH, long long abs_set_stride, long long abs_ear_stride,
                               int orient_per_set, int nyquist);
+
+// ---------------------------------------------------------------- gram_kernels.cu
+// F blocks of the Gram route: Fs [(nqs*P) x ne], Fa [(nqa*P) x ne] (see gram_kernels.cu)
+cudaError_t launch_build_F(cudaStream_t st, const double* Gh, int S, int N, const double* Y, int Mc,
+                           int P, int ne_ld, double* Fs, double* Fa);
+cudaError_t launch_gram_beta(cudaStream_t st, const cplx* bn, int N, int K, double* bre, double* bim);
+// Cholesky + inverse + condition bound of nbins*P packed Hermitian matrices; fail[0] counts all
+// refused matrices, fail[1 + bin] those of one bin.
+cudaError_t launch_gram_chol(cudaStream_t st, const double* Gre, const double* Gim, int Mc, int P,
+                             int ne_ld, int nbins, double thr, cplx* Pb, int* fail);
+// forward of every bin: Cv rows (j*2+ear)*2+{re,im} = b_k .* (Y_o^T W_{k-1})
+cudaError_t launch_fwd_small(cudaStream_t st, const double* Y, int Mc, int S, const int* roword,
+                             const cplx* bk, ProbMap pm, int num_prob, const cplx* Wsp,
+                             long long w_ear_stride, int K, int kprev, double* Cv);
+// backward of a Gram bin: W_k = (Y_o (conj(b_k) .* z)) * Pb
+cudaError_t launch_bwd_small(cudaStream_t st, const double* Y, int Mc, int S, const int* roword,
+                             const cplx* bk, const cplx* Pb, ProbMap pm, int num_prob, const double* z,
+                             long long z_set_stride, long long z_ear_stride, int z_shared, cplx* Wsp,
+                             long long w_ear_stride, int K, int k, int dc_fix);
 
 }  // namespace emagls

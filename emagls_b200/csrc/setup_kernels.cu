@@ -366,17 +366,7 @@ __global__ void tail_twiddle_kernel(int K, int nfft, int len, double delay, doub
   if (idx >= (long long)len * K) return;
   int tp = (int)(idx / K), k = (int)(idx % K);
   const int lo = nfft / 2 - len / 2;
-  // fade window
-  int nf = (int)floor(0.15 * (double)len + 0.5);
-  double win = 1.0;
-  if (nf > 0) {
-    double den = (double)(2 * nf - 1);
-    if (tp < nf) win = 0.5 * (1.0 - cos(2.0 * 3.141592653589793 * (double)tp / den));
-    else if (tp >= len - nf) {
-      int q = tp - (len - nf) + nf;  // index into hann(2*nf), second half
-      win = 0.5 * (1.0 - cos(2.0 * 3.141592653589793 * (double)q / den));
-    }
-  }
+  const double win = fade_window(tp, len);
   const double g = win / (double)nfft;
   // ramp
   const double omega = (double)k * (0.5 / (double)(K - 1));

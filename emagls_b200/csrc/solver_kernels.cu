@@ -177,14 +177,6 @@ factor_kernel(BlockPlan bp, RowSource src, OperatorSet ops, int kbase, int G, do
     for (int q = 0; q < PER; ++q) Rs[tid + q * FT] = tmp[q];
     __syncthreads();
   }
-  {
-    cplx* Rg = ops.Rc + oidx * ops.rc_stride;
-    for (int idx = tid; idx < Mc * Mc; idx += FT) {
-      int c = idx / Mc, r = idx % Mc;
-      Rg[idx] = Rs[c * MC + r];
-    }
-  }
-
   // ---------------- R^-1 (upper triangular) into region A2, row by row from the bottom
   cplx* Ri = Js;
   for (int idx = tid; idx < MC * MC; idx += FT) Ri[idx] = mk(0.0, 0.0);
@@ -397,62 +389,24 @@ __device__ void apply_qc(const BlockPlan& bp, const cplx* __restrict__ V, const 
   }
 }
 
-__global__ void chain_fwd_kernel(BlockPlan bp, OperatorSet ops, int slot, int G, int ops_mod,
-                                 const cplx* Wsp, long long w_ear_stride, int K, int kprev,
-                                 int num_prob, double* Cv) {
-  extern __shared__ __align__(16) unsigned char csm_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-  const int p = blockIdx.x * wpc + warp;
-  if (p >= num_prob) return;
-  const int S = bp.S, Mc = bp.Mc;
-  cplx* x0 = reinterpret_cast<cplx*>(csm_raw) + (size_t)warp * 2 * S;
-  cplx* x1 = x0 + S;
-  const long long oidx = (long long)(p % ops_mod) * G + slot;
-  const cplx* V = ops.V + oidx * ops.v_stride;
-  const cplx* tau = ops.tau + oidx * ops.tau_stride;
-  const cplx* Rc = ops.Rc + oidx * ops.rc_stride;
-  for (int i = lane; i < S; i += 32) { x0[i] = mk(0.0, 0.0); x1[i] = mk(0.0, 0.0); }
-  __syncwarp();
-  // u = R_C * w   (R_C column-major [Mc][Mc], upper)
-  const cplx* w0p = Wsp + ((long long)p * Mc) * K + kprev;
-  const cplx* w1p = w0p + w_ear_stride;
-  for (int i = lane; i < Mc; i += 32) {
-    cplx u0 = mk(0.0, 0.0), u1 = mk(0.0, 0.0);
-    for (int m = i; m < Mc; ++m) {
-      cplx r = Rc[m * Mc + i];
-      cfma(u0, r, w0p[(long long)m * K]);
-      cfma(u1, r, w1p[(long long)m * K]);
-    }
-    x0[i] = u0; x1[i] = u1;
-  }
-  __syncwarp();
-  apply_qc(bp, V, tau, x0, x1, false, lane);
-  double* c0 = Cv + ((long long)(p * 2 + 0) * 2) * S;
-  double* c1 = Cv + ((long long)(p * 2 + 1) * 2) * S;
-  for (int i = lane; i < S; i += 32) {
-    cplx a = x0[i], b = x1[i];
-    c0[i] = a.x; c0[S + i] = a.y;
-    c1[i] = b.x; c1[S + i] = b.y;
-  }
-}
-
 __global__ void chain_bwd_kernel(BlockPlan bp, OperatorSet ops, int slot, int G, const double* tq,
                                  long long tq_set_stride, long long tq_ear_stride, int tq_shared,
-                                 int orient_per_set, int ops_mod, cplx* Wsp, long long w_ear_stride,
+                                 ProbMap pm, cplx* Wsp, long long w_ear_stride,
                                  int K, int k, int dc_fix, int num_prob) {
   extern __shared__ __align__(16) unsigned char csm_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-  const int p = blockIdx.x * wpc + warp;
-  if (p >= num_prob) return;
+  const int j = blockIdx.x * wpc + warp;
+  if (j >= num_prob) return;
+  const long long p = pm.global(j);
   const int S = bp.S, Mc = bp.Mc;
   cplx* x0 = reinterpret_cast<cplx*>(csm_raw) + (size_t)warp * 2 * S;
   cplx* x1 = x0 + S;
-  const long long oidx = (long long)(p % ops_mod) * G + slot;
+  const long long oidx = (long long)(j % pm.oc) * G + slot;
   const cplx* V = ops.V + oidx * ops.v_stride;
   const cplx* tau = ops.tau + oidx * ops.tau_stride;
   const cplx* Pb = ops.Pb + oidx * ops.pb_stride;
-  const double* t0 = tq_shared ? tq + (long long)(p / orient_per_set) * tq_set_stride
-                               : tq + ((long long)(p * 2 + 0) * 2) * S;
+  const double* t0 = tq_shared ? tq + (long long)(j / pm.oc) * tq_set_stride
+                               : tq + ((long long)(j * 2 + 0) * 2) * S;
   const double* t1 = t0 + (tq_shared ? tq_ear_stride : 2 * (long long)S);
   for (int i = lane; i < S; i += 32) {
     x0[i] = mk(t0[i], t0[S + i]);
@@ -460,7 +414,7 @@ __global__ void chain_bwd_kernel(BlockPlan bp, OperatorSet ops, int slot, int G,
   }
   __syncwarp();
   apply_qc(bp, V, tau, x0, x1, true, lane);
-  cplx* w0p = Wsp + ((long long)p * Mc) * K + k;
+  cplx* w0p = Wsp + (p * Mc) * K + k;
   cplx* w1p = w0p + w_ear_stride;
   for (int m = lane; m < Mc; m += 32) {
     cplx a0 = mk(0.0, 0.0), a1 = mk(0.0, 0.0);
@@ -485,25 +439,9 @@ static int chain_warps(int S) {
   return w;
 }
 
-cudaError_t launch_chain_fwd(cudaStream_t st, const BlockPlan& bp, const OperatorSet& ops, int slot,
-                             int G, int ops_mod, const cplx* Wsp, long long w_ear_stride, int K,
-                             int kprev, int num_prob, double* Cv) {
-  int w = chain_warps(bp.S);
-  size_t smem = (size_t)w * 2 * bp.S * sizeof(cplx);
-  static size_t set_to = 0;
-  if (smem > 48 * 1024 && smem > set_to) {
-    cudaError_t e = cudaFuncSetAttribute(chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    set_to = smem;
-  }
-  chain_fwd_kernel<<<(num_prob + w - 1) / w, w * 32, smem, st>>>(bp, ops, slot, G, ops_mod, Wsp, w_ear_stride, K, kprev,
-                                                                 num_prob, Cv);
-  return cudaGetLastError();
-}
-
 cudaError_t launch_chain_bwd(cudaStream_t st, const BlockPlan& bp, const OperatorSet& ops, int slot,
                              int G, const double* tq, long long tq_set_stride,
-                             long long tq_ear_stride, int tq_shared, int orient_per_set, int ops_mod,
+                             long long tq_ear_stride, int tq_shared, ProbMap pm,
                              cplx* Wsp, long long w_ear_stride, int K, int k, int dc_fix, int num_prob) {
   int w = chain_warps(bp.S);
   size_t smem = (size_t)w * 2 * bp.S * sizeof(cplx);
@@ -514,8 +452,7 @@ cudaError_t launch_chain_bwd(cudaStream_t st, const BlockPlan& bp, const Operato
     set_to = smem;
   }
   chain_bwd_kernel<<<(num_prob + w - 1) / w, w * 32, smem, st>>>(bp, ops, slot, G, tq, tq_set_stride, tq_ear_stride, tq_shared,
-                                                                 orient_per_set, ops_mod, Wsp, w_ear_stride, K, k, dc_fix,
-                                                                 num_prob);
+                                                                 pm, Wsp, w_ear_stride, K, k, dc_fix, num_prob);
   return cudaGetLastError();
 }
 
