@@ -102,22 +102,22 @@ static int design_host(emagls_handle h, const emagls_config* cfg, Variant v, con
                        const double* ma, const double* mz, int M, int order, double fs, int len,
                        int ns, int no, const double* rot, double* wL, double* wR, double* sp) {
   return guarded(h, [&] {
-    EM_REQUIRE(cfg && hL && hR && ga && gz && ma && mz && wL && wR, "null argument");
+    EM_REQUIRE(cfg && hL && hR && ga && gz && ma && (mz || v == Variant::EMA_CH) && wL && wR, "null argument");
     EM_REQUIRE(T > 0 && D > 0 && M > 0 && ns > 0 && no > 0 && len > 0, "empty input");
     cudaStream_t st = h->stream;
     Arena ar(st);
-    const int Mc = (v == Variant::EMAGLS2) ? M : (order + 1) * (order + 1);
+    const int Mc = (v == Variant::EMAGLS2) ? M : (v == Variant::EMAGLS_SH ? (order + 1) * (order + 1) : 2 * order + 1);
     const int nfft = std::min(cfg->nfft_max_len, 2 * len);
     const int K = nfft / 2 + 1;
     const size_t P = (size_t)ns * no;
     DesignArgs a;
     // complex SH-domain output is interleaved complex (lib/getEMagLsFilters.m:117-120)
-    const size_t wn = (size_t)len * Mc * P * ((v == Variant::EMAGLS_SH && cfg->basis == EMAGLS_BASIS_COMPLEX) ? 2 : 1);
+    const size_t wn = (size_t)len * Mc * P * ((v != Variant::EMAGLS2 && cfg->basis == EMAGLS_BASIS_COMPLEX) ? 2 : 1);
     double* d_wL = ar.get<double>(wn);
     double* d_wR = ar.get<double>(wn);
     double* d_sp = sp ? ar.get<double>((size_t)2 * K * Mc * P * 2) : nullptr;
     fill_args(a, v, ar.upload(hL, (size_t)T * D * ns), ar.upload(hR, (size_t)T * D * ns), T, D,
-              ar.upload(ga, D), ar.upload(gz, D), r, ar.upload(ma, M), ar.upload(mz, M), M, order, fs, len,
+              ar.upload(ga, D), ar.upload(gz, D), r, ar.upload(ma, M), mz ? ar.upload(mz, M) : nullptr, M, order, fs, len,
               ns, no, rot ? ar.upload(rot, (size_t)no * 9) : nullptr, d_wL, d_wR, d_sp);
     design_factored(h, *cfg, a);
     EM_CUDA(cudaMemcpyAsync(wL, d_wL, wn * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -159,34 +159,106 @@ int emagls_design_emagls(emagls_handle h, const emagls_config* cfg, const double
                      mic_azi, mic_zen, num_mics, order, fs, len, num_sets, num_orient, rotations, wL, wR, spectra);
 }
 
-static int unsupported(emagls_handle h, const char* what) {
-  if (!h) return EMAGLS_ERR_INVALID;
-  h->err = std::string(what) + " is not built yet in this round";
-  return EMAGLS_ERR_UNSUPPORTED;
+
+int emagls_design_magls(emagls_handle h, const emagls_config* cfg, const double* hL, const double* hR,
+                        int num_samples, int num_dirs, const double* grid_azi, const double* grid_zen, int order,
+                        double fs, int len, double* wL, double* wR, double* spectra) {
+  return guarded(h, [&] {
+    EM_REQUIRE(cfg && hL && hR && grid_azi && grid_zen && wL && wR, "null argument");
+    EM_REQUIRE(num_samples > 0 && num_dirs > 0 && len > 0 && order >= 0, "empty input");
+    cudaStream_t st = h->stream;
+    Arena ar(st);
+    const int T = num_samples, D = num_dirs, Mc = (order + 1) * (order + 1);
+    const int K = std::min(cfg->nfft_max_len, 2 * len) / 2 + 1;
+    const size_t wn = (size_t)len * Mc * (cfg->basis == EMAGLS_BASIS_COMPLEX ? 2 : 1);
+    double* d_wL = ar.get<double>(wn);
+    double* d_wR = ar.get<double>(wn);
+    double* d_sp = spectra ? ar.get<double>((size_t)2 * K * Mc * 2) : nullptr;
+    design_magls(h, *cfg, ar.upload(hL, (size_t)T * D), ar.upload(hR, (size_t)T * D), T, D, ar.upload(grid_azi, D),
+                 ar.upload(grid_zen, D), order, fs, len, false, d_wL, d_wR, d_sp);
+    EM_CUDA(cudaMemcpyAsync(wL, d_wL, wn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaMemcpyAsync(wR, d_wR, wn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (spectra) EM_CUDA(cudaMemcpyAsync(spectra, d_sp, (size_t)2 * K * Mc * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaStreamSynchronize(st));
+  });
 }
 
-int emagls_design_magls(emagls_handle h, const emagls_config*, const double*, const double*, int, int,
-                        const double*, const double*, int, double, int, double*, double*, double*) {
-  return unsupported(h, "getMagLsFilters");
+int emagls_design_ls(emagls_handle h, const emagls_config* cfg, const double* hL, const double* hR,
+                     int num_samples, int num_dirs, const double* grid_azi, const double* grid_zen, int order,
+                     double* wL, double* wR) {
+  return guarded(h, [&] {
+    EM_REQUIRE(cfg && hL && hR && grid_azi && grid_zen && wL && wR, "null argument");
+    EM_REQUIRE(num_samples > 0 && num_dirs > 0 && order >= 0, "empty input");
+    cudaStream_t st = h->stream;
+    Arena ar(st);
+    const int T = num_samples, D = num_dirs, Mc = (order + 1) * (order + 1);
+    const size_t wn = (size_t)T * Mc * (cfg->basis == EMAGLS_BASIS_COMPLEX ? 2 : 1);
+    double* d_wL = ar.get<double>(wn);
+    double* d_wR = ar.get<double>(wn);
+    design_magls(h, *cfg, ar.upload(hL, (size_t)T * D), ar.upload(hR, (size_t)T * D), T, D, ar.upload(grid_azi, D),
+                 ar.upload(grid_zen, D), order, 0.0, 0, true, d_wL, d_wR, nullptr);
+    EM_CUDA(cudaMemcpyAsync(wL, d_wL, wn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaMemcpyAsync(wR, d_wR, wn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaStreamSynchronize(st));
+  });
 }
-int emagls_design_ls(emagls_handle h, const emagls_config*, const double*, const double*, int, int,
-                     const double*, const double*, int, double*, double*) {
-  return unsupported(h, "getLsFilters");
+int emagls_design_from_atf(emagls_handle h, const emagls_config* cfg, const double* hL, const double* hR,
+                           int num_samples, int num_dirs, const double* hrir_grid, const double* atf_irs,
+                           int atf_samples, int num_mics, int atf_dirs, const double* atf_grid, double fs,
+                           int filter_len, double f_trans, double* wL, double* wR, double* spectra,
+                           double* mean_grid_dev_deg) {
+  return guarded(h, [&] {
+    EM_REQUIRE(cfg && hL && hR && hrir_grid && atf_irs && atf_grid && wL && wR, "null argument");
+    EM_REQUIRE(num_samples > 0 && num_dirs > 0 && atf_samples > 0 && num_mics > 0 && atf_dirs > 0 && filter_len > 0,
+               "empty input");
+    cudaStream_t st = h->stream;
+    Arena ar(st);
+    const int T = num_samples, D = num_dirs, M = num_mics;
+    const int K = std::min(cfg->nfft_max_len, 2 * filter_len) / 2 + 1;
+    const size_t wn = (size_t)filter_len * M;
+    double* d_wL = ar.get<double>(wn);
+    double* d_wR = ar.get<double>(wn);
+    double* d_sp = spectra ? ar.get<double>((size_t)2 * K * M * 2) : nullptr;
+    design_from_atf(h, *cfg, ar.upload(hL, (size_t)T * D), ar.upload(hR, (size_t)T * D), T, D,
+                    ar.upload(hrir_grid, (size_t)2 * D), ar.upload(atf_irs, (size_t)atf_samples * M * atf_dirs),
+                    atf_samples, M, atf_dirs, ar.upload(atf_grid, (size_t)2 * atf_dirs), fs, filter_len, f_trans,
+                    d_wL, d_wR, d_sp, mean_grid_dev_deg);
+    EM_CUDA(cudaMemcpyAsync(wL, d_wL, wn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaMemcpyAsync(wR, d_wR, wn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (spectra) EM_CUDA(cudaMemcpyAsync(spectra, d_sp, (size_t)2 * K * M * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaStreamSynchronize(st));
+  });
 }
-int emagls_design_from_atf(emagls_handle h, const emagls_config*, const double*, const double*, int, int,
-                           const double*, const double*, int, int, int, const double*, double, int, double,
-                           double*, double*, double*, double*) {
-  return unsupported(h, "getEMagLsFiltersFromAtf");
+int emagls_design_ema_ch(emagls_handle h, const emagls_config* cfg, const double* hL, const double* hR,
+                         int num_samples, int num_dirs, const double* grid_azi, const double* grid_zen,
+                         double mic_radius, const double* mic_azi, int num_mics, int order, double fs, int len,
+                         double* wL, double* wR, double* spectra) {
+  return design_host(h, cfg, Variant::EMA_CH, hL, hR, num_samples, num_dirs, grid_azi, grid_zen, mic_radius,
+                     mic_azi, nullptr, num_mics, order, fs, len, 1, 1, nullptr, wL, wR, spectra);
 }
-int emagls_design_ema_ch(emagls_handle h, const emagls_config*, const double*, const double*, int, int,
-                         const double*, const double*, double, const double*, int, int, double, int,
-                         double*, double*, double*) {
-  return unsupported(h, "getEMagLsFiltersEMAinCH");
-}
-int emagls_design_ema_sh(emagls_handle h, const emagls_config*, const double*, const double*, int, int,
-                         const double*, const double*, double, const double*, int, int, double, int,
-                         double*, double*, double*) {
-  return unsupported(h, "getEMagLsFiltersEMAinSH");
+int emagls_design_ema_sh(emagls_handle h, const emagls_config* cfg, const double* hL, const double* hR,
+                         int num_samples, int num_dirs, const double* grid_azi, const double* grid_zen,
+                         double mic_radius, const double* mic_azi, int num_mics, int order, double fs, int len,
+                         double* wL, double* wR, double* spectra) {
+  return guarded(h, [&] {
+    EM_REQUIRE(cfg && hL && hR && grid_azi && grid_zen && mic_azi && wL && wR, "null argument");
+    EM_REQUIRE(num_samples > 0 && num_dirs > 0 && num_mics > 0 && len > 0 && order >= 0, "empty input");
+    cudaStream_t st = h->stream;
+    Arena ar(st);
+    const int T = num_samples, D = num_dirs, Mc = (order + 1) * (order + 1);
+    const int K = std::min(cfg->nfft_max_len, 2 * len) / 2 + 1;
+    const size_t wn = (size_t)len * Mc * (cfg->basis == EMAGLS_BASIS_COMPLEX ? 2 : 1);
+    double* d_wL = ar.get<double>(wn);
+    double* d_wR = ar.get<double>(wn);
+    double* d_sp = spectra ? ar.get<double>((size_t)2 * K * Mc * 2) : nullptr;
+    design_ema_sh(h, *cfg, ar.upload(hL, (size_t)T * D), ar.upload(hR, (size_t)T * D), T, D, ar.upload(grid_azi, D),
+                  ar.upload(grid_zen, D), mic_radius, ar.upload(mic_azi, num_mics), num_mics, order, fs, len,
+                  d_wL, d_wR, d_sp);
+    EM_CUDA(cudaMemcpyAsync(wL, d_wL, wn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaMemcpyAsync(wR, d_wR, wn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (spectra) EM_CUDA(cudaMemcpyAsync(spectra, d_sp, (size_t)2 * K * Mc * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaStreamSynchronize(st));
+  });
 }
 
 // ------------------------------------------------------------------------------------------

@@ -58,6 +58,28 @@ __global__ void real_to_cplx_kernel(const double* in, long long n, cplx* out) {
   if (idx < n) out[idx] = mk(in[idx], 0.0);
 }
 
+// At[m][c] = getCH(N, mic_azi, 'real')(m, c): [1, sqrt2 sin(q azi), sqrt2 cos(q azi)] ordered
+// [0, -1, +1, -2, +2, ...] (dependencies/getCH.m:17-28)
+__global__ void ch_rows_kernel(int N, const double* __restrict__ azi, int M, cplx* __restrict__ At) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nch = 2 * N + 1;
+  if (idx >= M * nch) return;
+  const int m = idx / nch, c = idx % nch;
+  double v = 1.0;
+  if (c > 0) {
+    const int q = (c + 1) / 2;
+    double sn, cs;
+    sincos((double)q * azi[m], &sn, &cs);
+    v = 1.4142135623730951 * ((c & 1) ? sn : cs);
+  }
+  At[idx] = mk(v, 0.0);
+}
+
+__global__ void fill_kernel(double* p, int n, double v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
 // L[c][m] = Re(W[(m&1)*npair + m/2][c])
 __global__ void extract_pinv_kernel(const cplx* W, int npair, int Mc, int M, double* L) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -66,75 +88,151 @@ __global__ void extract_pinv_kernel(const cplx* W, int npair, int Mc, int M, dou
   L[idx] = W[((long long)(m & 1) * npair + m / 2) * Mc + c].x;
 }
 
-// ---- complex SH basis (shDefinition = 'complex', lib/getEMagLsFilters.m:117-120) ---------------
+}  // namespace
+
+// ---- complex SH / CH basis (shDefinition = 'complex', lib/getEMagLsFilters.m:117-120) -----------
 // pwGrid_complex = conj(T) pwGrid_real with the unitary real->complex map Y_c = Y_r T^T
-// (getSH.m:25-49), so every bin but DC obeys W_c = W_r T^T; the DC fix W(1,:) = real(W(2,:)) acts on
-// the complex-basis coefficients (lib/getEMagLsFilters.m:110-111) and getShFreqDomainConjugate makes
-// the remaining spectrum the image of a real-basis Hermitian one.  Hence
-//   w_c = tail(W_r with DC := 0) T^T + fade/nfft * real(W_r(2,:) T^T).
-// T rows: m = 0: e_0;  m > 0: (-1)^m (e_m + i e_-m)/sqrt2;  m < 0: (e_|m| - i e_-|m|)/sqrt2.
-__device__ __forceinline__ cplx to_complex_basis(double ap, double am, int m) {
-  // ap, am: real-basis coefficients of (n, +|m|) and (n, -|m|); returns the complex-basis (n, m) one
+// (getSH.m:25-49, getCH.m:17-28), so every bin but DC obeys W_c = W_r T^T; the DC fix
+// W(1,:) = real(W(2,:)) acts on the complex-basis coefficients (lib/getEMagLsFilters.m:110-111) and
+// getShFreqDomainConjugate / getChFreqDomainConjugate make the remaining spectrum the image of a
+// real-basis Hermitian one.  Hence
+//   w_c = tail(W_r with DC := 0) T^T + fade/nfft * real(W_r(2,:) T^T)       (designers with a DC fix)
+//   w_c = tail(W_r) T^T                                                     (MagLS / LS: no DC fix)
+// T rows, SH (ACN, Condon-Shortley): m = 0: e_0; m > 0: (-1)^m (e_m + i e_-m)/sqrt2; m < 0: (e_|m| - i e_-|m|)/sqrt2.
+// T rows, CH ([0,-1,+1,-2,+2,..]):   the same without the (-1)^m.
+template <class V>
+__device__ __forceinline__ cplx to_complex_basis(V ap_, V am_, int m, int kind);
+template <>
+__device__ __forceinline__ cplx to_complex_basis<double>(double ap, double am, int m, int kind) {
   const double r = 0.7071067811865476;
   if (m == 0) return mk(ap, 0.0);
-  if (m > 0) { const double s = (m & 1) ? -r : r; return mk(s * ap, s * am); }
+  if (m > 0) { const double s = (kind == 0 && (m & 1)) ? -r : r; return mk(s * ap, s * am); }
   return mk(r * ap, -r * am);
 }
-__device__ __forceinline__ cplx to_complex_basis(cplx ap, cplx am, int m) {
+template <>
+__device__ __forceinline__ cplx to_complex_basis<cplx>(cplx ap, cplx am, int m, int kind) {
   const double r = 0.7071067811865476;
   if (m == 0) return ap;
-  if (m > 0) { const double s = (m & 1) ? -r : r; return mk(s * (ap.x - am.y), s * (ap.y + am.x)); }
+  if (m > 0) { const double s = (kind == 0 && (m & 1)) ? -r : r; return mk(s * (ap.x - am.y), s * (ap.y + am.x)); }
   return mk(r * (ap.x + am.y), r * (ap.y - am.x));
 }
+// channel j -> m and the channel indices of (+|m|, -|m|)
+__device__ __forceinline__ void basis_pair(int j, int kind, int& m, int& jp, int& jm) {
+  if (kind == 0) {
+    int n = (int)sqrt((double)j);
+    while ((n + 1) * (n + 1) <= j) ++n;
+    while (n * n > j) --n;
+    m = j - n * n - n;
+    const int am = m < 0 ? -m : m;
+    jp = n * n + n + am; jm = n * n + n - am;
+  } else {
+    const int am = (j + 1) / 2;
+    m = (j == 0) ? 0 : ((j & 1) ? -am : am);
+    jp = 2 * am; jm = (am == 0) ? 0 : 2 * am - 1;
+  }
+}
 
-// out (interleaved complex) [len x nsh x P]; wr [len x nsh x P] real tail of W_r with DC = 0;
-// Wsp_e: this ear's real-basis spectra [P][nsh][K]
-__global__ void complex_basis_filters_kernel(const double* __restrict__ wr, const cplx* __restrict__ Wsp_e,
-                                             int order, int len, int K, int nfft, long long P,
-                                             cplx* __restrict__ out) {
-  const int nsh = (order + 1) * (order + 1);
+// out (interleaved complex) [len x nch x P]; wr [len x nch x P] real-basis filters; optional DC term
+// from this ear's real-basis spectra Wsp_e [P][nch][K]
+__global__ void basis_change_filters_kernel(const double* __restrict__ wr, int kind, int nch, int len,
+                                            long long P, const cplx* __restrict__ Wsp_e, int K, int nfft,
+                                            cplx* __restrict__ out) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= P * nsh * len) return;
+  if (idx >= P * nch * len) return;
   const int t = (int)(idx % len);
-  const int j = (int)((idx / len) % nsh);
-  const long long p = idx / ((long long)len * nsh);
-  int n = (int)sqrt((double)j);
-  while ((n + 1) * (n + 1) <= j) ++n;
-  while (n * n > j) --n;
-  const int m = j - n * n - n, am = m < 0 ? -m : m;
-  const long long ip = p * nsh + n * n + n + am, im = p * nsh + n * n + n - am;
-  cplx v = to_complex_basis(wr[ip * len + t], wr[im * len + t], m);
-  const cplx dc = to_complex_basis(Wsp_e[ip * K + 1], Wsp_e[im * K + 1], m);
-  v.x += fade_window(t, len) / (double)nfft * dc.x;
+  const int j = (int)((idx / len) % nch);
+  const long long p = idx / ((long long)len * nch);
+  int m, jp, jm;
+  basis_pair(j, kind, m, jp, jm);
+  const long long ip = p * nch + jp, im = p * nch + jm;
+  cplx v = to_complex_basis<double>(wr[ip * len + t], wr[im * len + t], m, kind);
+  if (Wsp_e) {
+    const cplx dc = to_complex_basis<cplx>(Wsp_e[ip * K + 1], Wsp_e[im * K + 1], m, kind);
+    v.x += fade_window(t, len) / (double)nfft * dc.x;
+  }
   out[idx] = v;
 }
 
-// in place: spectra of one (ear, problem, order n, |m|) pair -> complex basis, DC := real(bin 1)
-__global__ void complex_basis_spectra_kernel(cplx* __restrict__ Wsp, int order, int K, long long EP) {
-  const int nsh = (order + 1) * (order + 1);
+// in place: spectra rows [EP][nch][K] -> complex basis; dc_quirk: DC := real(bin 1) in the new basis
+__global__ void basis_change_spectra_kernel(cplx* __restrict__ Wsp, int kind, int nch, int K, long long EP,
+                                            int dc_quirk) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= EP * nsh * K) return;
+  if (idx >= EP * nch * K) return;
   const int k = (int)(idx % K);
-  const int j = (int)((idx / K) % nsh);
-  const long long ep = idx / ((long long)K * nsh);
-  int n = (int)sqrt((double)j);
-  while ((n + 1) * (n + 1) <= j) ++n;
-  while (n * n > j) --n;
-  const int m = j - n * n - n;
-  if (m < 0 || k == 0) return;  // the thread of +m converts both rows; the thread of bin 1 also writes DC
-  cplx* rp = Wsp + (ep * nsh + n * n + n + m) * K;
-  cplx* rm = Wsp + (ep * nsh + n * n + n - m) * K;
+  const int j = (int)((idx / K) % nch);
+  const long long ep = idx / ((long long)K * nch);
+  int m, jp, jm;
+  basis_pair(j, kind, m, jp, jm);
+  if (m < 0 || (dc_quirk && k == 0)) return;  // the thread of +m converts both rows (and bin 1 writes DC)
+  cplx* rp = Wsp + (ep * nch + jp) * K;
+  cplx* rm = Wsp + (ep * nch + jm) * K;
   const cplx ap = rp[k], am = rm[k];
-  const cplx cp = to_complex_basis(ap, am, m), cm = to_complex_basis(ap, am, -m);
+  const cplx cp = to_complex_basis<cplx>(ap, am, m, kind), cm = to_complex_basis<cplx>(ap, am, -m, kind);
   rp[k] = cp;
   if (m > 0) rm[k] = cm;
-  if (k == 1) {
+  if (dc_quirk && k == 1) {
     rp[0] = mk(cp.x, 0.0);
     if (m > 0) rm[0] = mk(cm.x, 0.0);
   }
 }
 
-}  // namespace
+cudaError_t launch_basis_change_filters(cudaStream_t st, const double* wr, int kind, int nch, int len,
+                                        long long P, const cplx* Wsp_e, int K, int nfft, cplx* out) {
+  long long n = P * nch * len;
+  basis_change_filters_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(wr, kind, nch, len, P, Wsp_e, K, nfft, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_basis_change_spectra(cudaStream_t st, cplx* Wsp, int kind, int nch, int K, long long EP,
+                                        int dc_quirk) {
+  long long n = EP * nch * K;
+  basis_change_spectra_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Wsp, kind, nch, K, EP, dc_quirk);
+  return cudaGetLastError();
+}
+
+// median(grpdelay(sum(h,2), 1, f, fs)) per (set, ear)  (lib/getEMagLs2Filters.m:72-75)
+std::vector<double> group_delays(emagls_ctx* h, Arena& ar, const double* hL, const double* hR, int T, int D,
+                                 int K, double fs, int num_sets) {
+  cudaStream_t st = h->stream;
+  std::vector<double> grpD((size_t)num_sets * 2);
+  const int nchunk = 32;
+  double* partial = ar.get<double>((size_t)nchunk * T);
+  double* hsum = ar.get<double>((size_t)num_sets * 2 * T);
+  double* gd = ar.get<double>((size_t)num_sets * 2 * K);
+  for (int s = 0; s < num_sets; ++s)
+    for (int e = 0; e < 2; ++e) {
+      const double* hp = (e == 0 ? hL : hR) + (size_t)s * T * D;
+      EM_CUDA(launch_colsum(st, hp, T, D, partial, nchunk, hsum + ((size_t)s * 2 + e) * T));
+      EM_CUDA(launch_grpdelay(st, hsum + ((size_t)s * 2 + e) * T, T, K, fs, gd + ((size_t)s * 2 + e) * K));
+      h->launches += 3;
+    }
+  std::vector<double> gdh((size_t)num_sets * 2 * K);
+  EM_CUDA(cudaMemcpyAsync(gdh.data(), gd, gdh.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  EM_CUDA(cudaStreamSynchronize(st));
+  for (int i = 0; i < num_sets * 2; ++i)
+    grpD[i] = median_of(std::vector<double>(gdh.begin() + (size_t)i * K, gdh.begin() + (size_t)(i + 1) * K));
+  return grpD;
+}
+
+// Hd [D][2K] (interleaved complex rows) = fft(zero-padded h) .* exp(+i 2 pi omega delay_removed), the
+// Nyquist factor real (applySubsampleDelay.m:10-17 with delay = -delay_removed; an integer
+// delay_removed equals circshift(h, -delay_removed), lib/getEMagLsFiltersFromAtf.m:48-49).
+void hrir_spectrum(emagls_ctx* h, Arena& ar, const double* hp, int T, int D, int K, const double* tw,
+                   double delay_removed, double* Hd) {
+  cudaStream_t st = h->stream;
+  std::vector<cplx> ramp((size_t)K);
+  for (int k = 0; k < K; ++k) {
+    double omega = (double)k * (0.5 / (double)(K - 1));
+    double ang = 2.0 * M_PI * omega * delay_removed;
+    cplx r = mk(std::cos(ang), std::sin(ang));
+    if (k == K - 1) r.y = 0.0;
+    ramp[k] = r;
+  }
+  cplx* d_ramp = ar.upload(ramp.data(), ramp.size());
+  GemmOperand A{hp, T, 1}, B{tw, T, 1};  // (pageable H2D copies are staged before upload() returns)
+  EpiRamp epi{Hd, 2LL * K, d_ramp};
+  EM_CUDA(launch_gemm(st, A, B, GemmShape{D, 2 * K, T}, epi));
+  h->launches += 1;
+}
 
 // targets * Y_reg_inv for one steering matrix held as rows At [D][Mc] (lib/getEMagLs2Filters.m:87-94).
 // rows: [(pair*2 + ear)*2 + {re,im}][D];  W: [ear][pair][Mc].
@@ -177,16 +275,17 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
   EM_REQUIRE(simN <= MAX_SH_ORDER, "simulation order too high");
   const int S = (simN + 1) * (simN + 1);
   const int nsh = (a.order + 1) * (a.order + 1);
-  const int Mc = (a.variant == Variant::EMAGLS2) ? a.M : nsh;
+  const int Mc = (a.variant == Variant::EMAGLS2) ? a.M : (a.variant == Variant::EMAGLS_SH ? nsh : 2 * a.order + 1);
   EM_REQUIRE(Mc <= 64 && a.M <= 64, "more than 64 channels are not supported");
-  if (a.variant == Variant::EMAGLS_SH) EM_REQUIRE(a.M >= nsh, "fewer microphones than SH channels");
+  if (a.variant != Variant::EMAGLS2) EM_REQUIRE(a.M >= Mc, "fewer microphones than output channels");
   if (a.D < S)
     throw Fail{EMAGLS_ERR_UNSUPPORTED, "HRIR grid has fewer directions than simulation harmonics"};
   EM_REQUIRE(S >= Mc, "fewer simulation harmonics than channels");
   const int P = a.num_sets * a.num_orient;
   const int D = a.D, T = a.T;
   // complex SH-domain output: solved in the real basis, converted at the tail (see above)
-  const bool cplx_out = (a.variant == Variant::EMAGLS_SH && cfg.basis == EMAGLS_BASIS_COMPLEX);
+  const bool cplx_out = (a.variant != Variant::EMAGLS2 && cfg.basis == EMAGLS_BASIS_COMPLEX);
+  const int basis_kind = (a.variant == Variant::EMA_CH) ? 1 : 0;
   const int dc_fix = cplx_out ? 0 : 1;
   // bins (0-based): LS 1 .. kls1-1, MagLS kls1 .. K-1, with kls1 = k_cut - 1
   const int kls1 = std::min(std::max(k_cut - 1, 1), K);
@@ -243,22 +342,33 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
   double* Yo = nullptr;  // [num_orient][Mc][S]
   {
     double* Ym = ar.get<double>((size_t)a.num_orient * a.M * S);
-    EM_CUDA(launch_sh_mics(st, simN, a.mic_azi, a.mic_zen, a.M, a.rotations, a.num_orient, Ym));
+    const double* mic_zen = a.mic_zen;
+    if (!mic_zen) {  // equatorial array (lib/getEMagLsFiltersEMAinCH.m:57)
+      double* z = ar.get<double>(a.M);
+      fill_kernel<<<(a.M + 63) / 64, 64, 0, st>>>(z, a.M, 1.5707963267948966);
+      mic_zen = z;
+      h->launches += 1;
+    }
+    EM_CUDA(launch_sh_mics(st, simN, a.mic_azi, mic_zen, a.M, a.rotations, a.num_orient, Ym));
     h->launches += 1;
     Yo = Ym;
-    if (a.variant == Variant::EMAGLS_SH) {
-      // L = pinv(Y_Hi(:, 1:(order+1)^2)) at the microphones as given (getSMAIRMatrix.m:102),
-      // obtained from the same factorisation kernel with the clip disabled.
-      double* Ym0 = ar.get<double>((size_t)a.M * S);
-      EM_CUDA(launch_sh_mics(st, simN, a.mic_azi, a.mic_zen, a.M, nullptr, 1, Ym0));
-      cplx* At = ar.get<cplx>((size_t)a.M * nsh);
-      {
-        // At[m][c] = Y_lo[m][c]
-        double* tmp = ar.get<double>((size_t)a.M * nsh);
-        EM_CUDA(cudaMemcpy2DAsync(tmp, (size_t)nsh * sizeof(double), Ym0, (size_t)S * sizeof(double),
-                                  (size_t)nsh * sizeof(double), a.M, cudaMemcpyDeviceToDevice, st));
-        long long n = (long long)a.M * nsh;
+    if (a.variant != Variant::EMAGLS2) {
+      // L = pinv(Y_Hi(:, 1:(order+1)^2)) at the microphones as given (getSMAIRMatrix.m:102) or
+      // pinv(getCH(order, micAzi)) (lib/getEMagLsFiltersEMAinCH.m:71), obtained from the same
+      // factorisation kernel with the clip disabled.
+      cplx* At = ar.get<cplx>((size_t)a.M * Mc);
+      if (a.variant == Variant::EMAGLS_SH) {
+        double* Ym0 = ar.get<double>((size_t)a.M * S);
+        EM_CUDA(launch_sh_mics(st, simN, a.mic_azi, mic_zen, a.M, nullptr, 1, Ym0));
+        double* tmp = ar.get<double>((size_t)a.M * Mc);
+        EM_CUDA(cudaMemcpy2DAsync(tmp, (size_t)Mc * sizeof(double), Ym0, (size_t)S * sizeof(double),
+                                  (size_t)Mc * sizeof(double), a.M, cudaMemcpyDeviceToDevice, st));
+        long long n = (long long)a.M * Mc;
         real_to_cplx_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tmp, n, At);
+        h->launches += 2;
+      } else {
+        ch_rows_kernel<<<(a.M * Mc + 127) / 128, 128, 0, st>>>(a.order, a.mic_azi, a.M, At);
+        h->launches += 1;
       }
       const int npair = (a.M + 1) / 2;
       double* rows = ar.get<double>((size_t)npair * 4 * a.M);
@@ -266,38 +376,20 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
         long long n = (long long)npair * 4 * a.M;
         identity_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rows, npair, a.M, a.M);
       }
-      cplx* Wp = ar.get<cplx>((size_t)2 * npair * nsh);
-      regularized_apply_dev(h, ar, At, a.M, nsh, rows, npair, 0.0, Wp);
-      double* L = ar.get<double>((size_t)nsh * a.M);
-      extract_pinv_kernel<<<(nsh * a.M + 255) / 256, 256, 0, st>>>(Wp, npair, nsh, a.M, L);
-      double* Yeff = ar.get<double>((size_t)a.num_orient * nsh * S);
-      EM_CUDA(launch_left_mul(st, L, nsh, a.M, Ym, a.num_orient, S, Yeff));
+      cplx* Wp = ar.get<cplx>((size_t)2 * npair * Mc);
+      regularized_apply_dev(h, ar, At, a.M, Mc, rows, npair, 0.0, Wp);
+      double* L = ar.get<double>((size_t)Mc * a.M);
+      extract_pinv_kernel<<<(Mc * a.M + 255) / 256, 256, 0, st>>>(Wp, npair, Mc, a.M, L);
+      double* Yeff = ar.get<double>((size_t)a.num_orient * Mc * S);
+      EM_CUDA(launch_left_mul(st, L, Mc, a.M, Ym, a.num_orient, S, Yeff));
       EM_CUDA(cudaGetLastError());
-      h->launches += 6;
+      h->launches += 3;
       Yo = Yeff;
     }
   }
 
   // ---------------- HRTF sets: group delay, H, |H|, H*Q, H*Y_h
-  std::vector<double> grpD((size_t)a.num_sets * 2);
-  {
-    const int nchunk = 32;
-    double* partial = ar.get<double>((size_t)nchunk * T);
-    double* hsum = ar.get<double>((size_t)a.num_sets * 2 * T);
-    double* gd = ar.get<double>((size_t)a.num_sets * 2 * K);
-    for (int s = 0; s < a.num_sets; ++s)
-      for (int e = 0; e < 2; ++e) {
-        const double* hp = (e == 0 ? a.hL : a.hR) + (size_t)s * T * D;
-        EM_CUDA(launch_colsum(st, hp, T, D, partial, nchunk, hsum + ((size_t)s * 2 + e) * T));
-        EM_CUDA(launch_grpdelay(st, hsum + ((size_t)s * 2 + e) * T, T, K, a.fs, gd + ((size_t)s * 2 + e) * K));
-        h->launches += 3;
-      }
-    std::vector<double> gdh((size_t)a.num_sets * 2 * K);
-    EM_CUDA(cudaMemcpyAsync(gdh.data(), gd, gdh.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-    EM_CUDA(cudaStreamSynchronize(st));
-    for (int i = 0; i < a.num_sets * 2; ++i)
-      grpD[i] = median_of(std::vector<double>(gdh.begin() + (size_t)i * K, gdh.begin() + (size_t)(i + 1) * K));
-  }
+  const std::vector<double> grpD = group_delays(h, ar, a.hL, a.hR, T, D, K, a.fs, a.num_sets);
   double* absH = ar.get<double>((size_t)a.num_sets * 2 * K * D);                     // [set][ear][K][D]
   const size_t ls_elems = (size_t)a.num_sets * 2 * std::max(nLS, 1) * 2 * S;         // [set][ear][kls][c][S]
   double* Tls = ar.get<double>(ls_elems);   // H * Q
@@ -307,24 +399,12 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
     EM_CUDA(launch_dft_twiddle(st, K, T, nfft, tw));
     h->launches += 1;
     double* Hd = ar.get<double>((size_t)D * 2 * K);
-    std::vector<cplx> ramp((size_t)a.num_sets * 2 * K);
-    for (int i = 0; i < a.num_sets * 2; ++i)
-      for (int k = 0; k < K; ++k) {
-        double omega = (double)k * (0.5 / (double)(K - 1));
-        double ang = -2.0 * M_PI * omega * (-grpD[i]);
-        cplx r = mk(std::cos(ang), std::sin(ang));
-        if (k == K - 1) r.y = 0.0;
-        ramp[(size_t)i * K + k] = r;
-      }
-    cplx* d_ramp = ar.upload(ramp.data(), ramp.size());
     for (int s = 0; s < a.num_sets; ++s)
       for (int e = 0; e < 2; ++e) {
         const double* hp = (e == 0 ? a.hL : a.hR) + (size_t)s * T * D;
-        GemmOperand A{hp, T, 1}, B{tw, T, 1};
-        EpiRamp epi{Hd, 2LL * K, d_ramp + ((size_t)s * 2 + e) * K};
-        EM_CUDA(launch_gemm(st, A, B, GemmShape{D, 2 * K, T}, epi));
+        hrir_spectrum(h, ar, hp, T, D, K, tw, grpD[(size_t)s * 2 + e], Hd);
         EM_CUDA(launch_abs_transpose(st, Hd, D, K, absH + ((size_t)s * 2 + e) * K * D));
-        h->launches += 2;
+        h->launches += 1;
         if (nLS > 0) {
           GemmOperand A2{Hd + 2, 2LL * K, 0}, B2{Q, D, 1}, B3{Yh, D, 1};
           const size_t off = ((size_t)s * 2 + e) * nLS * 2 * S;
@@ -524,17 +604,12 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
         h->launches += 2;
         if (cplx_out) {
           cplx* outc = reinterpret_cast<cplx*>(e == 0 ? a.wL : a.wR) + out_off;
-          long long n = (long long)a.num_orient * Mc * a.len;
-          complex_basis_filters_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(wtmp, Wse_c, a.order, a.len, K, nfft,
-                                                                                   a.num_orient, outc);
-          EM_CUDA(cudaGetLastError());
+          EM_CUDA(launch_basis_change_filters(st, wtmp, basis_kind, Mc, a.len, a.num_orient, Wse_c, K, nfft, outc));
           h->launches += 1;
         }
       }
     if (cplx_out && a.spectra) {
-      long long n = (long long)2 * P * Mc * K;
-      complex_basis_spectra_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Wsp, a.order, K, 2LL * P);
-      EM_CUDA(cudaGetLastError());
+      EM_CUDA(launch_basis_change_spectra(st, Wsp, basis_kind, Mc, K, 2LL * P, 1));
       h->launches += 1;
     }
   }

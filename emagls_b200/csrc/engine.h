@@ -134,7 +134,7 @@ class ProfSpan {
 };
 
 // ---- design engine (engine.cu) ---------------------------------------------------------------
-enum class Variant { EMAGLS2, EMAGLS_SH };
+enum class Variant { EMAGLS2, EMAGLS_SH, EMA_CH };
 
 struct DesignArgs {
   Variant variant;
@@ -142,7 +142,7 @@ struct DesignArgs {
   int T, D;
   const double *grid_azi, *grid_zen;  // device [D]
   double mic_radius;
-  const double *mic_azi, *mic_zen;  // device [M]
+  const double *mic_azi, *mic_zen;  // device [M]; mic_zen == nullptr: equatorial array (zenith pi/2)
   int M, order;
   double fs;
   int len, num_sets, num_orient;
@@ -151,6 +151,25 @@ struct DesignArgs {
   double* spectra;          // device or nullptr: complex [K x Mc x P x 2]
 };
 void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& a);
+// real-basis -> complex-basis outputs (kind 0: SH in ACN order, 1: CH ordered [0,-1,+1,...]); see engine.cu
+cudaError_t launch_basis_change_filters(cudaStream_t st, const double* wr, int kind, int nch, int len,
+                                        long long P, const cplx* Wsp_e, int K, int nfft, cplx* out);
+cudaError_t launch_basis_change_spectra(cudaStream_t st, cplx* Wsp, int kind, int nch, int K, long long EP,
+                                        int dc_quirk);
+void design_magls(emagls_ctx* h, const emagls_config& cfg, const double* hL, const double* hR, int T, int D,
+                  const double* grid_azi, const double* grid_zen, int order, double fs, int len, bool ls_only,
+                  double* wL, double* wR, double* spectra);
+void design_from_atf(emagls_ctx* h, const emagls_config& cfg, const double* hL, const double* hR, int T, int D,
+                     const double* hrir_grid, const double* atf_irs, int Ta, int M, int Da, const double* atf_grid,
+                     double fs, int len, double f_trans, double* wL, double* wR, double* spectra,
+                     double* mean_dev_deg);
+void design_ema_sh(emagls_ctx* h, const emagls_config& cfg, const double* hL, const double* hR, int T, int D,
+                   const double* grid_azi, const double* grid_zen, double mic_radius, const double* mic_azi, int M,
+                   int order, double fs, int len, double* wL, double* wR, double* spectra);
+std::vector<double> group_delays(emagls_ctx* h, Arena& ar, const double* hL, const double* hR, int T, int D,
+                                 int K, double fs, int num_sets);
+void hrir_spectrum(emagls_ctx* h, Arena& ar, const double* hp, int T, int D, int K, const double* tw,
+                   double delay_removed, double* Hd);
 // targets * Y_reg_inv for one steering matrix given as rows At [D][Mc]; rows [(pair*2+ear)*2+{re,im}][D],
 // W [ear][pair][Mc]
 void regularized_apply_dev(emagls_ctx* h, Arena& ar, const cplx* At, int D, int Mc, const double* rows,

@@ -80,6 +80,17 @@ cudaError_t launch_phase_rows(cudaStream_t st, const double* Y, double* T, int n
                               const double* absH, long long abs_set_stride, long long abs_ear_stride,
                               int orient_per_set, int nyquist);
 
+// ---------------------------------------------------------------- ema_kernels.cu
+cudaError_t launch_ema_sh_rows(cudaStream_t st, int order, int simN, int M, int D, int K, int complex_basis,
+                               const double* azi, const double* zen, const cplx* dec, const double* Ym,
+                               const double* Yhor, const cplx* bn, cplx* At);
+cudaError_t launch_ch_rows(cudaStream_t st, int N, const double* azi, int M, int complex_basis, cplx* At);
+cudaError_t launch_ema_dec(cudaStream_t st, int N, int M, int npair, int complex_basis, const double* Ysh0,
+                           const cplx* pinvT, cplx* dec);
+cudaError_t launch_complex_tail_prep(cudaStream_t st, const cplx* W, int kind, int nch, int K, long long P,
+                                     cplx* X1, cplx* X2);
+cudaError_t launch_interleave(cudaStream_t st, const double* re, const double* im, long long n, cplx* out);
+
 // ---------------------------------------------------------------- gram_kernels.cu
 // F blocks of the Gram route: Fs [(nqs*P) x ne], Fa [(nqa*P) x ne] (see gram_kernels.cu)
 cudaError_t launch_build_F(cudaStream_t st, const double* Gh, int S, int N, const double* Y, int Mc,

@@ -11,6 +11,7 @@
 // When no singular value can be clipped (||R||_F ||R^-1||_F <= 1/c, a rigorous bound) the
 // Jacobi sweeps are skipped and Pb = R_C^-T (plain least squares).
 #include "kernels.h"
+#include "reflect.cuh"
 
 namespace emagls {
 
@@ -43,12 +44,6 @@ __device__ __forceinline__ double gsum8(double v, unsigned mask) {
   for (int m = 4; m > 0; m >>= 1) v += __shfl_xor_sync(mask, v, m);
   return v;
 }
-__device__ __forceinline__ double wsum(double v) {
-#pragma unroll
-  for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-  return v;
-}
-
 // Householder reflector for column `col`, pivot row j, tail rows [lo, hi); executed by one
 // aligned group of 8 lanes (LAPACK zlarfg conventions: beta real, H = I - tau v v^H, v_j = 1).
 __device__ __forceinline__ void gen_reflector(cplx* col, int j, int lo, int hi, int rl,
@@ -349,45 +344,6 @@ cudaError_t launch_factor(cudaStream_t st, const BlockPlan& bp, const RowSource&
 // chain kernels: one warp per problem, both ears; x (rows x 2 ears) lives in shared memory.
 // =============================================================================================
 constexpr int CH_MAXW = 4;
-
-__device__ __forceinline__ cplx wsumc(cplx v) { v.x = wsum(v.x); v.y = wsum(v.y); return v; }
-
-// apply Q_C (forward = false: Q_C * x, blocks/reflectors in reverse order with tau) or
-// Q_C^H (forward = true: blocks/reflectors in order with conj(tau)) to x0, x1 (length S)
-__device__ void apply_qc(const BlockPlan& bp, const cplx* __restrict__ V, const cplx* __restrict__ tau,
-                         cplx* x0, cplx* x1, bool adjoint, int lane) {
-  const int S = bp.S, Mc = bp.Mc;
-  for (int tt = 0; tt < bp.nblk; ++tt) {
-    const int t = adjoint ? tt : bp.nblk - 1 - tt;
-    const int r0 = (t == 0) ? 0 : bp.R0 + (t - 1) * bp.RB;
-    const int r1 = (t == 0) ? bp.R0 : min(S, r0 + bp.RB);
-    for (int jj = 0; jj < Mc; ++jj) {
-      const int j = adjoint ? jj : Mc - 1 - jj;
-      cplx ta = tau[t * bp.MC + j];
-      if (ta.x == 0.0 && ta.y == 0.0) continue;
-      if (adjoint) ta.y = -ta.y;
-      const int lo = (t == 0) ? j + 1 : r0;
-      const cplx* v = V + (long long)j * S;
-      cplx w0 = mk(0.0, 0.0), w1 = mk(0.0, 0.0);
-      if (lane == 0) { w0 = x0[j]; w1 = x1[j]; }
-      for (int i = lo + lane; i < r1; i += 32) {
-        cplx vi = v[i];
-        cfmac(w0, vi, x0[i]);
-        cfmac(w1, vi, x1[i]);
-      }
-      w0 = wsumc(w0); w1 = wsumc(w1);
-      cplx f0 = cmul(ta, w0), f1 = cmul(ta, w1);
-      if (lane == 0) { x0[j] = csub(x0[j], f0); x1[j] = csub(x1[j], f1); }
-      for (int i = lo + lane; i < r1; i += 32) {
-        cplx vi = v[i];
-        cplx a0 = x0[i], a1 = x1[i];
-        cfms(a0, f0, vi); cfms(a1, f1, vi);
-        x0[i] = a0; x1[i] = a1;
-      }
-      __syncwarp();
-    }
-  }
-}
 
 __global__ void chain_bwd_kernel(BlockPlan bp, OperatorSet ops, int slot, int G, const double* tq,
                                  long long tq_set_stride, long long tq_ear_stride, int tq_shared,

@@ -92,3 +92,118 @@ def test_orientation_chunking_is_transparent(em, h, c1, monkeypatch):
     xL, xR = em.getEMagLs2Filters(HL, HR, *args, rotations=R, handle=h)
     assert wL.shape == (512, 32, 10)
     assert rel(xL, wL) < 1e-9 and rel(xR, wR) < 1e-9
+
+
+# ------------------------------------------------------------------ getMagLsFilters / getLsFilters
+@pytest.mark.parametrize("basis", ["real", "complex"])
+def test_magls_matches_oracle(em, h, c1, basis):
+    wL, wR, sp = em.getMagLsFilters(c1["hL"], c1["hR"], c1["az"], c1["ze"], 4, c1["fs"], 512, basis, handle=h,
+                                    return_spectra=True)
+    oL, oR, osp = oracle.getMagLsFilters(c1["hL"], c1["hR"], c1["az"], c1["ze"], 4, c1["fs"], 512, basis,
+                                         return_spectra=True)
+    assert wL.shape == (512, 25) and wL.dtype == (np.complex128 if basis == "complex" else np.float64)
+    for e in range(2):
+        assert bin_err(sp[:, :, e], osp["W"][:, :, e]).max() <= 1e-10       # every bin, DC included (LS bin)
+    assert rel(wL, oL) < 1e-11 and rel(wR, oR) < 1e-11
+    assert np.all(wL[0] == 0) and np.all(wL[-1] == 0)
+
+
+@pytest.mark.parametrize("basis", ["real", "complex"])
+def test_ls_matches_oracle(em, h, c1, basis):
+    wL, wR = em.getLsFilters(c1["hL"], c1["hR"], c1["az"], c1["ze"], 4, basis, handle=h)
+    oL, oR = oracle.getLsFilters(c1["hL"], c1["hR"], c1["az"], c1["ze"], 4, basis)
+    assert wL.shape == (128, 25)
+    assert rel(wL, oL) < 1e-12 and rel(wR, oR) < 1e-12
+
+
+def test_magls_golden_pin_through_cabi(em, h, goldens):
+    """Golden pin (2) through the CUDA path: the order-4 surrogate HRIRs rebuilt from the reference's LS
+    golden reproduce the LS bins of the reference's MagLS golden (7e-6 .. 5e-3), and
+    the LS golden itself is reproduced from the surrogate exactly."""
+    G = goldens
+    az, ze = G["hrirGridAziRad"], G["hrirGridZenRad"]
+    Y4 = oracle.getSH(4, np.stack([az, ze], 1), "real")
+    h4L, h4R = G["real_LS_wLsL"] @ Y4.T, G["real_LS_wLsR"] @ Y4.T
+    lL, lR = em.getLsFilters(h4L, h4R, az, ze, 4, handle=h)
+    assert rel(lL, G["real_LS_wLsL"]) < 1e-11 and rel(lR, G["real_LS_wLsR"]) < 1e-11
+    for basis in ("real", "complex"):
+        wL, wR = em.getMagLsFilters(h4L, h4R, az, ze, 4, 48000, 512, basis, handle=h)
+        for w, key in ((wL, "wMlsL"), (wR, "wMlsR")):
+            A = np.fft.fft(w, 1024, axis=0)
+            Bq = np.fft.fft(G[f"{basis}_MagLS_woDC_{key}"], 1024, axis=0)
+            for lo, hi, tol in ((1, 10, 3e-5), (10, 30, 1e-3), (30, 42, 5e-2)):
+                assert np.abs(A[lo:hi] - Bq[lo:hi]).max() / np.abs(Bq[lo:hi]).max() < tol
+
+
+# ------------------------------------------------------------------ getEMagLsFiltersFromAtf
+@pytest.fixture(scope="module")
+def atf():
+    import os
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "atf_subset.npz"))
+    ag = np.deg2rad(d["atfGridAziEleDeg"].astype(float))
+    return d["atfIrs"].astype(float), np.stack([ag[:, 0], np.pi / 2 - ag[:, 1]], 1)
+
+
+@pytest.mark.parametrize("step", [3, 9])   # HRIR grid larger (901 > 407) and smaller (301 < 407) than the ATF grid
+def test_from_atf_matches_oracle(em, h, grids, atf, step, capsys):
+    atfIrs, ag = atf
+    az, ze = grids["hrirGridAziRad"][::step], grids["hrirGridZenRad"][::step]
+    hL, hR = synth.synth_hrirs(az, ze)
+    hg = np.stack([az, ze], 1)
+    wL, wR, sp, info = em.getEMagLsFiltersFromAtf(hL, hR, hg, atfIrs, ag, 48000, 256, 1000.0, handle=h,
+                                                  return_spectra=True, return_info=True)
+    oL, oR, osp = oracle.getEMagLsFiltersFromAtf(hL, hR, hg, atfIrs, ag, 48000, 256, 1000.0, return_spectra=True)
+    assert "average grid deviation" in capsys.readouterr().out            # the reference's disp() line (:96)
+    assert abs(info["meanGridDevDeg"] - osp["meanGridDevDeg"]) < 1e-9
+    assert wL.shape == (256, 8)
+    for e, Wo in enumerate((osp["W_l"], osp["W_r"])):
+        err = bin_err(sp[:, :, e], Wo)
+        assert err[1:].max() <= 1e-10, err[1:].max()                     # measured ATFs are benign (cond < 200)
+    assert rel(wL, oL) < 1e-10 and rel(wR, oR) < 1e-10
+    assert np.all(wL[0] == 0) and np.all(sp[0].imag == 0)
+
+
+# ------------------------------------------------------------------ EMA designers (config 4 shape at reduced radius)
+@pytest.fixture(scope="module")
+def ema(grids):
+    az, ze = grids["hrirGridAziRad"], grids["hrirGridZenRad"]
+    hL, hR = synth.synth_hrirs(az, ze)
+    maz = 2 * np.pi * np.arange(13) / 13
+    return dict(az=az, ze=ze, hL=hL, hR=hR, maz=maz)
+
+
+@pytest.mark.parametrize("basis", ["real", "complex"])
+@pytest.mark.parametrize("radius,order", [(0.042, 4), (0.08, 6)])
+def test_ema_ch_matches_oracle(em, h, ema, basis, radius, order):
+    args = (ema["az"], ema["ze"], radius, ema["maz"], order, 48000, 512)
+    wL, wR, sp = em.getEMagLsFiltersEMAinCH(ema["hL"], ema["hR"], *args, basis, handle=h, return_spectra=True)
+    oL, oR, osp = oracle.getEMagLsFiltersEMAinCH(ema["hL"], ema["hR"], *args, basis, return_spectra=True)
+    assert wL.shape == (512, 2 * order + 1)
+    assert wL.dtype == (np.complex128 if basis == "complex" else np.float64)
+    for e, Wo in enumerate((osp["W_l"], osp["W_r"])):
+        err = bin_err(sp[:, :, e], Wo)
+        assert err[16:].max() <= 1e-10, err[16:].max()
+        assert err[1:16].max() <= 1e-7, err[1:16].max()
+    assert rel(wL, oL) < 1e-8 and rel(wR, oR) < 1e-8
+
+
+@pytest.mark.parametrize("basis", ["real", "complex"])
+def test_ema_sh_matches_oracle(em, h, ema, basis):
+    args = (ema["az"], ema["ze"], 0.042, ema["maz"], 4, 48000, 512)
+    wL, wR, sp = em.getEMagLsFiltersEMAinSH(ema["hL"], ema["hR"], *args, basis, handle=h, return_spectra=True)
+    oL, oR, osp = oracle.getEMagLsFiltersEMAinSH(ema["hL"], ema["hR"], *args, basis, return_spectra=True)
+    assert wL.shape == (512, 25)
+    assert wL.dtype == (np.complex128 if basis == "complex" else np.float64)
+    for e, Wo in enumerate((osp["W_l"], osp["W_r"])):
+        err = bin_err(sp[:, :, e], Wo)
+        assert err[16:].max() <= 1e-10, err[16:].max()
+        assert err[1:16].max() <= 1e-7, err[1:16].max()
+    assert rel(wL, oL) < 1e-8 and rel(wR, oR) < 1e-8
+
+
+def test_variant_errors(em, h, c1, ema):
+    with pytest.raises(em.EmaglsError, match="len too short"):
+        em.getMagLsFilters(c1["hL"], c1["hR"], c1["az"], c1["ze"], 4, c1["fs"], 64, handle=h)
+    with pytest.raises(em.EmaglsError, match="fewer microphones"):
+        em.getEMagLsFiltersEMAinCH(ema["hL"], ema["hR"], ema["az"], ema["ze"], 0.042, ema["maz"][:5], 4, 48000, 512,
+                                   handle=h)
