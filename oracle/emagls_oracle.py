@@ -686,10 +686,10 @@ def getEMagLsFiltersEMAinCH(hL, hR, hrirGridAziRad, hrirGridZenRad, micRadius, m
     Y_hor_conj = np.conj(shFunction(simN, np.stack([az, ze], 1), shDefinition)).T
     Y_CH_Mic_pinv = np.linalg.pinv(chFunction(order, maz, shDefinition))
     # lib/getEMagLsFiltersEMAinCH.m:74-75 (two pagemtimes)
-    smairMat_CH = np.einsum("msk,sd->mdk", smairMat, Y_hor_conj)
-    smairMat_CH = np.einsum("cm,mdk->cdk", Y_CH_Mic_pinv, smairMat_CH)
+    smairMat_CH = np.matmul(smairMat.transpose(2, 0, 1), Y_hor_conj)   # [K, M, D] (batched BLAS)
+    smairMat_CH = np.matmul(Y_CH_Mic_pinv, smairMat_CH)                # [K, C, D]
     HL, HR, grpDL, grpDR = _prep_hrirs(hL, hR, nfft, f, fs)
-    W_l, W_r = _magls_loop(lambda k: smairMat_CH[:, :, k - 1], HL, HR, K, numHarm, k_cut,
+    W_l, W_r = _magls_loop(lambda k: smairMat_CH[k - 1], HL, HR, K, numHarm, k_cut,
                            cfg["SVD_REGUL_CONST"])
     is_real = np.isrealobj(Y_hor_conj)
     extend = _real_extend if is_real else getChFreqDomainConjugate
@@ -724,13 +724,13 @@ def getEMagLsFiltersEMAinSH(hL, hR, hrirGridAziRad, hrirGridZenRad, micRadius, m
     # lib/getEMagLsFiltersEMAinSH.m:68-69: directions projected onto the equator
     Y_hor_conj = np.conj(shFunction(simN, np.stack([az, np.full_like(az, np.pi / 2)], 1),
                                     shDefinition)).T
-    emaIrDir = np.einsum("msk,sd->kmd", emaIrMat, Y_hor_conj)  # K x M x D
+    emaIrDir = np.matmul(emaIrMat.transpose(2, 0, 1), Y_hor_conj)  # K x M x D
     numHarm = (order + 1) ** 2
     D = hL.shape[1]
     YCh = chFunction(order, maz, shDefinition)
     J = getChToShExpansionMatrix(order, shDefinition)
     dec = np.linalg.pinv(YCh.T) @ J.T  # M x numHarm   (:81-83)
-    emaIrDir_sh = np.einsum("kmd,mh->khd", emaIrDir, dec)  # K x H x D
+    emaIrDir_sh = np.matmul(dec.T, emaIrDir)  # K x H x D
     for d in range(D):  # :86-101
         if ze[d] != np.pi / 2:
             E = euler2rotationMatrix(-az[d], ze[d] - np.pi / 2, az[d], "zyz")
