@@ -48,7 +48,7 @@ ema_sh_rows_kernel(int order, int simN, int M, int D, int K, int complex_basis,
   const int nsh = (order + 1) * (order + 1), S = (simN + 1) * (simN + 1), L1 = simN + 1;
   const int d = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   double* Rr = reinterpret_cast<double*>(es_raw);            // [nsh][nsh] real rotation (block diagonal)
-  cplx* Rc = reinterpret_cast<cplx*>(Rr + nsh * nsh);        // [nsh][nsh] rotation in the output basis
+  cplx* Rc = reinterpret_cast<cplx*>(Rr + ((nsh * nsh + 1) & ~1));  // [nsh][nsh] rotation in the output basis
   cplx* Bd = Rc + nsh * nsh;                                 // [M][nsh]
   double* Pn = reinterpret_cast<double*>(Bd + M * nsh);      // [M][L1]
   cplx* Cn = reinterpret_cast<cplx*>(Pn + ((M * L1 + 1) & ~1));  // [L1][nsh]
@@ -181,7 +181,7 @@ cudaError_t launch_ema_sh_rows(cudaStream_t st, int order, int simN, int M, int 
                                const double* azi, const double* zen, const cplx* dec, const double* Ym,
                                const double* Yhor, const cplx* bn, cplx* At) {
   const int nsh = (order + 1) * (order + 1), L1 = simN + 1;
-  size_t smem = (size_t)nsh * nsh * 8 + (size_t)nsh * nsh * 16 + (size_t)M * nsh * 16 +
+  size_t smem = (size_t)((nsh * nsh + 1) & ~1) * 8 + (size_t)nsh * nsh * 16 + (size_t)M * nsh * 16 +
                 (size_t)((M * L1 + 1) & ~1) * 8 + (size_t)L1 * nsh * 16;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   static size_t set_to = 0;

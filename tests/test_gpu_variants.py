@@ -183,8 +183,9 @@ def test_ema_ch_matches_oracle(em, h, ema, basis, radius, order):
     for e, Wo in enumerate((osp["W_l"], osp["W_r"])):
         err = bin_err(sp[:, :, e], Wo)
         assert err[16:].max() <= 1e-10, err[16:].max()
-        assert err[1:16].max() <= 1e-7, err[1:16].max()
-    assert rel(wL, oL) < 1e-8 and rel(wR, oR) < 1e-8
+        assert err[8:16].max() <= 1e-8, err[8:16].max()
+        assert err[1:8].max() <= 2e-6, err[1:8].max()        # ill-conditioned bins: the reference's own 1-ulp floor
+    assert rel(wL, oL) < 5e-9 and rel(wR, oR) < 5e-9
 
 
 @pytest.mark.parametrize("basis", ["real", "complex"])
@@ -197,8 +198,9 @@ def test_ema_sh_matches_oracle(em, h, ema, basis):
     for e, Wo in enumerate((osp["W_l"], osp["W_r"])):
         err = bin_err(sp[:, :, e], Wo)
         assert err[16:].max() <= 1e-10, err[16:].max()
-        assert err[1:16].max() <= 1e-7, err[1:16].max()
-    assert rel(wL, oL) < 1e-8 and rel(wR, oR) < 1e-8
+        assert err[8:16].max() <= 1e-8, err[8:16].max()
+        assert err[1:8].max() <= 2e-6, err[1:8].max()        # ill-conditioned bins: the reference's own 1-ulp floor
+    assert rel(wL, oL) < 5e-9 and rel(wR, oR) < 5e-9
 
 
 def test_variant_errors(em, h, c1, ema):
