@@ -264,20 +264,45 @@ int emagls_design_ema_sh(emagls_handle h, const emagls_config* cfg, const double
 // ------------------------------------------------------------------------------------------
 // getSMAIRMatrix (dependencies/getSMAIRMatrix.m:86-127) for radialFilter = 'none'
 // ------------------------------------------------------------------------------------------
-__global__ void smair_raw_kernel(const double* __restrict__ Ym, const cplx* __restrict__ bn, int M, int S,
-                                 int N, int K, cplx* __restrict__ out) {
-  // out[(k*S + s)*M + m] = Ym[m][s] * bn[k][ord(s)]
+// out[(k*S + s)*rows + r] = Yrows[r][s] * bn[k][ord(s)]   (getSMAIRMatrix.m:112-122)
+__global__ void smair_kernel(const cplx* __restrict__ Yrows, const cplx* __restrict__ bn, int rows, int S,
+                             int N, int K, cplx* __restrict__ out) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)K * S * M) return;
-  int m = (int)(idx % M);
-  int s = (int)((idx / M) % S);
-  int k = (int)(idx / ((long long)M * S));
+  if (idx >= (long long)K * S * rows) return;
+  int r = (int)(idx % rows);
+  int s = (int)((idx / rows) % S);
+  int k = (int)(idx / ((long long)rows * S));
   int ord = (int)sqrt((double)s);
   while ((ord + 1) * (ord + 1) <= s) ++ord;
   while (ord * ord > s) --ord;
-  cplx b = bn[(long long)k * (N + 1) + ord];
-  double y = Ym[(long long)m * S + s];
-  out[idx] = mk(y * b.x, y * b.y);
+  out[idx] = cmul(Yrows[(long long)r * S + s], bn[(long long)k * (N + 1) + ord]);
+}
+
+// Ymic[m][s] (complex) from launch_sh_angles output [S][M] (real or complex basis)
+__global__ void sh_to_rows_kernel(const double* __restrict__ Y, int M, int S, int complex_basis,
+                                  cplx* __restrict__ rows) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * S) return;
+  int m = idx / S, s = idx % S;
+  rows[idx] = complex_basis ? reinterpret_cast<const cplx*>(Y)[(long long)s * M + m] : mk(Y[(long long)s * M + m], 0.0);
+}
+
+// Yout[c][s] = sum_m Lt[(m&1)*npair + m/2][c] * Ymic[m][s]   (pinv(Y_lo) * Y_Hi, getSMAIRMatrix.m:102,119-121)
+__global__ void smair_project_kernel(const cplx* __restrict__ Lt, int npair, int nsh, int M, int S,
+                                     const cplx* __restrict__ Ymic, cplx* __restrict__ Yout) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nsh * S) return;
+  int c = idx / S, s = idx % S;
+  cplx acc = mk(0.0, 0.0);
+  for (int m = 0; m < M; ++m) cfma(acc, Lt[((long long)(m & 1) * npair + m / 2) * nsh + c], Ymic[(long long)m * S + s]);
+  Yout[idx] = acc;
+}
+
+__global__ void unit_rows_kernel(double* rows, int npair, int D) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)npair * 4 * D) return;
+  const int d = (int)(idx % D), row = (int)(idx / D);
+  rows[idx] = ((row & 1) == 0 && (row >> 1) == d) ? 1.0 : 0.0;
 }
 
 int emagls_smair_matrix(emagls_handle h, const emagls_config* cfg, const double* mic_azi,
@@ -290,23 +315,49 @@ int emagls_smair_matrix(emagls_handle h, const emagls_config* cfg, const double*
     if (sim_order_out) *sim_order_out = simN;
     if (!out) return;
     EM_REQUIRE(simN <= MAX_SH_ORDER, "simulation order too high");
-    if (!return_raw_mic_sigs)
-      throw Fail{EMAGLS_ERR_UNSUPPORTED, "SH-domain getSMAIRMatrix output is wired in a later step"};
     cudaStream_t st = h->stream;
     Arena ar(st);
     const int S = (simN + 1) * (simN + 1), K = nfft / 2 + 1, M = num_mics;
+    const int nsh = (order + 1) * (order + 1);
+    const int cb = cfg->basis == EMAGLS_BASIS_COMPLEX ? 1 : 0;
     std::vector<double> kr(K);
     const double df = (fs / 2.0) / (double)(K - 1);
     for (int k = 0; k < K; ++k) kr[k] = 2.0 * M_PI * ((double)k * df) / cfg->speed_of_sound * sma_radius;
     cplx* bn = ar.get<cplx>((size_t)K * (simN + 1));
     EM_CUDA(launch_modal(st, simN, ar.upload(kr.data(), K), K, cfg->array_type, -1.0, 1, bn, simN + 1, 1));
-    double* Ym = ar.get<double>((size_t)M * S);
-    EM_CUDA(launch_sh_mics(st, simN, ar.upload(mic_azi, M), ar.upload(mic_zen, M), M, nullptr, 1, Ym));
-    cplx* d_out = ar.get<cplx>((size_t)K * S * M);
-    long long total = (long long)K * S * M;
-    smair_raw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Ym, bn, M, S, simN, K, d_out);
+    // Y_Hi = shFunction(simulationOrder, mics, shDefinition) as rows [M][S]
+    double* Y = ar.get<double>((size_t)M * S * (cb ? 2 : 1));
+    EM_CUDA(launch_sh_angles(st, simN, ar.upload(mic_azi, M), ar.upload(mic_zen, M), M, cb, Y));
+    cplx* Ymic = ar.get<cplx>((size_t)M * S);
+    sh_to_rows_kernel<<<(M * S + 255) / 256, 256, 0, st>>>(Y, M, S, cb, Ymic);
     EM_CUDA(cudaGetLastError());
     h->launches += 3;
+    const cplx* Yrows = Ymic;
+    int rows = M;
+    if (!return_raw_mic_sigs) {
+      EM_REQUIRE(M >= nsh && nsh <= 64 && M <= 4096, "fewer microphones than SH channels (or more than 64 channels)");
+      // pinv(Y_Hi(:, 1:(order+1)^2)) through the factorisation kernel with the clip disabled
+      cplx* Alo = ar.get<cplx>((size_t)M * nsh);
+      EM_CUDA(cudaMemcpy2DAsync(Alo, (size_t)nsh * sizeof(cplx), Ymic, (size_t)S * sizeof(cplx),
+                                (size_t)nsh * sizeof(cplx), M, cudaMemcpyDeviceToDevice, st));
+      const int npair = (M + 1) / 2;
+      double* urows = ar.get<double>((size_t)npair * 4 * M);
+      long long n = (long long)npair * 4 * M;
+      unit_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(urows, npair, M);
+      cplx* Lt = ar.get<cplx>((size_t)2 * npair * nsh);
+      regularized_apply_dev(h, ar, Alo, M, nsh, urows, npair, 0.0, Lt);
+      cplx* Yout = ar.get<cplx>((size_t)nsh * S);
+      smair_project_kernel<<<(nsh * S + 255) / 256, 256, 0, st>>>(Lt, npair, nsh, M, S, Ymic, Yout);
+      EM_CUDA(cudaGetLastError());
+      h->launches += 2;
+      Yrows = Yout;
+      rows = nsh;
+    }
+    cplx* d_out = ar.get<cplx>((size_t)K * S * rows);
+    long long total = (long long)K * S * rows;
+    smair_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Yrows, bn, rows, S, simN, K, d_out);
+    EM_CUDA(cudaGetLastError());
+    h->launches += 1;
     EM_CUDA(cudaMemcpyAsync(out, d_out, (size_t)total * sizeof(cplx), cudaMemcpyDeviceToHost, st));
     EM_CUDA(cudaStreamSynchronize(st));
   });

@@ -58,6 +58,18 @@ def test_smair_matrix_raw(em, h, grids):
     assert p["order"] == 4 and p["arrayType"] == "rigid"             # defaults echoed
 
 
+@pytest.mark.parametrize("raw,basis", [(False, "real"), (False, "complex"), (True, "complex")])
+def test_smair_matrix_sh_domain_and_complex_basis(em, h, grids, raw, basis):
+    params = dict(returnRawMicSigs=raw, order=4, fs=48000, irLen=512, oversamplingFactor=1, radialFilter="none",
+                  smaRadius=0.042, shDefinition=basis,
+                  smaDesignAziZenRad=np.stack([grids["micGridAziRad"], grids["micGridZenRad"]], 1))
+    sm, _ = em.getSMAIRMatrix(params, handle=h)
+    smo, _ = oracle.getSMAIRMatrix(params)
+    assert sm.shape == smo.shape == ((32 if raw else 25), 400, 257)
+    e = np.abs(sm - smo).max(axis=(0, 1)) / np.abs(smo).max(axis=(0, 1))
+    assert e.max() < 1e-12
+
+
 @pytest.mark.parametrize("Mc,D,grade,tol", [(32, 2702, 0, 1e-13), (8, 407, 0, 1e-13), (13, 2702, 3, 1e-11),
                                               (25, 2702, 5, 1e-9), (64, 3000, 4, 1e-10), (64, 1444, 0, 1e-13),
                                               (5, 5, 0, 1e-12), (1, 40, 0, 1e-13)])
