@@ -29,7 +29,7 @@ namespace {
 
 struct EpiRamp {  // H = fft(h) .* exp_omega  (applySubsampleDelay.m:10-17), columns (2k, 2k+1) = (re, im)
   double* C; long long ldc; const cplx* ramp;
-  __device__ __forceinline__ void operator()(int m, int n, double re, double im, int M, int N) const {
+  __device__ __forceinline__ void operator()(int m, int n, double re, double im, int M, int N, int) const {
     if (m >= M || n >= N) return;
     cplx r = ramp[n >> 1];
     double* q = C + (long long)m * ldc + n;
@@ -248,11 +248,11 @@ void regularized_apply_dev(emagls_ctx* h, Arena& ar, const cplx* At, int D, int 
   ops.info = ar.get<int>(1);
   RowSource src{};
   src.At = At; src.at_bin_stride = 0; src.at_prob_stride = 0;
-  EM_CUDA(launch_factor(st, bp, src, ops, 1, 0, 1, regul));
+  EM_CUDA(launch_factor(st, bp, src, ops, 1, 0, 1, regul, 1));
   // every pair of targets shares the one operator set: chain_bwd indexes operators by j % oc and
   // solutions by global(j), so oc = 1 addresses the pairs through the set index
   ProbMap pm1{1, 0, 1};
-  EM_CUDA(launch_chain_bwd(st, bp, ops, 0, 1, rows, 0, 0, 0, pm1, W, (long long)npair * Mc, 1, 0, 0, npair));
+  EM_CUDA(launch_chain_bwd(st, bp, ops, 0, 1, rows, 0, 0, 0, 1, 0, pm1, W, (long long)npair * Mc, 1, 0, 0, npair));
   h->launches += 2;
 }
 
@@ -425,7 +425,7 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
   const size_t per_orient =
       (size_t)Etot * 8 + (size_t)(nqs + nqa) * ne_ld * 8 + (size_t)2 * NB * ne_ld * 8 + (size_t)NB * pb_stride * 16 +
       (size_t)G * (v_stride + tau_stride + pb_stride) * 16 +
-      (size_t)a.num_sets * ((size_t)2 * 4 * S * 8 + (size_t)4 * D * 8);
+      (size_t)a.num_sets * ((size_t)(1 + 6) * 4 * S * 8 + (size_t)4 * D * 8);
   size_t free_b = 0, total_b = 0;
   EM_CUDA(cudaMemGetInfo(&free_b, &total_b));
   // memory still cached in the stream-ordered pool is reusable: plan against the larger figure
@@ -463,7 +463,8 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
   ops.info = ar.get<int>((size_t)OC * G);
   double* Cv = ar.get<double>((size_t)4 * PJ * S);
   double* Tt = ar.get<double>((size_t)D * 4 * PJ);
-  double* tq = ar.get<double>((size_t)4 * PJ * S);
+  constexpr int MAX_SPLITS = 6;
+  double* tq = ar.get<double>((size_t)MAX_SPLITS * 4 * PJ * S);   // split-K partials of t * Y_h
   // Gram route admissible iff cond_2(G) <= 1/c^2 (no singular value below c*s_max); the Frobenius
   // bound is tested with a factor-2 margin, and normal equations are never used beyond cond(G) = 1e4.
   double gram_thr = (cfg.svd_regul > 0.0) ? std::min(1e4, 0.5 / (cfg.svd_regul * cfg.svd_regul)) : 1e4;
@@ -529,7 +530,8 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
           while (Gn < G && kb + Gn < gb0 + nb && fail_h[1 + kb + Gn - gb0] != 0) ++Gn;
           {
             ProfSpan ps(h, EM_PROF_FACTOR);
-            EM_CUDA(launch_factor(st, bp, src, ops, oc, kb, Gn, cfg.svd_regul));
+            // bins refused by the Gram route skip the fast-path test (it cannot succeed there)
+            EM_CUDA(launch_factor(st, bp, src, ops, oc, kb, Gn, cfg.svd_regul, gram_thr > 0.0 ? 0 : 1));
           }
           h->launches += 1;
           slot_base = kb; slot_n = Gn;
@@ -551,10 +553,10 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
           const size_t off = (size_t)(kb - 1) * 2 * S;
           if (gram)
             EM_CUDA(launch_bwd_small(st, Yc, Mc, S, d_roword, bk, pbg, pm, pj, Zls + off, (long long)2 * nLS * 2 * S,
-                                     (long long)nLS * 2 * S, 1, Wsp, w_ear, K, kb, dc_fix));
+                                     (long long)nLS * 2 * S, 1, 1, 0, Wsp, w_ear, K, kb, dc_fix));
           else
             EM_CUDA(launch_chain_bwd(st, bp, ops, slot, slot_n, Tls + off, (long long)2 * nLS * 2 * S,
-                                     (long long)nLS * 2 * S, 1, pm, Wsp, w_ear, K, kb, dc_fix, pj));
+                                     (long long)nLS * 2 * S, 1, 1, 0, pm, Wsp, w_ear, K, kb, dc_fix, pj));
           h->launches += 1;
         } else {
           {
@@ -567,17 +569,22 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
             EpiPhase ep{Tt, 4LL * pj, absH + (size_t)kb * D, 2LL * K * D, (long long)K * D, oc, kb == K - 1 ? 1 : 0};
             EM_CUDA(launch_gemm(st, A3, B3, GemmShape{D, 4 * pj, S}, ep));
           }
+          int nsplit = 1;
+          const long long split_stride = 4LL * pj * S;
           {
             ProfSpan ps(h, EM_PROF_GEMM_BWD);
             GemmOperand A4{Tt, 4LL * pj, 0}, B4{gram ? Yh : Q, D, 1};
-            EM_CUDA(launch_gemm(st, A4, B4, GemmShape{4 * pj, S, D}, EpiStore{tq, S, 1.0}));
+            EM_CUDA(launch_gemm_splitk(st, A4, B4, GemmShape{4 * pj, S, D}, EpiStore{tq, S, 1.0, split_stride}, MAX_SPLITS,
+                                       &nsplit));
           }
           {
             ProfSpan ps(h, EM_PROF_CHAIN_BWD);
             if (gram)
-              EM_CUDA(launch_bwd_small(st, Yc, Mc, S, d_roword, bk, pbg, pm, pj, tq, 0, 0, 0, Wsp, w_ear, K, kb, dc_fix));
+              EM_CUDA(launch_bwd_small(st, Yc, Mc, S, d_roword, bk, pbg, pm, pj, tq, 0, 0, 0, nsplit, split_stride, Wsp,
+                                       w_ear, K, kb, dc_fix));
             else
-              EM_CUDA(launch_chain_bwd(st, bp, ops, slot, slot_n, tq, 0, 0, 0, pm, Wsp, w_ear, K, kb, dc_fix, pj));
+              EM_CUDA(launch_chain_bwd(st, bp, ops, slot, slot_n, tq, 0, 0, 0, nsplit, split_stride, pm, Wsp, w_ear, K,
+                                       kb, dc_fix, pj));
           }
           h->launches += 4;
         }

@@ -1,19 +1,22 @@
 // FP64 tensor-core GEMM used by every dense contraction of the design path:
 //   C[m][n] = epi( sum_k A(m,k) * B(n,k) )
-// CTA tile 128x128x16, 8 warps (2 x 4), warp tile 64x32 = 8x4 DMMA.8x8x4 tiles, 3-stage
-// cp.async (LDGSTS) ring.  A and B may be K-contiguous ([m][k]) or K-strided ([k][m]); the
-// tiles are staged in shared memory in their global orientation (padding chosen so both
-// fragment patterns are bank-conflict free) so no transposes are materialised in HBM.
+// DMMA.8x8x4 is the only FP64 MMA shape sm_100a executes natively (m16n8k{4,8,16} lower to it), so
+// the kernel is built from 8x8x4 tiles: CTA tile BM x BN x 16, 8 warps, multi-stage cp.async
+// (LDGSTS) ring.  Two configurations: 128x128 (2x4 warps of 64x32, 4 stages) for the wide
+// contractions and 128x80 (4x2 warps of 32x40, 3 stages, 2 CTAs/SM) for N = S = 400 and friends,
+// where 128-wide tiles would waste 22 % of the tensor work.  A and B may be K-contiguous ([m][k])
+// or K-strided ([k][m]); tiles are staged in their global orientation (padding chosen so both
+// fragment patterns are bank-conflict free), so no transposes are materialised in HBM.  The
+// cp.async traffic of the next stage is issued between the four k4 steps of the current one, so the
+// warps never leave the DMMA stream for a synchronised load phase.  Optional split-K (grid.z):
+// every split writes its own partial C (deterministic; the consumer adds the partials).
 #pragma once
 #include "common.cuh"
 
 namespace emagls {
 
-constexpr int GM_BM = 128, GM_BN = 128, GM_BK = 16, GM_STAGES = 3, GM_THREADS = 256;
+constexpr int GM_BK = 16, GM_THREADS = 256;
 constexpr int GM_LDK = GM_BK + 4;    // [row][k] orientation: row stride 20 doubles
-constexpr int GM_LDM = GM_BM + 4;    // [k][row] orientation: row stride 132 doubles
-constexpr int GM_TILE_DOUBLES = (GM_BM * GM_LDK > GM_BK * GM_LDM) ? GM_BM * GM_LDK : GM_BK * GM_LDM;
-constexpr size_t GM_SMEM_BYTES = (size_t)GM_STAGES * 2 * GM_TILE_DOUBLES * sizeof(double);
 
 struct GemmOperand {
   const double* p;
@@ -23,12 +26,12 @@ struct GemmOperand {
 
 struct GemmShape { int M, N, K; };
 
-// ---- epilogues -----------------------------------------------------------------------------
+// ---- epilogues (z = split-K index) -----------------------------------------------------------
 struct EpiStore {
-  double* C; long long ldc; double alpha;
-  __device__ __forceinline__ void operator()(int m, int n, double v0, double v1, int M, int N) const {
+  double* C; long long ldc; double alpha; long long split_stride = 0;
+  __device__ __forceinline__ void operator()(int m, int n, double v0, double v1, int M, int N, int z) const {
     if (m >= M) return;
-    double* q = C + (long long)m * ldc + n;
+    double* q = C + (long long)z * split_stride + (long long)m * ldc + n;
     if (n + 1 < N) {
       if ((((uintptr_t)q) & 15) == 0) { *reinterpret_cast<double2*>(q) = make_double2(alpha * v0, alpha * v1); }
       else { q[0] = alpha * v0; q[1] = alpha * v1; }
@@ -46,7 +49,7 @@ struct EpiPhase {
   long long abs_ear_stride;  // doubles between ears
   int orient_per_set;
   int nyquist;
-  __device__ __forceinline__ void operator()(int m, int n, double re, double im, int M, int N) const {
+  __device__ __forceinline__ void operator()(int m, int n, double re, double im, int M, int N, int) const {
     if (m >= M || n >= N) return;
     int j = n >> 1;                 // problem*2 + ear
     int ear = j & 1, prob = j >> 1;
@@ -64,125 +67,137 @@ struct EpiPhase {
   }
 };
 
-// ---- tile loader ---------------------------------------------------------------------------
-// Loads a [ROWS x BK] tile of an operand into shared memory (zero-filled out of range).
-template <int ROWS>
-__device__ __forceinline__ void load_tile(double* s, const GemmOperand& op, int row0, int k0,
-                                          int nrows, int K, bool vec16, int tid) {
-  if (op.kcontig) {
-    // smem [row][GM_LDK]; chunks run along k
-    if (vec16) {
-      constexpr int CH = GM_BK / 2;                   // 8 chunks per row
-      for (int c = tid; c < ROWS * CH; c += GM_THREADS) {
-        int r = c / CH, kk = (c % CH) * 2;
-        int gr = row0 + r, gk = k0 + kk;
-        bool ok = (gr < nrows) && (gk < K);
-        const double* g = op.p + (long long)(ok ? gr : 0) * op.ld + (ok ? gk : 0);
-        cp_async16(s + r * GM_LDK + kk, g, ok);
-      }
-    } else {
-      for (int c = tid; c < ROWS * GM_BK; c += GM_THREADS) {
-        int r = c / GM_BK, kk = c % GM_BK;
-        int gr = row0 + r, gk = k0 + kk;
-        bool ok = (gr < nrows) && (gk < K);
-        const double* g = op.p + (long long)(ok ? gr : 0) * op.ld + (ok ? gk : 0);
-        cp_async8(s + r * GM_LDK + kk, g, ok);
-      }
+// ---- tile configuration ----------------------------------------------------------------------
+template <int WM_, int WN_, int WARPS_M_, int WARPS_N_, int STAGES_, int MINB_>
+struct GemmCfg {
+  static constexpr int WM = WM_, WN = WN_, WARPS_M = WARPS_M_, WARPS_N = WARPS_N_, STAGES = STAGES_, MINB = MINB_;
+  static constexpr int BM = WARPS_M * WM * 8, BN = WARPS_N * WN * 8;
+  static constexpr int LDMA = BM + 4, LDMB = BN + 4;   // [k][row] orientation strides (== 4 mod 16)
+  static constexpr int TILE_A = (BM * GM_LDK > GM_BK * LDMA) ? BM * GM_LDK : GM_BK * LDMA;
+  static constexpr int TILE_B = (BN * GM_LDK > GM_BK * LDMB) ? BN * GM_LDK : GM_BK * LDMB;
+  static constexpr size_t SMEM = (size_t)STAGES * (TILE_A + TILE_B) * sizeof(double);
+  static_assert(WARPS_M * WARPS_N * 32 == GM_THREADS, "8 warps");
+  static_assert(LDMA % 16 == 4 && LDMB % 16 == 4, "k-strided tiles need a row stride of 4 mod 16 doubles");
+};
+using GemmWide = GemmCfg<8, 4, 2, 4, 4, 1>;    // 128 x 128, 160 KB, 1 CTA / SM
+using GemmNarrow = GemmCfg<4, 5, 4, 2, 3, 2>;  // 128 x 80,   98 KB, 2 CTAs / SM
+
+// ---- tile loader -----------------------------------------------------------------------------
+// Issues the part `part` of `nparts` of the cp.async traffic of a [ROWS x BK] operand tile
+// (zero-filled out of range).  LDM: row stride of the [k][row] orientation.
+template <int ROWS, int LDM>
+__device__ __forceinline__ void load_tile_part(double* s, const GemmOperand& op, int row0, int k0, int nrows,
+                                               int kend, bool vec16, int tid, int part, int nparts) {
+  if (vec16) {
+    constexpr int TOTAL = ROWS * GM_BK / 2;                        // 16-byte chunks
+    constexpr int PER = (TOTAL + GM_THREADS - 1) / GM_THREADS;     // chunks per thread
+    for (int i = part; i < PER; i += nparts) {
+      const int c = tid + i * GM_THREADS;
+      if (TOTAL % GM_THREADS != 0 && c >= TOTAL) break;
+      int r, kk, soff;
+      if (op.kcontig) { r = c / (GM_BK / 2); kk = (c % (GM_BK / 2)) * 2; soff = r * GM_LDK + kk; }
+      else { kk = c / (ROWS / 2); r = (c % (ROWS / 2)) * 2; soff = kk * LDM + r; }
+      const int gr = row0 + r, gk = k0 + kk;
+      const bool ok = (gr < nrows) && (gk < kend);
+      const double* g = op.kcontig ? op.p + (long long)(ok ? gr : 0) * op.ld + (ok ? gk : 0)
+                                   : op.p + (long long)(ok ? gk : 0) * op.ld + (ok ? gr : 0);
+      cp_async16(s + soff, g, ok);
     }
   } else {
-    // smem [k][GM_LDM]; chunks run along row
-    if (vec16) {
-      constexpr int CH = ROWS / 2;
-      for (int c = tid; c < GM_BK * CH; c += GM_THREADS) {
-        int kk = c / CH, r = (c % CH) * 2;
-        int gr = row0 + r, gk = k0 + kk;
-        bool ok = (gr < nrows) && (gk < K);
-        const double* g = op.p + (long long)(ok ? gk : 0) * op.ld + (ok ? gr : 0);
-        cp_async16(s + kk * GM_LDM + r, g, ok);
-      }
-    } else {
-      for (int c = tid; c < GM_BK * ROWS; c += GM_THREADS) {
-        int kk = c / ROWS, r = c % ROWS;
-        int gr = row0 + r, gk = k0 + kk;
-        bool ok = (gr < nrows) && (gk < K);
-        const double* g = op.p + (long long)(ok ? gk : 0) * op.ld + (ok ? gr : 0);
-        cp_async8(s + kk * GM_LDM + r, g, ok);
-      }
+    constexpr int TOTAL = ROWS * GM_BK;
+    constexpr int PER = (TOTAL + GM_THREADS - 1) / GM_THREADS;
+    for (int i = part; i < PER; i += nparts) {
+      const int c = tid + i * GM_THREADS;
+      if (TOTAL % GM_THREADS != 0 && c >= TOTAL) break;
+      int r, kk, soff;
+      if (op.kcontig) { r = c / GM_BK; kk = c % GM_BK; soff = r * GM_LDK + kk; }
+      else { kk = c / ROWS; r = c % ROWS; soff = kk * LDM + r; }
+      const int gr = row0 + r, gk = k0 + kk;
+      const bool ok = (gr < nrows) && (gk < kend);
+      const double* g = op.kcontig ? op.p + (long long)(ok ? gr : 0) * op.ld + (ok ? gk : 0)
+                                   : op.p + (long long)(ok ? gk : 0) * op.ld + (ok ? gr : 0);
+      cp_async8(s + soff, g, ok);
     }
   }
 }
 
-template <class Epi>
-__global__ void __launch_bounds__(GM_THREADS, 1)
-gemm_f64_kernel(GemmOperand A, GemmOperand B, GemmShape sh, int vecA, int vecB, Epi epi) {
+template <class Cfg, class Epi>
+__global__ void __launch_bounds__(GM_THREADS, Cfg::MINB)
+gemm_f64_kernel(GemmOperand A, GemmOperand B, GemmShape sh, int vecA, int vecB, int ksplit, Epi epi) {
   extern __shared__ __align__(16) double gsm[];
+  constexpr int WM = Cfg::WM, WN = Cfg::WN, STAGES = Cfg::STAGES;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3;          // 2 x 4 warps
-  const int m0 = blockIdx.y * GM_BM, n0 = blockIdx.x * GM_BN;
-  const int ktiles = (sh.K + GM_BK - 1) / GM_BK;
+  const int wm = warp / Cfg::WARPS_N, wn = warp % Cfg::WARPS_N;
+  const int m0 = blockIdx.y * Cfg::BM, n0 = blockIdx.x * Cfg::BN;
+  // split-K: this CTA contracts k in [kbeg, kend)
+  const int kbeg = blockIdx.z * ksplit;
+  const int kend = min(sh.K, kbeg + ksplit);
+  const int ktiles = (kend - kbeg + GM_BK - 1) / GM_BK;
 
-  double acc[8][4][2];
+  double acc[WM][WN][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < WM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    for (int j = 0; j < WN; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
-  auto stageA = [&](int s) { return gsm + (size_t)s * 2 * GM_TILE_DOUBLES; };
-  auto stageB = [&](int s) { return gsm + (size_t)s * 2 * GM_TILE_DOUBLES + GM_TILE_DOUBLES; };
+  auto stageA = [&](int s) { return gsm + (size_t)s * (Cfg::TILE_A + Cfg::TILE_B); };
+  auto stageB = [&](int s) { return gsm + (size_t)s * (Cfg::TILE_A + Cfg::TILE_B) + Cfg::TILE_A; };
 
 #pragma unroll
-  for (int s = 0; s < GM_STAGES - 1; ++s) {
+  for (int s = 0; s < STAGES - 1; ++s) {
     if (s < ktiles) {
-      load_tile<GM_BM>(stageA(s), A, m0, s * GM_BK, sh.M, sh.K, vecA, tid);
-      load_tile<GM_BN>(stageB(s), B, n0, s * GM_BK, sh.N, sh.K, vecB, tid);
+      load_tile_part<Cfg::BM, Cfg::LDMA>(stageA(s), A, m0, kbeg + s * GM_BK, sh.M, kend, vecA, tid, 0, 1);
+      load_tile_part<Cfg::BN, Cfg::LDMB>(stageB(s), B, n0, kbeg + s * GM_BK, sh.N, kend, vecB, tid, 0, 1);
     }
     cp_async_commit();
   }
 
   const int lr = lane >> 2, lk = lane & 3;
   for (int kt = 0; kt < ktiles; ++kt) {
-    cp_async_wait<GM_STAGES - 2>();
+    cp_async_wait<STAGES - 2>();
     __syncthreads();
-    {  // prefetch tile kt + STAGES - 1 into the slot freed by iteration kt - 1
-      int nk = kt + GM_STAGES - 1;
-      if (nk < ktiles) {
-        int s = nk % GM_STAGES;
-        load_tile<GM_BM>(stageA(s), A, m0, nk * GM_BK, sh.M, sh.K, vecA, tid);
-        load_tile<GM_BN>(stageB(s), B, n0, nk * GM_BK, sh.N, sh.K, vecB, tid);
-      }
-      cp_async_commit();
-    }
-    const double* As = stageA(kt % GM_STAGES);
-    const double* Bs = stageB(kt % GM_STAGES);
+    // tile kt + STAGES - 1 goes into the slot freed by iteration kt - 1; its cp.async traffic is
+    // spread over the four k4 steps below
+    const int nk = kt + STAGES - 1;
+    const bool pre = nk < ktiles;
+    double* nA = stageA(nk % STAGES);
+    double* nB = stageB(nk % STAGES);
+    const double* As = stageA(kt % STAGES);
+    const double* Bs = stageB(kt % STAGES);
 #pragma unroll
     for (int k4 = 0; k4 < GM_BK / 4; ++k4) {
-      double a[8], b[4];
+      double a[WM], b[WN];
       const int kk = k4 * 4 + lk;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        int r = wm * 64 + i * 8 + lr;
-        a[i] = A.kcontig ? As[r * GM_LDK + kk] : As[kk * GM_LDM + r];
+      for (int i = 0; i < WM; ++i) {
+        int r = wm * (WM * 8) + i * 8 + lr;
+        a[i] = A.kcontig ? As[r * GM_LDK + kk] : As[kk * Cfg::LDMA + r];
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        int c = wn * 32 + j * 8 + lr;
-        b[j] = B.kcontig ? Bs[c * GM_LDK + kk] : Bs[kk * GM_LDM + c];
+      for (int j = 0; j < WN; ++j) {
+        int c = wn * (WN * 8) + j * 8 + lr;
+        b[j] = B.kcontig ? Bs[c * GM_LDK + kk] : Bs[kk * Cfg::LDMB + c];
+      }
+      if (pre) {
+        load_tile_part<Cfg::BM, Cfg::LDMA>(nA, A, m0, kbeg + nk * GM_BK, sh.M, kend, vecA, tid, k4, GM_BK / 4);
+        load_tile_part<Cfg::BN, Cfg::LDMB>(nB, B, n0, kbeg + nk * GM_BK, sh.N, kend, vecB, tid, k4, GM_BK / 4);
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < WM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        for (int j = 0; j < WN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
+    cp_async_commit();
   }
   cp_async_wait<0>();
 
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < WM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int m = m0 + wm * 64 + i * 8 + lr;
-      int n = n0 + wn * 32 + j * 8 + 2 * lk;
-      epi(m, n, acc[i][j][0], acc[i][j][1], sh.M, sh.N);
+    for (int j = 0; j < WN; ++j) {
+      int m = m0 + wm * (WM * 8) + i * 8 + lr;
+      int n = n0 + wn * (WN * 8) + j * 8 + 2 * lk;
+      epi(m, n, acc[i][j][0], acc[i][j][1], sh.M, sh.N, (int)blockIdx.z);
     }
 }
 
@@ -193,18 +208,60 @@ inline int gemm_vec_ok(const GemmOperand& op, int rows, int K) {
   return aligned && (contig_extent % 2 == 0);
 }
 
-template <class Epi>
-inline cudaError_t launch_gemm(cudaStream_t st, GemmOperand A, GemmOperand B, GemmShape sh, Epi epi) {
+// Number of K splits that fills the 148 SMs best for a grid of `tiles` CTAs (1 = no split).
+inline int gemm_pick_splits(int tiles, int K, int ctas_per_sm, int max_splits) {
+  const int slots = 148 * ctas_per_sm;
+  int best = 1; double best_eff = 0.0;
+  for (int s = 1; s <= max_splits; ++s) {
+    if (s > 1 && K / s < 256) break;
+    const long long t = (long long)tiles * s;
+    const double eff = (double)t / (double)(((t + slots - 1) / slots) * slots);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+  }
+  return best;
+}
+
+template <class Cfg, class Epi>
+inline cudaError_t launch_gemm_cfg(cudaStream_t st, GemmOperand A, GemmOperand B, GemmShape sh, Epi epi, int splits) {
   static bool attr_set = false;
-  auto kern = gemm_f64_kernel<Epi>;
+  auto kern = gemm_f64_kernel<Cfg, Epi>;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GM_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  dim3 grid((sh.N + GM_BN - 1) / GM_BN, (sh.M + GM_BM - 1) / GM_BM);
-  kern<<<grid, GM_THREADS, GM_SMEM_BYTES, st>>>(A, B, sh, gemm_vec_ok(A, sh.M, sh.K), gemm_vec_ok(B, sh.N, sh.K), epi);
+  if (splits < 1) splits = 1;
+  int ksplit = (sh.K + splits - 1) / splits;
+  ksplit = (ksplit + GM_BK - 1) / GM_BK * GM_BK;      // splits start on a k-tile (keeps 16-byte chunks aligned)
+  splits = (sh.K + ksplit - 1) / ksplit;
+  dim3 grid((sh.N + Cfg::BN - 1) / Cfg::BN, (sh.M + Cfg::BM - 1) / Cfg::BM, splits);
+  kern<<<grid, GM_THREADS, Cfg::SMEM, st>>>(A, B, sh, gemm_vec_ok(A, sh.M, sh.K), gemm_vec_ok(B, sh.N, sh.K), ksplit, epi);
   return cudaGetLastError();
+}
+
+// Default: the wide tile, unless N is small enough that the narrow one wastes less.
+template <class Epi>
+inline cudaError_t launch_gemm(cudaStream_t st, GemmOperand A, GemmOperand B, GemmShape sh, Epi epi) {
+  const int nw = (sh.N + GemmWide::BN - 1) / GemmWide::BN * GemmWide::BN;
+  const int nn = (sh.N + GemmNarrow::BN - 1) / GemmNarrow::BN * GemmNarrow::BN;
+  if (nn < nw) return launch_gemm_cfg<GemmNarrow>(st, A, B, sh, epi, 1);
+  return launch_gemm_cfg<GemmWide>(st, A, B, sh, epi, 1);
+}
+
+// Split-K launch on the narrow tile; returns the number of splits actually used in *splits_out.
+// The epilogue must carry a split stride (EpiStore::split_stride).
+template <class Epi>
+inline cudaError_t launch_gemm_splitk(cudaStream_t st, GemmOperand A, GemmOperand B, GemmShape sh, Epi epi,
+                                      int max_splits, int* splits_out) {
+  const bool narrow = ((sh.N + GemmNarrow::BN - 1) / GemmNarrow::BN * GemmNarrow::BN) <
+                      ((sh.N + GemmWide::BN - 1) / GemmWide::BN * GemmWide::BN);
+  const int bn = narrow ? GemmNarrow::BN : GemmWide::BN, bm = 128;
+  const int tiles = ((sh.N + bn - 1) / bn) * ((sh.M + bm - 1) / bm);
+  int splits = gemm_pick_splits(tiles, sh.K, narrow ? 2 : 1, max_splits);
+  int ksplit = ((sh.K + splits - 1) / splits + GM_BK - 1) / GM_BK * GM_BK;
+  splits = (sh.K + ksplit - 1) / ksplit;
+  if (splits_out) *splits_out = splits;
+  return narrow ? launch_gemm_cfg<GemmNarrow>(st, A, B, sh, epi, splits) : launch_gemm_cfg<GemmWide>(st, A, B, sh, epi, splits);
 }
 
 }  // namespace emagls

@@ -236,7 +236,7 @@ static void run_generic(emagls_ctx* h, Arena& ar, const GenericProblem& g) {
     RowSource src{};
     src.At = g.At; src.at_bin_stride = (long long)g.D * g.Mc; src.at_prob_stride = 0;
     // one "problem", num_ops bin slots: operator index = slot
-    EM_CUDA(launch_factor(st, bp, src, ops, 1, 0, g.num_ops, g.regul));
+    EM_CUDA(launch_factor(st, bp, src, ops, 1, 0, g.num_ops, g.regul, 1));
     const size_t smem = (size_t)2 * g.D * sizeof(cplx);
     static size_t set_to = 0;
     if (smem > 48 * 1024 && smem > set_to) {

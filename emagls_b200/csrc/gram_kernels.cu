@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(256)
 bwd_small_kernel(const double* __restrict__ Y, int Mc, int S, const int* __restrict__ roword,
                  const cplx* __restrict__ bk, const cplx* __restrict__ Pb, ProbMap pm,
                  const double* __restrict__ z, long long z_set_stride, long long z_ear_stride,
-                 int z_shared, cplx* __restrict__ Wsp, long long w_ear_stride, int K, int k, int dc_fix) {
+                 int z_shared, int nsplit, long long split_stride, cplx* __restrict__ Wsp, long long w_ear_stride, int K, int k, int dc_fix) {
   extern __shared__ __align__(16) unsigned char bsm_raw[];
   cplx* zb = reinterpret_cast<cplx*>(bsm_raw);   // [2][S]
   cplx* v = zb + 2 * (size_t)S;                  // [2][Mc]
@@ -293,7 +293,11 @@ bwd_small_kernel(const double* __restrict__ Y, int Mc, int S, const int* __restr
   const double* z1 = z0 + (z_shared ? z_ear_stride : 2LL * S);
   for (int s = tid; s < S; s += blockDim.x) {
     const cplx b = bk[roword[s]];
-    const double r0 = z0[s], i0 = z0[S + s], r1 = z1[s], i1 = z1[S + s];
+    double r0 = z0[s], i0 = z0[S + s], r1 = z1[s], i1 = z1[S + s];
+    for (int q = 1; q < nsplit; ++q) {   // split-K partials of the backward GEMM, fixed order
+      const long long o = (long long)q * split_stride;
+      r0 += z0[o + s]; i0 += z0[o + S + s]; r1 += z1[o + s]; i1 += z1[o + S + s];
+    }
     // conj(b) * z
     zb[s] = mk(fma(b.x, r0, b.y * i0), fma(b.x, i0, -b.y * r0));
     zb[S + s] = mk(fma(b.x, r1, b.y * i1), fma(b.x, i1, -b.y * r1));
@@ -330,8 +334,8 @@ bwd_small_kernel(const double* __restrict__ Y, int Mc, int S, const int* __restr
 
 cudaError_t launch_bwd_small(cudaStream_t st, const double* Y, int Mc, int S, const int* roword,
                              const cplx* bk, const cplx* Pb, ProbMap pm, int num_prob, const double* z,
-                             long long z_set_stride, long long z_ear_stride, int z_shared, cplx* Wsp,
-                             long long w_ear_stride, int K, int k, int dc_fix) {
+                             long long z_set_stride, long long z_ear_stride, int z_shared, int nsplit,
+                             long long split_stride, cplx* Wsp, long long w_ear_stride, int K, int k, int dc_fix) {
   size_t smem = ((size_t)2 * S + 2 * Mc) * sizeof(cplx);
   static size_t set_to = 0;
   if (smem > 48 * 1024 && smem > set_to) {
@@ -340,7 +344,7 @@ cudaError_t launch_bwd_small(cudaStream_t st, const double* Y, int Mc, int S, co
     set_to = smem;
   }
   bwd_small_kernel<<<num_prob, 256, smem, st>>>(Y, Mc, S, roword, bk, Pb, pm, z, z_set_stride, z_ear_stride, z_shared,
-                                               Wsp, w_ear_stride, K, k, dc_fix);
+                                               nsplit, split_stride, Wsp, w_ear_stride, K, k, dc_fix);
   return cudaGetLastError();
 }
 

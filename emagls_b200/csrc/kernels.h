@@ -69,12 +69,14 @@ struct BlockPlan { int S, Mc, MC, RB, R0, nblk; };
 BlockPlan make_block_plan(int S, int Mc);
 size_t factor_smem_bytes(const BlockPlan& bp);
 cudaError_t launch_factor(cudaStream_t st, const BlockPlan& bp, const RowSource& src,
-                          const OperatorSet& ops, int num_prob, int kbase, int G, double regul);
-// backward: W[k] = (Q_C^H tq) * Pb; tq rows (j*2+e)*2+c, or shared per set when tq_shared != 0
+                          const OperatorSet& ops, int num_prob, int kbase, int G, double regul, int try_fast);
+// backward: W[k] = (Q_C^H tq) * Pb; tq rows (j*2+e)*2+c (sum of nsplit split-K partials), or shared per
+// set when tq_shared != 0
 cudaError_t launch_chain_bwd(cudaStream_t st, const BlockPlan& bp, const OperatorSet& ops, int slot,
                              int G, const double* tq, long long tq_set_stride,
-                             long long tq_ear_stride, int tq_shared, ProbMap pm,
-                             cplx* Wsp, long long w_ear_stride, int K, int k, int dc_fix, int num_prob);
+                             long long tq_ear_stride, int tq_shared, int nsplit, long long split_stride,
+                             ProbMap pm, cplx* Wsp, long long w_ear_stride, int K, int k, int dc_fix,
+                             int num_prob);
 // generic-path phase step on rows: t = absH * y/|y|
 cudaError_t launch_phase_rows(cudaStream_t st, const double* Y, double* T, int num_prob, int D,
                               const double* absH, long long abs_set_stride, long long abs_ear_stride,
@@ -107,7 +109,7 @@ cudaError_t launch_fwd_small(cudaStream_t st, const double* Y, int Mc, int S, co
 // backward of a Gram bin: W_k = (Y_o (conj(b_k) .* z)) * Pb
 cudaError_t launch_bwd_small(cudaStream_t st, const double* Y, int Mc, int S, const int* roword,
                              const cplx* bk, const cplx* Pb, ProbMap pm, int num_prob, const double* z,
-                             long long z_set_stride, long long z_ear_stride, int z_shared, cplx* Wsp,
-                             long long w_ear_stride, int K, int k, int dc_fix);
+                             long long z_set_stride, long long z_ear_stride, int z_shared, int nsplit,
+                             long long split_stride, cplx* Wsp, long long w_ear_stride, int K, int k, int dc_fix);
 
 }  // namespace emagls

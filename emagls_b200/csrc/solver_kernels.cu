@@ -28,7 +28,7 @@ BlockPlan make_block_plan(int S, int Mc) {
 }
 
 size_t factor_smem_bytes(const BlockPlan& bp) {
-  return (size_t)bp.MC * (bp.MC + bp.RB) * sizeof(cplx) + (size_t)(bp.MC + 72) * sizeof(cplx) + 256;
+  return (size_t)bp.MC * (bp.MC + bp.RB) * sizeof(cplx) + (size_t)(2 * bp.MC + 72) * sizeof(cplx) + 256;
 }
 
 __device__ __forceinline__ cplx gsum8(cplx v, unsigned mask) {
@@ -44,51 +44,83 @@ __device__ __forceinline__ double gsum8(double v, unsigned mask) {
   for (int m = 4; m > 0; m >>= 1) v += __shfl_xor_sync(mask, v, m);
   return v;
 }
-// Householder reflector for column `col`, pivot row j, tail rows [lo, hi); executed by one
-// aligned group of 8 lanes (LAPACK zlarfg conventions: beta real, H = I - tau v v^H, v_j = 1).
-__device__ __forceinline__ void gen_reflector(cplx* col, int j, int lo, int hi, int rl,
-                                              unsigned mask, cplx* tau_out) {
-  double xn = 0.0;
-  for (int i = lo + rl; i < hi; i += 8) xn += cabs2(col[i]);
-  xn = gsum8(xn, mask);
-  cplx alpha = col[j];
-  cplx tau = mk(0.0, 0.0);
-  if (!(xn == 0.0 && alpha.y == 0.0)) {
-    double beta = -copysign(sqrt(cabs2(alpha) + xn), alpha.x);
-    tau = mk((beta - alpha.x) / beta, -alpha.y / beta);
-    cplx sc = cdiv(mk(1.0, 0.0), mk(alpha.x - beta, alpha.y));
-    for (int i = lo + rl; i < hi; i += 8) col[i] = cmul(col[i], sc);
-    __syncwarp(mask);
-    if (rl == 0) col[j] = mk(beta, 0.0);
+// Householder reflector scalars for a column with pivot alpha and squared tail norm xn (LAPACK
+// zlarfg conventions: beta real, H = I - tau v v^H, v = [1; sc * x]).  The tail x is left unscaled in
+// shared memory; sc is applied on the fly and when the reflector is flushed.
+__device__ __forceinline__ void reflector_scalars(cplx alpha, double xn, double* beta_out, cplx* tau_out,
+                                                  cplx* sc_out) {
+  if (xn == 0.0 && alpha.y == 0.0) {
+    *beta_out = alpha.x; *tau_out = mk(0.0, 0.0); *sc_out = mk(0.0, 0.0);
+    return;
   }
-  if (rl == 0) *tau_out = tau;
+  const double s2 = cabs2(alpha) + xn;
+  const double nrm = sqrt(s2);
+  const double beta = -copysign(nrm, alpha.x);
+  const double ib = 1.0 / beta;
+  const cplx d = mk(alpha.x - beta, alpha.y);          // alpha - beta (no cancellation: signs agree)
+  const double id2 = 1.0 / cabs2(d);
+  *beta_out = beta;
+  *tau_out = mk((beta - alpha.x) * ib, -alpha.y * ib);
+  *sc_out = mk(d.x * id2, -d.y * id2);                 // 1 / (alpha - beta)
 }
 
 // In-place QR of one block held in shared memory (column-major, leading dimension LD).
 // first: rows [0, nrows) dense;  otherwise: upper-triangular top (Mc rows) + dense rows [Mc, Mc+nb).
-__device__ void qr_block(cplx* Wk, int LD, int Mc, bool first, int hi, cplx* tau_s) {
+// Groups of 8 lanes own one trailing column each; the group of column j+1 accumulates the tail norm
+// of its updated column inside the update loop, so the per-step critical path is one fused
+// dot/update pass, two 8-lane reductions and the reflector scalars.
+__device__ void qr_block(cplx* Wk, int LD, int Mc, bool first, int hi, cplx* tau_s, cplx* sc_s) {
   const int tid = threadIdx.x, group = tid >> 3, rl = tid & 7;
   const unsigned gmask = 0xffu << (threadIdx.x & 24);
-  if (group == 0) gen_reflector(Wk, 0, first ? 1 : Mc, hi, rl, gmask, &tau_s[0]);
+  if (group == 0) {
+    double xn = 0.0;
+    for (int i = (first ? 1 : Mc) + rl; i < hi; i += 8) xn += cabs2(Wk[i]);
+    xn = gsum8(xn, gmask);
+    if (rl == 0) {
+      double beta; cplx tau, sc;
+      reflector_scalars(Wk[0], xn, &beta, &tau, &sc);
+      Wk[0] = mk(beta, 0.0); tau_s[0] = tau; sc_s[0] = sc;
+    }
+  }
   __syncthreads();
   for (int j = 0; j < Mc; ++j) {
     const int lo = first ? j + 1 : Mc;
-    const cplx tau = tau_s[j];
+    const cplx tau = tau_s[j], sc = sc_s[j];
     const cplx* v = Wk + (size_t)j * LD;
-    if (tau.x != 0.0 || tau.y != 0.0) {
-      for (int c = j + 1 + group; c < Mc; c += FT / 8) {
-        cplx* a = Wk + (size_t)c * LD;
-        cplx w = (rl == 0) ? a[j] : mk(0.0, 0.0);
+    const bool active = (tau.x != 0.0 || tau.y != 0.0);
+    for (int c = j + 1 + group; c < Mc; c += FT / 8) {
+      cplx* a = Wk + (size_t)c * LD;
+      const bool next = (c == j + 1);
+      const int lo_next = first ? j + 2 : Mc;    // tail of column j+1 once it becomes the pivot column
+      double xn = 0.0;
+      if (active) {
+        cplx w = mk(0.0, 0.0);
         for (int i = lo + rl; i < hi; i += 8) cfmac(w, v[i], a[i]);
         w = gsum8(w, gmask);
-        cplx f = cmul(cconj(tau), w);  // H^H = I - conj(tau) v v^H
-        if (rl == 0) a[j] = csub(a[j], f);
-        for (int i = lo + rl; i < hi; i += 8) cfms(a[i], f, v[i]);
+        w = cmulc(w, sc);                          // conj(sc) * (x^H a)  ->  (sc x)^H a
+        const cplx aj = a[j];
+        w = cadd(w, aj);
+        const cplx f = cmul(cconj(tau), w);        // H^H = I - conj(tau) v v^H
+        const cplx fs = cmul(f, sc);
+        if (rl == 0) a[j] = csub(aj, f);
+        for (int i = lo + rl; i < hi; i += 8) {
+          cplx ai = a[i];
+          cfms(ai, fs, v[i]);
+          a[i] = ai;
+          if (next && i >= lo_next) xn += cabs2(ai);
+        }
+      } else if (next) {
+        for (int i = lo_next + rl; i < hi; i += 8) xn += cabs2(a[i]);
       }
-    }
-    if (group == 0 && j + 1 < Mc) {
-      __syncwarp(gmask);
-      gen_reflector(Wk + (size_t)(j + 1) * LD, j + 1, first ? j + 2 : Mc, hi, rl, gmask, &tau_s[j + 1]);
+      if (next) {
+        xn = gsum8(xn, gmask);
+        __syncwarp(gmask);
+        if (rl == 0) {
+          double beta; cplx t2, s2;
+          reflector_scalars(a[j + 1], xn, &beta, &t2, &s2);
+          a[j + 1] = mk(beta, 0.0); tau_s[j + 1] = t2; sc_s[j + 1] = s2;
+        }
+      }
     }
     __syncthreads();
   }
@@ -96,12 +128,13 @@ __device__ void qr_block(cplx* Wk, int LD, int Mc, bool first, int hi, cplx* tau
 
 template <int MC, int RB>
 __global__ void __launch_bounds__(FT, (MC == 32) ? 3 : 1)
-factor_kernel(BlockPlan bp, RowSource src, OperatorSet ops, int kbase, int G, double regul) {
+factor_kernel(BlockPlan bp, RowSource src, OperatorSet ops, int kbase, int G, double regul, int try_fast) {
   constexpr int LD = MC + RB;
   extern __shared__ __align__(16) unsigned char fsm_raw[];
   cplx* Wk = reinterpret_cast<cplx*>(fsm_raw);
   cplx* tau_s = Wk + (size_t)MC * LD;
-  cplx* bn_s = tau_s + MC;  // up to 64 orders
+  cplx* sc_s = tau_s + MC;
+  cplx* bn_s = sc_s + MC;   // up to 64 orders
   double* red = reinterpret_cast<double*>(bn_s + 72);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -145,11 +178,14 @@ factor_kernel(BlockPlan bp, RowSource src, OperatorSet ops, int kbase, int G, do
       }
     }
     __syncthreads();
-    qr_block(Wk, LD, Mc, t == 0, dst + nb, tau_s);
-    // flush reflectors of this block (qr_block ends with a barrier)
+    qr_block(Wk, LD, Mc, t == 0, dst + nb, tau_s, sc_s);
+    // flush reflectors of this block (qr_block ends with a barrier); the tails are stored scaled
+    // (v = [1; sc * x]) for the chain kernels
     for (int idx = tid; idx < nb * Mc; idx += FT) {
       int c = idx / nb, q = idx % nb;
-      Vg[(long long)c * S + r0 + q] = Wk[(size_t)c * LD + dst + q];
+      cplx val = Wk[(size_t)c * LD + dst + q];
+      if (t != 0 || q > c) val = cmul(val, sc_s[c]);
+      Vg[(long long)c * S + r0 + q] = val;
     }
     for (int c = tid; c < Mc; c += FT) taug[t * MC + c] = tau_s[c];
     __syncthreads();
@@ -172,41 +208,46 @@ factor_kernel(BlockPlan bp, RowSource src, OperatorSet ops, int kbase, int G, do
     for (int q = 0; q < PER; ++q) Rs[tid + q * FT] = tmp[q];
     __syncthreads();
   }
-  // ---------------- R^-1 (upper triangular) into region A2, row by row from the bottom
+  // ---------------- R^-1 (upper triangular) into region A2, row by row from the bottom: if
+  // ||R||_F ||R^-1||_F <= 1/c no singular value can be clipped and Pb = R^-T.  Skipped (try_fast == 0)
+  // for bins the Gram route has already refused: they go straight to the Jacobi SVD.
   cplx* Ri = Js;
-  for (int idx = tid; idx < MC * MC; idx += FT) Ri[idx] = mk(0.0, 0.0);
-  __syncthreads();
-  {
-    const int group = tid >> 3, rl = tid & 7;
-    const unsigned gmask = 0xffu << (threadIdx.x & 24);
-    for (int i = Mc - 1; i >= 0; --i) {
-      const cplx rii = Rs[i * MC + i];
-      for (int m = i + group; m < Mc; m += FT / 8) {
-        cplx sum = mk(0.0, 0.0);
-        for (int j = i + 1 + rl; j <= m; j += 8) cfma(sum, Rs[j * MC + i], Ri[m * MC + j]);
-        sum = gsum8(sum, gmask);
-        if (rl == 0) {
-          cplx num = mk((m == i ? 1.0 : 0.0) - sum.x, -sum.y);
-          Ri[m * MC + i] = cdiv(num, rii);   // Ri col-major: Ri[m*MC + i] = Rinv(i, m)
+  bool fast = false;
+  if (try_fast) {
+    for (int idx = tid; idx < MC * MC; idx += FT) Ri[idx] = mk(0.0, 0.0);
+    __syncthreads();
+    {
+      const int group = tid >> 3, rl = tid & 7;
+      const unsigned gmask = 0xffu << (threadIdx.x & 24);
+      for (int i = Mc - 1; i >= 0; --i) {
+        const cplx rii = Rs[i * MC + i];
+        for (int m = i + group; m < Mc; m += FT / 8) {
+          cplx sum = mk(0.0, 0.0);
+          for (int j = i + 1 + rl; j <= m; j += 8) cfma(sum, Rs[j * MC + i], Ri[m * MC + j]);
+          sum = gsum8(sum, gmask);
+          if (rl == 0) {
+            cplx num = mk((m == i ? 1.0 : 0.0) - sum.x, -sum.y);
+            Ri[m * MC + i] = cdiv(num, rii);   // Ri col-major: Ri[m*MC + i] = Rinv(i, m)
+          }
         }
+        __syncthreads();
       }
-      __syncthreads();
     }
+    // Frobenius norms
+    double fr = 0.0, fi = 0.0;
+    for (int idx = tid; idx < MC * MC; idx += FT) { fr += cabs2(Rs[idx]); fi += cabs2(Ri[idx]); }
+    fr = wsum(fr); fi = wsum(fi);
+    if (lane == 0) { red[warp] = fr; red[8 + warp] = fi; }
+    __syncthreads();
+    if (tid == 0) {
+      double a = 0.0, b = 0.0;
+      for (int w = 0; w < FT / 32; ++w) { a += red[w]; b += red[8 + w]; }
+      red[16] = sqrt(a) * sqrt(b);
+    }
+    __syncthreads();
+    const double condF = red[16];
+    fast = (regul > 0.0) ? (condF <= 1.0 / regul) : (condF < 1e300);  // NaN -> false
   }
-  // Frobenius norms
-  double fr = 0.0, fi = 0.0;
-  for (int idx = tid; idx < MC * MC; idx += FT) { fr += cabs2(Rs[idx]); fi += cabs2(Ri[idx]); }
-  fr = wsum(fr); fi = wsum(fi);
-  if (lane == 0) { red[warp] = fr; red[8 + warp] = fi; }
-  __syncthreads();
-  if (tid == 0) {
-    double a = 0.0, b = 0.0;
-    for (int w = 0; w < FT / 32; ++w) { a += red[w]; b += red[8 + w]; }
-    red[16] = sqrt(a) * sqrt(b);
-  }
-  __syncthreads();
-  const double condF = red[16];
-  const bool fast = (regul > 0.0) ? (condF <= 1.0 / regul) : (condF < 1e300);  // NaN -> false
   cplx* Ps = Rs;  // region A0 is reused for Pb (row-major [i][m], ld = MC)
   int sweeps = 0;
   if (fast) {
@@ -228,11 +269,15 @@ factor_kernel(BlockPlan bp, RowSource src, OperatorSet ops, int kbase, int G, do
     __syncthreads();
     const int ne = (Mc + 1) & ~1;  // even number of players (index Mc is a dummy when Mc is odd)
     const double tol = 2.220446049250313e-16 * sqrt((double)Mc);
-    constexpr int RPL = MC / 32;   // rows per lane
+    // one pair per half-warp: 16 lanes x (MC/16) rows, 4-step reductions; the 2 * FT/32 half-warps
+    // cover the ne/2 pairs of a round-robin round in one pass for Mc <= 32
+    constexpr int RPL = MC / 16;   // rows per lane
+    const int half = lane >> 4, hl = lane & 15;
+    const unsigned hmask = 0xffffu << (16 * half);
     for (sweeps = 1; sweeps <= 40; ++sweeps) {
       int rotated = 0;
       for (int r = 0; r < ne - 1; ++r) {
-        for (int pi = warp; pi < ne / 2; pi += FT / 32) {
+        for (int pi = warp * 2 + half; pi < ne / 2; pi += FT / 16) {
           int p, q;
           if (pi == 0) { p = ne - 1; q = r; }
           else { p = (r + pi) % (ne - 1); q = (r - pi + (ne - 1)) % (ne - 1); }
@@ -242,12 +287,16 @@ factor_kernel(BlockPlan bp, RowSource src, OperatorSet ops, int kbase, int G, do
           double a = 0.0, b = 0.0; cplx g = mk(0.0, 0.0);
 #pragma unroll
           for (int u = 0; u < RPL; ++u) {
-            int row = lane + 32 * u;
+            int row = hl + 16 * u;
             xp[u] = Xs[p * MC + row]; xq[u] = Xs[q * MC + row];
             a += cabs2(xp[u]); b += cabs2(xq[u]);
             cfmac(g, xp[u], xq[u]);
           }
-          a = wsum(a); b = wsum(b); g.x = wsum(g.x); g.y = wsum(g.y);
+#pragma unroll
+          for (int sft = 8; sft > 0; sft >>= 1) {
+            a += __shfl_xor_sync(hmask, a, sft); b += __shfl_xor_sync(hmask, b, sft);
+            g.x += __shfl_xor_sync(hmask, g.x, sft); g.y += __shfl_xor_sync(hmask, g.y, sft);
+          }
           double ag = sqrt(cabs2(g));
           if (ag > tol * sqrt(a * b) && ag > 0.0) {
             rotated = 1;
@@ -259,7 +308,7 @@ factor_kernel(BlockPlan bp, RowSource src, OperatorSet ops, int kbase, int G, do
             cplx sphc = mk(sph.x, -sph.y);        // s * conj(ph)
 #pragma unroll
             for (int u = 0; u < RPL; ++u) {
-              int row = lane + 32 * u;
+              int row = hl + 16 * u;
               cplx np_ = cscale(xp[u], cs); cfms(np_, sphc, xq[u]);
               cplx nq_ = cscale(xq[u], cs); cfma(nq_, sph, xp[u]);
               Xs[p * MC + row] = np_; Xs[q * MC + row] = nq_;
@@ -279,7 +328,7 @@ factor_kernel(BlockPlan bp, RowSource src, OperatorSet ops, int kbase, int G, do
     for (int j = warp; j < Mc; j += FT / 32) {
       double a = 0.0;
 #pragma unroll
-      for (int u = 0; u < RPL; ++u) a += cabs2(Xs[j * MC + lane + 32 * u]);
+      for (int u = 0; u < MC / 32; ++u) a += cabs2(Xs[j * MC + lane + 32 * u]);
       a = wsum(a);
       if (lane == 0) sv[j] = sqrt(a);
     }
@@ -317,7 +366,7 @@ factor_kernel(BlockPlan bp, RowSource src, OperatorSet ops, int kbase, int G, do
 }
 
 cudaError_t launch_factor(cudaStream_t st, const BlockPlan& bp, const RowSource& src,
-                          const OperatorSet& ops, int num_prob, int kbase, int G, double regul) {
+                          const OperatorSet& ops, int num_prob, int kbase, int G, double regul, int try_fast) {
   size_t smem = factor_smem_bytes(bp);
   cudaError_t e;
   if (bp.MC == 32) {
@@ -327,7 +376,7 @@ cudaError_t launch_factor(cudaStream_t st, const BlockPlan& bp, const RowSource&
       if (e != cudaSuccess) return e;
       set32 = true;
     }
-    factor_kernel<32, 96><<<num_prob * G, FT, smem, st>>>(bp, src, ops, kbase, G, regul);
+    factor_kernel<32, 96><<<num_prob * G, FT, smem, st>>>(bp, src, ops, kbase, G, regul, try_fast);
   } else {
     static bool set64 = false;
     if (!set64) {
@@ -335,7 +384,7 @@ cudaError_t launch_factor(cudaStream_t st, const BlockPlan& bp, const RowSource&
       if (e != cudaSuccess) return e;
       set64 = true;
     }
-    factor_kernel<64, 128><<<num_prob * G, FT, smem, st>>>(bp, src, ops, kbase, G, regul);
+    factor_kernel<64, 128><<<num_prob * G, FT, smem, st>>>(bp, src, ops, kbase, G, regul, try_fast);
   }
   return cudaGetLastError();
 }
@@ -347,7 +396,7 @@ constexpr int CH_MAXW = 4;
 
 __global__ void chain_bwd_kernel(BlockPlan bp, OperatorSet ops, int slot, int G, const double* tq,
                                  long long tq_set_stride, long long tq_ear_stride, int tq_shared,
-                                 ProbMap pm, cplx* Wsp, long long w_ear_stride,
+                                 int nsplit, long long split_stride, ProbMap pm, cplx* Wsp, long long w_ear_stride,
                                  int K, int k, int dc_fix, int num_prob) {
   extern __shared__ __align__(16) unsigned char csm_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
@@ -365,8 +414,13 @@ __global__ void chain_bwd_kernel(BlockPlan bp, OperatorSet ops, int slot, int G,
                                : tq + ((long long)(j * 2 + 0) * 2) * S;
   const double* t1 = t0 + (tq_shared ? tq_ear_stride : 2 * (long long)S);
   for (int i = lane; i < S; i += 32) {
-    x0[i] = mk(t0[i], t0[S + i]);
-    x1[i] = mk(t1[i], t1[S + i]);
+    double r0 = t0[i], i0 = t0[S + i], r1 = t1[i], i1 = t1[S + i];
+    for (int z = 1; z < nsplit; ++z) {   // split-K partials of the backward GEMM, fixed order
+      const long long o = (long long)z * split_stride;
+      r0 += t0[o + i]; i0 += t0[o + S + i]; r1 += t1[o + i]; i1 += t1[o + S + i];
+    }
+    x0[i] = mk(r0, i0);
+    x1[i] = mk(r1, i1);
   }
   __syncwarp();
   apply_qc(bp, V, tau, x0, x1, true, lane);
@@ -397,8 +451,9 @@ static int chain_warps(int S) {
 
 cudaError_t launch_chain_bwd(cudaStream_t st, const BlockPlan& bp, const OperatorSet& ops, int slot,
                              int G, const double* tq, long long tq_set_stride,
-                             long long tq_ear_stride, int tq_shared, ProbMap pm,
-                             cplx* Wsp, long long w_ear_stride, int K, int k, int dc_fix, int num_prob) {
+                             long long tq_ear_stride, int tq_shared, int nsplit, long long split_stride,
+                             ProbMap pm, cplx* Wsp, long long w_ear_stride, int K, int k, int dc_fix,
+                             int num_prob) {
   int w = chain_warps(bp.S);
   size_t smem = (size_t)w * 2 * bp.S * sizeof(cplx);
   static size_t set_to = 0;
@@ -408,7 +463,8 @@ cudaError_t launch_chain_bwd(cudaStream_t st, const BlockPlan& bp, const Operato
     set_to = smem;
   }
   chain_bwd_kernel<<<(num_prob + w - 1) / w, w * 32, smem, st>>>(bp, ops, slot, G, tq, tq_set_stride, tq_ear_stride, tq_shared,
-                                                                 pm, Wsp, w_ear_stride, K, k, dc_fix, num_prob);
+                                                                 nsplit, split_stride, pm, Wsp, w_ear_stride, K, k, dc_fix,
+                                                                 num_prob);
   return cudaGetLastError();
 }
 
