@@ -2,27 +2,18 @@
  * binauralOut = binauralDecode(in, inFs, decL, decR, decFs, compensateDelay)
  * (resampling, mono-signal convolution and horRotAngleRad fall through to the original .m file)
  * Build: mex -R2018a -I../include binauralDecode.c -L../emagls_b200/lib -lemagls_cuda  (needs MATLAB). */
-#include "mex.h"
-#include "emagls_cuda.h"
-
-static emagls_handle g_handle = NULL;
-static void at_exit(void) { if (g_handle) { emagls_destroy(g_handle); g_handle = NULL; } }
+#include "emagls_mex_common.h"
 
 void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   if (nrhs < 5) mexErrMsgIdAndTxt("eMagLS:nargin", "binauralDecode needs at least 5 arguments");
   if (nrhs > 6 || mxGetScalar(prhs[1]) != mxGetScalar(prhs[4]) || mxIsComplex(prhs[0]) || mxIsComplex(prhs[2])) {
     mexErrMsgIdAndTxt("eMagLS:fallback", "use the reference binauralDecode.m for this argument combination");
   }
-  if (!g_handle) {
-    if (emagls_create(0, &g_handle) != EMAGLS_OK) mexErrMsgIdAndTxt("eMagLS:cuda", "no usable CUDA device");
-    mexAtExit(at_exit);
-  }
   const long long n = (long long)mxGetM(prhs[0]);
   const int ch = (int)mxGetN(prhs[0]), len = (int)mxGetM(prhs[2]);
   const int comp = (nrhs > 5) && mxIsLogicalScalarTrue(prhs[5]);
   const long long rows = comp ? n - len / 2 + 1 : n;
   plhs[0] = mxCreateDoubleMatrix((mwSize)rows, 2, mxREAL);
-  int rc = emagls_binaural_decode(g_handle, mxGetDoubles(prhs[0]), n, ch, mxGetDoubles(prhs[2]),
-                                  mxGetDoubles(prhs[3]), len, comp, mxGetDoubles(plhs[0]));
-  if (rc != EMAGLS_OK) mexErrMsgIdAndTxt("eMagLS:cuda", "%s", emagls_last_error(g_handle));
+  emx_check(emagls_binaural_decode(emx_handle(), mxGetDoubles(prhs[0]), n, ch, mxGetDoubles(prhs[2]),
+                                  mxGetDoubles(prhs[3]), len, comp, mxGetDoubles(plhs[0])));
 }

@@ -1,0 +1,52 @@
+/* Shared helpers of the MEX drop-ins (interleaved-complex API: build with `mex -R2018a`).
+ * NOTE: none of the gateways can be compiled in this repo's build image (no MATLAB, no mex.h); the C ABI
+ * they bind is exercised through the Python ctypes binding. */
+#ifndef EMAGLS_MEX_COMMON_H
+#define EMAGLS_MEX_COMMON_H
+#include <string.h>
+#include "mex.h"
+#include "emagls_cuda.h"
+
+static emagls_handle g_handle = NULL;
+static void emx_at_exit(void) { if (g_handle) { emagls_destroy(g_handle); g_handle = NULL; } }
+
+static emagls_handle emx_handle(void) {
+  if (!g_handle) {
+    if (emagls_create(0, &g_handle) != EMAGLS_OK) mexErrMsgIdAndTxt("eMagLS:cuda", "no usable CUDA device");
+    mexAtExit(emx_at_exit);
+  }
+  return g_handle;
+}
+
+/* shDefinition argument ('real' | 'complex', default 'real') */
+static int emx_basis(int nrhs, const mxArray* prhs[], int idx) {
+  char def[16] = "real";
+  if (nrhs > idx && !mxIsEmpty(prhs[idx])) mxGetString(prhs[idx], def, sizeof def);
+  return strcmp(def, "complex") == 0 ? EMAGLS_BASIS_COMPLEX : EMAGLS_BASIS_REAL;
+}
+
+/* shFunction / chFunction handles: only the defaults can be evaluated on the device */
+static void emx_require_default_handle(int nrhs, const mxArray* prhs[], int idx, const char* expected) {
+  if (nrhs > idx && !mxIsEmpty(prhs[idx])) {
+    mxArray* name; char buf[64];
+    mexCallMATLAB(1, &name, 1, (mxArray**)&prhs[idx], "func2str");
+    mxGetString(name, buf, sizeof buf);
+    if (strcmp(buf, expected) != 0)
+      mexErrMsgIdAndTxt("eMagLS:handle", "only @%s is supported by the CUDA drop-in", expected);
+  }
+}
+
+static mxArray* emx_out(mwSize rows, mwSize cols, int basis) {
+  return mxCreateDoubleMatrix(rows, cols, basis == EMAGLS_BASIS_COMPLEX ? mxCOMPLEX : mxREAL);
+}
+static double* emx_ptr(mxArray* a) {
+  return mxIsComplex(a) ? (double*)mxGetComplexDoubles(a) : mxGetDoubles(a);
+}
+static void emx_check(int rc) {
+  if (rc != EMAGLS_OK) mexErrMsgIdAndTxt("eMagLS:cuda", "%s", emagls_last_error(g_handle)); /* e.g. 'len too short' */
+}
+static void emx_return2(int nlhs, mxArray* plhs[], mxArray* wL, mxArray* wR) {
+  plhs[0] = wL;
+  if (nlhs > 1) plhs[1] = wR; else mxDestroyArray(wR);
+}
+#endif

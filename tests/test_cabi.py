@@ -66,3 +66,20 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_mex_gateways_match_the_c_abi():
+    """The MEX drop-ins cannot be built without MATLAB; compile them against a stub mex.h so that every
+    call into libemagls_cuda is at least type-checked against include/emagls_cuda.h."""
+    import glob
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    srcs = sorted(glob.glob(os.path.join(root, "mex", "*.c")))
+    names = {os.path.basename(s)[:-2] for s in srcs}
+    assert {"getLsFilters", "getMagLsFilters", "getEMagLsFilters", "getEMagLs2Filters", "getEMagLsFiltersEMAinCH",
+            "getEMagLsFiltersEMAinSH", "getEMagLsFiltersFromAtf", "getSMAIRMatrix", "binauralDecode"} <= names
+    for s in srcs:
+        r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-Wno-unused-function",
+                            "-I" + os.path.join(root, "tests", "mex_stub"), "-I" + os.path.join(root, "include"), s],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
