@@ -40,7 +40,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--orient", type=int, default=3600, help="orientations per rank per step")
-    ap.add_argument("--render-seconds", type=float, default=60.0)
+    ap.add_argument("--render-seconds", type=float, default=600.0,
+                    help="length of the rendered 32-channel signal (SURVEY.md 8-d: 10 min)")
     ap.add_argument("--no-render", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -264,8 +265,18 @@ def main():
     dom = max(("gemm_fwd", "gemm_bwd"), key=lambda k: prof[k]["ms"])
     avg_ms = prof[dom]["ms"] / max(prof[dom]["n"], 1)
     achieved = flops_per_launch[dom] / (avg_ms * 1e-3) / 1e12
+    # DRAM bytes of that launch from the committed `ncu --set full` capture at this shape (profiles/)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")))
+        want = "EpiPhase" if dom == "gemm_fwd" else "EpiStore"
+        if B == 3600:
+            traffic = next(x["traffic_bytes"] for x in tj["launches"] if want in x["kernel"])
+    except Exception:
+        pass
     roofline = {"kernel": f"gemm_f64_kernel ({dom})", "bound": "tensor", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": (achieved / peak) if peak else None, "traffic": None,
+                "unit": "TFLOP/s", "frac": (achieved / peak) if peak else None, "traffic": traffic,
+                "traffic_source": "profiles/r01_gemm_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, bytes/launch)",
                 "peak_source": peak_src, "flops_per_launch": flops_per_launch[dom],
                 "avg_launch_ms": avg_ms, "class_time_share": shares,
                 "algorithmic_tflops_whole_job": value / world * ALGO_GFLOP_PER_SET / 1e3}

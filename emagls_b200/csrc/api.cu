@@ -36,6 +36,7 @@ int emagls_destroy(emagls_handle h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  emagls::destroy_render_plans(h);
   cudaStreamDestroy(h->stream);
   delete h;
   return EMAGLS_OK;

@@ -35,6 +35,11 @@ struct emagls_ctx {
   std::vector<Span> spans;
   double prof_ms[EM_PROF_NUM] = {0};
   long long prof_n[EM_PROF_NUM] = {0};
+  // render: cuFFT plans are expensive to build (milliseconds), so they live with the handle
+  struct RenderPlans {
+    int N = 0, num_ch = 0, chunk = 0;
+    int fwd = 0, inv = 0, filt = 0;   // cufftHandle values (0 = not created)
+  } render_plans;
 };
 
 namespace emagls {
@@ -151,6 +156,7 @@ struct DesignArgs {
   double* spectra;          // device or nullptr: complex [K x Mc x P x 2]
 };
 void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& a);
+void destroy_render_plans(emagls_ctx* h);  // render.cu
 // real-basis -> complex-basis outputs (kind 0: SH in ACN order, 1: CH ordered [0,-1,+1,...]); see engine.cu
 cudaError_t launch_basis_change_filters(cudaStream_t st, const double* wr, int kind, int nch, int len,
                                         long long P, const cplx* Wsp_e, int K, int nfft, cplx* out);

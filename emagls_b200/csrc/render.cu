@@ -18,10 +18,26 @@ namespace {
       throw ::emagls::Fail{EMAGLS_ERR_CUDA, std::string(#expr) + ": cufft error " + std::to_string((int)_r)}; \
   } while (0)
 
-struct Plan {
-  cufftHandle p = 0;
-  ~Plan() { if (p) cufftDestroy(p); }
-};
+// (Re)build the three plans of the render for this geometry; cached in the handle between calls.
+void ensure_plans(emagls_ctx* h, int N, int num_ch, int chunk, long long seg_len) {
+  auto& rp = h->render_plans;
+  if (rp.N == N && rp.num_ch == num_ch && rp.chunk == chunk && rp.fwd && rp.inv && rp.filt) return;
+  if (rp.fwd) cufftDestroy(rp.fwd);
+  if (rp.inv) cufftDestroy(rp.inv);
+  if (rp.filt) cufftDestroy(rp.filt);
+  rp = emagls_ctx::RenderPlans{};
+  const int L = N / 2, F = N / 2 + 1;
+  int n[1] = {N};
+  cufftHandle pf = 0, pi = 0, pw = 0;
+  EM_FFT(cufftPlanMany(&pw, 1, n, nullptr, 1, N, nullptr, 1, F, CUFFT_D2Z, 2 * num_ch));
+  int inembed[1] = {(int)std::min<long long>(seg_len, 1 << 30)}, onembed[1] = {F};
+  EM_FFT(cufftPlanMany(&pf, 1, n, inembed, 1, L, onembed, 1, F, CUFFT_D2Z, num_ch * (chunk + 1)));
+  EM_FFT(cufftPlanMany(&pi, 1, n, nullptr, 1, F, nullptr, 1, N, CUFFT_Z2D, 2 * chunk));
+  EM_FFT(cufftSetStream(pw, h->stream));
+  EM_FFT(cufftSetStream(pf, h->stream));
+  EM_FFT(cufftSetStream(pi, h->stream));
+  rp.N = N; rp.num_ch = num_ch; rp.chunk = chunk; rp.fwd = pf; rp.inv = pi; rp.filt = pw;
+}
 
 // xp[ch][L + n] = in[ch][n0 + n - L ...]: segment buffer for one chunk of blocks.  For chunk
 // starting at sample s0 (multiple of L) the buffer holds samples [s0 - L, s0 + nb*L + L) per
@@ -111,9 +127,14 @@ void binaural_decode_dev(emagls_ctx* h, const double* in, long long num_samples,
   const long long out_rows = num_samples - skip;
   EM_REQUIRE(out_rows > 0, "signal shorter than the compensated delay");
   const long long nblk_total = (num_samples + L - 1) / L;
-  int chunk_max = 512;
+  int chunk_max = 2048;
   if (const char* e = getenv("EMAGLS_RENDER_CHUNK")) chunk_max = std::max(1, atoi(e));
   const int chunk = (int)std::min<long long>(nblk_total, chunk_max);
+  // every channel holds (chunk + 1) hops of L samples (+ L at the very end) so that the overlapping
+  // D2Z batch has a uniform signal distance of L
+  const long long seg_len = (long long)(chunk + 1) * L;
+  ensure_plans(h, N, num_ch, chunk, seg_len);
+  const auto& rp = h->render_plans;
 
   // filter spectra Hw[ear][ch][F]
   cplx* Hw = ar.get<cplx>((size_t)2 * num_ch * F);
@@ -122,32 +143,15 @@ void binaural_decode_dev(emagls_ctx* h, const double* in, long long num_samples,
     int total = 2 * num_ch * N;
     pad_filters_kernel<<<(total + 255) / 256, 256, 0, st>>>(wL, wR, len, num_ch, N, wp);
     EM_CUDA(cudaGetLastError());
-    Plan pf;
-    int n[1] = {N};
-    EM_FFT(cufftPlanMany(&pf.p, 1, n, nullptr, 1, N, nullptr, 1, F, CUFFT_D2Z, 2 * num_ch));
-    EM_FFT(cufftSetStream(pf.p, st));
-    EM_FFT(cufftExecD2Z(pf.p, wp, reinterpret_cast<cufftDoubleComplex*>(Hw)));
+    EM_FFT(cufftExecD2Z(rp.filt, wp, reinterpret_cast<cufftDoubleComplex*>(Hw)));
     h->launches += 1;
-    EM_CUDA(cudaStreamSynchronize(st));  // plan is destroyed at scope exit
   }
 
-  // per-chunk buffers: every channel holds (chunk + 1) hops of L samples (+ L at the very end) so
-  // that the overlapping D2Z batch has a uniform signal distance of L
-  const long long seg_len = (long long)(chunk + 1) * L;
   double* xp = ar.get<double>((size_t)seg_len * num_ch + L);
   cplx* X = ar.get<cplx>((size_t)num_ch * (chunk + 1) * F);
   cplx* Y = ar.get<cplx>((size_t)2 * chunk * F);
   double* yseg = ar.get<double>((size_t)2 * chunk * N);
   EM_CUDA(cudaMemsetAsync(xp + seg_len * num_ch, 0, (size_t)L * sizeof(double), st));
-  Plan fwd, inv;
-  {
-    int n[1] = {N};
-    int inembed[1] = {(int)std::min<long long>(seg_len, 1 << 30)}, onembed[1] = {F};
-    EM_FFT(cufftPlanMany(&fwd.p, 1, n, inembed, 1, L, onembed, 1, F, CUFFT_D2Z, num_ch * (chunk + 1)));
-    EM_FFT(cufftSetStream(fwd.p, st));
-    EM_FFT(cufftPlanMany(&inv.p, 1, n, nullptr, 1, F, nullptr, 1, N, CUFFT_Z2D, 2 * chunk));
-    EM_FFT(cufftSetStream(inv.p, st));
-  }
   for (long long b0 = 0; b0 < nblk_total; b0 += chunk) {
     const long long s0 = b0 * L;
     {
@@ -158,7 +162,7 @@ void binaural_decode_dev(emagls_ctx* h, const double* in, long long num_samples,
     }
     {
       ProfSpan ps(h, EM_PROF_RENDER_FFT);
-      EM_FFT(cufftExecD2Z(fwd.p, xp, reinterpret_cast<cufftDoubleComplex*>(X)));
+      EM_FFT(cufftExecD2Z(rp.fwd, xp, reinterpret_cast<cufftDoubleComplex*>(X)));
     }
     {
       ProfSpan ps(h, EM_PROF_RENDER_MAC);
@@ -170,7 +174,7 @@ void binaural_decode_dev(emagls_ctx* h, const double* in, long long num_samples,
     }
     {
       ProfSpan ps(h, EM_PROF_RENDER_FFT);
-      EM_FFT(cufftExecZ2D(inv.p, reinterpret_cast<cufftDoubleComplex*>(Y), yseg));
+      EM_FFT(cufftExecZ2D(rp.inv, reinterpret_cast<cufftDoubleComplex*>(Y), yseg));
     }
     {
       ProfSpan ps(h, EM_PROF_RENDER_STAGE);
@@ -181,7 +185,15 @@ void binaural_decode_dev(emagls_ctx* h, const double* in, long long num_samples,
     }
     h->launches += 3;
   }
-  EM_CUDA(cudaStreamSynchronize(st));  // plans die with this scope
+  // stream-ordered: the arena's cudaFreeAsync calls queue behind the work above
+}
+
+void destroy_render_plans(emagls_ctx* h) {
+  auto& rp = h->render_plans;
+  if (rp.fwd) cufftDestroy(rp.fwd);
+  if (rp.inv) cufftDestroy(rp.inv);
+  if (rp.filt) cufftDestroy(rp.filt);
+  rp = emagls_ctx::RenderPlans{};
 }
 
 }  // namespace emagls
