@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <string>
+#include <utility>
 #include <vector>
 #include "../../include/emagls_cuda.h"
 #include "kernels.h"
@@ -37,8 +38,10 @@ struct emagls_ctx {
   long long prof_n[EM_PROF_NUM] = {0};
   // render: cuFFT plans are expensive to build (milliseconds), so they live with the handle
   struct RenderPlans {
-    int N = 0, num_ch = 0, chunk = 0;
+    int N = 0, L = 0, num_ch = 0, chunk = 0;
     int fwd = 0, inv = 0, filt = 0;   // cufftHandle values (0 = not created)
+    int edge = 0;                     // one boundary block of every channel (zero-padded staging)
+    std::vector<std::pair<int, int>> direct;  // (batch, plan): interior blocks read straight from the input
   } render_plans;
 };
 

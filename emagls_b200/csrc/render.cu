@@ -4,6 +4,7 @@
 // multiply-accumulate over channels (the HBM-bound part) is the hand-written kernel below.
 #include <cufft.h>
 #include <algorithm>
+#include <cstdint>
 #include <cstdlib>
 #include <vector>
 #include "engine.h"
@@ -18,39 +19,70 @@ namespace {
       throw ::emagls::Fail{EMAGLS_ERR_CUDA, std::string(#expr) + ": cufft error " + std::to_string((int)_r)}; \
   } while (0)
 
-// (Re)build the three plans of the render for this geometry; cached in the handle between calls.
-void ensure_plans(emagls_ctx* h, int N, int num_ch, int chunk, long long seg_len) {
+constexpr int MAX_EDGE = 8;  // staged boundary blocks per chunk (head + tail)
+
+void drop_plans(emagls_ctx* h) {
   auto& rp = h->render_plans;
-  if (rp.N == N && rp.num_ch == num_ch && rp.chunk == chunk && rp.fwd && rp.inv && rp.filt) return;
   if (rp.fwd) cufftDestroy(rp.fwd);
   if (rp.inv) cufftDestroy(rp.inv);
   if (rp.filt) cufftDestroy(rp.filt);
+  if (rp.edge) cufftDestroy(rp.edge);
+  for (auto& d : rp.direct) cufftDestroy(d.second);
   rp = emagls_ctx::RenderPlans{};
-  const int L = N / 2, F = N / 2 + 1;
+}
+
+// (Re)build the plans of the render for this geometry; cached in the handle between calls.
+void ensure_plans(emagls_ctx* h, int N, int L, int num_ch, int chunk, int nbc) {
+  auto& rp = h->render_plans;
+  if (rp.N == N && rp.L == L && rp.num_ch == num_ch && rp.chunk == chunk && rp.fwd && rp.inv && rp.filt) return;
+  drop_plans(h);
+  const int F = N / 2 + 1;
   int n[1] = {N};
   cufftHandle pf = 0, pi = 0, pw = 0;
   EM_FFT(cufftPlanMany(&pw, 1, n, nullptr, 1, N, nullptr, 1, F, CUFFT_D2Z, 2 * num_ch));
-  int inembed[1] = {(int)std::min<long long>(seg_len, 1 << 30)}, onembed[1] = {F};
-  EM_FFT(cufftPlanMany(&pf, 1, n, inembed, 1, L, onembed, 1, F, CUFFT_D2Z, num_ch * (chunk + 1)));
+  // overlapping input batches: block j of channel ch starts at (ch * nbc + j) * L
+  int inembed[1] = {N}, onembed[1] = {F};
+  EM_FFT(cufftPlanMany(&pf, 1, n, inembed, 1, L, onembed, 1, F, CUFFT_D2Z, num_ch * nbc));
   EM_FFT(cufftPlanMany(&pi, 1, n, nullptr, 1, F, nullptr, 1, N, CUFFT_Z2D, 2 * chunk));
+  // boundary block e of every channel: in xe[ch][e][N], out X[ch][b][F]
+  cufftHandle pe = 0;
+  int e_in[1] = {N};
+  EM_FFT(cufftPlanMany(&pe, 1, n, e_in, 1, MAX_EDGE * N, onembed, 1, nbc * F, CUFFT_D2Z, num_ch));
   EM_FFT(cufftSetStream(pw, h->stream));
   EM_FFT(cufftSetStream(pf, h->stream));
   EM_FFT(cufftSetStream(pi, h->stream));
-  rp.N = N; rp.num_ch = num_ch; rp.chunk = chunk; rp.fwd = pf; rp.inv = pi; rp.filt = pw;
+  EM_FFT(cufftSetStream(pe, h->stream));
+  rp.N = N; rp.L = L; rp.num_ch = num_ch; rp.chunk = chunk; rp.fwd = pf; rp.inv = pi; rp.filt = pw; rp.edge = pe;
 }
 
-// xp[ch][L + n] = in[ch][n0 + n - L ...]: segment buffer for one chunk of blocks.  For chunk
-// starting at sample s0 (multiple of L) the buffer holds samples [s0 - L, s0 + nb*L + L) per
-// channel, zero outside [0, num_samples).
+// interior blocks of one channel straight from the caller's signal: `batch` overlapping transforms at
+// distance L (cuFFT plans have a fixed batch: one plan per distinct count, normally one or two)
+cufftHandle direct_plan(emagls_ctx* h, int N, int L, int batch) {
+  auto& rp = h->render_plans;
+  for (auto& d : rp.direct)
+    if (d.first == batch) return d.second;
+  const int F = N / 2 + 1;
+  int n[1] = {N}, inembed[1] = {N}, onembed[1] = {F};
+  cufftHandle p = 0;
+  EM_FFT(cufftPlanMany(&p, 1, n, inembed, 1, L, onembed, 1, F, CUFFT_D2Z, batch));
+  EM_FFT(cufftSetStream(p, h->stream));
+  if (rp.direct.size() >= 4) { cufftDestroy(rp.direct.front().second); rp.direct.erase(rp.direct.begin()); }
+  rp.direct.emplace_back(batch, p);
+  return p;
+}
+
+// Segment buffer of one chunk of blocks: xp[ch][i] = in[ch][s_first + i] (zero outside the signal),
+// i in [0, seg_len).  Block j of a channel is the N samples starting at xp[ch][j * L].
 __global__ void stage_input_kernel(const double* __restrict__ in, long long num_samples, int num_ch,
-                                   long long s0, long long seg_len, double* __restrict__ xp) {
+                                   long long s_first, long long seg_len, long long ch_stride,
+                                   double* __restrict__ xp) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = seg_len * num_ch;
   if (idx >= total) return;
   int ch = (int)(idx / seg_len);
   long long i = idx % seg_len;
-  long long n = s0 + i;
-  xp[idx] = (n >= 0 && n < num_samples) ? in[(long long)ch * num_samples + n] : 0.0;
+  long long n = s_first + i;
+  xp[(long long)ch * ch_stride + i] = (n >= 0 && n < num_samples) ? in[(long long)ch * num_samples + n] : 0.0;
 }
 
 __global__ void pad_filters_kernel(const double* __restrict__ wL, const double* __restrict__ wR, int len,
@@ -62,42 +94,62 @@ __global__ void pad_filters_kernel(const double* __restrict__ wL, const double* 
   wp[idx] = (t < len) ? w[(long long)ch * len + t] : 0.0;
 }
 
-// Y[ear][b][f] = sum_ch X[ch][b][f] * Hw[ear][ch][f].  One thread per (b, f); the channel loop is
-// unrolled so 8 independent 16-byte loads are in flight per thread.
-__global__ void __launch_bounds__(256)
-spectral_mac_kernel(const cplx* __restrict__ X, const cplx* __restrict__ Hw, int num_ch, int nbt,
+// Y[ear][b][f] = sum_ch X[ch][b][f] * Hw[ear][ch][f].  One thread per (f, BT consecutive blocks):
+// each pair of filter-spectrum values (L2-resident) is used for BT blocks, and the channel loop is
+// unrolled by CU so CU * (BT + 2) independent 16-byte loads are in flight per thread.
+template <int BT, int CU>
+__global__ void __launch_bounds__(128)
+spectral_mac_kernel(const cplx* __restrict__ X, const cplx* __restrict__ Hw, int num_ch, int nbc,
                     int nb, int F, cplx* __restrict__ Y) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)nb * F) return;
-  int f = (int)(idx % F);
-  int b = (int)(idx / F);
-  const cplx* x = X + (long long)b * F + f;
-  const long long xs = (long long)nbt * F;  // channel stride of X
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b0 = blockIdx.y * BT;
+  if (f >= F) return;
+  const long long xs = (long long)nbc * F;  // channel stride of X
+  const cplx* x = X + (long long)b0 * F + f;
   const cplx* hl = Hw + f;
   const cplx* hr = Hw + (long long)num_ch * F + f;
-  cplx yl = mk(0.0, 0.0), yr = mk(0.0, 0.0);
+  cplx yl[BT], yr[BT];
+#pragma unroll
+  for (int t = 0; t < BT; ++t) { yl[t] = mk(0.0, 0.0); yr[t] = mk(0.0, 0.0); }
+  // blocks past nb inside the same channel segment still exist (nbc > nb), so full tiles never
+  // read out of range; the stores are guarded
+  const int bt = min(BT, nbc - b0);
   int ch = 0;
-  for (; ch + 8 <= num_ch; ch += 8) {
-    cplx xv[8];
+  if (bt == BT) {
+    for (; ch + CU <= num_ch; ch += CU) {
+      cplx xv[CU][BT], a[CU], c[CU];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) xv[u] = x[(long long)(ch + u) * xs];
+      for (int u = 0; u < CU; ++u) {
+        a[u] = hl[(long long)(ch + u) * F];
+        c[u] = hr[(long long)(ch + u) * F];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      cfma(yl, xv[u], hl[(long long)(ch + u) * F]);
-      cfma(yr, xv[u], hr[(long long)(ch + u) * F]);
+        for (int t = 0; t < BT; ++t) xv[u][t] = x[(long long)(ch + u) * xs + (long long)t * F];
+      }
+#pragma unroll
+      for (int u = 0; u < CU; ++u)
+#pragma unroll
+        for (int t = 0; t < BT; ++t) { cfma(yl[t], xv[u][t], a[u]); cfma(yr[t], xv[u][t], c[u]); }
     }
   }
   for (; ch < num_ch; ++ch) {
-    cplx xv = x[(long long)ch * xs];
-    cfma(yl, xv, hl[(long long)ch * F]);
-    cfma(yr, xv, hr[(long long)ch * F]);
+    const cplx a = hl[(long long)ch * F], c = hr[(long long)ch * F];
+#pragma unroll
+    for (int t = 0; t < BT; ++t)
+      if (t < bt) {
+        const cplx xv = x[(long long)ch * xs + (long long)t * F];
+        cfma(yl[t], xv, a); cfma(yr[t], xv, c);
+      }
   }
-  Y[(long long)b * F + f] = yl;
-  Y[((long long)nb + b) * F + f] = yr;
+#pragma unroll
+  for (int t = 0; t < BT; ++t)
+    if (b0 + t < nb) {
+      Y[(long long)(b0 + t) * F + f] = yl[t];
+      Y[((long long)nb + b0 + t) * F + f] = yr[t];
+    }
 }
 
-// out[ear][row] = yseg[ear][b][L + i] / N for full-signal sample n = s0 + b*L + i, row = n - skip
-__global__ void unstage_output_kernel(const double* __restrict__ yseg, int nb, int N, int L, long long s0,
+// out[ear][row] = yseg[ear][b][ov + i] / N for full-signal sample n = s0 + b*L + i, row = n - skip
+__global__ void unstage_output_kernel(const double* __restrict__ yseg, int nb, int N, int L, int ov, long long s0,
                                       long long num_samples, long long skip, long long out_rows,
                                       double* __restrict__ out) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -108,11 +160,21 @@ __global__ void unstage_output_kernel(const double* __restrict__ yseg, int nb, i
   int ear = (int)(idx / ((long long)L * nb));
   long long n = s0 + (long long)b * L + i;
   if (n >= num_samples || n < skip) return;
-  out[(long long)ear * out_rows + (n - skip)] = yseg[((long long)ear * nb + b) * N + L + i] * (1.0 / (double)N);
+  out[(long long)ear * out_rows + (n - skip)] = yseg[((long long)ear * nb + b) * N + ov + i] * (1.0 / (double)N);
+}
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
 }
 
 }  // namespace
 
+// Overlap-save geometry: FFT size N (power of two), overlap ov >= len - 1 (even), hop L = N - ov.
+// Block b takes the N input samples starting at b*L - ov and yields output samples [b*L, (b+1)*L).
+// Large N amortises the overlap (N = 8 len: 12.5 % redundant input, 0.57 spectrum bins per output
+// frame instead of 1.0 at N = 2 len); the chunk (blocks per cuFFT batch) is sized so that the
+// staged input, its spectra and the ear spectra of one chunk stay L2-resident between the kernels.
 void binaural_decode_dev(emagls_ctx* h, const double* in, long long num_samples, int num_ch,
                          const double* wL, const double* wR, int len, int compensate_delay, double* out) {
   EM_REQUIRE(in && wL && wR && out, "null argument");
@@ -120,20 +182,41 @@ void binaural_decode_dev(emagls_ctx* h, const double* in, long long num_samples,
   EM_REQUIRE(!compensate_delay || len % 2 == 0, "compensateDelay needs an even filter length");
   cudaStream_t st = h->stream;
   Arena ar(st);
-  int N = 2;
-  while (N < 2 * len) N <<= 1;
-  const int L = N / 2, F = N / 2 + 1;
+  const int ov = (len + 1) & ~1;
+  int Nmin = 16;
+  while (Nmin < 2 * len) Nmin <<= 1;
+  int N = Nmin;
+  {
+    int want = env_int("EMAGLS_RENDER_FFT", 0);
+    if (want <= 0) want = 8 * Nmin / 2;                       // default N = 8 len (next power of two)
+    // no point in blocks much longer than the signal
+    while (N < want && (long long)(N - ov) < num_samples) N <<= 1;
+  }
+  const int L = N - ov, F = N / 2 + 1;
   const long long skip = compensate_delay ? (len / 2 - 1) : 0;  // out(del:end,:), binauralDecode.m:55-56
   const long long out_rows = num_samples - skip;
   EM_REQUIRE(out_rows > 0, "signal shorter than the compensated delay");
   const long long nblk_total = (num_samples + L - 1) / L;
-  int chunk_max = 2048;
-  if (const char* e = getenv("EMAGLS_RENDER_CHUNK")) chunk_max = std::max(1, atoi(e));
-  const int chunk = (int)std::min<long long>(nblk_total, chunk_max);
-  // every channel holds (chunk + 1) hops of L samples (+ L at the very end) so that the overlapping
-  // D2Z batch has a uniform signal distance of L
-  const long long seg_len = (long long)(chunk + 1) * L;
-  ensure_plans(h, N, num_ch, chunk, seg_len);
+  const int nex = (ov + L - 1) / L;   // extra hops per channel so that the overlapping batch has a uniform distance L
+  // blocks per chunk: as many as a memory budget allows (measured on B200: launch-bound below a few
+  // hundred blocks; one chunk for a 10-minute signal is fastest, the intermediates do not need to stay
+  // in L2).  EMAGLS_RENDER_CHUNK / EMAGLS_RENDER_WS_MB override.
+  int chunk_max;
+  if (const char* e = getenv("EMAGLS_RENDER_CHUNK")) {
+    chunk_max = std::max(1, atoi(e));
+  } else {
+    size_t free_b = 0, total_b = 0;
+    EM_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    double budget = std::min(0.4 * (double)free_b, 16.0 * 1073741824.0);
+    const int ws_mb = env_int("EMAGLS_RENDER_WS_MB", 0);
+    if (ws_mb > 0) budget = (double)ws_mb * 1048576.0;
+    const double per_block = (double)num_ch * ((double)L * 8 + (double)F * 16) + 2.0 * F * 16 + 2.0 * N * 8;
+    chunk_max = (int)std::max(1.0, std::min(65535.0 * 4, budget / per_block));
+  }
+  const int chunk = (int)std::min<long long>({nblk_total, (long long)chunk_max, 65535LL * 4});
+  const int nbc = chunk + nex;
+  const long long seg_len = (long long)nbc * L;
+  ensure_plans(h, N, L, num_ch, chunk, nbc);
   const auto& rp = h->render_plans;
 
   // filter spectra Hw[ear][ch][F]
@@ -147,29 +230,77 @@ void binaural_decode_dev(emagls_ctx* h, const double* in, long long num_samples,
     h->launches += 1;
   }
 
-  double* xp = ar.get<double>((size_t)seg_len * num_ch + L);
-  cplx* X = ar.get<cplx>((size_t)num_ch * (chunk + 1) * F);
+  // Forward transforms.  Direct route (default when every channel of the caller's signal is 16-byte
+  // aligned): interior blocks are transformed in place from `in`, one cuFFT call per channel, and only
+  // the blocks that overlap the ends of the signal are staged zero-padded.  Staged route: the whole
+  // chunk is copied into a segment buffer first (one cuFFT call per chunk).
+  const bool direct = env_int("EMAGLS_RENDER_DIRECT", 1) != 0 && (num_samples % 2 == 0) &&
+                      (reinterpret_cast<uintptr_t>(in) % 16 == 0);
+  const long long b_int_lo = nex;                                                   // input starts at >= 0
+  const long long b_int_hi = (num_samples - N + ov >= 0) ? (num_samples - N + ov) / L : -1;  // ends inside
+  // the last nex blocks of the last channel read up to N samples past the staged segments
+  double* xp = direct ? ar.get<double>((size_t)MAX_EDGE * N * num_ch) : ar.get<double>((size_t)seg_len * num_ch + N);
+  cplx* X = ar.get<cplx>((size_t)num_ch * nbc * F);
   cplx* Y = ar.get<cplx>((size_t)2 * chunk * F);
   double* yseg = ar.get<double>((size_t)2 * chunk * N);
-  EM_CUDA(cudaMemsetAsync(xp + seg_len * num_ch, 0, (size_t)L * sizeof(double), st));
+  if (!direct) EM_CUDA(cudaMemsetAsync(xp + seg_len * num_ch, 0, (size_t)N * sizeof(double), st));
+  constexpr int BT = 4, CU = 4;
   for (long long b0 = 0; b0 < nblk_total; b0 += chunk) {
     const long long s0 = b0 * L;
-    {
-      ProfSpan ps(h, EM_PROF_RENDER_STAGE);
-      long long total = seg_len * num_ch;
-      stage_input_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, num_samples, num_ch, s0 - L, seg_len, xp);
-      EM_CUDA(cudaGetLastError());
-    }
-    {
-      ProfSpan ps(h, EM_PROF_RENDER_FFT);
-      EM_FFT(cufftExecD2Z(rp.fwd, xp, reinterpret_cast<cufftDoubleComplex*>(X)));
+    if (direct) {
+      const long long nbk = std::min<long long>(chunk, nblk_total - b0);
+      const long long lo = std::max(b0, b_int_lo), hi = std::min(b0 + nbk - 1, b_int_hi);
+      if (hi >= lo) {
+        ProfSpan ps(h, EM_PROF_RENDER_FFT);
+        cufftHandle pd = direct_plan(h, N, L, (int)(hi - lo + 1));
+        for (int ch = 0; ch < num_ch; ++ch)
+          EM_FFT(cufftExecD2Z(pd, const_cast<double*>(in) + (long long)ch * num_samples + lo * L - ov,
+                              reinterpret_cast<cufftDoubleComplex*>(X + ((long long)ch * nbc + (lo - b0)) * F)));
+      }
+      // boundary blocks of this chunk, MAX_EDGE at a time
+      long long eb[MAX_EDGE];
+      int ne = 0;
+      auto flush = [&]() {
+        for (int e = 0; e < ne; ++e) {
+          ProfSpan ps(h, EM_PROF_RENDER_STAGE);
+          long long total = (long long)N * num_ch;
+          stage_input_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, num_samples, num_ch, eb[e] * L - ov, N,
+                                                                            (long long)MAX_EDGE * N, xp + (long long)e * N);
+          EM_CUDA(cudaGetLastError());
+        }
+        for (int e = 0; e < ne; ++e) {
+          ProfSpan ps(h, EM_PROF_RENDER_FFT);
+          EM_FFT(cufftExecD2Z(rp.edge, xp + (long long)e * N, reinterpret_cast<cufftDoubleComplex*>(X + (eb[e] - b0) * F)));
+        }
+        h->launches += ne;
+        ne = 0;
+      };
+      for (long long b = b0; b < b0 + nbk; ++b) {
+        if (b >= lo && b <= hi) { b = hi; continue; }
+        eb[ne++] = b;
+        if (ne == MAX_EDGE) flush();
+      }
+      flush();
+    } else {
+      {
+        ProfSpan ps(h, EM_PROF_RENDER_STAGE);
+        long long total = seg_len * num_ch;
+        stage_input_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, num_samples, num_ch, s0 - ov, seg_len,
+                                                                          seg_len, xp);
+        EM_CUDA(cudaGetLastError());
+      }
+      {
+        ProfSpan ps(h, EM_PROF_RENDER_FFT);
+        EM_FFT(cufftExecD2Z(rp.fwd, xp, reinterpret_cast<cufftDoubleComplex*>(X)));
+      }
+      h->launches += 1;
     }
     {
       ProfSpan ps(h, EM_PROF_RENDER_MAC);
-      long long total = (long long)chunk * F;
       // Y is laid out [ear][chunk][F] for the fixed-size inverse plan (a partial last chunk
       // computes a few unused blocks)
-      spectral_mac_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, Hw, num_ch, chunk + 1, chunk, F, Y);
+      dim3 grid((unsigned)((F + 127) / 128), (unsigned)((chunk + BT - 1) / BT));
+      spectral_mac_kernel<BT, CU><<<grid, 128, 0, st>>>(X, Hw, num_ch, nbc, chunk, F, Y);
       EM_CUDA(cudaGetLastError());
     }
     {
@@ -179,22 +310,16 @@ void binaural_decode_dev(emagls_ctx* h, const double* in, long long num_samples,
     {
       ProfSpan ps(h, EM_PROF_RENDER_STAGE);
       long long total = (long long)2 * chunk * L;
-      unstage_output_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(yseg, chunk, N, L, s0, num_samples, skip,
+      unstage_output_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(yseg, chunk, N, L, ov, s0, num_samples, skip,
                                                                            out_rows, out);
       EM_CUDA(cudaGetLastError());
     }
-    h->launches += 3;
+    h->launches += 2;
   }
   // stream-ordered: the arena's cudaFreeAsync calls queue behind the work above
 }
 
-void destroy_render_plans(emagls_ctx* h) {
-  auto& rp = h->render_plans;
-  if (rp.fwd) cufftDestroy(rp.fwd);
-  if (rp.inv) cufftDestroy(rp.inv);
-  if (rp.filt) cufftDestroy(rp.filt);
-  rp = emagls_ctx::RenderPlans{};
-}
+void destroy_render_plans(emagls_ctx* h) { drop_plans(h); }
 
 }  // namespace emagls
 

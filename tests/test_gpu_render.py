@@ -47,6 +47,26 @@ def test_chunk_boundaries(em, h, monkeypatch):
         assert rel(em.binauralDecode(x, 48000, wl, wr, 48000, handle=h), yo) < 1e-9
 
 
+@pytest.mark.parametrize("direct", ["0", "1"])
+@pytest.mark.parametrize("fft", ["1024", "2048", "4096", "16384"])
+def test_overlap_save_geometries(em, h, monkeypatch, direct, fft):
+    """Every FFT size / hop and both forward routes (input transformed in place vs. staged) give the
+    reference convolution; even and odd signal lengths (odd lengths always take the staged route)."""
+    monkeypatch.setenv("EMAGLS_RENDER_DIRECT", direct)
+    monkeypatch.setenv("EMAGLS_RENDER_FFT", fft)
+    rng = np.random.default_rng(21)
+    wl, wr = rng.standard_normal((512, 5)), rng.standard_normal((512, 5))
+    for n in (40000, 40001, 3584 * 4, 3584 * 4 + 512, 700):
+        x = rng.standard_normal((n, 5))
+        yo = oracle.binauralDecode(x, 48000, wl, wr, 48000)
+        assert rel(em.binauralDecode(x, 48000, wl, wr, 48000, handle=h), yo) < 1e-9
+    for chunk in ("1", "3"):
+        monkeypatch.setenv("EMAGLS_RENDER_CHUNK", chunk)
+        x = rng.standard_normal((30000, 5))
+        yo = oracle.binauralDecode(x, 48000, wl, wr, 48000, True)
+        assert rel(em.binauralDecode(x, 48000, wl, wr, 48000, True, handle=h), yo) < 1e-9
+
+
 def test_linearity_and_impulse_properties_at_full_size(em, h):
     """Size-independent properties on a 10 s, 32-channel signal: linearity and the impulse response."""
     rng = np.random.default_rng(12)
