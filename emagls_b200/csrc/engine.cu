@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 #include "engine.h"
 #include "gemm.cuh"
@@ -414,6 +415,26 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
         }
       }
   }
+  // ---------------- int8 tensor-core route for the two direction-grid contractions (ozaki.cuh)
+  int oz_T = 7;
+  if (const char* e = getenv("EMAGLS_OZAKI_SLICES")) oz_T = atoi(e);
+  bool use_oz = true;
+  if (const char* e = getenv("EMAGLS_GEMM")) use_oz = std::string(e) != "dmma";
+  if (oz_T < 6 || oz_T > 8 || K - kls1 <= 0) use_oz = false;
+  const int KpS = oz_pad32(S), KpD = oz_pad32(D);
+  int8_t *YhA_q = nullptr, *YhB_q = nullptr, *QB_q = nullptr;
+  double *sYhA = nullptr, *sYhB = nullptr, *sQB = nullptr, *upH = nullptr, *scH = nullptr;
+  if (use_oz) {
+    YhA_q = ar.get<int8_t>((size_t)oz_T * D * KpS); sYhA = ar.get<double>(D);
+    YhB_q = ar.get<int8_t>((size_t)oz_T * S * KpD); sYhB = ar.get<double>(S);
+    QB_q = ar.get<int8_t>((size_t)oz_T * S * KpD);  sQB = ar.get<double>(S);
+    upH = ar.get<double>((size_t)a.num_sets * 2 * K); scH = ar.get<double>((size_t)a.num_sets * 2 * K);
+    EM_CUDA(launch_slice_rows(st, Yh, 1, D, D, S, KpS, oz_T, YhA_q, sYhA));   // rows = directions
+    EM_CUDA(launch_slice_rows(st, Yh, D, 1, S, D, KpD, oz_T, YhB_q, sYhB));   // rows = harmonics
+    EM_CUDA(launch_slice_rows(st, Q, D, 1, S, D, KpD, oz_T, QB_q, sQB));
+    EM_CUDA(launch_row_scale(st, absH, (long long)a.num_sets * 2 * K, D, upH, scH));
+    h->launches += 4;
+  }
   delete setup_span; setup_span = nullptr;
 
   // ---------------- memory plan: orientation chunks of OC, Gram bin groups of NB, TSQR slots of G
@@ -462,7 +483,11 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
   ops.Pb = ar.get<cplx>((size_t)OC * G * pb_stride);
   ops.info = ar.get<int>((size_t)OC * G);
   double* Cv = ar.get<double>((size_t)4 * PJ * S);
-  double* Tt = ar.get<double>((size_t)D * 4 * PJ);
+  double* Tt = use_oz ? nullptr : ar.get<double>((size_t)D * 4 * PJ);
+  int8_t* Cv_q = use_oz ? ar.get<int8_t>((size_t)oz_T * 4 * PJ * KpS) : nullptr;
+  int8_t* Tt_q = use_oz ? ar.get<int8_t>((size_t)oz_T * 4 * PJ * KpD) : nullptr;
+  double* sCv = use_oz ? ar.get<double>((size_t)4 * PJ) : nullptr;
+  double* sTt = use_oz ? ar.get<double>((size_t)4 * PJ) : nullptr;
   constexpr int MAX_SPLITS = 6;
   double* tq = ar.get<double>((size_t)MAX_SPLITS * 4 * PJ * S);   // split-K partials of t * Y_h
   // Gram route admissible iff cond_2(G) <= 1/c^2 (no singular value below c*s_max); the Frobenius
@@ -493,6 +518,8 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
       EM_CUDA(launch_build_F(st, Gh, S, simN, Yc, Mc, oc, ne_ld, Fs, Fa));
       h->launches += 1;
     }
+    // the padding columns D..KpD-1 of the t digits must read as zero (their position depends on pj)
+    if (use_oz) EM_CUDA(cudaMemsetAsync(Tt_q, 0, (size_t)oz_T * 4 * pj * KpD, st));
     RowSource src{};
     src.E = E; src.Etot = Etot; src.rowoff = d_rowoff; src.roword = d_roword; src.bn = bn; src.N = simN;
 
@@ -563,19 +590,35 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
             ProfSpan ps(h, EM_PROF_CHAIN_FWD);
             EM_CUDA(launch_fwd_small(st, Yc, Mc, S, d_roword, bk, pm, pj, Wsp, w_ear, K, kb - 1, Cv));
           }
-          {
-            ProfSpan ps(h, EM_PROF_GEMM_FWD);
-            GemmOperand A3{Yh, D, 0}, B3{Cv, S, 1};
-            EpiPhase ep{Tt, 4LL * pj, absH + (size_t)kb * D, 2LL * K * D, (long long)K * D, oc, kb == K - 1 ? 1 : 0};
-            EM_CUDA(launch_gemm(st, A3, B3, GemmShape{D, 4 * pj, S}, ep));
-          }
           int nsplit = 1;
           const long long split_stride = 4LL * pj * S;
-          {
-            ProfSpan ps(h, EM_PROF_GEMM_BWD);
-            GemmOperand A4{Tt, 4LL * pj, 0}, B4{gram ? Yh : Q, D, 1};
-            EM_CUDA(launch_gemm_splitk(st, A4, B4, GemmShape{4 * pj, S, D}, EpiStore{tq, S, 1.0, split_stride}, MAX_SPLITS,
-                                       &nsplit));
+          if (use_oz) {
+            {
+              ProfSpan ps(h, EM_PROF_GEMM_FWD);
+              EM_CUDA(launch_slice_rows(st, Cv, S, 1, 4 * pj, S, KpS, oz_T, Cv_q, sCv));
+              OzFwdArgs fa{YhA_q, sYhA, D, KpS, Cv_q, sCv, 4 * pj, oz_T, Tt_q, KpD, sTt,
+                           absH + (size_t)kb * D, 2LL * K * D, (long long)K * D, upH + kb, scH + kb, K, oc,
+                           kb == K - 1 ? 1 : 0};
+              EM_CUDA(launch_oz_fwd(st, fa));
+            }
+            {
+              ProfSpan ps(h, EM_PROF_GEMM_BWD);
+              EM_CUDA(launch_oz_bwd(st, Tt_q, sTt, 4 * pj, gram ? YhB_q : QB_q, gram ? sYhB : sQB, S, KpD, oz_T, tq));
+            }
+            h->launches += 1;
+          } else {
+            {
+              ProfSpan ps(h, EM_PROF_GEMM_FWD);
+              GemmOperand A3{Yh, D, 0}, B3{Cv, S, 1};
+              EpiPhase ep{Tt, 4LL * pj, absH + (size_t)kb * D, 2LL * K * D, (long long)K * D, oc, kb == K - 1 ? 1 : 0};
+              EM_CUDA(launch_gemm(st, A3, B3, GemmShape{D, 4 * pj, S}, ep));
+            }
+            {
+              ProfSpan ps(h, EM_PROF_GEMM_BWD);
+              GemmOperand A4{Tt, 4LL * pj, 0}, B4{gram ? Yh : Q, D, 1};
+              EM_CUDA(launch_gemm_splitk(st, A4, B4, GemmShape{4 * pj, S, D}, EpiStore{tq, S, 1.0, split_stride}, MAX_SPLITS,
+                                         &nsplit));
+            }
           }
           {
             ProfSpan ps(h, EM_PROF_CHAIN_BWD);

@@ -112,4 +112,26 @@ cudaError_t launch_bwd_small(cudaStream_t st, const double* Y, int Mc, int S, co
                              long long z_set_stride, long long z_ear_stride, int z_shared, int nsplit,
                              long long split_stride, cplx* Wsp, long long w_ear_stride, int K, int k, int dc_fix);
 
+// ---------------------------------------------------------------- ozaki_kernels.cu
+// FP64-accurate GEMMs on the int8 tensor cores (tcgen05 + TMEM + TMA); see ozaki.cuh.
+int oz_pad32(int k);
+// x(r, k) = src[r*rs + k*cs] -> digits out[T][R][Kpad] (int8) and scale[r] = 2^(e_r - 6)
+cudaError_t launch_slice_rows(cudaStream_t st, const double* src, long long rs, long long cs, int R, int K, int Kpad,
+                              int T, int8_t* out, double* scale);
+// per row of x [rows][D]: up = 2^(6-e), sc = 2^(e-6) with 2^e > max |x(row, :)|
+cudaError_t launch_row_scale(cudaStream_t st, const double* x, long long rows, int D, double* up, double* sc);
+struct OzFwdArgs {
+  const int8_t* YhA_q; const double* sYhA; int D, KpS;   // [T][D][KpS]: rows = directions, K = harmonics
+  const int8_t* Cv_q; const double* sCv; int rows;       // [T][rows][KpS]: rows = (problem, ear, re/im)
+  int T;
+  int8_t* Tt_q; int KpD; double* sT;                     // out: digits of t [T][rows][KpD], scales [rows]
+  const double* absH; long long abs_set_stride, abs_ear_stride;
+  const double* up; const double* sc; int scale_stride;  // this bin's |H| scales, indexed (set*2+ear)*scale_stride
+  int orient_per_set, nyquist;
+};
+cudaError_t launch_oz_fwd(cudaStream_t st, const OzFwdArgs& a);
+// tq [rows][S] = t^T B with B_q [T][S][KpD] (rows = harmonics, K = directions)
+cudaError_t launch_oz_bwd(cudaStream_t st, const int8_t* Tt_q, const double* sT, int rows, const int8_t* B_q,
+                          const double* sB, int S, int KpD, int T, double* tq);
+
 }  // namespace emagls

@@ -1,0 +1,384 @@
+// FP64-accurate GEMM on the 5th-generation tensor cores: error-free slicing (Ozaki scheme I) of both
+// operands into signed 7-bit digits, int8 x int8 -> int32 `tcgen05.mma.kind::i8` products with the
+// accumulators in TMEM, operands staged by TMA, FP64 recombination in the epilogue.
+//
+//   x(r, k) = 2^(e_r) * sum_s q_s(r, k) 2^(-6 - 7 s),  |q_s| <= 64          (slice_rows_kernel)
+//   C(m, n) = sA(m) sB(n) sum_{d < T} 2^(-7 d) sum_{i + j = d} sum_k qA_i(m, k) qB_j(n, k)
+//
+// with sA = 2^(e - 6).  Products of slices are exact in int32 (64 * 64 * K * T < 2^31 for K <= 2^16);
+// pairs with i + j >= T are dropped, so the result carries 7 T - 1 bits relative to max|a| max|b| K
+// (T = 7: 2^-48; the native FP64 dot product carries 2^-53 relative to sum |a||b|).
+//
+// Layout: one CTA = one 128 x 64 output tile at a time (persistent over tiles), T accumulators of
+// 64 TMEM columns (one per diagonal i + j = d), K streamed in tiles of 64 bytes per slice through a
+// 2-stage TMA -> smem ring (64-byte swizzle, K-major operands).  Warp 0: TMA producer, warp 1: MMA
+// issuer (one elected thread), warps 2..5: epilogue (TMEM -> registers -> FP64 -> functor).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace emagls {
+namespace oz {
+
+constexpr int TILE_M = 128, TILE_N = 64, TILE_K = 64, STAGES = 2, MAX_SLICES = 8;
+constexpr int A_SLICE_BYTES = TILE_M * TILE_K;   // 8 KB
+constexpr int B_SLICE_BYTES = TILE_N * TILE_K;   // 4 KB
+constexpr int THREADS = 192;
+
+// ------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol error becomes a trap (launch failure) instead of a hung GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {  // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {    // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, int8 x int8 -> int32
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 8 consecutive 32-bit columns: thread i of the warp receives lane (base lane + i)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile, rows of 64 bytes, 64-byte swizzle (cute::UMMA::SmemDescriptor, canonical
+// layout Swizzle<2,4,3> o ((8,n),2):((4,SBO),1) in 16-byte units): start address >> 4, LBO = 1
+// (unused for swizzled K-major), SBO = 8 rows * 64 B = 512 B, version 1 (Blackwell), layout 4.
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor: c_format S32 (2) @4, a/b format INT8 (1) @7/@10, K-major both,
+// n_dim = N >> 3 @17, m_dim = M >> 4 @24
+__device__ __forceinline__ uint32_t instr_desc_i8(int m, int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------- slicing
+// One warp per row r: x(r, k) = src[r * rs + k * cs], k < K.  out[s][r][Kpad] (int8), scale[r] = 2^(e-6)
+// with 2^e > max_k |x|.  Columns K..Kpad-1 are written as zero.
+__global__ void slice_rows_kernel(const double* __restrict__ src, long long rs, long long cs, int R, int K, int Kpad,
+                                  int T, int8_t* __restrict__ out, double* __restrict__ scale) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const double* x = src + (long long)r * rs;
+  double mx = 0.0;
+  for (int k = lane; k < K; k += 32) mx = fmax(mx, fabs(x[(long long)k * cs]));
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+  int e = 0;
+  if (mx > 0.0 && mx < 1e300) frexp(mx, &e);   // mx = f 2^e, f in [0.5, 1)
+  if (lane == 0) scale[r] = scalbn(1.0, e - 6);
+  for (int k = lane; k < Kpad; k += 32) {
+    double v = (k < K) ? scalbn(x[(long long)k * cs], 6 - e) : 0.0;
+    for (int s = 0; s < T; ++s) {
+      const double q = rint(v);
+      out[((long long)s * R + r) * Kpad + k] = (int8_t)(int)q;
+      v = (v - q) * 128.0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------- GEMM
+struct GemmArgs {
+  int M, N, Kpad;           // C is M x N; Kpad multiple of 32 (bytes per slice row of both operands)
+  const double* sA;         // [M] row scales of A
+  const double* sB;         // [N] row scales of B
+  int dbg;                  // microbenchmark switches: 1 = skip the epilogue work, 2 = skip the MMAs
+};
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// Epilogue functor: operator()(m, n0, v[8], M, N) receives 8 consecutive columns n0..n0+7 of row m
+// (already scaled, FP64).  Called only for m < M; columns >= N hold zeros and must be skipped.
+struct EpiStoreF64 {
+  double* C; long long ldc;
+  __device__ __forceinline__ void operator()(int m, int n0, const double (&v)[8], int M, int N) const {
+    double* p = C + (long long)m * ldc + n0;
+    if (n0 + 8 <= N) {
+#pragma unroll
+      for (int q = 0; q < 8; q += 2) *reinterpret_cast<double2*>(p + q) = make_double2(v[q], v[q + 1]);
+    } else {
+      for (int q = 0; q < 8 && n0 + q < N; ++q) p[q] = v[q];
+    }
+  }
+};
+
+template <int T, class Epi>
+__global__ void __launch_bounds__(THREADS, 1)
+ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g, Epi epi) {
+  extern __shared__ uint8_t oz_smem_raw[];
+  // 1024-byte aligned carve-up: [stage][A slices | B slices]
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int stage_bytes = T * (A_SLICE_BYTES + B_SLICE_BYTES);
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar, tmem_empty_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (g.M + TILE_M - 1) / TILE_M, n_tiles = (g.N + TILE_N - 1) / TILE_N;
+  const int num_tiles = m_tiles * n_tiles;
+  const int ksteps_total = g.Kpad / 32;
+  const int num_kt = (g.Kpad + TILE_K - 1) / TILE_K;
+  constexpr uint32_t tmem_cols = (T * TILE_N <= 256) ? 256u : 512u;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    mbar_init(&tmem_empty_bar, 4);   // one arrival per epilogue warp
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ================================================================= TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % m_tiles) * TILE_M, n0 = (tile / m_tiles) * TILE_N;
+        for (int kt = 0; kt < num_kt; ++kt) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = base + (size_t)stage * stage_bytes;
+          uint8_t* sb = sa + (size_t)T * A_SLICE_BYTES;
+          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          tma_load_3d(sa, &tmA, &full_bar[stage], kt * TILE_K, m0, 0);
+          tma_load_3d(sb, &tmB, &full_bar[stage], kt * TILE_K, n0, 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= MMA issuer
+    // The whole warp walks the pipeline (uniform control flow); one elected lane issues.  The
+    // T (T + 1) / 2 slice pairs of a k-step are straight-line code: every descriptor is the stage's
+    // base descriptor plus a compile-time constant, so issue cost stays below the 32 cycles one
+    // 128 x 64 x 32 MMA occupies the tensor pipe.
+    int stage = 0; uint32_t phase = 0, acc_phase = 0;
+    const bool leader = elect_one();
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n0 = (tile / m_tiles) * TILE_N;
+      const int n_mma = min(TILE_N, ((g.N - n0) + 15) & ~15);
+      const uint32_t idesc = instr_desc_i8(TILE_M, n_mma);
+      mbar_wait(&tmem_empty_bar, acc_phase ^ 1);   // epilogue has drained the accumulators
+      tc_fence_after();
+      for (int kt = 0; kt < num_kt; ++kt) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t sa = smem_u32(base + (size_t)stage * stage_bytes);
+          const uint64_t adesc0 = smem_desc_sw64(sa);
+          const uint64_t bdesc0 = smem_desc_sw64(sa + (uint32_t)T * A_SLICE_BYTES);
+          const int nks = min(TILE_K / 32, ksteps_total - kt * (TILE_K / 32));
+          if (!(g.dbg & 2)) {
+#pragma unroll
+            for (int ks = 0; ks < TILE_K / 32; ++ks) {
+              if (ks < nks) {
+#pragma unroll
+                for (int d = 0; d < T; ++d) {
+#pragma unroll
+                  for (int i = 0; i <= d; ++i) {
+                    const uint64_t ad = adesc0 + (uint64_t)((i * A_SLICE_BYTES + ks * 32) >> 4);
+                    const uint64_t bd = bdesc0 + (uint64_t)(((d - i) * B_SLICE_BYTES + ks * 32) >> 4);
+                    const uint32_t accum = (ks > 0 || i > 0) ? 1u : (uint32_t)(kt > 0);
+                    umma_i8(tmem_base + (uint32_t)d * TILE_N, ad, bd, idesc, accum);
+                  }
+                }
+              }
+            }
+          }
+          umma_commit(&empty_bar[stage]);            // smem slot reusable once these MMAs retire
+          if (kt == num_kt - 1) umma_commit(&tmem_full_bar);   // accumulators complete
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      acc_phase ^= 1;
+    }
+  } else {
+    // ================================================================= epilogue (warps 2..5)
+    const int lg = warp & 3;                          // TMEM lane group this warp may access
+    uint32_t acc_phase = 0;
+    const double w_hi = scalbn(1.0, -7 * ((T < 4 ? T : 4) - 1)), w_lo = scalbn(1.0, -7 * (T - 1));
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % m_tiles) * TILE_M, n0 = (tile / m_tiles) * TILE_N;
+      const int n_mma = min(TILE_N, ((g.N - n0) + 15) & ~15);
+      const int m = m0 + lg * 32 + lane;
+      mbar_wait(&tmem_full_bar, acc_phase);
+      tc_fence_after();
+      const double sa = (m < g.M) ? g.sA[m] : 0.0;
+      for (int c0 = 0; c0 < ((g.dbg & 1) ? 0 : n_mma); c0 += 8) {
+        int32_t a[MAX_SLICES][8];
+#pragma unroll
+        for (int d = 0; d < MAX_SLICES; ++d)
+          if (d < T) tmem_ld8(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(d * TILE_N + c0), a[d]);
+        tmem_ld_wait();
+        double v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          long long hi = 0, lo = 0;
+#pragma unroll
+          for (int d = 0; d < 4; ++d)
+            if (d < T) hi = hi * 128 + a[d][q];
+#pragma unroll
+          for (int d = 4; d < MAX_SLICES; ++d)
+            if (d < T) lo = lo * 128 + a[d][q];
+          const int n = n0 + c0 + q;
+          const double sb = (n < g.N) ? g.sB[n] : 0.0;
+          v[q] = fma((double)lo, w_lo, (double)hi * w_hi) * (sa * sb);
+        }
+        if (m < g.M) epi(m, n0 + c0, v, g.M, g.N);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar);
+      acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// Sliced operand [T][rows][Kpad] int8 -> 3-D tensor map, box {TILE_K, box_rows, T}, 64-byte swizzle,
+// out-of-range rows / columns read as zero.
+inline bool make_operand_map(CUtensorMap* tm, const int8_t* ptr, int rows, int Kpad, int T, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)Kpad, (cuuint64_t)rows, (cuuint64_t)T};
+  cuuint64_t strides[2] = {(cuuint64_t)Kpad, (cuuint64_t)Kpad * (cuuint64_t)rows};
+  cuuint32_t box[3] = {(cuuint32_t)TILE_K, (cuuint32_t)box_rows, (cuuint32_t)T};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+inline size_t gemm_smem_bytes(int T) { return (size_t)STAGES * T * (A_SLICE_BYTES + B_SLICE_BYTES) + 1024; }
+
+template <int T, class Epi>
+cudaError_t launch_ozaki_gemm_t(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g,
+                                Epi epi, int num_sms) {
+  const size_t smem = gemm_smem_bytes(T);
+  cudaError_t e = cudaFuncSetAttribute(ozaki_gemm_kernel<T, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int tiles = ((g.M + TILE_M - 1) / TILE_M) * ((g.N + TILE_N - 1) / TILE_N);
+  ozaki_gemm_kernel<T, Epi><<<tiles < num_sms ? tiles : num_sms, THREADS, smem, st>>>(tmA, tmB, g, epi);
+  return cudaGetLastError();
+}
+
+// C = A * B^T from sliced operands Aq [T][M][Kpad], Bq [T][N][Kpad]
+template <class Epi>
+cudaError_t launch_ozaki_gemm(cudaStream_t st, const int8_t* Aq, const double* sA, const int8_t* Bq, const double* sB,
+                              int M, int N, int Kpad, int T, Epi epi, int num_sms, int dbg = 0) {
+  if (Kpad % 32 != 0) return cudaErrorInvalidValue;
+  CUtensorMap tmA, tmB;
+  if (!make_operand_map(&tmA, Aq, M, Kpad, T, TILE_M) || !make_operand_map(&tmB, Bq, N, Kpad, T, TILE_N))
+    return cudaErrorInvalidValue;
+  GemmArgs g{M, N, Kpad, sA, sB, dbg};
+  switch (T) {
+    case 6: return launch_ozaki_gemm_t<6>(st, tmA, tmB, g, epi, num_sms);
+    case 7: return launch_ozaki_gemm_t<7>(st, tmA, tmB, g, epi, num_sms);
+    case 8: return launch_ozaki_gemm_t<8>(st, tmA, tmB, g, epi, num_sms);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace oz
+}  // namespace emagls

@@ -1,0 +1,120 @@
+// The two direction-grid contractions of the MagLS recursion on the int8 tensor cores (see ozaki.cuh):
+//   forward : y = Y_h c  (D x 4P, contraction over the S simulation harmonics) with the phase
+//             continuation t = |H_k| y / |y| (lib/getEMagLs2Filters.m:95-103) fused into the epilogue,
+//             which also slices t into the int8 digits the backward product consumes;
+//   backward: t^T Y_h (or t^T Q)  (4P x S, contraction over the D directions), FP64 out.
+#include "kernels.h"
+#include "ozaki.cuh"
+
+namespace emagls {
+
+namespace {
+
+template <int T>
+struct EpiPhaseSlice {
+  int8_t* Tq; long long slice_stride; int Kpad;   // [T][rows][Kpad], element (n, m) at n * Kpad + m
+  double* sT;                                     // [rows] scale of row n (written by the m == 0 lanes)
+  const double* absH; long long abs_set_stride, abs_ear_stride;   // this bin: [set][ear][dir]
+  const double* up; const double* sc; int scale_stride;           // 2^(6-e), 2^(e-6) at [(set*2+ear)*scale_stride]
+  int orient_per_set; int nyquist;
+  __device__ __forceinline__ void operator()(int m, int n0, const double (&v)[8], int M, int N) const {
+#pragma unroll
+    for (int q = 0; q < 8; q += 2) {
+      const int n = n0 + q;
+      if (n >= N) break;
+      const int j = n >> 1, ear = j & 1, set = (j >> 1) / orient_per_set;
+      const double mag = absH[(long long)set * abs_set_stride + (long long)ear * abs_ear_stride + m];
+      const double re = v[q], im = v[q + 1];
+      const double a2 = fma(re, re, im * im);
+      double tr, ti;
+      if (a2 > 1e-290 && a2 < 1e290) {
+        const double inv = mag * rsqrt(a2);
+        tr = re * inv; ti = im * inv;
+      } else if (a2 > 0.0) {
+        const double inv = mag / sqrt(a2);
+        tr = re * inv; ti = im * inv;
+      } else { tr = mag; ti = 0.0; }          // angle(0) = 0
+      if (nyquist) ti = 0.0;
+      const int si = (set * 2 + ear) * scale_stride;
+      const double u = up[si];
+      double a = tr * u, b = ti * u;          // |a|, |b| <= 64 (u = 2^(6-e), 2^e > max_d |H_k|)
+      int8_t* p = Tq + (long long)n * Kpad + m;
+#pragma unroll
+      for (int s = 0; s < T; ++s) {
+        const double qa = rint(a), qb = rint(b);
+        p[(long long)s * slice_stride] = (int8_t)(int)qa;
+        p[(long long)s * slice_stride + Kpad] = (int8_t)(int)qb;
+        a = (a - qa) * 128.0; b = (b - qb) * 128.0;
+      }
+      if (m == 0) { const double s_ = sc[si]; sT[n] = s_; sT[n + 1] = s_; }
+    }
+  }
+};
+
+// one warp per row: 2^e > max_d |x(row, d)|  ->  up = 2^(6-e), sc = 2^(e-6)
+__global__ void row_scale_kernel(const double* __restrict__ x, long long rows, int D, double* __restrict__ up,
+                                 double* __restrict__ sc) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  double mx = 0.0;
+  for (int d = lane; d < D; d += 32) mx = fmax(mx, fabs(x[r * D + d]));
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+  int e = 0;
+  if (mx > 0.0 && mx < 1e300) frexp(mx, &e);
+  if (lane == 0) { up[r] = scalbn(1.0, 6 - e); sc[r] = scalbn(1.0, e - 6); }
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+}  // namespace
+
+int oz_pad32(int k) { return (k + 31) & ~31; }
+
+cudaError_t launch_slice_rows(cudaStream_t st, const double* src, long long rs, long long cs, int R, int K, int Kpad,
+                              int T, int8_t* out, double* scale) {
+  oz::slice_rows_kernel<<<(R + 7) / 8, 256, 0, st>>>(src, rs, cs, R, K, Kpad, T, out, scale);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_row_scale(cudaStream_t st, const double* x, long long rows, int D, double* up, double* sc) {
+  row_scale_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, rows, D, up, sc);
+  return cudaGetLastError();
+}
+
+template <int T>
+static cudaError_t oz_fwd_t(cudaStream_t st, const OzFwdArgs& a) {
+  CUtensorMap tmA, tmB;
+  if (!oz::make_operand_map(&tmA, a.YhA_q, a.D, a.KpS, T, oz::TILE_M) ||
+      !oz::make_operand_map(&tmB, a.Cv_q, a.rows, a.KpS, T, oz::TILE_N))
+    return cudaErrorInvalidValue;
+  oz::GemmArgs g{a.D, a.rows, a.KpS, a.sYhA, a.sCv, 0};
+  EpiPhaseSlice<T> epi{a.Tt_q, (long long)a.rows * a.KpD, a.KpD, a.sT, a.absH, a.abs_set_stride, a.abs_ear_stride,
+                       a.up, a.sc, a.scale_stride, a.orient_per_set, a.nyquist};
+  return oz::launch_ozaki_gemm_t<T>(st, tmA, tmB, g, epi, sm_count());
+}
+
+cudaError_t launch_oz_fwd(cudaStream_t st, const OzFwdArgs& a) {
+  switch (a.T) {
+    case 6: return oz_fwd_t<6>(st, a);
+    case 7: return oz_fwd_t<7>(st, a);
+    case 8: return oz_fwd_t<8>(st, a);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launch_oz_bwd(cudaStream_t st, const int8_t* Tt_q, const double* sT, int rows, const int8_t* B_q,
+                          const double* sB, int S, int KpD, int T, double* tq) {
+  return oz::launch_ozaki_gemm(st, Tt_q, sT, B_q, sB, rows, S, KpD, T, oz::EpiStoreF64{tq, (long long)S}, sm_count());
+}
+
+}  // namespace emagls
