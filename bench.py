@@ -241,45 +241,87 @@ def main():
     e2e_s = emdist.max_over_ranks(time.perf_counter() - t0, dev)
     e2e_value = world * B * e2e_steps / e2e_s
 
-    # ---------------- roofline of the dominant kernel class
+    # ---------------- roofline of the dominant tensor kernel
+    # The two direction-grid contractions run on the int8 tensor cores (tcgen05.mma kind::i8, FP64
+    # accuracy through T = 7 error-free slices: T (T + 1) / 2 = 28 int8 GEMMs per product).  The roofline
+    # counts the int8 operations the kernel EXECUTES against the int8 tensor peak; the FP64-equivalent
+    # rate and the DGEMM (DMMA) peak of this GPU are reported next to it.
     S = (19 + 1) ** 2
-    peak = None
-    peak_src = "live cuBLAS DGEMM 8192^3, best of 5 (MEASURED_PEAKS.json has no FP64 entry)"
+    use_oz = os.environ.get("EMAGLS_GEMM", "") != "dmma"
+    oz_T = int(os.environ.get("EMAGLS_OZAKI_SLICES", "7"))
+    pairs = oz_T * (oz_T + 1) // 2
+    KpS, KpD = (S + 31) // 32 * 32, (D + 31) // 32 * 32
+    dgemm_peak = i8_peak = None
+    i8_src = None
     if rank == 0:
+        def best_ms(fn, n=5):
+            fn()
+            best = 1e9
+            for _ in range(n):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            return best
         a = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
         b = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
-        torch.matmul(a, b)
-        best = 1e9
-        for _ in range(5):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            torch.matmul(a, b)
-            e1.record()
-            torch.cuda.synchronize()
-            best = min(best, e0.elapsed_time(e1))
-        peak = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+        dgemm_peak = 2 * 8192 ** 3 / (best_ms(lambda: torch.matmul(a, b)) * 1e-3) / 1e12
         del a, b
-    flops_per_launch = {"gemm_fwd": 2.0 * D * 4 * B * S, "gemm_bwd": 2.0 * 4 * B * S * D}
+        try:   # library int8 GEMM (cuBLASLt) as the measured int8 tensor peak
+            ai = torch.randint(-64, 64, (8192, 8192), dtype=torch.int8, device=dev)
+            bi = torch.randint(-64, 64, (8192, 8192), dtype=torch.int8, device=dev).t()
+            i8_peak = 2 * 8192 ** 3 / (best_ms(lambda: torch._int_mm(ai, bi)) * 1e-3) / 1e12
+            i8_src = "live torch._int_mm (cuBLASLt int8) 8192^3, best of 5"
+            del ai, bi
+        except Exception as ex:  # noqa: BLE001
+            i8_peak = None
+            i8_src = f"torch._int_mm unavailable ({type(ex).__name__})"
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            alt = 2.0 * float(mp["bf16_tflops"])
+            if i8_peak is None or i8_peak < alt:
+                i8_peak, i8_src = alt, ("2 x MEASURED_PEAKS.json bf16_tflops (burst): tcgen05 kind::i8 runs at twice "
+                                        "the bf16 rate; " + (i8_src or ""))
+        except Exception:
+            if i8_peak is None:
+                i8_peak, i8_src = 4500.0, "nominal dense int8 (B200_PROFILING.md fallback)"
+    fp64_flops = {"gemm_fwd": 2.0 * D * 4 * B * S, "gemm_bwd": 2.0 * 4 * B * S * D}
+    i8_ops = {"gemm_fwd": 2.0 * D * 4 * B * KpS * pairs, "gemm_bwd": 2.0 * 4 * B * S * KpD * pairs}
     tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
     shares = {k: round(v["ms"] / tot_ms, 4) for k, v in prof.items() if v["n"]}
     dom = max(("gemm_fwd", "gemm_bwd"), key=lambda k: prof[k]["ms"])
     avg_ms = prof[dom]["ms"] / max(prof[dom]["n"], 1)
-    achieved = flops_per_launch[dom] / (avg_ms * 1e-3) / 1e12
-    # DRAM bytes of that launch from the committed `ncu --set full` capture at this shape (profiles/)
-    traffic = None
+    fp64_equiv = fp64_flops[dom] / (avg_ms * 1e-3) / 1e12
+    traffic, traffic_src = None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")))
-        want = "EpiPhase" if dom == "gemm_fwd" else "EpiStore"
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_oz_traffic.json" if use_oz else "r01_gemm_traffic.json")))
+        want = ("EpiPhase" if dom == "gemm_fwd" else "EpiStore")
         if B == 3600:
             traffic = next(x["traffic_bytes"] for x in tj["launches"] if want in x["kernel"])
+            traffic_src = ("profiles/" + ("r01_oz_traffic.json" if use_oz else "r01_gemm_traffic.json") +
+                           " (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full launch)")
     except Exception:
         pass
-    roofline = {"kernel": f"gemm_f64_kernel ({dom})", "bound": "tensor", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": (achieved / peak) if peak else None, "traffic": traffic,
-                "traffic_source": "profiles/r01_gemm_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, bytes/launch)",
-                "peak_source": peak_src, "flops_per_launch": flops_per_launch[dom],
-                "avg_launch_ms": avg_ms, "class_time_share": shares,
-                "algorithmic_tflops_whole_job": value / world * ALGO_GFLOP_PER_SET / 1e3}
+    if use_oz:
+        achieved = i8_ops[dom] / (avg_ms * 1e-3) / 1e12
+        roofline = {"kernel": f"ozaki_gemm_kernel<{oz_T}> ({dom}: tcgen05.mma kind::i8, TMEM accumulators, TMA operands)",
+                    "bound": "tensor", "achieved": achieved, "peak": i8_peak, "unit": "TOP/s (int8, executed)",
+                    "frac": (achieved / i8_peak) if i8_peak else None, "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": i8_src, "int8_ops_per_launch": i8_ops[dom], "slice_pairs": pairs,
+                    "fp64_equivalent_tflops": fp64_equiv, "fp64_flops_per_launch": fp64_flops[dom],
+                    "dgemm_peak_tflops": dgemm_peak, "fp64_equivalent_vs_dgemm_peak": (fp64_equiv / dgemm_peak) if dgemm_peak else None,
+                    "dgemm_peak_source": "live cuBLAS DGEMM 8192^3, best of 5 (MEASURED_PEAKS.json has no FP64 entry)",
+                    "avg_launch_ms": avg_ms, "class_time_share": shares,
+                    "algorithmic_tflops_whole_job": value / world * ALGO_GFLOP_PER_SET / 1e3}
+    else:
+        roofline = {"kernel": f"gemm_f64_kernel ({dom}, DMMA.8x8x4)", "bound": "tensor", "achieved": fp64_equiv,
+                    "peak": dgemm_peak, "unit": "TFLOP/s", "frac": (fp64_equiv / dgemm_peak) if dgemm_peak else None,
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": "live cuBLAS DGEMM 8192^3, best of 5 (MEASURED_PEAKS.json has no FP64 entry)",
+                    "flops_per_launch": fp64_flops[dom], "avg_launch_ms": avg_ms, "class_time_share": shares,
+                    "algorithmic_tflops_whole_job": value / world * ALGO_GFLOP_PER_SET / 1e3}
 
     # ---------------- render (secondary metric: Msamples/s of the 32 -> 2 channel, 512-tap FIR)
     render = None

@@ -589,13 +589,13 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
           {
             ProfSpan ps(h, EM_PROF_CHAIN_FWD);
             EM_CUDA(launch_fwd_small(st, Yc, Mc, S, d_roword, bk, pm, pj, Wsp, w_ear, K, kb - 1, Cv));
+            if (use_oz) EM_CUDA(launch_slice_rows(st, Cv, S, 1, 4 * pj, S, KpS, oz_T, Cv_q, sCv));
           }
           int nsplit = 1;
           const long long split_stride = 4LL * pj * S;
           if (use_oz) {
             {
-              ProfSpan ps(h, EM_PROF_GEMM_FWD);
-              EM_CUDA(launch_slice_rows(st, Cv, S, 1, 4 * pj, S, KpS, oz_T, Cv_q, sCv));
+              ProfSpan ps(h, EM_PROF_GEMM_FWD);   // exactly one launch: the int8 tensor-core GEMM
               OzFwdArgs fa{YhA_q, sYhA, D, KpS, Cv_q, sCv, 4 * pj, oz_T, Tt_q, KpD, sTt,
                            absH + (size_t)kb * D, 2LL * K * D, (long long)K * D, upH + kb, scH + kb, K, oc,
                            kb == K - 1 ? 1 : 0};

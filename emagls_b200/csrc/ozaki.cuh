@@ -12,7 +12,7 @@
 // Layout: one CTA = one 128 x 64 output tile at a time (persistent over tiles), T accumulators of
 // 64 TMEM columns (one per diagonal i + j = d), K streamed in tiles of 64 bytes per slice through a
 // 2-stage TMA -> smem ring (64-byte swizzle, K-major operands).  Warp 0: TMA producer, warp 1: MMA
-// issuer (one elected thread), warps 2..5: epilogue (TMEM -> registers -> FP64 -> functor).
+// issuer (one elected thread), warps 2..9: epilogue (TMEM -> registers -> FP64 -> functor).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -24,7 +24,8 @@ namespace oz {
 constexpr int TILE_M = 128, TILE_N = 64, TILE_K = 64, STAGES = 2, MAX_SLICES = 8;
 constexpr int A_SLICE_BYTES = TILE_M * TILE_K;   // 8 KB
 constexpr int B_SLICE_BYTES = TILE_N * TILE_K;   // 4 KB
-constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 8;                    // two warps per TMEM lane group, alternating 8-column chunks
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
 
 // ------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -120,10 +121,36 @@ __device__ __forceinline__ uint32_t instr_desc_i8(int m, int n) {
 }
 
 // ------------------------------------------------------------------------------------- slicing
+// Signed base-128 digits of a (|a| <= 64): a = sum_{s < T} q_s 128^-s + r, |r| <= 128^-(T-1) / 2, |q_s| <= 64.
+// Two int32 limbs (hi: digits 0..nh-1, lo: the rest) are rounded out of the FP64 value, then the
+// digits are peeled off with integer shifts (round to nearest: next = (x + 64) >> 7).
+template <int T, class Store>
+__device__ __forceinline__ void slice_digits(double a, Store&& store) {
+  constexpr int nh = T / 2, nl = T - nh;
+  const double ah = a * (double)(1 << (7 * (nh - 1)));
+  int hi = __double2int_rn(ah);
+  int lo = __double2int_rn((ah - (double)hi) * (double)(1 << (7 * nl)));
+#pragma unroll
+  for (int s = T - 1; s > nh; --s) {
+    const int nx = (lo + 64) >> 7;
+    store(s, lo - (nx << 7));
+    lo = nx;
+  }
+  store(nh, lo);
+#pragma unroll
+  for (int s = nh - 1; s > 0; --s) {
+    const int nx = (hi + 64) >> 7;
+    store(s, hi - (nx << 7));
+    hi = nx;
+  }
+  store(0, hi);
+}
+
 // One warp per row r: x(r, k) = src[r * rs + k * cs], k < K.  out[s][r][Kpad] (int8), scale[r] = 2^(e-6)
 // with 2^e > max_k |x|.  Columns K..Kpad-1 are written as zero.
+template <int T>
 __global__ void slice_rows_kernel(const double* __restrict__ src, long long rs, long long cs, int R, int K, int Kpad,
-                                  int T, int8_t* __restrict__ out, double* __restrict__ scale) {
+                                  int8_t* __restrict__ out, double* __restrict__ scale) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= R) return;
@@ -135,13 +162,11 @@ __global__ void slice_rows_kernel(const double* __restrict__ src, long long rs, 
   int e = 0;
   if (mx > 0.0 && mx < 1e300) frexp(mx, &e);   // mx = f 2^e, f in [0.5, 1)
   if (lane == 0) scale[r] = scalbn(1.0, e - 6);
+  const double up = scalbn(1.0, 6 - e);
   for (int k = lane; k < Kpad; k += 32) {
-    double v = (k < K) ? scalbn(x[(long long)k * cs], 6 - e) : 0.0;
-    for (int s = 0; s < T; ++s) {
-      const double q = rint(v);
-      out[((long long)s * R + r) * Kpad + k] = (int8_t)(int)q;
-      v = (v - q) * 128.0;
-    }
+    const double v = (k < K) ? x[(long long)k * cs] * up : 0.0;
+    int8_t* o = out + (long long)r * Kpad + k;
+    slice_digits<T>(v, [&](int s, int q) { o[(long long)s * R * Kpad] = (int8_t)q; });
   }
 }
 
@@ -165,7 +190,7 @@ struct EpiStoreF64 {
   double* C; long long ldc;
   __device__ __forceinline__ void operator()(int m, int n0, const double (&v)[8], int M, int N) const {
     double* p = C + (long long)m * ldc + n0;
-    if (n0 + 8 <= N) {
+    if (n0 + 8 <= N && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {   // odd ldc: rows alternate in alignment
 #pragma unroll
       for (int q = 0; q < 8; q += 2) *reinterpret_cast<double2*>(p + q) = make_double2(v[q], v[q + 1]);
     } else {
@@ -196,7 +221,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tmem_full_bar, 1);
-    mbar_init(&tmem_empty_bar, 4);   // one arrival per epilogue warp
+    mbar_init(&tmem_empty_bar, EPI_WARPS);   // one arrival per epilogue warp
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_s, tmem_cols);
@@ -270,8 +295,10 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       acc_phase ^= 1;
     }
   } else {
-    // ================================================================= epilogue (warps 2..5)
+    // ================================================================= epilogue (warps 2..)
     const int lg = warp & 3;                          // TMEM lane group this warp may access
+    const int chunk0 = ((warp - 2) >> 2) * 8;         // first 8-column chunk of this warp
+    constexpr int chunk_step = 8 * (EPI_WARPS / 4);
     uint32_t acc_phase = 0;
     const double w_hi = scalbn(1.0, -7 * ((T < 4 ? T : 4) - 1)), w_lo = scalbn(1.0, -7 * (T - 1));
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -281,7 +308,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&tmem_full_bar, acc_phase);
       tc_fence_after();
       const double sa = (m < g.M) ? g.sA[m] : 0.0;
-      for (int c0 = 0; c0 < ((g.dbg & 1) ? 0 : n_mma); c0 += 8) {
+      for (int c0 = chunk0; c0 < ((g.dbg & 1) ? 0 : n_mma); c0 += chunk_step) {
         int32_t a[MAX_SLICES][8];
 #pragma unroll
         for (int d = 0; d < MAX_SLICES; ++d)

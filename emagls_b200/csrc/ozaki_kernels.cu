@@ -37,15 +37,9 @@ struct EpiPhaseSlice {
       if (nyquist) ti = 0.0;
       const int si = (set * 2 + ear) * scale_stride;
       const double u = up[si];
-      double a = tr * u, b = ti * u;          // |a|, |b| <= 64 (u = 2^(6-e), 2^e > max_d |H_k|)
-      int8_t* p = Tq + (long long)n * Kpad + m;
-#pragma unroll
-      for (int s = 0; s < T; ++s) {
-        const double qa = rint(a), qb = rint(b);
-        p[(long long)s * slice_stride] = (int8_t)(int)qa;
-        p[(long long)s * slice_stride + Kpad] = (int8_t)(int)qb;
-        a = (a - qa) * 128.0; b = (b - qb) * 128.0;
-      }
+      int8_t* p = Tq + (long long)n * Kpad + m;   // |tr u|, |ti u| <= 64 (u = 2^(6-e), 2^e > max_d |H_k|)
+      oz::slice_digits<T>(tr * u, [&](int s, int q_) { p[(long long)s * slice_stride] = (int8_t)q_; });
+      oz::slice_digits<T>(ti * u, [&](int s, int q_) { p[(long long)s * slice_stride + Kpad] = (int8_t)q_; });
       if (m == 0) { const double s_ = sc[si]; sT[n] = s_; sT[n + 1] = s_; }
     }
   }
@@ -82,7 +76,13 @@ int oz_pad32(int k) { return (k + 31) & ~31; }
 
 cudaError_t launch_slice_rows(cudaStream_t st, const double* src, long long rs, long long cs, int R, int K, int Kpad,
                               int T, int8_t* out, double* scale) {
-  oz::slice_rows_kernel<<<(R + 7) / 8, 256, 0, st>>>(src, rs, cs, R, K, Kpad, T, out, scale);
+  const dim3 grid((R + 7) / 8), block(256);
+  switch (T) {
+    case 6: oz::slice_rows_kernel<6><<<grid, block, 0, st>>>(src, rs, cs, R, K, Kpad, out, scale); break;
+    case 7: oz::slice_rows_kernel<7><<<grid, block, 0, st>>>(src, rs, cs, R, K, Kpad, out, scale); break;
+    case 8: oz::slice_rows_kernel<8><<<grid, block, 0, st>>>(src, rs, cs, R, K, Kpad, out, scale); break;
+    default: return cudaErrorInvalidValue;
+  }
   return cudaGetLastError();
 }
 

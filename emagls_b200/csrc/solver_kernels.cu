@@ -31,19 +31,23 @@ size_t factor_smem_bytes(const BlockPlan& bp) {
   return (size_t)bp.MC * (bp.MC + bp.RB) * sizeof(cplx) + (size_t)(2 * bp.MC + 72) * sizeof(cplx) + 256;
 }
 
-__device__ __forceinline__ cplx gsum8(cplx v, unsigned mask) {
+template <int GW>
+__device__ __forceinline__ cplx gsum(cplx v, unsigned mask) {
 #pragma unroll
-  for (int m = 4; m > 0; m >>= 1) {
+  for (int m = GW / 2; m > 0; m >>= 1) {
     v.x += __shfl_xor_sync(mask, v.x, m);
     v.y += __shfl_xor_sync(mask, v.y, m);
   }
   return v;
 }
-__device__ __forceinline__ double gsum8(double v, unsigned mask) {
+template <int GW>
+__device__ __forceinline__ double gsum(double v, unsigned mask) {
 #pragma unroll
-  for (int m = 4; m > 0; m >>= 1) v += __shfl_xor_sync(mask, v, m);
+  for (int m = GW / 2; m > 0; m >>= 1) v += __shfl_xor_sync(mask, v, m);
   return v;
 }
+__device__ __forceinline__ cplx gsum8(cplx v, unsigned mask) { return gsum<8>(v, mask); }
+__device__ __forceinline__ double gsum8(double v, unsigned mask) { return gsum<8>(v, mask); }
 // Householder reflector scalars for a column with pivot alpha and squared tail norm xn (LAPACK
 // zlarfg conventions: beta real, H = I - tau v v^H, v = [1; sc * x]).  The tail x is left unscaled in
 // shared memory; sc is applied on the fly and when the reflector is flushed.
@@ -64,11 +68,58 @@ __device__ __forceinline__ void reflector_scalars(cplx alpha, double xn, double*
   *sc_out = mk(d.x * id2, -d.y * id2);                 // 1 / (alpha - beta)
 }
 
+// One Householder step of qr_block with groups of GW lanes per trailing column: apply reflector j to
+// the columns c > j; the group of column j+1 accumulates the tail norm of its updated column inside
+// the update loop and produces the next reflector's scalars.
+template <int GW>
+__device__ __forceinline__ void qr_step(cplx* Wk, int LD, int Mc, bool first, int hi, int j, cplx* tau_s, cplx* sc_s) {
+  const int tid = threadIdx.x, group = tid / GW, rl = tid % GW;
+  const unsigned gmask = (GW == 32) ? 0xffffffffu : (((1u << GW) - 1u) << (threadIdx.x & (32 - GW) & 31));
+  const int lo = first ? j + 1 : Mc;
+  const cplx tau = tau_s[j], sc = sc_s[j];
+  const cplx* v = Wk + (size_t)j * LD;
+  const bool active = (tau.x != 0.0 || tau.y != 0.0);
+  for (int c = j + 1 + group; c < Mc; c += FT / GW) {
+    cplx* a = Wk + (size_t)c * LD;
+    const bool next = (c == j + 1);
+    const int lo_next = first ? j + 2 : Mc;    // tail of column j+1 once it becomes the pivot column
+    double xn = 0.0;
+    if (active) {
+      cplx w = mk(0.0, 0.0);
+      for (int i = lo + rl; i < hi; i += GW) cfmac(w, v[i], a[i]);
+      w = gsum<GW>(w, gmask);
+      w = cmulc(w, sc);                          // conj(sc) * (x^H a)  ->  (sc x)^H a
+      const cplx aj = a[j];
+      w = cadd(w, aj);
+      const cplx f = cmul(cconj(tau), w);        // H^H = I - conj(tau) v v^H
+      const cplx fs = cmul(f, sc);
+      if (rl == 0) a[j] = csub(aj, f);
+      for (int i = lo + rl; i < hi; i += GW) {
+        cplx ai = a[i];
+        cfms(ai, fs, v[i]);
+        a[i] = ai;
+        if (next && i >= lo_next) xn += cabs2(ai);
+      }
+    } else if (next) {
+      for (int i = lo_next + rl; i < hi; i += GW) xn += cabs2(a[i]);
+    }
+    if (next) {
+      xn = gsum<GW>(xn, gmask);
+      __syncwarp(gmask);
+      if (rl == 0) {
+        double beta; cplx t2, s2;
+        reflector_scalars(a[j + 1], xn, &beta, &t2, &s2);
+        a[j + 1] = mk(beta, 0.0); tau_s[j + 1] = t2; sc_s[j + 1] = s2;
+      }
+    }
+  }
+}
+
 // In-place QR of one block held in shared memory (column-major, leading dimension LD).
 // first: rows [0, nrows) dense;  otherwise: upper-triangular top (Mc rows) + dense rows [Mc, Mc+nb).
-// Groups of 8 lanes own one trailing column each; the group of column j+1 accumulates the tail norm
-// of its updated column inside the update loop, so the per-step critical path is one fused
-// dot/update pass, two 8-lane reductions and the reflector scalars.
+// Groups of 8 lanes own one trailing column each (16 / 32 lanes once no more than 16 / 8 columns
+// remain), so the per-step critical path is one fused dot/update pass, two group reductions and the
+// reflector scalars.
 __device__ void qr_block(cplx* Wk, int LD, int Mc, bool first, int hi, cplx* tau_s, cplx* sc_s) {
   const int tid = threadIdx.x, group = tid >> 3, rl = tid & 7;
   const unsigned gmask = 0xffu << (threadIdx.x & 24);
@@ -84,44 +135,10 @@ __device__ void qr_block(cplx* Wk, int LD, int Mc, bool first, int hi, cplx* tau
   }
   __syncthreads();
   for (int j = 0; j < Mc; ++j) {
-    const int lo = first ? j + 1 : Mc;
-    const cplx tau = tau_s[j], sc = sc_s[j];
-    const cplx* v = Wk + (size_t)j * LD;
-    const bool active = (tau.x != 0.0 || tau.y != 0.0);
-    for (int c = j + 1 + group; c < Mc; c += FT / 8) {
-      cplx* a = Wk + (size_t)c * LD;
-      const bool next = (c == j + 1);
-      const int lo_next = first ? j + 2 : Mc;    // tail of column j+1 once it becomes the pivot column
-      double xn = 0.0;
-      if (active) {
-        cplx w = mk(0.0, 0.0);
-        for (int i = lo + rl; i < hi; i += 8) cfmac(w, v[i], a[i]);
-        w = gsum8(w, gmask);
-        w = cmulc(w, sc);                          // conj(sc) * (x^H a)  ->  (sc x)^H a
-        const cplx aj = a[j];
-        w = cadd(w, aj);
-        const cplx f = cmul(cconj(tau), w);        // H^H = I - conj(tau) v v^H
-        const cplx fs = cmul(f, sc);
-        if (rl == 0) a[j] = csub(aj, f);
-        for (int i = lo + rl; i < hi; i += 8) {
-          cplx ai = a[i];
-          cfms(ai, fs, v[i]);
-          a[i] = ai;
-          if (next && i >= lo_next) xn += cabs2(ai);
-        }
-      } else if (next) {
-        for (int i = lo_next + rl; i < hi; i += 8) xn += cabs2(a[i]);
-      }
-      if (next) {
-        xn = gsum8(xn, gmask);
-        __syncwarp(gmask);
-        if (rl == 0) {
-          double beta; cplx t2, s2;
-          reflector_scalars(a[j + 1], xn, &beta, &t2, &s2);
-          a[j + 1] = mk(beta, 0.0); tau_s[j + 1] = t2; sc_s[j + 1] = s2;
-        }
-      }
-    }
+    const int rem = Mc - 1 - j;
+    if (rem > FT / 16) qr_step<8>(Wk, LD, Mc, first, hi, j, tau_s, sc_s);
+    else if (rem > FT / 32) qr_step<16>(Wk, LD, Mc, first, hi, j, tau_s, sc_s);
+    else qr_step<32>(Wk, LD, Mc, first, hi, j, tau_s, sc_s);
     __syncthreads();
   }
 }
@@ -268,14 +285,18 @@ factor_kernel(BlockPlan bp, RowSource src, OperatorSet ops, int kbase, int G, do
     for (int idx = tid; idx < MC * MC; idx += FT) Js[idx] = mk((idx / MC == idx % MC) ? 1.0 : 0.0, 0.0);
     __syncthreads();
     const int ne = (Mc + 1) & ~1;  // even number of players (index Mc is a dummy when Mc is odd)
-    const double tol = 2.220446049250313e-16 * sqrt((double)Mc);
+    const double tol2 = 4.930380657631324e-32 * (double)Mc;   // (eps sqrt(Mc))^2
     // one pair per half-warp: 16 lanes x (MC/16) rows, 4-step reductions; the 2 * FT/32 half-warps
     // cover the ne/2 pairs of a round-robin round in one pass for Mc <= 32
     constexpr int RPL = MC / 16;   // rows per lane
     const int half = lane >> 4, hl = lane & 15;
     const unsigned hmask = 0xffffu << (16 * half);
+    // Rotation scalars without divisions by |g| (t ph = 2 g sign(d) / (|d| + sqrt(d^2 + 4 |g|^2)),
+    // d = b - a): one rsqrt-based square root, one reciprocal, one rsqrt.  A sweep whose largest
+    // cosine stayed below 1e-9 leaves every pair orthogonal to ~30 * 1e-18 << tol (quadratic
+    // convergence), so no trailing check sweep is run after it.
     for (sweeps = 1; sweeps <= 40; ++sweeps) {
-      int rotated = 0;
+      int big = 0;
       for (int r = 0; r < ne - 1; ++r) {
         for (int pi = warp * 2 + half; pi < ne / 2; pi += FT / 16) {
           int p, q;
@@ -297,15 +318,17 @@ factor_kernel(BlockPlan bp, RowSource src, OperatorSet ops, int kbase, int G, do
             a += __shfl_xor_sync(hmask, a, sft); b += __shfl_xor_sync(hmask, b, sft);
             g.x += __shfl_xor_sync(hmask, g.x, sft); g.y += __shfl_xor_sync(hmask, g.y, sft);
           }
-          double ag = sqrt(cabs2(g));
-          if (ag > tol * sqrt(a * b) && ag > 0.0) {
-            rotated = 1;
-            cplx ph = mk(g.x / ag, g.y / ag);
-            double zeta = (b - a) / (2.0 * ag);
-            double tt = ((zeta >= 0.0) ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-            double cs = 1.0 / sqrt(1.0 + tt * tt), sn = cs * tt;
-            cplx sph = cscale(ph, sn);            // s * ph
-            cplx sphc = mk(sph.x, -sph.y);        // s * conj(ph)
+          const double gg = cabs2(g), ab = a * b;
+          if (gg > tol2 * ab && gg > 0.0) {
+            if (gg > 1e-18 * ab) big = 1;
+            const double d = b - a;
+            const double s2 = fma(d, d, 4.0 * gg);
+            const double root = s2 * rsqrt(s2);
+            const double rden = __drcp_rn(fabs(d) + root);
+            const double tw = copysign(2.0 * rden, d);        // t / |g|, signed
+            const double cs = rsqrt(fma(tw * tw, gg, 1.0));    // 1 / sqrt(1 + t^2)
+            const cplx sph = cscale(g, cs * tw);              // s * ph
+            const cplx sphc = mk(sph.x, -sph.y);              // s * conj(ph)
 #pragma unroll
             for (int u = 0; u < RPL; ++u) {
               int row = hl + 16 * u;
@@ -321,7 +344,7 @@ factor_kernel(BlockPlan bp, RowSource src, OperatorSet ops, int kbase, int G, do
         }
         __syncthreads();
       }
-      if (!__syncthreads_or(rotated)) break;
+      if (!__syncthreads_or(big)) break;
     }
     // singular values = column norms of X; gains 1/(s * max(s, c*smax))
     double* sv = reinterpret_cast<double*>(bn_s);  // reuse (>= 64 doubles)

@@ -43,8 +43,13 @@ int run(int M, int N, int K, int T, int reps, int grade, int dbg = 0) {
   CK(cudaMemcpy(dA, hA.data(), hA.size() * 8, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dB, hB.data(), hB.size() * 8, cudaMemcpyHostToDevice));
   CK(cudaMemset(dC, 0xff, (size_t)M * N * 8));
-  slice_rows_kernel<<<(M + 7) / 8, 256>>>(dA, K, 1, M, K, Kpad, T, qA, sA);
-  slice_rows_kernel<<<(N + 7) / 8, 256>>>(dB, K, 1, N, K, Kpad, T, qB, sB);
+  auto slice = [&](const double* d, int R, int8_t* q, double* sc) {
+    if (T == 6) slice_rows_kernel<6><<<(R + 7) / 8, 256>>>(d, K, 1, R, K, Kpad, q, sc);
+    else if (T == 7) slice_rows_kernel<7><<<(R + 7) / 8, 256>>>(d, K, 1, R, K, Kpad, q, sc);
+    else slice_rows_kernel<8><<<(R + 7) / 8, 256>>>(d, K, 1, R, K, Kpad, q, sc);
+  };
+  slice(dA, M, qA, sA);
+  slice(dB, N, qB, sB);
   CK(cudaGetLastError());
   ref_gemm<<<dim3((N + 127) / 128, M), 128>>>(dA, dB, M, N, K, dR, dNrm);
   CK(cudaGetLastError());
