@@ -21,6 +21,12 @@ class Config(C.Structure):
                 ("reserved", C.c_int * 6)]
 
 
+class RadialParams(C.Structure):
+    """struct emagls_radial_params (include/emagls_cuda.h)."""
+    _fields_ = [("kind", C.c_int), ("regul_const", C.c_double), ("noise_gain_db", C.c_double),
+                ("array_type", C.c_int)]
+
+
 _DESIGN_ARGS = [C.c_void_p, C.POINTER(Config), c_dp, c_dp, C.c_int, C.c_int, c_dp, c_dp, C.c_double, c_dp, c_dp,
                 C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp]
 
@@ -55,6 +61,33 @@ SIGNATURES = {
     "emagls_get_sh": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, C.c_int, C.c_int, c_dp]),
     "emagls_sph_modal_coeffs": (C.c_int, [C.c_void_p, C.c_int, c_dp, C.c_int, C.c_int, c_dp]),
     "emagls_regularized_apply": (C.c_int, [C.c_void_p, c_dp, C.c_int, C.c_int, c_dp, C.c_int, C.c_double, c_dp]),
+    # ---- SURVEY.md section 8(f) rows (frontend.cu)
+    "emagls_radial_params_default": (None, [C.POINTER(RadialParams)]),
+    "emagls_radial_filter": (C.c_int, [C.c_void_p, C.POINTER(Config), C.POINTER(RadialParams), C.c_int, C.c_double,
+                                       C.c_double, C.c_int, c_dp]),
+    "emagls_apply_radial_filter_rows": (C.c_longlong, [C.c_longlong, C.c_int]),
+    "emagls_apply_radial_filter": (C.c_int, [C.c_void_p, C.POINTER(Config), C.POINTER(RadialParams), c_dp,
+                                             C.c_longlong, C.c_int, C.c_double, C.c_double, C.c_int, c_dp]),
+    "emagls_apply_radial_filter_dev": (C.c_int, [C.c_void_p, C.POINTER(Config), C.POINTER(RadialParams), c_dp,
+                                                 C.c_longlong, C.c_int, C.c_double, C.c_double, C.c_int, c_dp]),
+    "emagls_smair_matrix_radial": (C.c_int, [C.c_void_p, C.POINTER(Config), C.POINTER(RadialParams), c_dp, c_dp,
+                                             C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, c_dp,
+                                             C.POINTER(C.c_int)]),
+    "emagls_sh_encode": (C.c_int, [C.c_void_p, C.POINTER(Config), c_dp, C.c_longlong, C.c_int, c_dp, c_dp, C.c_int,
+                                   c_dp]),
+    "emagls_sh_encode_dev": (C.c_int, [C.c_void_p, C.POINTER(Config), c_dp, C.c_longlong, C.c_int, c_dp, c_dp,
+                                       C.c_int, c_dp]),
+    "emagls_ch_encode": (C.c_int, [C.c_void_p, C.POINTER(Config), c_dp, C.c_longlong, C.c_int, c_dp, C.c_int, c_dp]),
+    "emagls_rotate_sh": (C.c_int, [C.c_void_p, c_dp, C.c_longlong, C.c_int, C.c_double, C.c_double, C.c_double,
+                                   c_dp]),
+    "emagls_rotate_sh_dev": (C.c_int, [C.c_void_p, c_dp, C.c_longlong, C.c_int, C.c_double, C.c_double, C.c_double,
+                                       c_dp]),
+    "emagls_design_magls_2d": (C.c_int, [C.c_void_p, C.POINTER(Config), c_dp, c_dp, C.c_int, C.c_int, c_dp, C.c_int,
+                                         C.c_double, C.c_int, c_dp, c_dp, c_dp]),
+    "emagls_spherical_head_filter": (C.c_int, [C.c_void_p, C.POINTER(Config), C.c_double, C.c_int, C.c_double,
+                                               C.c_int, c_dp, c_dp]),
+    "emagls_array_diffuse_filter": (C.c_int, [C.c_void_p, C.POINTER(Config), C.c_double, c_dp, c_dp, C.c_int,
+                                              C.c_int, C.c_double, C.c_int, c_dp]),
 }
 
 _lib = None

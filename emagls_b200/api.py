@@ -19,12 +19,13 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import Config, EmaglsError, Handle, default_handle  # noqa: F401
+from ._lib import Config, EmaglsError, Handle, RadialParams, default_handle  # noqa: F401
 
 __all__ = ["getEMagLs2Filters", "getEMagLsFilters", "getMagLsFilters", "getLsFilters",
            "getEMagLsFiltersFromAtf", "getEMagLsFiltersEMAinCH", "getEMagLsFiltersEMAinSH",
            "getSMAIRMatrix", "binauralDecode", "getSH", "sphModalCoeffs", "regularizedApply",
-           "Handle", "EmaglsError"]
+           "getRadialFilter", "applyRadialFilter", "encodeSH", "encodeCH", "rotateSH", "getMagLsFilters2D",
+           "getMagLsSphericalHeadFilter", "getMagLsArrayDiffuseFilter", "Handle", "EmaglsError"]
 
 
 def _f(x):
@@ -277,9 +278,7 @@ def getSMAIRMatrix(params: dict, *, handle=None):
     p.setdefault("shDefinition", "real")
     p["sourceDist"] = float(np.linalg.norm(p["sourcePosCart"]))
     _check_sh_function(p.get("shFunction"))
-    if str(p["radialFilter"]).lower() != "none" and not p["returnRawMicSigs"]:
-        raise NotImplementedError("Unkown radialFilter on the device path: only 'none' is built "
-                                  "(getRadialFilter is a 'next' row, SURVEY.md 8(f))")
+    radial = str(p["radialFilter"]).lower() != "none" and not p["returnRawMicSigs"]
     if p["arrayType"] not in ("rigid", "open"):
         raise ValueError("Wrong array type")
     h = handle or default_handle()
@@ -297,6 +296,12 @@ def getSMAIRMatrix(params: dict, *, handle=None):
     rows = maz.size if raw else (int(p["order"]) + 1) ** 2
     K = nfft // 2 + 1
     out = np.zeros((rows, S, K), dtype=np.complex128, order="F")
+    if radial:   # getSMAIRMatrix.m:129-139
+        rp = _radial_params(h, p)
+        h.check(h.lib.emagls_smair_matrix_radial(h.ptr, C.byref(cfg), C.byref(rp), _p(maz), _p(mze), maz.size,
+                                                 int(p["order"]), float(p["fs"]), float(p["smaRadius"]), nfft,
+                                                 _p(out), C.byref(simN)))
+        return out, p
     h.check(h.lib.emagls_smair_matrix(h.ptr, C.byref(cfg), _p(maz), _p(mze), maz.size, int(p["order"]),
                                       float(p["fs"]), float(p["smaRadius"]), nfft, raw, _p(out), C.byref(simN)))
     return out, p
@@ -324,6 +329,153 @@ def binauralDecode(inp, inFs, decodingFilterLeft, decodingFilterRight, decodingF
     h.check(h.lib.emagls_binaural_decode(h.ptr, _p(x), n, ch, _p(wL), _p(wR), ln, 1 if compensateDelay else 0,
                                          _p(out)))
     return out
+
+
+# ---- callers either side of the hot path --------------------------------
+_RADIAL_KINDS = {"none": 0, "tikhonov": 1, "softlimit": 2, "full": 3}
+
+
+def _radial_params(h, p) -> RadialParams:
+    rp = RadialParams()
+    h.lib.emagls_radial_params_default(C.byref(rp))
+    kind = str(p.get("radialFilter", "tikhonov")).lower()
+    if kind not in _RADIAL_KINDS:
+        raise ValueError(f'Unkown radialFilter parameter "{p.get("radialFilter")}".')   # getRadialFilter.m:65
+    if str(p.get("waveModel", "planeWave")).lower() == "pointsource" and kind != "none":
+        raise NotImplementedError('WaveModel parameter "pointSource" not yet implemented.')   # :37-40
+    at = p.get("arrayType", "rigid")
+    if at not in ("rigid", "open"):
+        raise ValueError("Wrong array type")
+    rp.kind = _RADIAL_KINDS[kind]
+    rp.regul_const = float(p.get("regulConst", 1e-2))
+    if kind == "softlimit":
+        rp.noise_gain_db = float(p["noiseGainDb"])
+    rp.array_type = 0 if at == "rigid" else 1
+    return rp
+
+
+def getRadialFilter(params: dict, *, handle=None):
+    """radFilts = getRadialFilter(params) -- dependencies/getRadialFilter.m:1 ([nfft/2+1, order+1])."""
+    h = handle or default_handle()
+    p = dict(params)
+    nfft = int(p.get("oversamplingFactor", 2) * p.get("irLen", 256))
+    rp = _radial_params(h, p)
+    N = int(p["order"])
+    out = np.zeros((nfft // 2 + 1, N + 1), dtype=np.complex128, order="F")
+    cfg = h.default_config()
+    h.check(h.lib.emagls_radial_filter(h.ptr, C.byref(cfg), C.byref(rp), N, float(p["fs"]), float(p["smaRadius"]),
+                                       nfft, _p(out)))
+    return out.real.copy() if rp.kind == 0 else out
+
+
+def applyRadialFilter(inSig, params: dict, *, handle=None):
+    """sigFiltered = applyRadialFilter(inSig, params) -- dependencies/applyRadialFilter.m:1."""
+    h = handle or default_handle()
+    p = dict(params)
+    rp = _radial_params(h, p)
+    N = int(p["order"])
+    nfft = int(p["nfft"])
+    if nfft != int(p.get("oversamplingFactor", 2) * p.get("irLen", 256)):
+        raise ValueError("params.nfft must equal oversamplingFactor * irLen (the reference would fail in "
+                         "applySubsampleDelay otherwise)")
+    x = _f(inSig)
+    if x.ndim != 2 or x.shape[1] != (N + 1) ** 2:
+        raise ValueError("inSig must be [samples, (order+1)^2]")
+    rows = int(h.lib.emagls_apply_radial_filter_rows(x.shape[0], nfft))
+    out = np.zeros((rows, x.shape[1]), order="F")
+    cfg = h.default_config()
+    h.check(h.lib.emagls_apply_radial_filter(h.ptr, C.byref(cfg), C.byref(rp), _p(x), x.shape[0], N, float(p["fs"]),
+                                             float(p["smaRadius"]), nfft, _p(out)))
+    return out
+
+
+def encodeSH(sig, micGridAziRad, micGridZenRad, order, shDefinition="real", shFunction=None, *, handle=None):
+    """shRecording = sig * pinv(getSH(order, [azi zen], shDefinition).')  -- verifyEMagLs.m:235-236."""
+    _check_sh_function(shFunction)
+    h = handle or default_handle()
+    cfg = _config(h, None, shDefinition)
+    x = _f(sig)
+    maz, mze = _vec(micGridAziRad), _vec(micGridZenRad)
+    if x.ndim != 2 or x.shape[1] != maz.size or mze.size != maz.size:
+        raise ValueError("sig must be [samples, mics]")
+    out = np.zeros((x.shape[0], (int(order) + 1) ** 2), dtype=np.complex128 if cfg.basis else np.float64, order="F")
+    h.check(h.lib.emagls_sh_encode(h.ptr, C.byref(cfg), _p(x), x.shape[0], maz.size, _p(maz), _p(mze), int(order),
+                                   _p(out)))
+    return out
+
+
+def encodeCH(sig, micGridAziRad, order, chDefinition="real", *, handle=None):
+    """chSig = sig * pinv(getCH(order, azi, chDefinition).')  -- testEMagLs.m:99-102."""
+    h = handle or default_handle()
+    cfg = _config(h, None, chDefinition)
+    x = _f(sig)
+    maz = _vec(micGridAziRad)
+    if x.ndim != 2 or x.shape[1] != maz.size:
+        raise ValueError("sig must be [samples, mics]")
+    out = np.zeros((x.shape[0], 2 * int(order) + 1), dtype=np.complex128 if cfg.basis else np.float64, order="F")
+    h.check(h.lib.emagls_ch_encode(h.ptr, C.byref(cfg), _p(x), x.shape[0], maz.size, _p(maz), int(order), _p(out)))
+    return out
+
+
+def rotateSH(sig, yawRad, pitchRad=0.0, rollRad=0.0, *, handle=None):
+    """rotateHOA_N3D(sig, yaw, pitch, roll) as called at dependencies/binauralDecode.m:26-30 (radians)."""
+    h = handle or default_handle()
+    x = _f(sig)
+    N = int(round(np.sqrt(x.shape[1]))) - 1
+    if x.ndim != 2 or (N + 1) ** 2 != x.shape[1]:
+        raise ValueError("sig must be [samples, (order+1)^2]")
+    out = np.zeros_like(x, order="F")
+    h.check(h.lib.emagls_rotate_sh(h.ptr, _p(x), x.shape[0], N, float(yawRad), float(pitchRad), float(rollRad),
+                                   _p(out)))
+    return out
+
+
+def getMagLsFilters2D(hLHor, hRHor, horHrirGridAziRad, order, fs, len, chDefinition="real", *, handle=None,
+                      config=None, return_spectra=False):
+    """[wMlsL, wMlsR] = getMagLsFilters2D(...)  -- lib/getMagLsFilters2D.m:1."""
+    h = handle or default_handle()
+    cfg = _config(h, config, chDefinition)
+    hL, hR, T, D, sets = _prep_hrirs(hLHor, hRHor)
+    if sets != 1:
+        raise ValueError("getMagLsFilters2D is not batched")
+    az = _vec(horHrirGridAziRad)
+    if az.size != D:
+        raise ValueError("HRIR grid size does not match hLHor")
+    H = 2 * int(order) + 1
+    K = min(cfg.nfft_max_len, 2 * int(len)) // 2 + 1
+    odt = np.complex128 if cfg.basis == 1 else np.float64
+    wL = np.zeros((int(len), H), dtype=odt, order="F")
+    wR = np.zeros((int(len), H), dtype=odt, order="F")
+    sp = np.zeros((K, H, 2), dtype=np.complex128, order="F") if return_spectra else None
+    h.check(h.lib.emagls_design_magls_2d(h.ptr, C.byref(cfg), _p(hL), _p(hR), T, D, _p(az), int(order), float(fs),
+                                         int(len), _p(wL), _p(wR), _p(sp)))
+    return (wL, wR, sp) if return_spectra else (wL, wR)
+
+
+def getMagLsSphericalHeadFilter(micRadius, order, fs, len, *, handle=None, config=None):
+    """[wShf, W_Shf] = getMagLsSphericalHeadFilter(micRadius, order, fs, len)
+    -- lib/getMagLsSphericalHeadFilter.m:1."""
+    h = handle or default_handle()
+    cfg = config if config is not None else h.default_config()
+    nfft = min(cfg.nfft_max_len, 2 * int(len))
+    w = np.zeros(int(len))
+    W = np.zeros(nfft)
+    h.check(h.lib.emagls_spherical_head_filter(h.ptr, C.byref(cfg), float(micRadius), int(order), float(fs),
+                                               int(len), _p(w), _p(W)))
+    return w, W
+
+
+def getMagLsArrayDiffuseFilter(micRadius, micGridAziRad, micGridZenRad, order, fs, len, shDefinition="real",
+                               shFunction=None, *, handle=None, config=None):
+    """wAdf = getMagLsArrayDiffuseFilter(...)  -- lib/getMagLsArrayDiffuseFilter.m:1."""
+    _check_sh_function(shFunction)
+    h = handle or default_handle()
+    cfg = _config(h, config, shDefinition)
+    maz, mze = _vec(micGridAziRad), _vec(micGridZenRad)
+    w = np.zeros(int(len))
+    h.check(h.lib.emagls_array_diffuse_filter(h.ptr, C.byref(cfg), float(micRadius), _p(maz), _p(mze), maz.size,
+                                              int(order), float(fs), int(len), _p(w)))
+    return w
 
 
 # ---- building blocks (each mirrors one reference function) -------------------------------------

@@ -37,6 +37,7 @@ int emagls_destroy(emagls_handle h) {
   cudaStreamSynchronize(h->stream);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   emagls::destroy_render_plans(h);
+  emagls::destroy_fir_plans(h);
   cudaStreamDestroy(h->stream);
   delete h;
   return EMAGLS_OK;
@@ -306,9 +307,26 @@ __global__ void unit_rows_kernel(double* rows, int npair, int D) {
   rows[idx] = ((row & 1) == 0 && (row >> 1) == d) ? 1.0 : 0.0;
 }
 
-int emagls_smair_matrix(emagls_handle h, const emagls_config* cfg, const double* mic_azi,
-                        const double* mic_zen, int num_mics, int order, double fs, double sma_radius,
-                        int nfft, int return_raw_mic_sigs, double* out, int* sim_order_out) {
+// smairMat(r, :, k) *= rad(k, ord(r)), and once more by real(rad) at the Nyquist bin
+// (getSMAIRMatrix.m:131-138: the k == numPosFreqs branch multiplies the already filtered page again)
+__global__ void smair_radial_kernel(cplx* __restrict__ out, const cplx* __restrict__ rad, int rows, int S, int K,
+                                    int L1) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)K * S * rows) return;
+  const int r = (int)(idx % rows);
+  const int k = (int)(idx / ((long long)rows * S));
+  int ord = (int)sqrt((double)r);
+  while ((ord + 1) * (ord + 1) <= r) ++ord;
+  while (ord * ord > r) --ord;
+  const cplx f = rad[(long long)k * L1 + ord];
+  cplx v = cmul(f, out[idx]);
+  if (k == K - 1) v = mk(f.x * v.x, f.x * v.y);
+  out[idx] = v;
+}
+
+static int smair_impl(emagls_handle h, const emagls_config* cfg, const emagls_radial_params* rp, const double* mic_azi,
+                      const double* mic_zen, int num_mics, int order, double fs, double sma_radius,
+                      int nfft, int return_raw_mic_sigs, double* out, int* sim_order_out) {
   return guarded(h, [&] {
     EM_REQUIRE(cfg && mic_azi && mic_zen && num_mics > 0, "null argument");
     EM_REQUIRE(nfft > 0 && nfft % 2 == 0, "nfft must be even");  // getSMAIRMatrix.m:89
@@ -359,7 +377,55 @@ int emagls_smair_matrix(emagls_handle h, const emagls_config* cfg, const double*
     smair_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Yrows, bn, rows, S, simN, K, d_out);
     EM_CUDA(cudaGetLastError());
     h->launches += 1;
+    if (rp && rp->kind != EMAGLS_RADIAL_NONE && !return_raw_mic_sigs) {
+      cplx* rad = ar.get<cplx>((size_t)K * (order + 1));
+      radial_filter_dev(h, ar, *cfg, *rp, order, fs, sma_radius, nfft, 0, rad);
+      smair_radial_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_out, rad, rows, S, K, order + 1);
+      EM_CUDA(cudaGetLastError());
+      h->launches += 1;
+    }
     EM_CUDA(cudaMemcpyAsync(out, d_out, (size_t)total * sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+int emagls_smair_matrix(emagls_handle h, const emagls_config* cfg, const double* mic_azi,
+                        const double* mic_zen, int num_mics, int order, double fs, double sma_radius,
+                        int nfft, int return_raw_mic_sigs, double* out, int* sim_order_out) {
+  return smair_impl(h, cfg, nullptr, mic_azi, mic_zen, num_mics, order, fs, sma_radius, nfft, return_raw_mic_sigs,
+                    out, sim_order_out);
+}
+
+int emagls_smair_matrix_radial(emagls_handle h, const emagls_config* cfg, const emagls_radial_params* rp,
+                               const double* mic_azi, const double* mic_zen, int num_mics, int order, double fs,
+                               double sma_radius, int nfft, double* out, int* sim_order_out) {
+  if (!h) return EMAGLS_ERR_INVALID;
+  if (!rp || rp->kind < EMAGLS_RADIAL_NONE || rp->kind > EMAGLS_RADIAL_FULL) {
+    h->err = "Unkown radialFilter parameter";   // getRadialFilter.m:65
+    return EMAGLS_ERR_INVALID;
+  }
+  return smair_impl(h, cfg, rp, mic_azi, mic_zen, num_mics, order, fs, sma_radius, nfft, 0, out, sim_order_out);
+}
+
+int emagls_design_magls_2d(emagls_handle h, const emagls_config* cfg, const double* hL, const double* hR,
+                           int num_samples, int num_dirs, const double* grid_azi, int order, double fs, int len,
+                           double* wL, double* wR, double* spectra) {
+  return guarded(h, [&] {
+    EM_REQUIRE(cfg && hL && hR && grid_azi && wL && wR, "null argument");
+    EM_REQUIRE(num_samples > 0 && num_dirs > 0 && len > 0 && order >= 0, "empty input");
+    cudaStream_t st = h->stream;
+    Arena ar(st);
+    const int T = num_samples, D = num_dirs, Mc = 2 * order + 1;
+    const int K = std::min(cfg->nfft_max_len, 2 * len) / 2 + 1;
+    const size_t wn = (size_t)len * Mc * (cfg->basis == EMAGLS_BASIS_COMPLEX ? 2 : 1);
+    double* d_wL = ar.get<double>(wn);
+    double* d_wR = ar.get<double>(wn);
+    double* d_sp = spectra ? ar.get<double>((size_t)2 * K * Mc * 2) : nullptr;
+    design_magls(h, *cfg, ar.upload(hL, (size_t)T * D), ar.upload(hR, (size_t)T * D), T, D, ar.upload(grid_azi, D),
+                 nullptr, order, fs, len, false, d_wL, d_wR, d_sp, 1);
+    EM_CUDA(cudaMemcpyAsync(wL, d_wL, wn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaMemcpyAsync(wR, d_wR, wn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (spectra) EM_CUDA(cudaMemcpyAsync(spectra, d_sp, (size_t)2 * K * Mc * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     EM_CUDA(cudaStreamSynchronize(st));
   });
 }

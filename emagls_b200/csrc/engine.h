@@ -43,6 +43,9 @@ struct emagls_ctx {
     int edge = 0;                     // one boundary block of every channel (zero-padded staging)
     std::vector<std::pair<int, int>> direct;  // (batch, plan): interior blocks read straight from the input
   } render_plans;
+  // per-channel FIR of the front end (frontend.cu): cuFFT plans keyed by (size, batch, direction)
+  struct FirPlan { int N, batch, inverse, plan; };
+  std::vector<FirPlan> fir_plans;
 };
 
 namespace emagls {
@@ -160,6 +163,10 @@ struct DesignArgs {
 };
 void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& a);
 void destroy_render_plans(emagls_ctx* h);  // render.cu
+void destroy_fir_plans(emagls_ctx* h);     // frontend.cu
+// radFilts [K][(order+1)] (row index k) on the device (getRadialFilter.m:42-70)
+void radial_filter_dev(emagls_ctx* h, Arena& ar, const emagls_config& cfg, const emagls_radial_params& rp, int order,
+                       double fs, double radius, int nfft, int nan_to_zero, cplx* out);
 // real-basis -> complex-basis outputs (kind 0: SH in ACN order, 1: CH ordered [0,-1,+1,...]); see engine.cu
 cudaError_t launch_basis_change_filters(cudaStream_t st, const double* wr, int kind, int nch, int len,
                                         long long P, const cplx* Wsp_e, int K, int nfft, cplx* out);
@@ -167,7 +174,7 @@ cudaError_t launch_basis_change_spectra(cudaStream_t st, cplx* Wsp, int kind, in
                                         int dc_quirk);
 void design_magls(emagls_ctx* h, const emagls_config& cfg, const double* hL, const double* hR, int T, int D,
                   const double* grid_azi, const double* grid_zen, int order, double fs, int len, bool ls_only,
-                  double* wL, double* wR, double* spectra);
+                  double* wL, double* wR, double* spectra, int harmonics_kind = 0);
 void design_from_atf(emagls_ctx* h, const emagls_config& cfg, const double* hL, const double* hR, int T, int D,
                      const double* hrir_grid, const double* atf_irs, int Ta, int M, int Da, const double* atf_grid,
                      double fs, int len, double f_trans, double* wL, double* wR, double* spectra,

@@ -289,26 +289,31 @@ static void tail_real(emagls_ctx* h, Arena& ar, const cplx* Wsp, int P, int Mc, 
 // ------------------------------------------------------------------------------------------
 void design_magls(emagls_ctx* h, const emagls_config& cfg, const double* hL, const double* hR, int T, int D,
                   const double* grid_azi, const double* grid_zen, int order, double fs, int len, bool ls_only,
-                  double* wL, double* wR, double* spectra) {
+                  double* wL, double* wR, double* spectra, int harmonics_kind) {
+  // harmonics_kind 0: spherical harmonics (getMagLsFilters / getLsFilters); 1: circular harmonics of the
+  // azimuth only (lib/getMagLsFilters2D.m:44-45), channels ordered [0,-1,+1,...]
   cudaStream_t st = h->stream;
   EM_REQUIRE(T > 0 && D > 0, "empty input");
   EM_REQUIRE(order >= 0 && order <= MAX_SH_ORDER, "order out of range");
-  const int Mc = (order + 1) * (order + 1);
+  const int Mc = harmonics_kind == 1 ? 2 * order + 1 : (order + 1) * (order + 1);
   EM_REQUIRE(Mc <= 64, "more than 64 channels are not supported");
   EM_REQUIRE(D >= Mc, "fewer directions than harmonics");
   const bool cplx_out = cfg.basis == EMAGLS_BASIS_COMPLEX;
   Arena ar(st);
   ProfSpan* setup_span = new ProfSpan(h, EM_PROF_SETUP);
   // Y_conj.' rows in the real basis; a complex basis is a unitary change of the output (engine.cu)
-  double* Y = ar.get<double>((size_t)Mc * D);
-  EM_CUDA(launch_sh_angles(st, order, grid_azi, grid_zen, D, 0, Y));
   cplx* At = ar.get<cplx>((size_t)D * Mc);
-  {
+  if (harmonics_kind == 1) {
+    EM_CUDA(launch_ch_rows(st, order, grid_azi, D, 0, At));
+    h->launches += 1;
+  } else {
+    double* Y = ar.get<double>((size_t)Mc * D);
+    EM_CUDA(launch_sh_angles(st, order, grid_azi, grid_zen, D, 0, Y));
     long long n = (long long)D * Mc;
     sh_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Y, D, Mc, At);
     EM_CUDA(cudaGetLastError());
+    h->launches += 2;
   }
-  h->launches += 2;
   GenericProblem g{};
   g.At = At; g.num_ops = 1; g.D = D; g.Mc = Mc; g.regul = 0.0; g.num_prob = 1;
   if (ls_only) {
@@ -333,7 +338,7 @@ void design_magls(emagls_ctx* h, const emagls_config& cfg, const double* hL, con
       EM_CUDA(cudaMemcpy2DAsync(cplx_out ? tmp : out, sizeof(double), We, sizeof(cplx), sizeof(double),
                                 (size_t)Mc * T, cudaMemcpyDeviceToDevice, st));
       if (cplx_out) {
-        EM_CUDA(launch_basis_change_filters(st, tmp, 0, Mc, T, 1, nullptr, 0, 1, reinterpret_cast<cplx*>(out)));
+        EM_CUDA(launch_basis_change_filters(st, tmp, harmonics_kind, Mc, T, 1, nullptr, 0, 1, reinterpret_cast<cplx*>(out)));
         h->launches += 1;
       }
     }
@@ -373,10 +378,10 @@ void design_magls(emagls_ctx* h, const emagls_config& cfg, const double* hL, con
   } else {
     double* tmp = ar.get<double>((size_t)2 * Mc * len);
     tail_real(h, ar, Wsp, 1, Mc, K, nfft, len, dl, dr, tmp, tmp + (size_t)Mc * len);
-    EM_CUDA(launch_basis_change_filters(st, tmp, 0, Mc, len, 1, nullptr, 0, 1, reinterpret_cast<cplx*>(wL)));
-    EM_CUDA(launch_basis_change_filters(st, tmp + (size_t)Mc * len, 0, Mc, len, 1, nullptr, 0, 1,
+    EM_CUDA(launch_basis_change_filters(st, tmp, harmonics_kind, Mc, len, 1, nullptr, 0, 1, reinterpret_cast<cplx*>(wL)));
+    EM_CUDA(launch_basis_change_filters(st, tmp + (size_t)Mc * len, harmonics_kind, Mc, len, 1, nullptr, 0, 1,
                                         reinterpret_cast<cplx*>(wR)));
-    if (spectra) EM_CUDA(launch_basis_change_spectra(st, Wsp, 0, Mc, K, 2, 0));
+    if (spectra) EM_CUDA(launch_basis_change_spectra(st, Wsp, harmonics_kind, Mc, K, 2, 0));
     h->launches += 3;
   }
 }

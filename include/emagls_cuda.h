@@ -155,6 +155,87 @@ int emagls_binaural_decode_dev(emagls_handle h, const double* in, long long num_
                                int num_ch, const double* wL, const double* wR, int len,
                                int compensate_delay, double* out);
 
+/* ======================================================================================================
+ * Callers either side of the hot path: radial filters, SH/CH encoding and
+ * rotation of the recording in front of the render, the remaining lib/ designers.
+ * ====================================================================================================== */
+typedef enum {
+  EMAGLS_RADIAL_NONE = 0,       /* 'none'      (getRadialFilter.m:29-33)  */
+  EMAGLS_RADIAL_TIKHONOV = 1,   /* 'tikhonov'  (:45-52), the default      */
+  EMAGLS_RADIAL_SOFTLIMIT = 2,  /* 'softlimit' (:54-59)                   */
+  EMAGLS_RADIAL_FULL = 3        /* 'full'      (:61-62)                   */
+} emagls_radial_kind;
+
+/* The fields of the reference `params` struct that getRadialFilter reads (getRadialFilter.m:9-23,48-56). */
+typedef struct {
+  int kind;              /* emagls_radial_kind; anything else -> EMAGLS_ERR_INVALID ("Unkown radialFilter") */
+  double regul_const;    /* params.regulConst  (default 1e-2)  */
+  double noise_gain_db;  /* params.noiseGainDb (softlimit)     */
+  int array_type;        /* emagls_array_type ('directional' is not built) */
+} emagls_radial_params;
+void emagls_radial_params_default(emagls_radial_params* rp);
+
+/* radFilts = getRadialFilter(params) (dependencies/getRadialFilter.m:1): out interleaved complex
+ * [nfft/2+1 x (order+1)] column-major, nfft = oversamplingFactor * irLen.  NaN entries (e.g. softlimit
+ * at kr = 0) are returned as NaN, exactly as the reference does.                                      */
+int emagls_radial_filter(emagls_handle h, const emagls_config* cfg, const emagls_radial_params* rp,
+                         int order, double fs, double sma_radius, int nfft, double* out);
+
+/* sigFiltered = applyRadialFilter(inSig, params) (dependencies/applyRadialFilter.m:1):
+ * in [num_samples x (order+1)^2]; out [emagls_apply_radial_filter_rows(num_samples, nfft) x (order+1)^2]
+ * (= max(num_samples, nfft) - nfft/2 rows: zero padding of short signals, filter delay removed).     */
+long long emagls_apply_radial_filter_rows(long long num_samples, int nfft);
+int emagls_apply_radial_filter(emagls_handle h, const emagls_config* cfg, const emagls_radial_params* rp,
+                               const double* in, long long num_samples, int order, double fs,
+                               double sma_radius, int nfft, double* out);
+int emagls_apply_radial_filter_dev(emagls_handle h, const emagls_config* cfg,
+                                   const emagls_radial_params* rp, const double* in,
+                                   long long num_samples, int order, double fs, double sma_radius,
+                                   int nfft, double* out);
+
+/* getSMAIRMatrix with params.radialFilter ~= 'none' (dependencies/getSMAIRMatrix.m:129-139, SH-domain
+ * output only; includes the reference's double application of real(BnTi) at the Nyquist bin).       */
+int emagls_smair_matrix_radial(emagls_handle h, const emagls_config* cfg, const emagls_radial_params* rp,
+                               const double* mic_azi, const double* mic_zen, int num_mics, int order,
+                               double fs, double sma_radius, int nfft, double* out, int* sim_order_out);
+
+/* shRecording = smaRecording * pinv(getSH(order, mics, shDefinition).') (verifyEMagLs.m:235-236,
+ * testEMagLs.m:98): in [num_samples x num_mics]; out [num_samples x (order+1)^2], interleaved complex
+ * for cfg->basis == COMPLEX.  emagls_ch_encode: the same with getCH(order, mic_azi) (testEMagLs.m:99-102),
+ * out [num_samples x (2*order+1)].                                                                   */
+int emagls_sh_encode(emagls_handle h, const emagls_config* cfg, const double* in, long long num_samples,
+                     int num_mics, const double* mic_azi, const double* mic_zen, int order, double* out);
+int emagls_sh_encode_dev(emagls_handle h, const emagls_config* cfg, const double* in,
+                         long long num_samples, int num_mics, const double* mic_azi,
+                         const double* mic_zen, int order, double* out);
+int emagls_ch_encode(emagls_handle h, const emagls_config* cfg, const double* in, long long num_samples,
+                     int num_mics, const double* mic_azi, int order, double* out);
+
+/* Rotation of a real-SH-domain signal, the rotateHOA_N3D(in, yaw, pitch, roll) call of
+ * dependencies/binauralDecode.m:26-30 (angles in radians here): out = in * getSHrotMtx(
+ * euler2rotationMatrix(-yaw, -pitch, roll, 'zyx'), order, 'real').'; in/out [num_samples x (order+1)^2]. */
+int emagls_rotate_sh(emagls_handle h, const double* in, long long num_samples, int order,
+                     double yaw_rad, double pitch_rad, double roll_rad, double* out);
+int emagls_rotate_sh_dev(emagls_handle h, const double* in, long long num_samples, int order,
+                         double yaw_rad, double pitch_rad, double roll_rad, double* out);
+
+/* [wMlsL, wMlsR] = getMagLsFilters2D(hLHor, hRHor, horHrirGridAziRad, order, fs, len, chDefinition)
+ * (lib/getMagLsFilters2D.m:1): outputs [len x (2*order+1)], interleaved complex for COMPLEX;
+ * spectra (optional) complex [K x (2*order+1) x 2 ears].                                             */
+int emagls_design_magls_2d(emagls_handle h, const emagls_config* cfg, const double* hL, const double* hR,
+                           int num_samples, int num_dirs, const double* grid_azi, int order, double fs,
+                           int len, double* wL, double* wR, double* spectra);
+
+/* [wShf, W_Shf] = getMagLsSphericalHeadFilter(micRadius, order, fs, len)
+ * (lib/getMagLsSphericalHeadFilter.m:1): w [len]; W_full (optional) [min(nfft_max_len, 2 len)] real.  */
+int emagls_spherical_head_filter(emagls_handle h, const emagls_config* cfg, double mic_radius, int order,
+                                 double fs, int len, double* w, double* W_full);
+/* wAdf = getMagLsArrayDiffuseFilter(micRadius, micGridAziRad, micGridZenRad, order, fs, len, shDefinition)
+ * (lib/getMagLsArrayDiffuseFilter.m:1): w [len]; shDefinition = cfg->basis (the result depends on it). */
+int emagls_array_diffuse_filter(emagls_handle h, const emagls_config* cfg, double mic_radius,
+                                const double* mic_azi, const double* mic_zen, int num_mics, int order,
+                                double fs, int len, double* w);
+
 /* ---- building blocks exposed for parity tests (each mirrors one reference function) --------- */
 /* getSH(N, [azi zen], basis) (dependencies/Spherical-Harmonic-Transform/getSH.m:1):
  * out [num_dirs x (N+1)^2] column-major; interleaved complex for COMPLEX.                      */

@@ -49,4 +49,32 @@ static void emx_return2(int nlhs, mxArray* plhs[], mxArray* wL, mxArray* wR) {
   plhs[0] = wL;
   if (nlhs > 1) plhs[1] = wR; else mxDestroyArray(wR);
 }
+
+/* struct field helpers + the getRadialFilter parameter block (getRadialFilter.m:9-23, 48-56) */
+static double emx_fld(const mxArray* s, const char* name, double dflt) {
+  const mxArray* f = mxGetField(s, 0, name);
+  return (f && !mxIsEmpty(f)) ? mxGetScalar(f) : dflt;
+}
+static void emx_radial_params(const mxArray* p, emagls_radial_params* rp) {
+  char buf[32] = "tikhonov";
+  const mxArray* f = mxGetField(p, 0, "radialFilter");
+  emagls_radial_params_default(rp);
+  if (f) mxGetString(f, buf, sizeof buf);
+  if (strcmp(buf, "none") == 0) rp->kind = EMAGLS_RADIAL_NONE;
+  else if (strcmp(buf, "tikhonov") == 0) rp->kind = EMAGLS_RADIAL_TIKHONOV;
+  else if (strcmp(buf, "softlimit") == 0) rp->kind = EMAGLS_RADIAL_SOFTLIMIT;
+  else if (strcmp(buf, "full") == 0) rp->kind = EMAGLS_RADIAL_FULL;
+  else mexErrMsgIdAndTxt("eMagLS:radialFilter", "Unkown radialFilter parameter \"%s\".", buf);
+  rp->regul_const = emx_fld(p, "regulConst", 1e-2);
+  rp->noise_gain_db = emx_fld(p, "noiseGainDb", 20.0);
+  strcpy(buf, "rigid");
+  f = mxGetField(p, 0, "arrayType");
+  if (f) mxGetString(f, buf, sizeof buf);
+  rp->array_type = strcmp(buf, "open") == 0 ? EMAGLS_ARRAY_OPEN : EMAGLS_ARRAY_RIGID;
+  strcpy(buf, "planeWave");
+  f = mxGetField(p, 0, "waveModel");
+  if (f) mxGetString(f, buf, sizeof buf);
+  if (rp->kind != EMAGLS_RADIAL_NONE && strcmp(buf, "pointSource") == 0)
+    mexErrMsgIdAndTxt("eMagLS:waveModel", "WaveModel parameter \"%s\" not yet implemented.", buf);
+}
 #endif

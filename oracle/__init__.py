@@ -15,3 +15,4 @@ to 7e-6, eMagLS/eMagLS2 conventions to a few percent.  The end-to-end hot loop
 itself is therefore "parity unpinned" by any runnable in-tree reference test.
 """
 from .emagls_oracle import *  # noqa: F401,F403
+from .frontend_oracle import *  # noqa: F401,F403,E402  (SURVEY.md section 8(f) rows)

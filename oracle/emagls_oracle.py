@@ -237,8 +237,12 @@ def getSMAIRMatrix(params: dict):
         return pMics, p
     smairMat = np.einsum("om,msk->osk", Y_Lo_pinv, pMics)
     if str(p["radialFilter"]).lower() != "none":
-        raise NotImplementedError("radialFilter != 'none' is outside the hot path "
-                                  "(SURVEY.md section 8(f) rank 1)")
+        # getSMAIRMatrix.m:129-139.  At the Nyquist bin the reference multiplies by BnTi and then
+        # once more by real(BnTi) (the result of the first product is overwritten in place).
+        from .frontend_oracle import getRadialFilter
+        rad = sh_repToOrder(getRadialFilter(p).T)[:numShsOut, :]  # numShsOut x K
+        smairMat = rad[:, None, :] * smairMat
+        smairMat[:, :, -1] = rad[:, None, -1].real * smairMat[:, :, -1]
     return smairMat, p
 
 
