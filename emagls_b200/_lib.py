@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libemagls_cuda.so")
+# EMAGLS_LIB_PATH: A/B runs of alternative builds of the same library (tools/); never a fallback
+LIB_PATH = os.environ.get("EMAGLS_LIB_PATH") or os.path.join(_HERE, "lib", "libemagls_cuda.so")
 
 c_dp = C.c_void_p  # double* / const double*
 

@@ -24,7 +24,10 @@ namespace oz {
 constexpr int TILE_M = 128, TILE_N = 64, TILE_K = 64, STAGES = 2, MAX_SLICES = 8;
 constexpr int A_SLICE_BYTES = TILE_M * TILE_K;   // 8 KB
 constexpr int B_SLICE_BYTES = TILE_N * TILE_K;   // 4 KB
-constexpr int EPI_WARPS = 8;                    // two warps per TMEM lane group, alternating 8-column chunks
+#ifndef EMAGLS_OZ_EPI_WARPS
+#define EMAGLS_OZ_EPI_WARPS 16
+#endif
+constexpr int EPI_WARPS = EMAGLS_OZ_EPI_WARPS;  // EPI_WARPS / 4 warps per TMEM lane group, interleaved 8-column chunks
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
 
 // ------------------------------------------------------------------------------------- PTX wrappers
@@ -176,7 +179,16 @@ struct GemmArgs {
   const double* sA;         // [M] row scales of A
   const double* sB;         // [N] row scales of B
   int dbg;                  // microbenchmark switches: 1 = skip the epilogue work, 2 = skip the MMAs
+  int n_fastest;            // tile order: consecutive tiles share the A rows (1) or the B rows (0)
 };
+
+// Persistent tile index -> (m0, n0).  Consecutive tiles run concurrently on neighbouring SMs, so the
+// operand indexed by the slow dimension is fetched from DRAM once and re-read from L2 by its
+// neighbours: the large operand must be the one shared (backward product: A = 274 MB of digits).
+__device__ __forceinline__ void tile_origin(const GemmArgs& g, int tile, int m_tiles, int n_tiles, int& m0, int& n0) {
+  if (g.n_fastest) { n0 = (tile % n_tiles) * TILE_N; m0 = (tile / n_tiles) * TILE_M; }
+  else { m0 = (tile % m_tiles) * TILE_M; n0 = (tile / m_tiles) * TILE_N; }
+}
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -235,7 +247,8 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % m_tiles) * TILE_M, n0 = (tile / m_tiles) * TILE_N;
+        int m0, n0;
+        tile_origin(g, tile, m_tiles, n_tiles, m0, n0);
         for (int kt = 0; kt < num_kt; ++kt) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = base + (size_t)stage * stage_bytes;
@@ -256,7 +269,8 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int stage = 0; uint32_t phase = 0, acc_phase = 0;
     const bool leader = elect_one();
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int n0 = (tile / m_tiles) * TILE_N;
+      int m0, n0;
+      tile_origin(g, tile, m_tiles, n_tiles, m0, n0);
       const int n_mma = min(TILE_N, ((g.N - n0) + 15) & ~15);
       const uint32_t idesc = instr_desc_i8(TILE_M, n_mma);
       mbar_wait(&tmem_empty_bar, acc_phase ^ 1);   // epilogue has drained the accumulators
@@ -299,40 +313,54 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int lg = warp & 3;                          // TMEM lane group this warp may access
     const int chunk0 = ((warp - 2) >> 2) * 8;         // first 8-column chunk of this warp
     constexpr int chunk_step = 8 * (EPI_WARPS / 4);
+    constexpr int CH_PER_WARP = (TILE_N + chunk_step - 1) / chunk_step;
     uint32_t acc_phase = 0;
     const double w_hi = scalbn(1.0, -7 * ((T < 4 ? T : 4) - 1)), w_lo = scalbn(1.0, -7 * (T - 1));
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % m_tiles) * TILE_M, n0 = (tile / m_tiles) * TILE_N;
+      int m0, n0;
+      tile_origin(g, tile, m_tiles, n_tiles, m0, n0);
       const int n_mma = min(TILE_N, ((g.N - n0) + 15) & ~15);
       const int m = m0 + lg * 32 + lane;
       mbar_wait(&tmem_full_bar, acc_phase);
       tc_fence_after();
       const double sa = (m < g.M) ? g.sA[m] : 0.0;
-      for (int c0 = chunk0; c0 < ((g.dbg & 1) ? 0 : n_mma); c0 += chunk_step) {
-        int32_t a[MAX_SLICES][8];
+      const int n_lim = (g.dbg & 1) ? 0 : n_mma;
+      // Phase 1 (drain): this warp's chunks go TMEM -> registers -> FP64; the accumulators are then
+      // handed back, so the MMA warp starts the next tile while phase 2 (the functor: phase
+      // continuation, slicing, global stores) runs from registers.
+      double v[CH_PER_WARP][8];
 #pragma unroll
-        for (int d = 0; d < MAX_SLICES; ++d)
-          if (d < T) tmem_ld8(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(d * TILE_N + c0), a[d]);
-        tmem_ld_wait();
-        double v[8];
+      for (int ci = 0; ci < CH_PER_WARP; ++ci) {
+        const int c0 = chunk0 + ci * chunk_step;
+        if (c0 < n_lim) {
+          int32_t a[MAX_SLICES][8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          long long hi = 0, lo = 0;
+          for (int d = 0; d < MAX_SLICES; ++d)
+            if (d < T) tmem_ld8(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(d * TILE_N + c0), a[d]);
+          tmem_ld_wait();
 #pragma unroll
-          for (int d = 0; d < 4; ++d)
-            if (d < T) hi = hi * 128 + a[d][q];
+          for (int q = 0; q < 8; ++q) {
+            long long hi = 0, lo = 0;
 #pragma unroll
-          for (int d = 4; d < MAX_SLICES; ++d)
-            if (d < T) lo = lo * 128 + a[d][q];
-          const int n = n0 + c0 + q;
-          const double sb = (n < g.N) ? g.sB[n] : 0.0;
-          v[q] = fma((double)lo, w_lo, (double)hi * w_hi) * (sa * sb);
+            for (int d = 0; d < 4; ++d)
+              if (d < T) hi = hi * 128 + a[d][q];
+#pragma unroll
+            for (int d = 4; d < MAX_SLICES; ++d)
+              if (d < T) lo = lo * 128 + a[d][q];
+            const int n = n0 + c0 + q;
+            const double sb = (n < g.N) ? g.sB[n] : 0.0;
+            v[ci][q] = fma((double)lo, w_lo, (double)hi * w_hi) * (sa * sb);
+          }
         }
-        if (m < g.M) epi(m, n0 + c0, v, g.M, g.N);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar);
+#pragma unroll
+      for (int ci = 0; ci < CH_PER_WARP; ++ci) {
+        const int c0 = chunk0 + ci * chunk_step;
+        if (c0 < n_lim && m < g.M) epi(m, n0 + c0, v[ci], g.M, g.N);
+      }
       acc_phase ^= 1;
     }
   }
@@ -398,7 +426,8 @@ cudaError_t launch_ozaki_gemm(cudaStream_t st, const int8_t* Aq, const double* s
   CUtensorMap tmA, tmB;
   if (!make_operand_map(&tmA, Aq, M, Kpad, T, TILE_M) || !make_operand_map(&tmB, Bq, N, Kpad, T, TILE_N))
     return cudaErrorInvalidValue;
-  GemmArgs g{M, N, Kpad, sA, sB, dbg};
+  const int m_tiles = (M + TILE_M - 1) / TILE_M, n_tiles = (N + TILE_N - 1) / TILE_N;
+  GemmArgs g{M, N, Kpad, sA, sB, dbg, n_tiles < m_tiles ? 1 : 0};
   switch (T) {
     case 6: return launch_ozaki_gemm_t<6>(st, tmA, tmB, g, epi, num_sms);
     case 7: return launch_ozaki_gemm_t<7>(st, tmA, tmB, g, epi, num_sms);

@@ -97,7 +97,7 @@ static cudaError_t oz_fwd_t(cudaStream_t st, const OzFwdArgs& a) {
   if (!oz::make_operand_map(&tmA, a.YhA_q, a.D, a.KpS, T, oz::TILE_M) ||
       !oz::make_operand_map(&tmB, a.Cv_q, a.rows, a.KpS, T, oz::TILE_N))
     return cudaErrorInvalidValue;
-  oz::GemmArgs g{a.D, a.rows, a.KpS, a.sYhA, a.sCv, 0};
+  oz::GemmArgs g{a.D, a.rows, a.KpS, a.sYhA, a.sCv, 0, 0};   // m fastest: the 42 MB of Cv digits are the shared operand
   EpiPhaseSlice<T> epi{a.Tt_q, (long long)a.rows * a.KpD, a.KpD, a.sT, a.absH, a.abs_set_stride, a.abs_ear_stride,
                        a.up, a.sc, a.scale_stride, a.orient_per_set, a.nyquist};
   return oz::launch_ozaki_gemm_t<T>(st, tmA, tmB, g, epi, sm_count());

@@ -61,6 +61,14 @@ def rotate_grid(azi, zen, R):
     return angles_from_vectors(v)
 
 
+def fibonacci_sphere(n):
+    """n-point Fibonacci sphere (azi, zen) -- the 64-microphone layout of BASELINE config 5."""
+    i = np.arange(n) + 0.5
+    zen = np.arccos(1.0 - 2.0 * i / n)
+    azi = np.mod(i * math.pi * (3.0 - math.sqrt(5.0)), 2 * math.pi)
+    return azi, zen
+
+
 def _rigid_bn(N, x):
     """4 pi i^n (j_n - j_n'/h_n' h_n), h_n = j_n - i y_n, for x > 0: [len(x), N+1]."""
     n = np.arange(N + 1)[None, :]

@@ -160,3 +160,57 @@ def test_other_filter_lengths_and_rates(em, h, grids):
     assert wL.shape == (96, 32)
     err = np.abs(sp[:, :, 0] - osp["W_l"]).max(1) / np.abs(osp["W_l"]).max(1)
     assert err[6:].max() < 1e-9 and rel(wL, oL) < 1e-7 and rel(wR, oR) < 1e-7
+
+
+def test_stress_config_shape_at_reduced_length(em, h, grids):
+    """BASELINE config 5 shape (64-microphone Fibonacci sphere, SH order 7, 96 kHz: simulation order 37,
+    1444 harmonics) at a filter length the oracle finishes in seconds."""
+    az, ze = grids["hrirGridAziRad"], grids["hrirGridZenRad"]
+    hL, hR = synth.synth_hrirs(az, ze, fs=96000.0, taps=128, delay=40)
+    maz, mze = synth.fibonacci_sphere(64)
+    args = (az, ze, 0.042, maz, mze, 7, 96000.0, 128)
+    wL, wR, sp = em.getEMagLs2Filters(hL, hR, *args, handle=h, return_spectra=True)
+    oL, oR, osp = oracle.getEMagLs2Filters(hL, hR, *args, return_spectra=True)
+    assert wL.shape == (128, 64)
+    for e, Wo in enumerate((osp["W_l"], osp["W_r"])):
+        err = np.abs(sp[:, :, e] - Wo).max(1) / np.abs(Wo).max(1)
+        assert err[8:].max() <= 1e-8, err[8:].max()      # 750 Hz bins: same conditioning classes as config 1
+        assert err[1:8].max() <= 2e-6, err[1:8].max()
+    assert rel(wL, oL) < 5e-8 and rel(wR, oR) < 5e-8
+    # SH-domain variant of the same array (64 channels)
+    wL, wR = em.getEMagLsFilters(hL, hR, *args, handle=h)
+    oL, oR = oracle.getEMagLsFilters(hL, hR, *args)
+    assert wL.shape == (128, 64) and rel(wL, oL) < 1e-8 and rel(wR, oR) < 1e-8
+
+
+def test_stress_config_full_length_properties(em, h, grids):
+    """BASELINE config 5 at its full size for one (HRTF set, two orientations): 4096 taps at 96 kHz need
+    NFFT_MAX_LEN lifted to 8192 (K = 4097 bins).  The oracle would need minutes, so the
+    checks are size-independent properties: LS bins of single reference-style solves, zero end taps,
+    identity orientation inside a batch equals the single call."""
+    az, ze = grids["hrirGridAziRad"], grids["hrirGridZenRad"]
+    hL, hR = synth.synth_hrirs(az, ze, fs=96000.0, taps=256, delay=60)
+    maz, mze = synth.fibonacci_sphere(64)
+    cfg = h.default_config()
+    cfg.nfft_max_len = 8192
+    args = (az, ze, 0.042, maz, mze, 7, 96000.0, 4096)
+    R = np.stack([synth.rotation_yaw_pitch(33.0, 15.0), np.eye(3)])
+    wL, wR, sp = em.getEMagLs2Filters(hL, hR, *args, rotations=R, handle=h, config=cfg, return_spectra=True)
+    assert wL.shape == (4096, 64, 2) and np.all(np.isfinite(wL)) and np.all(np.isfinite(wR))
+    assert np.all(wL[0] == 0) and np.all(wL[-1] == 0)
+    sL, sR = em.getEMagLs2Filters(hL, hR, *args, handle=h, config=cfg)
+    assert rel(wL[:, :, 1], sL) < 1e-8 and rel(wR[:, :, 1], sR) < 1e-8
+    # LS bins (below k_cut = 299) against the oracle's per-bin solve (lib/getEMagLs2Filters.m:86-92)
+    nfft, K = 8192, 4097
+    f = np.linspace(0, 48000.0, K)
+    Ymic = oracle.getSH(37, np.stack([maz, mze], 1), "real")                   # [64, 1444]
+    Yc = oracle.getSH(37, np.stack([az, ze], 1), "real").T                     # [1444, 2702]
+    hp = np.zeros((nfft, az.size))
+    hp[:256] = hL
+    grp = float(np.median(oracle.grpdelay(hp.sum(1), f, 96000.0)))
+    HL = np.fft.fft(oracle.applySubsampleDelay(hp, -grp), axis=0)
+    for k in (150, 220, 290):   # cond(pwGrid) <= 3e5 there; lower bins sit on the 1e-7 noise floor (DESIGN.md 2)
+        bn = -oracle.sphModalCoeffs(37, np.array([2 * np.pi * f[k] / 343.0 * 0.042]))[0]
+        pw = (Ymic * oracle.sh_repToOrder(bn[:, None])[:, 0][None, :]) @ Yc
+        Wo = HL[k] @ oracle.regularized_inverse(pw)
+        assert np.abs(sp[k, :, 1, 0] - Wo).max() <= 1e-8 * np.abs(Wo).max(), k
