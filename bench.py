@@ -243,12 +243,12 @@ def main():
 
     # ---------------- roofline of the dominant tensor kernel
     # The two direction-grid contractions run on the int8 tensor cores (tcgen05.mma kind::i8, FP64
-    # accuracy through T = 7 error-free slices: T (T + 1) / 2 = 28 int8 GEMMs per product).  The roofline
+    # accuracy through T = 6 error-free base-256 slices: T (T + 1) / 2 = 21 int8 GEMMs per product).  The roofline
     # counts the int8 operations the kernel EXECUTES against the int8 tensor peak; the FP64-equivalent
     # rate and the DGEMM (DMMA) peak of this GPU are reported next to it.
     S = (19 + 1) ** 2
     use_oz = os.environ.get("EMAGLS_GEMM", "") != "dmma"
-    oz_T = int(os.environ.get("EMAGLS_OZAKI_SLICES", "7"))
+    oz_T = int(os.environ.get("EMAGLS_OZAKI_SLICES", "6"))
     pairs = oz_T * (oz_T + 1) // 2
     KpS, KpD = (S + 31) // 32 * 32, (D + 31) // 32 * 32
     dgemm_peak = i8_peak = None

@@ -119,7 +119,7 @@ gram_chol_kernel(const double* __restrict__ Gre, const double* __restrict__ Gim,
                  long long nmat, double thr, cplx* __restrict__ Pb, int* __restrict__ fail) {
   extern __shared__ __align__(16) unsigned char gsm_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long id = (long long)blockIdx.x * GC_WPC + warp;
+  const long long id = (long long)blockIdx.x * (blockDim.x >> 5) + warp;   // blockDim.x / 32 matrices per CTA
   if (id >= nmat) return;
   const int LD = Mc + 1;
   const int ne = Mc * (Mc + 1) / 2;
@@ -220,14 +220,17 @@ cudaError_t launch_gram_chol(cudaStream_t st, const double* Gre, const double* G
                              int ne_ld, int nbins, double thr, cplx* Pb, int* fail) {
   const long long nmat = (long long)nbins * P;
   size_t per_warp = ((size_t)Mc * (Mc + 1) + (Mc + 1) / 2) * sizeof(cplx);
-  size_t smem = per_warp * GC_WPC;
+  // as many warps (matrices) per CTA as the 227 KB of shared memory hold (4 up to Mc = 58, 3 at Mc = 64)
+  int wpc = GC_WPC;
+  while (wpc > 1 && per_warp * wpc > 227 * 1024) --wpc;
+  size_t smem = per_warp * wpc;
   static size_t set_to = 0;
   if (smem > 48 * 1024 && smem > set_to) {
     cudaError_t e = cudaFuncSetAttribute(gram_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     set_to = smem;
   }
-  gram_chol_kernel<<<(unsigned)((nmat + GC_WPC - 1) / GC_WPC), GC_WPC * 32, smem, st>>>(Gre, Gim, Mc, P, ne_ld, nmat, thr,
+  gram_chol_kernel<<<(unsigned)((nmat + wpc - 1) / wpc), wpc * 32, smem, st>>>(Gre, Gim, Mc, P, ne_ld, nmat, thr,
                                                                                     Pb, fail);
   return cudaGetLastError();
 }

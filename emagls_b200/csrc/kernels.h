@@ -115,7 +115,9 @@ cudaError_t launch_bwd_small(cudaStream_t st, const double* Y, int Mc, int S, co
 // ---------------------------------------------------------------- ozaki_kernels.cu
 // FP64-accurate GEMMs on the int8 tensor cores (tcgen05 + TMEM + TMA); see ozaki.cuh.
 int oz_pad32(int k);
-// x(r, k) = src[r*rs + k*cs] -> digits out[T][R][Kpad] (int8) and scale[r] = 2^(e_r - 6)
+// int32 accumulation of T slice pairs of 2^14 over Kpad terms must stay below 2^31 (Kpad <= 21845 at T = 6)
+bool oz_contraction_fits(int Kpad, int T);
+// x(r, k) = src[r*rs + k*cs] -> balanced base-256 digits out[T][R][Kpad] (int8) and scale[r] = 2^(e_r - 6)
 cudaError_t launch_slice_rows(cudaStream_t st, const double* src, long long rs, long long cs, int R, int K, int Kpad,
                               int T, int8_t* out, double* scale);
 // per row of x [rows][D]: up = 2^(6-e), sc = 2^(e-6) with 2^e > max |x(row, :)|

@@ -1,18 +1,22 @@
 // FP64-accurate GEMM on the 5th-generation tensor cores: error-free slicing (Ozaki scheme I) of both
-// operands into signed 7-bit digits, int8 x int8 -> int32 `tcgen05.mma.kind::i8` products with the
-// accumulators in TMEM, operands staged by TMA, FP64 recombination in the epilogue.
+// operands into balanced base-256 digits (int8), int8 x int8 -> int32 `tcgen05.mma.kind::i8` products
+// with the accumulators in TMEM, operands staged by TMA, FP64 recombination in the epilogue.
 //
-//   x(r, k) = 2^(e_r) * sum_s q_s(r, k) 2^(-6 - 7 s),  |q_s| <= 64          (slice_rows_kernel)
-//   C(m, n) = sA(m) sB(n) sum_{d < T} 2^(-7 d) sum_{i + j = d} sum_k qA_i(m, k) qB_j(n, k)
+//   x(r, k) = 2^(e_r - 6) * sum_{s < T} q_s(r, k) 256^-s,   |q_0| <= 64, q_s in [-128, 127]   (slice_rows_kernel)
+//   C(m, n) = sA(m) sB(n) sum_{d < T} 256^-d sum_{i + j = d} sum_k qA_i(m, k) qB_j(n, k)
 //
-// with sA = 2^(e - 6).  Products of slices are exact in int32 (64 * 64 * K * T < 2^31 for K <= 2^16);
-// pairs with i + j >= T are dropped, so the result carries 7 T - 1 bits relative to max|a| max|b| K
-// (T = 7: 2^-48; the native FP64 dot product carries 2^-53 relative to sum |a||b|).
+// with sA = 2^(e - 6).  Products of slices are exact in int32 (T * 2^14 * K < 2^31, i.e. K <= 21845 for
+// T = 6; the host refuses longer contractions); pairs with i + j >= T are dropped, so the result carries
+// 8 T - 2 bits relative to max|a| max|b| K (T = 6: 2^-46, measured 5e-14 of |a|.|b|; the native FP64 dot
+// product carries 2^-53 relative to sum |a||b|).  Base 256 uses all 8 bits of the int8 operands: the same
+// 48 bits need T = 6 slices (21 slice pairs) instead of the 7 slices (28 pairs) of 7-bit digits, and the
+// digits of a value are the bytes of (x + 0x808080) ^ 0x808080 -- two integer instructions per limb.
 //
 // Layout: one CTA = one 128 x 64 output tile at a time (persistent over tiles), T accumulators of
 // 64 TMEM columns (one per diagonal i + j = d), K streamed in tiles of 64 bytes per slice through a
-// 2-stage TMA -> smem ring (64-byte swizzle, K-major operands).  Warp 0: TMA producer, warp 1: MMA
-// issuer (one elected thread), warps 2..9: epilogue (TMEM -> registers -> FP64 -> functor).
+// 3-stage TMA -> smem ring (64-byte swizzle, K-major operands).  Warp 0: TMA producer, warp 1: MMA
+// issuer (one elected thread), warps 2..17: epilogue (TMEM -> registers -> FP64, accumulators released,
+// then the functor).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -21,7 +25,7 @@
 namespace emagls {
 namespace oz {
 
-constexpr int TILE_M = 128, TILE_N = 64, TILE_K = 64, STAGES = 2, MAX_SLICES = 8;
+constexpr int TILE_M = 128, TILE_N = 64, TILE_K = 64, STAGES = 3, MAX_SLICES = 6;
 constexpr int A_SLICE_BYTES = TILE_M * TILE_K;   // 8 KB
 constexpr int B_SLICE_BYTES = TILE_N * TILE_K;   // 4 KB
 #ifndef EMAGLS_OZ_EPI_WARPS
@@ -124,29 +128,28 @@ __device__ __forceinline__ uint32_t instr_desc_i8(int m, int n) {
 }
 
 // ------------------------------------------------------------------------------------- slicing
-// Signed base-128 digits of a (|a| <= 64): a = sum_{s < T} q_s 128^-s + r, |r| <= 128^-(T-1) / 2, |q_s| <= 64.
-// Two int32 limbs (hi: digits 0..nh-1, lo: the rest) are rounded out of the FP64 value, then the
-// digits are peeled off with integer shifts (round to nearest: next = (x + 64) >> 7).
+// Balanced base-256 digits of a (|a| <= 64): a = sum_{s < T} q_s 256^-s + r, |r| <= 256^-(T-1) / 2,
+// |q_0| <= 64, q_s in [-128, 127].  Two int32 limbs (hi: digits 0..T-4, lo: the last three) are rounded
+// out of the FP64 value; the balanced digits of a limb x are the bytes of (x + 0x808080) ^ 0x808080
+// (adding 128 to every byte propagates the carries, the xor subtracts it again as a signed byte), and
+// the carry out of the low limb (its top digit rounding up) moves into the high limb.
 template <int T, class Store>
 __device__ __forceinline__ void slice_digits(double a, Store&& store) {
-  constexpr int nh = T / 2, nl = T - nh;
-  const double ah = a * (double)(1 << (7 * (nh - 1)));
+  static_assert(T >= 4 && T <= 6, "hi limb: 1..3 digits, lo limb: 3 digits");
+  constexpr int nh = T - 3;
+  constexpr int bias_hi = (nh == 3) ? 0x808080 : (nh == 2 ? 0x8080 : 0x80);
+  const double ah = a * (double)(1 << (8 * (nh - 1)));
   int hi = __double2int_rn(ah);
-  int lo = __double2int_rn((ah - (double)hi) * (double)(1 << (7 * nl)));
+  const int lo = __double2int_rn((ah - (double)hi) * 16777216.0);     // |lo| <= 2^23
+  const int yl = lo + 0x808080;                                       // in (0, 2^25)
+  hi += yl >> 24;                                                     // carry (0 or 1)
+  const int zl = yl ^ 0x808080;
+  store(T - 1, (int)(signed char)(zl));
+  store(T - 2, (int)(signed char)(zl >> 8));
+  store(T - 3, (int)(signed char)(zl >> 16));
+  const int zh = (hi + bias_hi) ^ bias_hi;                            // |hi| <= 2^22 + 1: no carry out
 #pragma unroll
-  for (int s = T - 1; s > nh; --s) {
-    const int nx = (lo + 64) >> 7;
-    store(s, lo - (nx << 7));
-    lo = nx;
-  }
-  store(nh, lo);
-#pragma unroll
-  for (int s = nh - 1; s > 0; --s) {
-    const int nx = (hi + 64) >> 7;
-    store(s, hi - (nx << 7));
-    hi = nx;
-  }
-  store(0, hi);
+  for (int j = 0; j < nh; ++j) store(nh - 1 - j, (int)(signed char)(zh >> (8 * j)));
 }
 
 // One warp per row r: x(r, k) = src[r * rs + k * cs], k < K.  out[s][r][Kpad] (int8), scale[r] = 2^(e-6)
@@ -315,7 +318,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     constexpr int chunk_step = 8 * (EPI_WARPS / 4);
     constexpr int CH_PER_WARP = (TILE_N + chunk_step - 1) / chunk_step;
     uint32_t acc_phase = 0;
-    const double w_hi = scalbn(1.0, -7 * ((T < 4 ? T : 4) - 1)), w_lo = scalbn(1.0, -7 * (T - 1));
+    const double w_hi = scalbn(1.0, -8 * ((T < 3 ? T : 3) - 1)), w_lo = scalbn(1.0, -8 * (T - 1));
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m0, n0;
       tile_origin(g, tile, m_tiles, n_tiles, m0, n0);
@@ -342,11 +345,11 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int q = 0; q < 8; ++q) {
             long long hi = 0, lo = 0;
 #pragma unroll
-            for (int d = 0; d < 4; ++d)
-              if (d < T) hi = hi * 128 + a[d][q];
+            for (int d = 0; d < 3; ++d)
+              if (d < T) hi = hi * 256 + a[d][q];
 #pragma unroll
-            for (int d = 4; d < MAX_SLICES; ++d)
-              if (d < T) lo = lo * 128 + a[d][q];
+            for (int d = 3; d < MAX_SLICES; ++d)
+              if (d < T) lo = lo * 256 + a[d][q];
             const int n = n0 + c0 + q;
             const double sb = (n < g.N) ? g.sB[n] : 0.0;
             v[ci][q] = fma((double)lo, w_lo, (double)hi * w_hi) * (sa * sb);
@@ -405,6 +408,9 @@ inline bool make_operand_map(CUtensorMap* tm, const int8_t* ptr, int rows, int K
   return r == CUDA_SUCCESS;
 }
 
+// int32 accumulators: a diagonal holds at most T pairs of products bounded by 2^14 each
+inline bool contraction_fits(int Kpad, int T) { return (long long)T * 16384LL * Kpad < (1LL << 31); }
+
 inline size_t gemm_smem_bytes(int T) { return (size_t)STAGES * T * (A_SLICE_BYTES + B_SLICE_BYTES) + 1024; }
 
 template <int T, class Epi>
@@ -422,16 +428,15 @@ cudaError_t launch_ozaki_gemm_t(cudaStream_t st, const CUtensorMap& tmA, const C
 template <class Epi>
 cudaError_t launch_ozaki_gemm(cudaStream_t st, const int8_t* Aq, const double* sA, const int8_t* Bq, const double* sB,
                               int M, int N, int Kpad, int T, Epi epi, int num_sms, int dbg = 0) {
-  if (Kpad % 32 != 0) return cudaErrorInvalidValue;
+  if (Kpad % 32 != 0 || !contraction_fits(Kpad, T)) return cudaErrorInvalidValue;
   CUtensorMap tmA, tmB;
   if (!make_operand_map(&tmA, Aq, M, Kpad, T, TILE_M) || !make_operand_map(&tmB, Bq, N, Kpad, T, TILE_N))
     return cudaErrorInvalidValue;
   const int m_tiles = (M + TILE_M - 1) / TILE_M, n_tiles = (N + TILE_N - 1) / TILE_N;
   GemmArgs g{M, N, Kpad, sA, sB, dbg, n_tiles < m_tiles ? 1 : 0};
   switch (T) {
+    case 5: return launch_ozaki_gemm_t<5>(st, tmA, tmB, g, epi, num_sms);
     case 6: return launch_ozaki_gemm_t<6>(st, tmA, tmB, g, epi, num_sms);
-    case 7: return launch_ozaki_gemm_t<7>(st, tmA, tmB, g, epi, num_sms);
-    case 8: return launch_ozaki_gemm_t<8>(st, tmA, tmB, g, epi, num_sms);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -73,14 +73,14 @@ int sm_count() {
 }  // namespace
 
 int oz_pad32(int k) { return (k + 31) & ~31; }
+bool oz_contraction_fits(int Kpad, int T) { return oz::contraction_fits(Kpad, T); }
 
 cudaError_t launch_slice_rows(cudaStream_t st, const double* src, long long rs, long long cs, int R, int K, int Kpad,
                               int T, int8_t* out, double* scale) {
   const dim3 grid((R + 7) / 8), block(256);
   switch (T) {
+    case 5: oz::slice_rows_kernel<5><<<grid, block, 0, st>>>(src, rs, cs, R, K, Kpad, out, scale); break;
     case 6: oz::slice_rows_kernel<6><<<grid, block, 0, st>>>(src, rs, cs, R, K, Kpad, out, scale); break;
-    case 7: oz::slice_rows_kernel<7><<<grid, block, 0, st>>>(src, rs, cs, R, K, Kpad, out, scale); break;
-    case 8: oz::slice_rows_kernel<8><<<grid, block, 0, st>>>(src, rs, cs, R, K, Kpad, out, scale); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -104,10 +104,10 @@ static cudaError_t oz_fwd_t(cudaStream_t st, const OzFwdArgs& a) {
 }
 
 cudaError_t launch_oz_fwd(cudaStream_t st, const OzFwdArgs& a) {
+  if (!oz::contraction_fits(a.KpS, a.T)) return cudaErrorInvalidValue;
   switch (a.T) {
+    case 5: return oz_fwd_t<5>(st, a);
     case 6: return oz_fwd_t<6>(st, a);
-    case 7: return oz_fwd_t<7>(st, a);
-    case 8: return oz_fwd_t<8>(st, a);
     default: return cudaErrorInvalidValue;
   }
 }

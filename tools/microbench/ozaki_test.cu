@@ -44,9 +44,8 @@ int run(int M, int N, int K, int T, int reps, int grade, int dbg = 0) {
   CK(cudaMemcpy(dB, hB.data(), hB.size() * 8, cudaMemcpyHostToDevice));
   CK(cudaMemset(dC, 0xff, (size_t)M * N * 8));
   auto slice = [&](const double* d, int R, int8_t* q, double* sc) {
-    if (T == 6) slice_rows_kernel<6><<<(R + 7) / 8, 256>>>(d, K, 1, R, K, Kpad, q, sc);
-    else if (T == 7) slice_rows_kernel<7><<<(R + 7) / 8, 256>>>(d, K, 1, R, K, Kpad, q, sc);
-    else slice_rows_kernel<8><<<(R + 7) / 8, 256>>>(d, K, 1, R, K, Kpad, q, sc);
+    if (T == 5) slice_rows_kernel<5><<<(R + 7) / 8, 256>>>(d, K, 1, R, K, Kpad, q, sc);
+    else slice_rows_kernel<6><<<(R + 7) / 8, 256>>>(d, K, 1, R, K, Kpad, q, sc);
   };
   slice(dA, M, qA, sA);
   slice(dB, N, qB, sB);
@@ -99,15 +98,15 @@ int main(int argc, char** argv) {
     fails += run(atoi(argv[1]), atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argc > 5 ? atoi(argv[5]) : 5, argc > 6 ? atoi(argv[6]) : 0);
     return fails;
   }
-  fails += run(128, 64, 64, 7, 0, 0);
-  fails += run(300, 200, 400, 8, 0, 4);
-  fails += run(1000, 400, 2702, 6, 0, 0);
+  fails += run(128, 64, 64, 6, 0, 0);
+  fails += run(300, 200, 400, 6, 0, 4);
+  fails += run(1000, 400, 2702, 5, 0, 0);
   for (int dbg = 0; dbg < 4; ++dbg) {
-    fails += run(2702, 14400, 400, 7, 10, 0, dbg);
-    fails += run(14400, 400, 2702, 7, 10, 0, dbg);
+    fails += run(2702, 14400, 400, 6, 10, 0, dbg);
+    fails += run(14400, 400, 2702, 6, 10, 0, dbg);
   }
-  fails += run(2702, 14400, 400, 8, 10, 0);
-  fails += run(14400, 400, 2702, 8, 10, 0);
+  fails += run(2702, 14400, 400, 5, 10, 0);
+  fails += run(14400, 400, 2702, 5, 10, 0);
   printf("%s (%d failing)\n", fails ? "FAIL" : "PASS", fails);
   return fails != 0;
 }
