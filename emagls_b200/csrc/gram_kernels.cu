@@ -12,6 +12,7 @@
 // A warp-per-matrix Cholesky in shared memory then yields G^-1 and the rigorous bound
 // cond_2(G) <= ||G||_F ||G^-1||_F that decides whether the bin may use this route; bins that fail
 // it go through the TSQR + Jacobi kernel (solver_kernels.cu).
+#include <cstdlib>
 #include "kernels.h"
 
 namespace emagls {
@@ -216,9 +217,104 @@ gram_chol_kernel(const double* __restrict__ Gre, const double* __restrict__ Gim,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Register-resident variant for Mc <= 32: lane i of a warp holds row i of the (padded 32 x 32)
+// Hermitian matrix and the warp inverts it in place by sweeps,
+//   sweep(k): d = A_kk;  A_kk <- -1/d;  A_ik <- A_ik / d;  A_ij <- A_ij - A_ik conj(A_jk) / d   (i, j != k),
+// after which A = -G^-1.  The pivots are the Cholesky pivots (Schur-complement diagonals), so the
+// positive-definiteness test is the same; every step is a full rank-1 update with no triangular load
+// imbalance, no square root and one reciprocal; only the pivot column (512 B per warp) goes through
+// shared memory and is read back as broadcasts.  The k loop is fully unrolled so that the row stays in
+// registers.  Same output and refusal rule as gram_chol_kernel.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GC_WPC * 32, 3)
+gram_sweep_kernel(const double* __restrict__ Gre, const double* __restrict__ Gim, int Mc, int P, int ne_ld,
+                  long long nmat, double thr, cplx* __restrict__ Pb, int* __restrict__ fail) {
+  __shared__ cplx colbuf[GC_WPC][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long id = (long long)blockIdx.x * GC_WPC + warp;
+  if (id >= nmat) return;
+  const double* gr = Gre + id * ne_ld;
+  const double* gi = Gim + id * ne_ld;
+  cplx* col = colbuf[warp];
+  cplx a[32];
+  double fro = 0.0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (lane < Mc && j < Mc) {
+      const int hi = max(lane, j), lo = min(lane, j);
+      const int e = hi * (hi + 1) / 2 + lo;
+      const double re = gr[e];
+      double im = (hi == lo) ? 0.0 : gi[e];       // packed entry (hi, lo); row lane, column j
+      if (j > lane) im = -im;                      // upper triangle: conj
+      a[j] = mk(re, im);
+      fro += fma(re, re, im * im);
+    } else {
+      a[j] = mk((j == lane) ? 1.0 : 0.0, 0.0);     // identity padding: inert under the sweeps
+    }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) fro += __shfl_xor_sync(0xffffffffu, fro, s);
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    if (ok && k < Mc) {                            // uniform across the warp
+      col[lane] = a[k];
+      __syncwarp();
+      const double d = col[k].x;
+      if (!(d > 0.0) || !(d < 1e300)) {
+        ok = false;
+      } else {
+        const double inv = 1.0 / d;
+        if (lane == k) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a[j] = (j == k) ? mk(-inv, 0.0) : mk(a[j].x * inv, a[j].y * inv);
+        } else {
+          const cplx f = mk(a[k].x * inv, a[k].y * inv);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j == k) continue;
+            const cplx cj = col[j];                // broadcast
+            // a_ij -= f * conj(A_jk)
+            a[j].x = fma(-f.x, cj.x, a[j].x); a[j].x = fma(-f.y, cj.y, a[j].x);
+            a[j].y = fma(-f.y, cj.x, a[j].y); a[j].y = fma(f.x, cj.y, a[j].y);
+          }
+          a[k] = f;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  if (!ok) {
+    if (lane == 0) atomicAdd(fail, 1), atomicAdd(fail + 1 + (int)(id / P), 1);
+    return;
+  }
+  // Ginv = -A;  Pb[m][i] = Ginv[i][m]  (W = v * Pb): lane i writes column i, coalesced over the lanes
+  double froi = 0.0;
+  cplx* out = Pb + id * (long long)Mc * Mc;
+#pragma unroll
+  for (int m = 0; m < 32; ++m) {
+    if (lane < Mc && m < Mc) {
+      out[(long long)m * Mc + lane] = mk(-a[m].x, -a[m].y);
+      froi += cabs2(a[m]);
+    }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) froi += __shfl_xor_sync(0xffffffffu, froi, s);
+  const double condF = sqrt(fro) * sqrt(froi);
+  if (!(condF <= thr)) {
+    if (lane == 0) atomicAdd(fail, 1), atomicAdd(fail + 1 + (int)(id / P), 1);
+  }
+}
+
 cudaError_t launch_gram_chol(cudaStream_t st, const double* Gre, const double* Gim, int Mc, int P,
                              int ne_ld, int nbins, double thr, cplx* Pb, int* fail) {
   const long long nmat = (long long)nbins * P;
+  if (Mc <= 32 && !getenv("EMAGLS_GRAM_CHOL")) {   // EMAGLS_GRAM_CHOL: A/B switch back to the shared-memory Cholesky
+    gram_sweep_kernel<<<(unsigned)((nmat + GC_WPC - 1) / GC_WPC), GC_WPC * 32, 0, st>>>(Gre, Gim, Mc, P, ne_ld, nmat, thr,
+                                                                                    Pb, fail);
+    return cudaGetLastError();
+  }
   size_t per_warp = ((size_t)Mc * (Mc + 1) + (Mc + 1) / 2) * sizeof(cplx);
   // as many warps (matrices) per CTA as the 227 KB of shared memory hold (4 up to Mc = 58, 3 at Mc = 64)
   int wpc = GC_WPC;
