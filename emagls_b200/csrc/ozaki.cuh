@@ -26,8 +26,13 @@ namespace emagls {
 namespace oz {
 
 constexpr int TILE_M = 128, TILE_N = 64, TILE_K = 64, STAGES = 3, MAX_SLICES = 6;
+// Tile width / ring depth per use: 64 x 3 stages by default; 80 x 2 stages for the backward product
+// (N = 400 = 5 x 80: no padded columns, the 235 MB A operand streams through L2 5 instead of 7 times;
+// 6 x 80 = 480 TMEM columns).
+template <int NT_, int ST_> struct TileCfg { static constexpr int NT = NT_, ST = ST_; };
+using TileDefault = TileCfg<TILE_N, STAGES>;
+using TileWide = TileCfg<80, 2>;
 constexpr int A_SLICE_BYTES = TILE_M * TILE_K;   // 8 KB
-constexpr int B_SLICE_BYTES = TILE_N * TILE_K;   // 4 KB
 #ifndef EMAGLS_OZ_EPI_WARPS
 #define EMAGLS_OZ_EPI_WARPS 16
 #endif
@@ -183,14 +188,15 @@ struct GemmArgs {
   const double* sB;         // [N] row scales of B
   int dbg;                  // microbenchmark switches: 1 = skip the epilogue work, 2 = skip the MMAs
   int n_fastest;            // tile order: consecutive tiles share the A rows (1) or the B rows (0)
+  int tile_n;               // Cfg::NT of the launched instance (tile_origin)
 };
 
 // Persistent tile index -> (m0, n0).  Consecutive tiles run concurrently on neighbouring SMs, so the
 // operand indexed by the slow dimension is fetched from DRAM once and re-read from L2 by its
 // neighbours: the large operand must be the one shared (backward product: A = 274 MB of digits).
 __device__ __forceinline__ void tile_origin(const GemmArgs& g, int tile, int m_tiles, int n_tiles, int& m0, int& n0) {
-  if (g.n_fastest) { n0 = (tile % n_tiles) * TILE_N; m0 = (tile / n_tiles) * TILE_M; }
-  else { m0 = (tile % m_tiles) * TILE_M; n0 = (tile / m_tiles) * TILE_N; }
+  if (g.n_fastest) { n0 = (tile % n_tiles) * g.tile_n; m0 = (tile / n_tiles) * TILE_M; }
+  else { m0 = (tile % m_tiles) * TILE_M; n0 = (tile / m_tiles) * g.tile_n; }
 }
 
 __device__ __forceinline__ bool elect_one() {
@@ -214,27 +220,28 @@ struct EpiStoreF64 {
   }
 };
 
-template <int T, class Epi>
+template <int T, class Epi, class Cfg = TileDefault>
 __global__ void __launch_bounds__(THREADS, 1)
 ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g, Epi epi) {
   extern __shared__ uint8_t oz_smem_raw[];
   // 1024-byte aligned carve-up: [stage][A slices | B slices]
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int NT = Cfg::NT, ST = Cfg::ST, B_SLICE_BYTES = NT * TILE_K;
   constexpr int stage_bytes = T * (A_SLICE_BYTES + B_SLICE_BYTES);
-  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar, tmem_empty_bar;
+  __shared__ __align__(8) uint64_t full_bar[ST], empty_bar[ST], tmem_full_bar, tmem_empty_bar;
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tiles = (g.M + TILE_M - 1) / TILE_M, n_tiles = (g.N + TILE_N - 1) / TILE_N;
+  const int m_tiles = (g.M + TILE_M - 1) / TILE_M, n_tiles = (g.N + NT - 1) / NT;
   const int num_tiles = m_tiles * n_tiles;
   const int ksteps_total = g.Kpad / 32;
   const int num_kt = (g.Kpad + TILE_K - 1) / TILE_K;
-  constexpr uint32_t tmem_cols = (T * TILE_N <= 256) ? 256u : 512u;
+  constexpr uint32_t tmem_cols = (T * NT <= 256) ? 256u : 512u;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < ST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tmem_full_bar, 1);
     mbar_init(&tmem_empty_bar, EPI_WARPS);   // one arrival per epilogue warp
     fence_barrier_init();
@@ -259,7 +266,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
           tma_load_3d(sa, &tmA, &full_bar[stage], kt * TILE_K, m0, 0);
           tma_load_3d(sb, &tmB, &full_bar[stage], kt * TILE_K, n0, 0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == ST) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -274,7 +281,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m0, n0;
       tile_origin(g, tile, m_tiles, n_tiles, m0, n0);
-      const int n_mma = min(TILE_N, ((g.N - n0) + 15) & ~15);
+      const int n_mma = min(NT, ((g.N - n0) + 15) & ~15);
       const uint32_t idesc = instr_desc_i8(TILE_M, n_mma);
       mbar_wait(&tmem_empty_bar, acc_phase ^ 1);   // epilogue has drained the accumulators
       tc_fence_after();
@@ -297,7 +304,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     const uint64_t ad = adesc0 + (uint64_t)((i * A_SLICE_BYTES + ks * 32) >> 4);
                     const uint64_t bd = bdesc0 + (uint64_t)(((d - i) * B_SLICE_BYTES + ks * 32) >> 4);
                     const uint32_t accum = (ks > 0 || i > 0) ? 1u : (uint32_t)(kt > 0);
-                    umma_i8(tmem_base + (uint32_t)d * TILE_N, ad, bd, idesc, accum);
+                    umma_i8(tmem_base + (uint32_t)d * NT, ad, bd, idesc, accum);
                   }
                 }
               }
@@ -307,7 +314,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (kt == num_kt - 1) umma_commit(&tmem_full_bar);   // accumulators complete
         }
         __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == ST) { stage = 0; phase ^= 1; }
       }
       acc_phase ^= 1;
     }
@@ -316,13 +323,13 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int lg = warp & 3;                          // TMEM lane group this warp may access
     const int chunk0 = ((warp - 2) >> 2) * 8;         // first 8-column chunk of this warp
     constexpr int chunk_step = 8 * (EPI_WARPS / 4);
-    constexpr int CH_PER_WARP = (TILE_N + chunk_step - 1) / chunk_step;
+    constexpr int CH_PER_WARP = (NT + chunk_step - 1) / chunk_step;
     uint32_t acc_phase = 0;
     const double w_hi = scalbn(1.0, -8 * ((T < 3 ? T : 3) - 1)), w_lo = scalbn(1.0, -8 * (T - 1));
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m0, n0;
       tile_origin(g, tile, m_tiles, n_tiles, m0, n0);
-      const int n_mma = min(TILE_N, ((g.N - n0) + 15) & ~15);
+      const int n_mma = min(NT, ((g.N - n0) + 15) & ~15);
       const int m = m0 + lg * 32 + lane;
       mbar_wait(&tmem_full_bar, acc_phase);
       tc_fence_after();
@@ -339,7 +346,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           int32_t a[MAX_SLICES][8];
 #pragma unroll
           for (int d = 0; d < MAX_SLICES; ++d)
-            if (d < T) tmem_ld8(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(d * TILE_N + c0), a[d]);
+            if (d < T) tmem_ld8(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(d * NT + c0), a[d]);
           tmem_ld_wait();
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -411,32 +418,35 @@ inline bool make_operand_map(CUtensorMap* tm, const int8_t* ptr, int rows, int K
 // int32 accumulators: a diagonal holds at most T pairs of products bounded by 2^14 each
 inline bool contraction_fits(int Kpad, int T) { return (long long)T * 16384LL * Kpad < (1LL << 31); }
 
-inline size_t gemm_smem_bytes(int T) { return (size_t)STAGES * T * (A_SLICE_BYTES + B_SLICE_BYTES) + 1024; }
+template <class Cfg>
+inline size_t gemm_smem_bytes(int T) { return (size_t)Cfg::ST * T * (A_SLICE_BYTES + Cfg::NT * TILE_K) + 1024; }
 
-template <int T, class Epi>
-cudaError_t launch_ozaki_gemm_t(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g,
+template <int T, class Epi, class Cfg = TileDefault>
+cudaError_t launch_ozaki_gemm_t(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs g,
                                 Epi epi, int num_sms) {
-  const size_t smem = gemm_smem_bytes(T);
-  cudaError_t e = cudaFuncSetAttribute(ozaki_gemm_kernel<T, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static_assert(T * Cfg::NT <= 512 && Cfg::NT % 16 == 0, "TMEM holds 512 columns; UMMA N is a multiple of 16");
+  const size_t smem = gemm_smem_bytes<Cfg>(T);
+  cudaError_t e = cudaFuncSetAttribute(ozaki_gemm_kernel<T, Epi, Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const int tiles = ((g.M + TILE_M - 1) / TILE_M) * ((g.N + TILE_N - 1) / TILE_N);
-  ozaki_gemm_kernel<T, Epi><<<tiles < num_sms ? tiles : num_sms, THREADS, smem, st>>>(tmA, tmB, g, epi);
+  g.tile_n = Cfg::NT;
+  const int tiles = ((g.M + TILE_M - 1) / TILE_M) * ((g.N + Cfg::NT - 1) / Cfg::NT);
+  ozaki_gemm_kernel<T, Epi, Cfg><<<tiles < num_sms ? tiles : num_sms, THREADS, smem, st>>>(tmA, tmB, g, epi);
   return cudaGetLastError();
 }
 
 // C = A * B^T from sliced operands Aq [T][M][Kpad], Bq [T][N][Kpad]
-template <class Epi>
+template <class Epi, class Cfg = TileDefault>
 cudaError_t launch_ozaki_gemm(cudaStream_t st, const int8_t* Aq, const double* sA, const int8_t* Bq, const double* sB,
                               int M, int N, int Kpad, int T, Epi epi, int num_sms, int dbg = 0) {
   if (Kpad % 32 != 0 || !contraction_fits(Kpad, T)) return cudaErrorInvalidValue;
   CUtensorMap tmA, tmB;
-  if (!make_operand_map(&tmA, Aq, M, Kpad, T, TILE_M) || !make_operand_map(&tmB, Bq, N, Kpad, T, TILE_N))
+  if (!make_operand_map(&tmA, Aq, M, Kpad, T, TILE_M) || !make_operand_map(&tmB, Bq, N, Kpad, T, Cfg::NT))
     return cudaErrorInvalidValue;
-  const int m_tiles = (M + TILE_M - 1) / TILE_M, n_tiles = (N + TILE_N - 1) / TILE_N;
-  GemmArgs g{M, N, Kpad, sA, sB, dbg, n_tiles < m_tiles ? 1 : 0};
+  const int m_tiles = (M + TILE_M - 1) / TILE_M, n_tiles = (N + Cfg::NT - 1) / Cfg::NT;
+  GemmArgs g{M, N, Kpad, sA, sB, dbg, n_tiles < m_tiles ? 1 : 0, Cfg::NT};
   switch (T) {
-    case 5: return launch_ozaki_gemm_t<5>(st, tmA, tmB, g, epi, num_sms);
-    case 6: return launch_ozaki_gemm_t<6>(st, tmA, tmB, g, epi, num_sms);
+    case 5: return launch_ozaki_gemm_t<5, Epi, Cfg>(st, tmA, tmB, g, epi, num_sms);
+    case 6: return launch_ozaki_gemm_t<6, Epi, Cfg>(st, tmA, tmB, g, epi, num_sms);
     default: return cudaErrorInvalidValue;
   }
 }

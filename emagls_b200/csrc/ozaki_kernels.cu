@@ -3,6 +3,7 @@
 //             continuation t = |H_k| y / |y| (lib/getEMagLs2Filters.m:95-103) fused into the epilogue,
 //             which also slices t into the int8 digits the backward product consumes;
 //   backward: t^T Y_h (or t^T Q)  (4P x S, contraction over the D directions), FP64 out.
+#include <cstdlib>
 #include "kernels.h"
 #include "ozaki.cuh"
 
@@ -18,11 +19,16 @@ struct EpiPhaseSlice {
   const double* up; const double* sc; int scale_stride;           // 2^(6-e), 2^(e-6) at [(set*2+ear)*scale_stride]
   int orient_per_set; int nyquist;
   __device__ __forceinline__ void operator()(int m, int n0, const double (&v)[8], int M, int N) const {
+    // columns n0..n0+7 are the (re, im) pairs of four consecutive (problem, ear) indices j = n / 2;
+    // the HRTF set of a problem is found with one division per call and then tracked incrementally
+    int prob = n0 >> 2;
+    int set = prob / orient_per_set;
+    int left = (set + 1) * orient_per_set - prob;     // problems left in this set, >= 1
 #pragma unroll
     for (int q = 0; q < 8; q += 2) {
       const int n = n0 + q;
       if (n >= N) break;
-      const int j = n >> 1, ear = j & 1, set = (j >> 1) / orient_per_set;
+      const int ear = (n >> 1) & 1;
       const double mag = absH[(long long)set * abs_set_stride + (long long)ear * abs_ear_stride + m];
       const double re = v[q], im = v[q + 1];
       const double a2 = fma(re, re, im * im);
@@ -41,6 +47,7 @@ struct EpiPhaseSlice {
       oz::slice_digits<T>(tr * u, [&](int s, int q_) { p[(long long)s * slice_stride] = (int8_t)q_; });
       oz::slice_digits<T>(ti * u, [&](int s, int q_) { p[(long long)s * slice_stride + Kpad] = (int8_t)q_; });
       if (m == 0) { const double s_ = sc[si]; sT[n] = s_; sT[n + 1] = s_; }
+      if (ear == 1 && --left == 0) { ++set; left = orient_per_set; }   // next pair belongs to the next problem
     }
   }
 };
@@ -97,7 +104,7 @@ static cudaError_t oz_fwd_t(cudaStream_t st, const OzFwdArgs& a) {
   if (!oz::make_operand_map(&tmA, a.YhA_q, a.D, a.KpS, T, oz::TILE_M) ||
       !oz::make_operand_map(&tmB, a.Cv_q, a.rows, a.KpS, T, oz::TILE_N))
     return cudaErrorInvalidValue;
-  oz::GemmArgs g{a.D, a.rows, a.KpS, a.sYhA, a.sCv, 0, 0};   // m fastest: the 42 MB of Cv digits are the shared operand
+  oz::GemmArgs g{a.D, a.rows, a.KpS, a.sYhA, a.sCv, 0, 0, oz::TILE_N};   // m fastest: the 42 MB of Cv digits are the shared operand
   EpiPhaseSlice<T> epi{a.Tt_q, (long long)a.rows * a.KpD, a.KpD, a.sT, a.absH, a.abs_set_stride, a.abs_ear_stride,
                        a.up, a.sc, a.scale_stride, a.orient_per_set, a.nyquist};
   return oz::launch_ozaki_gemm_t<T>(st, tmA, tmB, g, epi, sm_count());
@@ -114,6 +121,11 @@ cudaError_t launch_oz_fwd(cudaStream_t st, const OzFwdArgs& a) {
 
 cudaError_t launch_oz_bwd(cudaStream_t st, const int8_t* Tt_q, const double* sT, int rows, const int8_t* B_q,
                           const double* sB, int S, int KpD, int T, double* tq) {
+  // 80-column tiles when they leave fewer padded columns than 64-column tiles (S = 400: 5 x 80 against 7 x 64)
+  const bool wide = ((S + 79) / 80) * 80 < ((S + 63) / 64) * 64 && !getenv("EMAGLS_OZ_NARROW");
+  if (wide)
+    return oz::launch_ozaki_gemm<oz::EpiStoreF64, oz::TileWide>(st, Tt_q, sT, B_q, sB, rows, S, KpD, T,
+                                                                oz::EpiStoreF64{tq, (long long)S}, sm_count());
   return oz::launch_ozaki_gemm(st, Tt_q, sT, B_q, sB, rows, S, KpD, T, oz::EpiStoreF64{tq, (long long)S}, sm_count());
 }
 

@@ -231,32 +231,42 @@ cudaError_t launch_householder_qr(cudaStream_t st, double* A, int D, int S, doub
 // ---------------------------------------------------------------------------------------------
 // E rows:  E[o][rowoff[i] + (n-ord(i))*Mc + c] = sum_{j in block n, j >= i} R[i][j] Ym[o][c][j]
 // ---------------------------------------------------------------------------------------------
-__global__ void build_E_kernel(const double* __restrict__ R, int S, int N, const double* __restrict__ Ym,
-                               int Mc, int B, const int* __restrict__ rowoff, const int* __restrict__ roword,
-                               long long Etot, double* __restrict__ E) {
-  // grid: (row i, orientation o); threads over (n, c)
-  const int i = blockIdx.x, o = blockIdx.y;
-  const int ord = roword[i];
-  const int cnt = (N + 1 - ord) * Mc;
-  const double* Ri = R + (long long)i * S;
+// One CTA per (order block n, orientation o): the block's columns of Ym[o] are staged in shared memory
+// ([Mc][2n+1], odd pitch: conflict free), one warp per row i < (n+1)^2 with the lanes over the channels c,
+// so the R entries are warp-uniform loads and the stores are contiguous.
+__global__ void __launch_bounds__(256)
+build_E_kernel(const double* __restrict__ R, int S, int N, const double* __restrict__ Ym,
+               int Mc, int B, const int* __restrict__ rowoff, const int* __restrict__ roword,
+               long long Etot, double* __restrict__ E) {
+  extern __shared__ double be_y[];
+  const int n = blockIdx.x, o = blockIdx.y, w = 2 * n + 1, s0 = n * n;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const double* Yo = Ym + (long long)o * Mc * S;
-  double* Eo = E + (long long)o * Etot + rowoff[i];
-  for (int idx = threadIdx.x; idx < cnt; idx += blockDim.x) {
-    int n = ord + idx / Mc, c = idx % Mc;
-    int j0 = n * n, j1 = (n + 1) * (n + 1);
-    if (j0 < i) j0 = i;  // R is upper triangular
-    const double* y = Yo + (long long)c * S;
-    double acc = 0.0;
-    for (int j = j0; j < j1; ++j) acc = fma(Ri[j], y[j], acc);
-    Eo[idx] = acc;
+  for (int idx = tid; idx < Mc * w; idx += blockDim.x) be_y[idx] = Yo[(long long)(idx / w) * S + s0 + idx % w];
+  __syncthreads();
+  const int nrows = min(S, (n + 1) * (n + 1));
+  double* Eo = E + (long long)o * Etot;
+  for (int i = warp; i < nrows; i += nw) {
+    const int ord = roword[i];
+    const int j0 = max(s0, i), j1 = s0 + w;   // R is upper triangular
+    const double* Ri = R + (long long)i * S;
+    double* e = Eo + rowoff[i] + (long long)(n - ord) * Mc;
+    for (int c = lane; c < Mc; c += 32) {
+      const double* y = be_y + c * w - s0;
+      double acc = 0.0;
+      for (int j = j0; j < j1; ++j) acc = fma(Ri[j], y[j], acc);
+      e[c] = acc;
+    }
   }
 }
 
 cudaError_t launch_build_E(cudaStream_t st, const double* R, int S, int N, const double* Ym,
                            int Mc, int B, const int* rowoff, const int* roword, long long Etot,
                            double* E) {
-  dim3 grid(S, B);
-  build_E_kernel<<<grid, 128, 0, st>>>(R, S, N, Ym, Mc, B, rowoff, roword, Etot, E);
+  dim3 grid(N + 1, B);
+  const size_t smem = (size_t)Mc * (2 * N + 1) * sizeof(double);
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  build_E_kernel<<<grid, 256, smem, st>>>(R, S, N, Ym, Mc, B, rowoff, roword, Etot, E);
   return cudaGetLastError();
 }
 

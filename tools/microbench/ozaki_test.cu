@@ -24,7 +24,8 @@ __global__ void ref_gemm(const double* A, const double* B, int M, int N, int K, 
   nrm[(size_t)m * N + n] = sqrt(na * nb);
 }
 
-int run(int M, int N, int K, int T, int reps, int grade, int dbg = 0) {
+template <class Cfg>
+int run_cfg(int M, int N, int K, int T, int reps, int grade, int dbg) {
   const int Kpad = (K + 31) & ~31;
   std::mt19937_64 rng(1234 + M + N + K);
   std::normal_distribution<double> nd(0.0, 1.0);
@@ -56,7 +57,7 @@ int run(int M, int N, int K, int T, int reps, int grade, int dbg = 0) {
   int sms = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   EpiStoreF64 epi{dC, N};
-  CK(launch_ozaki_gemm(0, qA, sA, qB, sB, M, N, Kpad, T, epi, sms));
+  CK((launch_ozaki_gemm<EpiStoreF64, Cfg>(0, qA, sA, qB, sB, M, N, Kpad, T, epi, sms)));
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("M=%d N=%d K=%d T=%d: kernel failed: %s\n", M, N, K, T, cudaGetErrorString(e)); return 1; }
   std::vector<double> hC((size_t)M * N), hR((size_t)M * N), hN((size_t)M * N);
@@ -74,23 +75,25 @@ int run(int M, int N, int K, int T, int reps, int grade, int dbg = 0) {
   float ms = 0.f;
   if (reps > 0) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-    for (int i = 0; i < 2; ++i) launch_ozaki_gemm(0, qA, sA, qB, sB, M, N, Kpad, T, epi, sms, dbg);
+    for (int i = 0; i < 2; ++i) launch_ozaki_gemm<EpiStoreF64, Cfg>(0, qA, sA, qB, sB, M, N, Kpad, T, epi, sms, dbg);
     cudaEventRecord(a);
-    for (int i = 0; i < reps; ++i) launch_ozaki_gemm(0, qA, sA, qB, sB, M, N, Kpad, T, epi, sms, dbg);
+    for (int i = 0; i < reps; ++i) launch_ozaki_gemm<EpiStoreF64, Cfg>(0, qA, sA, qB, sB, M, N, Kpad, T, epi, sms, dbg);
     cudaEventRecord(b);
     CK(cudaDeviceSynchronize());
     cudaEventElapsedTime(&ms, a, b); ms /= reps;
   }
   const double flop = 2.0 * M * N * K;
-  const double iops = 2.0 * M * (double)((N + 63) / 64 * 64) * Kpad * (T * (T + 1) / 2);
-  printf("M=%5d N=%5d K=%4d T=%d grade=%d: err/(|a||b|) max %.2e (at m=%zu n=%zu: got %.15g want %.15g)  rel(typical) %.2e  nan %zu",
-         M, N, K, T, grade, emax, where / N, where % N, hC[where], hR[where], erel, bad);
+  const double iops = 2.0 * M * (double)((N + Cfg::NT - 1) / Cfg::NT * Cfg::NT) * Kpad * (T * (T + 1) / 2);
+  printf("NT=%d M=%5d N=%5d K=%4d T=%d grade=%d: err/(|a||b|) max %.2e (at m=%zu n=%zu: got %.15g want %.15g)  rel(typical) %.2e  nan %zu",
+         Cfg::NT, M, N, K, T, grade, emax, where / N, where % N, hC[where], hR[where], erel, bad);
   if (reps > 0) printf("  dbg=%d %.3f ms  %.1f TFLOP/s fp64-equivalent  %.0f int8 TOP/s", dbg, ms, flop / ms / 1e9, iops / ms / 1e9);
   printf("\n");
   fflush(stdout);
   cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dR); cudaFree(dNrm); cudaFree(sA); cudaFree(sB); cudaFree(qA); cudaFree(qB);
   return (bad == 0 && emax < 1e-9) ? 0 : 1;
 }
+
+int run(int M, int N, int K, int T, int reps, int grade, int dbg = 0) { return run_cfg<TileDefault>(M, N, K, T, reps, grade, dbg); }
 
 int main(int argc, char** argv) {
   int fails = 0;
@@ -105,6 +108,10 @@ int main(int argc, char** argv) {
     fails += run(2702, 14400, 400, 6, 10, 0, dbg);
     fails += run(14400, 400, 2702, 6, 10, 0, dbg);
   }
+  fails += run_cfg<TileWide>(300, 200, 400, 6, 0, 4, 0);
+  fails += run_cfg<TileWide>(1000, 400, 2702, 6, 0, 0, 0);
+  for (int dbg = 0; dbg < 4; ++dbg) fails += run_cfg<TileWide>(14400, 400, 2702, 6, 10, 0, dbg);
+  fails += run_cfg<TileWide>(2702, 14400, 400, 6, 10, 0, 0);
   fails += run(2702, 14400, 400, 5, 10, 0);
   fails += run(14400, 400, 2702, 5, 10, 0);
   printf("%s (%d failing)\n", fails ? "FAIL" : "PASS", fails);
