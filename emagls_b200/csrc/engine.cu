@@ -503,6 +503,8 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
     const int oc = std::min(OC, a.num_orient - o0);
     const int pj = a.num_sets * oc;
     const ProbMap pm{oc, o0, a.num_orient};
+    bool cv_ready = false;                                      // digits of u_kb already produced by a fused tail
+    const bool fuse_fwd = getenv("EMAGLS_NO_FUSE") == nullptr;  // A/B switch
     const double* Yc = Yo + (size_t)o0 * Mc * S;
     {
       ProfSpan ps(h, EM_PROF_SETUP);
@@ -551,6 +553,7 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
         fprintf(stderr, "orient chunk %d: bins %d..%d: %d Gram bins, %d TSQR bins\n", o0, gb0, gb0 + nb - 1, ng, nb - ng);
       }
       int slot_base = -1, slot_n = 0;  // bins [slot_base, slot_base + slot_n) hold valid TSQR operators
+      if (gb0 == 1) cv_ready = false;
       for (int kb = gb0; kb < gb0 + nb; ++kb) {
         const bool gram = fail_h[1 + kb - gb0] == 0;
         const cplx* bk = bn + (size_t)kb * (simN + 1);
@@ -588,11 +591,12 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
                                      (long long)nLS * 2 * S, 1, 1, 0, pm, Wsp, w_ear, K, kb, dc_fix, pj));
           h->launches += 1;
         } else {
-          {
+          if (!cv_ready) {   // else: the digits of u_kb were written by the fused tail of the previous Gram bin
             ProfSpan ps(h, EM_PROF_CHAIN_FWD);
             EM_CUDA(launch_fwd_small(st, Yc, Mc, S, d_roword, bk, pm, pj, Wsp, w_ear, K, kb - 1, Cv));
             if (use_oz) EM_CUDA(launch_slice_rows(st, Cv, S, 1, 4 * pj, S, KpS, oz_T, Cv_q, sCv));
           }
+          cv_ready = false;
           int nsplit = 1;
           const long long split_stride = 4LL * pj * S;
           if (use_oz) {
@@ -624,10 +628,13 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
           }
           {
             ProfSpan ps(h, EM_PROF_CHAIN_BWD);
-            if (gram)
+            if (gram) {
+              const bool fuse = use_oz && fuse_fwd && kb + 1 < K;
               EM_CUDA(launch_bwd_small(st, Yc, Mc, S, d_roword, bk, pbg, pm, pj, tq, 0, 0, 0, nsplit, split_stride, Wsp,
-                                       w_ear, K, kb, dc_fix));
-            else
+                                       w_ear, K, kb, dc_fix, fuse ? bn + (size_t)(kb + 1) * (simN + 1) : nullptr, Cv_q, sCv,
+                                       KpS, oz_T));
+              cv_ready = fuse;
+            } else
               EM_CUDA(launch_chain_bwd(st, bp, ops, slot, slot_n, tq, 0, 0, 0, nsplit, split_stride, pm, Wsp, w_ear, K,
                                        kb, dc_fix, pj));
           }

@@ -14,6 +14,7 @@
 // it go through the TSQR + Jacobi kernel (solver_kernels.cu).
 #include <cstdlib>
 #include "kernels.h"
+#include "ozaki.cuh"
 
 namespace emagls {
 
@@ -377,14 +378,27 @@ cudaError_t launch_fwd_small(cudaStream_t st, const double* Y, int Mc, int S, co
 // backward (Gram bins): v = Y_o (conj(b_k) .* z),  W_k = v * Pb.   z rows like Cv, or shared per
 // (set, ear) for the LS bins (z_shared != 0: z + set*z_set_stride + ear*z_ear_stride, [re | im]).
 // ---------------------------------------------------------------------------------------------
+// Fused tail (T > 0): the forward contraction of the NEXT bin, u = b_{k+1} .* (Y_o^T W_k) (fwd_small_kernel),
+// and its slicing into int8 digits (slice_rows_kernel), computed while Y_o is still L2-hot and W_k is in
+// shared memory: the per-orientation harmonics (102 KB) are fetched from HBM once per bin instead of
+// twice, and the FP64 vector u never exists in HBM.  Same arithmetic, in the same order, as the two
+// separate kernels.
+struct FwdFuse {
+  const cplx* bk_next;     // b_n(k+1) [N+1]; nullptr: no fused tail
+  int8_t* Cv_q; double* sCv; int KpS; long long rows;   // digits [T][rows][KpS], rows = 4 * num_prob
+};
+
+template <int T>
 __global__ void __launch_bounds__(256)
 bwd_small_kernel(const double* __restrict__ Y, int Mc, int S, const int* __restrict__ roword,
                  const cplx* __restrict__ bk, const cplx* __restrict__ Pb, ProbMap pm,
                  const double* __restrict__ z, long long z_set_stride, long long z_ear_stride,
-                 int z_shared, int nsplit, long long split_stride, cplx* __restrict__ Wsp, long long w_ear_stride, int K, int k, int dc_fix) {
+                 int z_shared, int nsplit, long long split_stride, cplx* __restrict__ Wsp, long long w_ear_stride, int K, int k, int dc_fix,
+                 FwdFuse ff) {
   extern __shared__ __align__(16) unsigned char bsm_raw[];
   cplx* zb = reinterpret_cast<cplx*>(bsm_raw);   // [2][S]
   cplx* v = zb + 2 * (size_t)S;                  // [2][Mc]
+  cplx* wk = v + 2 * Mc;                         // [2][Mc]: W_k for the fused tail
   const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const int ol = j % pm.oc;
   const long long p = pm.global(j);
@@ -428,23 +442,88 @@ bwd_small_kernel(const double* __restrict__ Y, int Mc, int S, const int* __restr
     cplx* wp = Wsp + (long long)e * w_ear_stride + (p * Mc + m) * K + k;
     *wp = acc;
     if (dc_fix && k == 1) wp[-1] = mk(acc.x, 0.0);  // W(1,:) = real(W(2,:)), lib/getEMagLs2Filters.m:109-110
+    if (T > 0) wk[idx] = acc;
   }
+  if constexpr (T > 0) {
+    __shared__ double red[4][8];
+    __shared__ double up_s[4];
+    __syncthreads();
+    double* cv = reinterpret_cast<double*>(zb);   // [4][S]: rows e*2 + {re, im} (zb is no longer needed)
+    double mx[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int s2 = tid; s2 < S; s2 += blockDim.x) {
+      double a0r = 0.0, a0i = 0.0, a1r = 0.0, a1i = 0.0;
+#pragma unroll 8
+      for (int m = 0; m < Mc; ++m) {
+        const double y = Yo[(long long)m * S + s2];
+        a0r = fma(y, wk[m].x, a0r); a0i = fma(y, wk[m].y, a0i);
+        a1r = fma(y, wk[Mc + m].x, a1r); a1i = fma(y, wk[Mc + m].y, a1i);
+      }
+      const cplx b = ff.bk_next[roword[s2]];
+      const double c0 = fma(b.x, a0r, -b.y * a0i), c1 = fma(b.x, a0i, b.y * a0r);
+      const double c2 = fma(b.x, a1r, -b.y * a1i), c3 = fma(b.x, a1i, b.y * a1r);
+      cv[s2] = c0; cv[S + s2] = c1; cv[2 * S + s2] = c2; cv[3 * S + s2] = c3;
+      mx[0] = fmax(mx[0], fabs(c0)); mx[1] = fmax(mx[1], fabs(c1));
+      mx[2] = fmax(mx[2], fabs(c2)); mx[3] = fmax(mx[3], fabs(c3));
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) mx[r] = fmax(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], sh));
+      if (lane == 0) red[r][warp] = mx[r];
+    }
+    __syncthreads();
+    if (tid < 4) {
+      double m4 = 0.0;
+      for (int w = 0; w < nw; ++w) m4 = fmax(m4, red[tid][w]);
+      int e = 0;
+      if (m4 > 0.0 && m4 < 1e300) frexp(m4, &e);           // slice_rows_kernel: 2^e > max |x|
+      ff.sCv[(long long)j * 4 + tid] = scalbn(1.0, e - 6);
+      up_s[tid] = scalbn(1.0, 6 - e);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 4 * ff.KpS; idx += blockDim.x) {
+      const int r = idx / ff.KpS, s2 = idx - r * ff.KpS;
+      const double x = (s2 < S) ? cv[r * S + s2] * up_s[r] : 0.0;
+      int8_t* o = ff.Cv_q + ((long long)j * 4 + r) * ff.KpS + s2;
+      oz::slice_digits<T>(x, [&](int t, int q) { o[(long long)t * ff.rows * ff.KpS] = (int8_t)q; });
+    }
+  }
+}
+
+template <int T>
+static cudaError_t launch_bwd_small_t(cudaStream_t st, size_t smem, int num_prob, const double* Y, int Mc, int S,
+                                      const int* roword, const cplx* bk, const cplx* Pb, ProbMap pm, const double* z,
+                                      long long z_set_stride, long long z_ear_stride, int z_shared, int nsplit,
+                                      long long split_stride, cplx* Wsp, long long w_ear_stride, int K, int k, int dc_fix,
+                                      FwdFuse ff) {
+  static size_t set_to = 0;
+  if (smem > 48 * 1024 && smem > set_to) {
+    cudaError_t e = cudaFuncSetAttribute(bwd_small_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    set_to = smem;
+  }
+  bwd_small_kernel<T><<<num_prob, 256, smem, st>>>(Y, Mc, S, roword, bk, Pb, pm, z, z_set_stride, z_ear_stride, z_shared,
+                                                  nsplit, split_stride, Wsp, w_ear_stride, K, k, dc_fix, ff);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_bwd_small(cudaStream_t st, const double* Y, int Mc, int S, const int* roword,
                              const cplx* bk, const cplx* Pb, ProbMap pm, int num_prob, const double* z,
                              long long z_set_stride, long long z_ear_stride, int z_shared, int nsplit,
-                             long long split_stride, cplx* Wsp, long long w_ear_stride, int K, int k, int dc_fix) {
-  size_t smem = ((size_t)2 * S + 2 * Mc) * sizeof(cplx);
-  static size_t set_to = 0;
-  if (smem > 48 * 1024 && smem > set_to) {
-    cudaError_t e = cudaFuncSetAttribute(bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    set_to = smem;
+                             long long split_stride, cplx* Wsp, long long w_ear_stride, int K, int k, int dc_fix,
+                             const cplx* bk_next, int8_t* Cv_q, double* sCv, int KpS, int T) {
+  const size_t smem = ((size_t)2 * S + 4 * Mc) * sizeof(cplx);
+  FwdFuse ff{bk_next, Cv_q, sCv, KpS, 4LL * num_prob};
+  const int Tf = bk_next ? T : 0;
+#define EM_BWD_ARGS st, smem, num_prob, Y, Mc, S, roword, bk, Pb, pm, z, z_set_stride, z_ear_stride, z_shared, nsplit, \
+                    split_stride, Wsp, w_ear_stride, K, k, dc_fix, ff
+  switch (Tf) {
+    case 0: return launch_bwd_small_t<0>(EM_BWD_ARGS);
+    case 5: return launch_bwd_small_t<5>(EM_BWD_ARGS);
+    case 6: return launch_bwd_small_t<6>(EM_BWD_ARGS);
+    default: return cudaErrorInvalidValue;
   }
-  bwd_small_kernel<<<num_prob, 256, smem, st>>>(Y, Mc, S, roword, bk, Pb, pm, z, z_set_stride, z_ear_stride, z_shared,
-                                               nsplit, split_stride, Wsp, w_ear_stride, K, k, dc_fix);
-  return cudaGetLastError();
+#undef EM_BWD_ARGS
 }
 
 }  // namespace emagls

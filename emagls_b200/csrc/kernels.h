@@ -110,7 +110,10 @@ cudaError_t launch_fwd_small(cudaStream_t st, const double* Y, int Mc, int S, co
 cudaError_t launch_bwd_small(cudaStream_t st, const double* Y, int Mc, int S, const int* roword,
                              const cplx* bk, const cplx* Pb, ProbMap pm, int num_prob, const double* z,
                              long long z_set_stride, long long z_ear_stride, int z_shared, int nsplit,
-                             long long split_stride, cplx* Wsp, long long w_ear_stride, int K, int k, int dc_fix);
+                             long long split_stride, cplx* Wsp, long long w_ear_stride, int K, int k, int dc_fix,
+                             // fused forward of the next bin + slicing (bk_next != nullptr): see gram_kernels.cu
+                             const cplx* bk_next = nullptr, int8_t* Cv_q = nullptr, double* sCv = nullptr,
+                             int KpS = 0, int T = 0);
 
 // ---------------------------------------------------------------- ozaki_kernels.cu
 // FP64-accurate GEMMs on the int8 tensor cores (tcgen05 + TMEM + TMA); see ozaki.cuh.
