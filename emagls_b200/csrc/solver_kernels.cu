@@ -10,6 +10,7 @@
 //     Y_reg_inv = B * conj(Q_C) * Pb,     Pb = conj(J) diag(1/(s max(s, c s_max))) X^T.
 // When no singular value can be clipped (||R||_F ||R^-1||_F <= 1/c, a rigorous bound) the
 // Jacobi sweeps are skipped and Pb = R_C^-T (plain least squares).
+#include <cstdlib>
 #include "kernels.h"
 #include "reflect.cuh"
 
@@ -21,7 +22,11 @@ BlockPlan make_block_plan(int S, int Mc) {
   BlockPlan bp;
   bp.S = S; bp.Mc = Mc;
   bp.MC = (Mc <= 32) ? 32 : 64;
-  bp.RB = (bp.MC == 32) ? 96 : 128;
+  // MC = 32: row blocks of 96 (three CTAs per SM).  EMAGLS_FACTOR_RB=64 selects blocks of 64 (52 KB working
+  // set, four CTAs of <= 64 registers per thread per SM): measured on B200 the factor kernel gains 2.7 %
+  // and the reflector chain, which then has 192 instead of 128 reflectors per problem, loses as much.
+  static const int rb32 = [] { const char* e = getenv("EMAGLS_FACTOR_RB"); return (e && atoi(e) == 64) ? 64 : 96; }();
+  bp.RB = (bp.MC == 32) ? rb32 : 128;
   bp.R0 = (S < Mc + bp.RB) ? S : Mc + bp.RB;
   bp.nblk = 1 + (S - bp.R0 + bp.RB - 1) / bp.RB;
   return bp;
@@ -144,7 +149,7 @@ __device__ void qr_block(cplx* Wk, int LD, int Mc, bool first, int hi, cplx* tau
 }
 
 template <int MC, int RB>
-__global__ void __launch_bounds__(FT, (MC == 32) ? 3 : 1)
+__global__ void __launch_bounds__(FT, (MC == 32) ? (RB <= 64 ? 4 : 3) : 1)
 factor_kernel(BlockPlan bp, RowSource src, OperatorSet ops, int kbase, int G, double regul, int try_fast) {
   constexpr int LD = MC + RB;
   extern __shared__ __align__(16) unsigned char fsm_raw[];
@@ -392,7 +397,15 @@ cudaError_t launch_factor(cudaStream_t st, const BlockPlan& bp, const RowSource&
                           const OperatorSet& ops, int num_prob, int kbase, int G, double regul, int try_fast) {
   size_t smem = factor_smem_bytes(bp);
   cudaError_t e;
-  if (bp.MC == 32) {
+  if (bp.MC == 32 && bp.RB == 64) {
+    static bool set32n = false;
+    if (!set32n) {
+      e = cudaFuncSetAttribute(factor_kernel<32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      set32n = true;
+    }
+    factor_kernel<32, 64><<<num_prob * G, FT, smem, st>>>(bp, src, ops, kbase, G, regul, try_fast);
+  } else if (bp.MC == 32) {
     static bool set32 = false;
     if (!set32) {
       e = cudaFuncSetAttribute(factor_kernel<32, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
