@@ -323,6 +323,21 @@ def main():
                            " (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full launch)")
     except Exception:
         pass
+    # The largest single class of the step is the per-(orientation, bin) TSQR + Jacobi kernel of the clipped
+    # bins (FP64 on the CUDA cores, neither an HBM nor a tensor-core roofline): reported beside the GEMM.
+    # Algorithmic flops per problem: 8 (S M^2 - M^3 / 3) for the QR, ~1800 flops per rotated column pair
+    # x M (M - 1) / 2 pairs x the measured 9 sweeps, 8 M^3 for the projector.
+    fac = None
+    if prof.get("factor", {}).get("n"):
+        fl = 8.0 * (S * M * M - M ** 3 / 3.0) + 9 * 1800.0 * M * (M - 1) / 2 + 8.0 * M ** 3
+        fac_ms = prof["factor"]["ms"] / args.steps
+        fac = {"kernel": "factor_kernel (TSQR + one-sided Jacobi, FP64 CUDA cores)", "ms_per_step": fac_ms,
+               "share": shares.get("factor"), "algorithmic_mflop_per_problem": fl / 1e6,
+               "note": "problems per step = clipped bins x orientations (em32 @48 kHz: 87 x orientations); "
+                       "peak = the measured DGEMM figure (the FP64 pipe of this part)"}
+        if M == 32 and abs(pr["fs"] - 48000.0) < 1:
+            fac["achieved_tflops"] = fl * 87 * B / (fac_ms * 1e-3) / 1e12
+            fac["frac_of_dgemm_peak"] = (fac["achieved_tflops"] / dgemm_peak) if dgemm_peak else None
     if use_oz:
         achieved = i8_ops[dom] / (avg_ms * 1e-3) / 1e12
         roofline = {"kernel": f"ozaki_gemm_kernel<{oz_T}> ({dom}: tcgen05.mma kind::i8, TMEM accumulators, TMA operands)",
@@ -341,6 +356,8 @@ def main():
                     "peak_source": "live cuBLAS DGEMM 8192^3, best of 5 (MEASURED_PEAKS.json has no FP64 entry)",
                     "flops_per_launch": fp64_flops[dom], "avg_launch_ms": avg_ms, "class_time_share": shares,
                     "algorithmic_tflops_whole_job": value / world * ALGO_GFLOP_PER_SET / 1e3}
+
+    roofline["largest_class"] = fac
 
     # ---------------- render (secondary metric: Msamples/s of the 32 -> 2 channel, 512-tap FIR)
     render = None
