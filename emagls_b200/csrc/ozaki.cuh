@@ -133,11 +133,6 @@ __device__ __forceinline__ uint32_t instr_desc_i8(int m, int n) {
 }
 
 // ------------------------------------------------------------------------------------- slicing
-constexpr double RN_MAGIC = 6755399441055744.0;   // 1.5 * 2^52: (x + RN_MAGIC) has rn(x) in its low mantissa bits for |x| < 2^31
-// exact int64 -> double for |v| < 2^51 without I2F.S64: add v to the mantissa of 1.5 * 2^52, subtract the constant
-__device__ __forceinline__ double ll2double_small(long long v) {
-  return __longlong_as_double(v + 0x4338000000000000LL) - RN_MAGIC;
-}
 // Balanced base-256 digits of a (|a| <= 64): a = sum_{s < T} q_s 256^-s + r, |r| <= 256^-(T-1) / 2,
 // |q_0| <= 64, q_s in [-128, 127].  Two int32 limbs (hi: digits 0..T-4, lo: the last three) are rounded
 // out of the FP64 value; the balanced digits of a limb x are the bytes of (x + 0x808080) ^ 0x808080
@@ -148,12 +143,9 @@ __device__ __forceinline__ void slice_digits(double a, Store&& store) {
   static_assert(T >= 4 && T <= 6, "hi limb: 1..3 digits, lo limb: 3 digits");
   constexpr int nh = T - 3;
   constexpr int bias_hi = (nh == 3) ? 0x808080 : (nh == 2 ? 0x8080 : 0x80);
-  // round to nearest even without F2I / I2F (a slow pipe): x + 1.5 * 2^52 holds rn(x) in its low word
   const double ah = a * (double)(1 << (8 * (nh - 1)));
-  const double th = ah + RN_MAGIC;
-  int hi = __double2loint(th);                                        // rn(ah), |hi| <= 2^22
-  const double tl = (ah - (th - RN_MAGIC)) * 16777216.0 + RN_MAGIC;
-  const int lo = __double2loint(tl);                                  // |lo| <= 2^23
+  int hi = __double2int_rn(ah);
+  const int lo = __double2int_rn((ah - (double)hi) * 16777216.0);     // |lo| <= 2^23
   const int yl = lo + 0x808080;                                       // in (0, 2^25)
   hi += yl >> 24;                                                     // carry (0 or 1)
   const int zl = yl ^ 0x808080;
@@ -339,22 +331,10 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tile_origin(g, tile, m_tiles, n_tiles, m0, n0);
       const int n_mma = min(NT, ((g.N - n0) + 15) & ~15);
       const int m = m0 + lg * 32 + lane;
-      const int n_lim = (g.dbg & 1) ? 0 : n_mma;
-      // operand scales: fetched before the accumulators are waited for.  They are powers of two (or 0),
-      // so only the high word of each is kept in a register.
-      const double sa = (m < g.M) ? g.sA[m] : 0.0;
-      int sbv[CH_PER_WARP][8];
-#pragma unroll
-      for (int ci = 0; ci < CH_PER_WARP; ++ci) {
-        const int c0 = chunk0 + ci * chunk_step;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int n = n0 + c0 + q;
-          sbv[ci][q] = (c0 < n_lim && n < g.N) ? __double2hiint(g.sB[n]) : 0;
-        }
-      }
       mbar_wait(&tmem_full_bar, acc_phase);
       tc_fence_after();
+      const double sa = (m < g.M) ? g.sA[m] : 0.0;
+      const int n_lim = (g.dbg & 1) ? 0 : n_mma;
       // Phase 1 (drain): this warp's chunks go TMEM -> registers -> FP64; the accumulators are then
       // handed back, so the MMA warp starts the next tile while phase 2 (the functor: phase
       // continuation, slicing, global stores) runs from registers.
@@ -377,7 +357,9 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int d = 3; d < MAX_SLICES; ++d)
               if (d < T) lo = lo * 256 + a[d][q];
-            v[ci][q] = fma(ll2double_small(lo), w_lo, ll2double_small(hi) * w_hi) * (sa * __hiloint2double(sbv[ci][q], 0));
+            const int n = n0 + c0 + q;
+            const double sb = (n < g.N) ? g.sB[n] : 0.0;
+            v[ci][q] = fma((double)lo, w_lo, (double)hi * w_hi) * (sa * sb);
           }
         }
       }

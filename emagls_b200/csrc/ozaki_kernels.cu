@@ -24,38 +24,30 @@ struct EpiPhaseSlice {
     int prob = n0 >> 2;
     int set = prob / orient_per_set;
     int left = (set + 1) * orient_per_set - prob;     // problems left in this set, >= 1
-    // all loads of the call first (|H_k| and its scale per pair), so their latencies overlap
-    double mag[4], us[4];
-    int sis[4];
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      const int ear = h & 1;
-      sis[h] = (set * 2 + ear) * scale_stride;
-      mag[h] = absH[(long long)set * abs_set_stride + (long long)ear * abs_ear_stride + m];
-      us[h] = up[sis[h]];
-      if (ear == 1 && --left == 0) { ++set; left = orient_per_set; }   // next pair belongs to the next problem
-    }
 #pragma unroll
     for (int q = 0; q < 8; q += 2) {
       const int n = n0 + q;
       if (n >= N) break;
+      const int ear = (n >> 1) & 1;
+      const double mag = absH[(long long)set * abs_set_stride + (long long)ear * abs_ear_stride + m];
       const double re = v[q], im = v[q + 1];
       const double a2 = fma(re, re, im * im);
-      const double mg = mag[q >> 1];
       double tr, ti;
       if (a2 > 1e-290 && a2 < 1e290) {
-        const double inv = mg * rsqrt(a2);
+        const double inv = mag * rsqrt(a2);
         tr = re * inv; ti = im * inv;
       } else if (a2 > 0.0) {
-        const double inv = mg / sqrt(a2);
+        const double inv = mag / sqrt(a2);
         tr = re * inv; ti = im * inv;
-      } else { tr = mg; ti = 0.0; }           // angle(0) = 0
+      } else { tr = mag; ti = 0.0; }          // angle(0) = 0
       if (nyquist) ti = 0.0;
-      const double u = us[q >> 1];
+      const int si = (set * 2 + ear) * scale_stride;
+      const double u = up[si];
       int8_t* p = Tq + (long long)n * Kpad + m;   // |tr u|, |ti u| <= 64 (u = 2^(6-e), 2^e > max_d |H_k|)
       oz::slice_digits<T>(tr * u, [&](int s, int q_) { p[(long long)s * slice_stride] = (int8_t)q_; });
       oz::slice_digits<T>(ti * u, [&](int s, int q_) { p[(long long)s * slice_stride + Kpad] = (int8_t)q_; });
-      if (m == 0) { const double s_ = sc[sis[q >> 1]]; sT[n] = s_; sT[n + 1] = s_; }
+      if (m == 0) { const double s_ = sc[si]; sT[n] = s_; sT[n + 1] = s_; }
+      if (ear == 1 && --left == 0) { ++set; left = orient_per_set; }   // next pair belongs to the next problem
     }
   }
 };
