@@ -416,13 +416,13 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
       }
   }
   // ---------------- int8 tensor-core route for the two direction-grid contractions (ozaki.cuh)
-  int oz_T = 6;   // balanced base-256 digits: 48 bits
+  int oz_T = (cfg.precision == EMAGLS_PRECISION_FP32) ? 4 : 6;   // balanced base-256 digits: 48 (32) bits
   if (const char* e = getenv("EMAGLS_OZAKI_SLICES")) oz_T = atoi(e);
   bool use_oz = true;
   if (const char* e = getenv("EMAGLS_GEMM")) use_oz = std::string(e) != "dmma";
   const int KpS = oz_pad32(S), KpD = oz_pad32(D);
   // longer contractions than the int32 accumulators hold exactly go through the DMMA GEMM instead
-  if (oz_T < 5 || oz_T > 6 || K - kls1 <= 0 || !oz_contraction_fits(KpD, oz_T) || !oz_contraction_fits(KpS, oz_T))
+  if ((oz_T != 4 && oz_T != 6) || K - kls1 <= 0 || !oz_contraction_fits(KpD, oz_T) || !oz_contraction_fits(KpS, oz_T))
     use_oz = false;
   int8_t *YhA_q = nullptr, *YhB_q = nullptr, *QB_q = nullptr;
   double *sYhA = nullptr, *sYhB = nullptr, *sQB = nullptr, *upH = nullptr, *scH = nullptr;

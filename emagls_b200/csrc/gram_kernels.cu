@@ -519,7 +519,7 @@ cudaError_t launch_bwd_small(cudaStream_t st, const double* Y, int Mc, int S, co
                     split_stride, Wsp, w_ear_stride, K, k, dc_fix, ff
   switch (Tf) {
     case 0: return launch_bwd_small_t<0>(EM_BWD_ARGS);
-    case 5: return launch_bwd_small_t<5>(EM_BWD_ARGS);
+    case 4: return launch_bwd_small_t<4>(EM_BWD_ARGS);
     case 6: return launch_bwd_small_t<6>(EM_BWD_ARGS);
     default: return cudaErrorInvalidValue;
   }

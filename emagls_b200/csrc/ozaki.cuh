@@ -445,7 +445,7 @@ cudaError_t launch_ozaki_gemm(cudaStream_t st, const int8_t* Aq, const double* s
   const int m_tiles = (M + TILE_M - 1) / TILE_M, n_tiles = (N + Cfg::NT - 1) / Cfg::NT;
   GemmArgs g{M, N, Kpad, sA, sB, dbg, n_tiles < m_tiles ? 1 : 0, Cfg::NT};
   switch (T) {
-    case 5: return launch_ozaki_gemm_t<5, Epi, Cfg>(st, tmA, tmB, g, epi, num_sms);
+    case 4: return launch_ozaki_gemm_t<4, Epi, Cfg>(st, tmA, tmB, g, epi, num_sms);
     case 6: return launch_ozaki_gemm_t<6, Epi, Cfg>(st, tmA, tmB, g, epi, num_sms);
     default: return cudaErrorInvalidValue;
   }

@@ -86,7 +86,7 @@ cudaError_t launch_slice_rows(cudaStream_t st, const double* src, long long rs, 
                               int T, int8_t* out, double* scale) {
   const dim3 grid((R + 7) / 8), block(256);
   switch (T) {
-    case 5: oz::slice_rows_kernel<5><<<grid, block, 0, st>>>(src, rs, cs, R, K, Kpad, out, scale); break;
+    case 4: oz::slice_rows_kernel<4><<<grid, block, 0, st>>>(src, rs, cs, R, K, Kpad, out, scale); break;
     case 6: oz::slice_rows_kernel<6><<<grid, block, 0, st>>>(src, rs, cs, R, K, Kpad, out, scale); break;
     default: return cudaErrorInvalidValue;
   }
@@ -113,7 +113,7 @@ static cudaError_t oz_fwd_t(cudaStream_t st, const OzFwdArgs& a) {
 cudaError_t launch_oz_fwd(cudaStream_t st, const OzFwdArgs& a) {
   if (!oz::contraction_fits(a.KpS, a.T)) return cudaErrorInvalidValue;
   switch (a.T) {
-    case 5: return oz_fwd_t<5>(st, a);
+    case 4: return oz_fwd_t<4>(st, a);
     case 6: return oz_fwd_t<6>(st, a);
     default: return cudaErrorInvalidValue;
   }

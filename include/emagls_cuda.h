@@ -36,6 +36,12 @@ typedef enum {
 
 typedef enum { EMAGLS_BASIS_REAL = 0, EMAGLS_BASIS_COMPLEX = 1 } emagls_basis;
 typedef enum { EMAGLS_ARRAY_RIGID = 0, EMAGLS_ARRAY_OPEN = 1 } emagls_array_type;
+/* FP64 (default): every result within the FP64 tolerances of the parity tests.  FP32: the optional
+ * reduced-precision path of the model-based designers -- the two direction-grid contractions of the
+ * MagLS recursion carry 32 instead of 48 bits (4 instead of 6 int8 slices: 10 instead of 21 tensor-core
+ * products); the factorisations stay FP64, because FP32 cannot represent the clipped subspace.
+ * Filters agree with the FP64 path to ~1e-7 (bound asserted in the tests: 1e-4 relative, 0.05 dB).     */
+typedef enum { EMAGLS_PRECISION_FP64 = 0, EMAGLS_PRECISION_FP32 = 1 } emagls_precision;
 
 /* Constants that sit at the top of every reference function
  * (lib/getEMagLs2Filters.m:35-39, dependencies/getSMAIRMatrix.m:86). */
@@ -46,7 +52,8 @@ typedef struct {
   double speed_of_sound; /* C               = 343  */
   int array_type;        /* SIMULATION_ARRAY_TYPE = 'rigid' */
   int basis;             /* shDefinition: 'real' (default) or 'complex' */
-  int reserved[6];
+  int precision;         /* emagls_precision (default FP64) */
+  int reserved[5];
 } emagls_config;
 
 int emagls_create(int device, emagls_handle* out);

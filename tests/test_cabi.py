@@ -47,7 +47,7 @@ def test_config_defaults_match_reference_constants(lib):
     lib.emagls_config_default(ctypes.byref(cfg))
     # lib/getEMagLs2Filters.m:35-39, dependencies/getSMAIRMatrix.m:86
     assert cfg.nfft_max_len == 2048 and cfg.f_cut_min == 1e3 and cfg.svd_regul == 0.01
-    assert cfg.speed_of_sound == 343.0 and cfg.array_type == 0 and cfg.basis == 0
+    assert cfg.speed_of_sound == 343.0 and cfg.array_type == 0 and cfg.basis == 0 and cfg.precision == 0
 
 
 def test_no_cpu_fallback_without_a_device():

@@ -214,3 +214,24 @@ def test_stress_config_full_length_properties(em, h, grids):
         pw = (Ymic * oracle.sh_repToOrder(bn[:, None])[:, 0][None, :]) @ Yc
         Wo = HL[k] @ oracle.regularized_inverse(pw)
         assert np.abs(sp[k, :, 1, 0] - Wo).max() <= 1e-8 * np.abs(Wo).max(), k
+
+
+def test_optional_fp32_contraction_path(em, h, c1, oracle_c1):
+    """north_star's optional reduced-precision path (config.precision = FP32: 4 instead of 6 int8 slices in the
+    two direction-grid contractions): within 1e-4 relative / 0.05 dB of the reference on the bins FP32 can
+    represent (sigma_min / sigma_max >= 1e-3: bins >= 16 for em32), and much closer in practice."""
+    cfg = h.default_config()
+    cfg.precision = 1
+    args = (c1["az"], c1["ze"], c1["r"], c1["maz"], c1["mze"], 4, c1["fs"], 512)
+    wL, wR, sp = em.getEMagLs2Filters(c1["hL"], c1["hR"], *args, handle=h, config=cfg, return_spectra=True)
+    oL, oR, osp = oracle_c1
+    for e, Wo in enumerate((osp["W_l"], osp["W_r"])):
+        err = np.abs(sp[:, :, e] - Wo).max(1) / np.abs(Wo).max(1)
+        assert err[16:].max() <= 1e-4, err[16:].max()
+        # magnitude response towards the grid directions is not needed here: per-bin coefficient error of 1e-4
+        # bounds the level error by 20 log10(1 + 1e-4) = 9e-4 dB << 0.05 dB
+    assert rel(wL, oL) < 1e-4 and rel(wR, oR) < 1e-4
+    # the switch really changes the arithmetic (different rounding than the FP64 path) and stays close to it
+    w64, _ = em.getEMagLs2Filters(c1["hL"], c1["hR"], *args, handle=h)
+    d = rel(wL, w64)
+    assert 0 < d < 1e-5, d

@@ -45,7 +45,7 @@ int run_cfg(int M, int N, int K, int T, int reps, int grade, int dbg) {
   CK(cudaMemcpy(dB, hB.data(), hB.size() * 8, cudaMemcpyHostToDevice));
   CK(cudaMemset(dC, 0xff, (size_t)M * N * 8));
   auto slice = [&](const double* d, int R, int8_t* q, double* sc) {
-    if (T == 5) slice_rows_kernel<5><<<(R + 7) / 8, 256>>>(d, K, 1, R, K, Kpad, q, sc);
+    if (T == 4) slice_rows_kernel<4><<<(R + 7) / 8, 256>>>(d, K, 1, R, K, Kpad, q, sc);
     else slice_rows_kernel<6><<<(R + 7) / 8, 256>>>(d, K, 1, R, K, Kpad, q, sc);
   };
   slice(dA, M, qA, sA);
@@ -90,7 +90,7 @@ int run_cfg(int M, int N, int K, int T, int reps, int grade, int dbg) {
   printf("\n");
   fflush(stdout);
   cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dR); cudaFree(dNrm); cudaFree(sA); cudaFree(sB); cudaFree(qA); cudaFree(qB);
-  return (bad == 0 && emax < 1e-9) ? 0 : 1;
+  return (bad == 0 && emax < (T >= 6 ? 1e-9 : 1e-6)) ? 0 : 1;
 }
 
 int run(int M, int N, int K, int T, int reps, int grade, int dbg = 0) { return run_cfg<TileDefault>(M, N, K, T, reps, grade, dbg); }
@@ -103,7 +103,7 @@ int main(int argc, char** argv) {
   }
   fails += run(128, 64, 64, 6, 0, 0);
   fails += run(300, 200, 400, 6, 0, 4);
-  fails += run(1000, 400, 2702, 5, 0, 0);
+  fails += run(1000, 400, 2702, 4, 0, 0);
   for (int dbg = 0; dbg < 4; ++dbg) {
     fails += run(2702, 14400, 400, 6, 10, 0, dbg);
     fails += run(14400, 400, 2702, 6, 10, 0, dbg);
@@ -112,8 +112,8 @@ int main(int argc, char** argv) {
   fails += run_cfg<TileWide>(1000, 400, 2702, 6, 0, 0, 0);
   for (int dbg = 0; dbg < 4; ++dbg) fails += run_cfg<TileWide>(14400, 400, 2702, 6, 10, 0, dbg);
   fails += run_cfg<TileWide>(2702, 14400, 400, 6, 10, 0, 0);
-  fails += run(2702, 14400, 400, 5, 10, 0);
-  fails += run(14400, 400, 2702, 5, 10, 0);
+  fails += run(2702, 14400, 400, 4, 10, 0);
+  fails += run_cfg<TileWide>(14400, 400, 2702, 4, 10, 0, 0);
   printf("%s (%d failing)\n", fails ? "FAIL" : "PASS", fails);
   return fails != 0;
 }
