@@ -420,6 +420,7 @@ bwd_small_kernel(const double* __restrict__ Y, int Mc, int S, const int* __restr
   for (int i = warp; i < Mc; i += nw) {
     const double* y = Yo + (long long)i * S;
     double a0r = 0.0, a0i = 0.0, a1r = 0.0, a1i = 0.0;
+#pragma unroll 4
     for (int s = lane; s < S; s += 32) {
       const double yv = y[s];
       const cplx q0 = zb[s], q1 = zb[S + s];
@@ -438,6 +439,7 @@ bwd_small_kernel(const double* __restrict__ Y, int Mc, int S, const int* __restr
   for (int idx = tid; idx < 2 * Mc; idx += blockDim.x) {
     const int e = idx / Mc, m = idx % Mc;
     cplx acc = mk(0.0, 0.0);
+#pragma unroll 8
     for (int i = 0; i < Mc; ++i) cfma(acc, v[e * Mc + i], pb[i * Mc + m]);
     cplx* wp = Wsp + (long long)e * w_ear_stride + (p * Mc + m) * K + k;
     *wp = acc;
