@@ -173,7 +173,8 @@ void fir_channels_dev(emagls_ctx* h, Arena& ar, const double* in, long long n, i
   EM_REQUIRE(nb < (1LL << 31), "signal too long");
   size_t free_b = 0, total_b = 0;
   EM_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  const double budget = std::min(0.3 * (double)free_b, 8.0 * 1073741824.0);
+  double budget = std::min(0.3 * (double)free_b, 8.0 * 1073741824.0);
+  if (const char* e = getenv("EMAGLS_FIR_WS_MB")) budget = std::max(1.0, atof(e)) * 1048576.0;   // tests: force chunking
   const double per_block = (double)N * 8 + (double)F * 16;
   const long long Bc = std::max<long long>(1, std::min<long long>(TB, (long long)(budget / per_block)));
   int* map = ar.upload(map_host, C);

@@ -72,6 +72,18 @@ def test_apply_radial_filter_matches_oracle(em, h, grids, n, kind, order, nfft):
     assert rel(y, yo) < 1e-11
 
 
+def test_apply_radial_filter_chunked_workspace(em, h, grids, monkeypatch):
+    """The per-channel FIR processes (channel, block) pairs in chunks when the workspace budget is small:
+    same result with a 1 MB budget (many chunks, ragged last chunk) as with the default single chunk."""
+    p = radial_params(grids, "tikhonov", 2, 256, 1)
+    x = np.random.default_rng(11).standard_normal((50001, 9))    # 9 channels x 28 blocks = 252 = 7 x 32 + 28
+    y1 = em.applyRadialFilter(x, p, handle=h)
+    monkeypatch.setenv("EMAGLS_FIR_WS_MB", "1")
+    y2 = em.applyRadialFilter(x, p, handle=h)
+    assert np.array_equal(y1, y2)
+    assert rel(y2, oracle.applyRadialFilter(x, p)) < 1e-11
+
+
 def test_apply_radial_filter_linearity_full_size(em, h, grids):
     """Size-independent property at the length of the shipped recording: linear, and an impulse
     returns the (delay-compensated) radial-filter IR of its order."""
