@@ -163,6 +163,122 @@ __global__ void unstage_output_kernel(const double* __restrict__ yseg, int nb, i
   out[(long long)ear * out_rows + (n - skip)] = yseg[((long long)ear * nb + b) * N + ov + i] * (1.0 / (double)N);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused overlap-save block: one CTA per block of L output frames.  For every channel the N-point real
+// FFT (as an N/2-point complex Stockham FFT, radix 4 with a leading radix-2 stage when log2(N/2) is odd,
+// ping-pong in shared memory), the multiply-accumulate with both ears' filter spectra into two
+// accumulators in shared memory, then the two inverse transforms and the store of the valid L frames.
+// The channel spectra never reach HBM: the kernel reads the input once (plus the N/L overlap) and the
+// L2-resident filter spectra, and writes the two output channels.
+//   rfft:  X[k] = (Z[k] + conj(Z[M-k])) / 2 - (i/2) W_N^k (Z[k] - conj(Z[M-k])),  z[n] = x[2n] + i x[2n+1]
+//   irfft: Zy[k] = (Y[k] + conj(Y[M-k])) + i conj(W_N^k) (Y[k] - conj(Y[M-k])),  y[2n] + i y[2n+1] = IFFT_M(Zy) / N
+// WM[q] = exp(-2 pi i q / M) (q < M/2), WN[k] = exp(-2 pi i k / N) (k <= M), M = N / 2.
+// ---------------------------------------------------------------------------------------------
+__global__ void render_twiddle_kernel(int M, cplx* __restrict__ WM, cplx* __restrict__ WN) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < M / 2) { double s_, c_; sincospi(-2.0 * (double)i / (double)M, &s_, &c_); WM[i] = mk(c_, s_); }
+  if (i <= M) { double s_, c_; sincospi(-(double)i / (double)M, &s_, &c_); WN[i] = mk(c_, s_); }
+}
+
+// in-place-free Stockham FFT of length M on the ping-pong buffers; returns the buffer holding the result
+template <bool INV>
+__device__ __forceinline__ cplx* stockham_fft(cplx* src, cplx* dst, int M, int logM, const cplx* __restrict__ WM,
+                                              int tid, int nt) {
+  int p = 1;
+  if (logM & 1) {
+    for (int j = tid; j < M / 2; j += nt) {
+      const cplx u0 = src[j], u1 = src[j + M / 2];
+      dst[2 * j] = cadd(u0, u1); dst[2 * j + 1] = csub(u0, u1);
+    }
+    __syncthreads();
+    cplx* t_ = src; src = dst; dst = t_;
+    p = 2;
+  }
+  const int T = M / 4;
+  while (p < M) {
+    const int tw = M / (4 * p);
+    for (int t = tid; t < T; t += nt) {
+      const int k = t & (p - 1);
+      cplx w1 = WM[k * tw], w2 = WM[2 * k * tw];
+      if (INV) { w1.y = -w1.y; w2.y = -w2.y; }
+      const cplx w3 = cmul(w1, w2);
+      const cplx u0 = src[t], u1 = cmul(src[t + T], w1), u2 = cmul(src[t + 2 * T], w2), u3 = cmul(src[t + 3 * T], w3);
+      const cplx v0 = cadd(u0, u2), v1 = csub(u0, u2), v2 = cadd(u1, u3);
+      cplx v3 = csub(u1, u3);
+      v3 = INV ? mk(-v3.y, v3.x) : mk(v3.y, -v3.x);          // * (+i) inverse, * (-i) forward
+      const int j = ((t - k) << 2) + k;
+      dst[j] = cadd(v0, v2); dst[j + p] = cadd(v1, v3); dst[j + 2 * p] = csub(v0, v2); dst[j + 3 * p] = csub(v1, v3);
+    }
+    __syncthreads();
+    cplx* t_ = src; src = dst; dst = t_;
+    p <<= 2;
+  }
+  return src;
+}
+
+__global__ void __launch_bounds__(512, 1)
+fused_render_kernel(const double* __restrict__ in, long long num_samples, int num_ch, const cplx* __restrict__ Hw,
+                    const cplx* __restrict__ WM, const cplx* __restrict__ WN, int N, int logM, int L, int ov,
+                    long long skip, long long out_rows, double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char fr_raw[];
+  const int M = N / 2, F = M + 1, tid = threadIdx.x, nt = blockDim.x;
+  cplx* A = reinterpret_cast<cplx*>(fr_raw);
+  cplx* Bf = A + M;
+  cplx* accL = Bf + M;
+  cplx* accR = accL + F;
+  const long long b = blockIdx.x;
+  const long long s_first = b * (long long)L - ov;          // even: L and ov are even
+  for (int k = tid; k < F; k += nt) { accL[k] = mk(0.0, 0.0); accR[k] = mk(0.0, 0.0); }
+  for (int ch = 0; ch < num_ch; ++ch) {
+    const double* x = in + (long long)ch * num_samples;     // 16-byte aligned: num_samples is even
+    for (int n = tid; n < M; n += nt) {
+      const long long i0 = s_first + 2LL * n;
+      cplx v;
+      if (i0 >= 0 && i0 + 1 < num_samples) {
+        const double2 d = *reinterpret_cast<const double2*>(x + i0);
+        v = mk(d.x, d.y);
+      } else {
+        v = mk((i0 >= 0 && i0 < num_samples) ? x[i0] : 0.0, (i0 + 1 >= 0 && i0 + 1 < num_samples) ? x[i0 + 1] : 0.0);
+      }
+      A[n] = v;
+    }
+    __syncthreads();
+    const cplx* Z = stockham_fft<false>(A, Bf, M, logM, WM, tid, nt);
+    const cplx* hl = Hw + (long long)ch * F;
+    const cplx* hr = Hw + ((long long)num_ch + ch) * F;
+    for (int k = tid; k < F; k += nt) {
+      const cplx zk = Z[k & (M - 1)], zm = cconj(Z[(M - k) & (M - 1)]);
+      const cplx sm_ = cadd(zk, zm), df = cmul(WN[k], csub(zk, zm));
+      // X = sm/2 - (i/2) df
+      const cplx X = mk(0.5 * (sm_.x + df.y), 0.5 * (sm_.y - df.x));
+      cfma(accL[k], X, hl[k]);
+      cfma(accR[k], X, hr[k]);
+    }
+    __syncthreads();
+  }
+  const double inv_n = 1.0 / (double)N;
+  for (int ear = 0; ear < 2; ++ear) {
+    const cplx* acc = ear ? accR : accL;
+    for (int k = tid; k < M; k += nt) {
+      const cplx yk = acc[k], ym = cconj(acc[M - k]);
+      const cplx sm_ = cadd(yk, ym), df = cmul(cconj(WN[k]), csub(yk, ym));
+      A[k] = mk(sm_.x - df.y, sm_.y + df.x);               // sm + i df
+    }
+    __syncthreads();
+    const cplx* zy = stockham_fft<true>(A, Bf, M, logM, WM, tid, nt);
+    for (int n = tid; n < M; n += nt) {
+      const int i = 2 * n;
+      if (i + 1 < ov) continue;
+      const cplx v = zy[n];
+      const long long s0 = b * (long long)L + (i - ov);
+      if (i >= ov && s0 < num_samples && s0 >= skip) out[(long long)ear * out_rows + (s0 - skip)] = v.x * inv_n;
+      const long long s1 = s0 + 1;
+      if (s1 >= 0 && s1 < num_samples && s1 >= skip) out[(long long)ear * out_rows + (s1 - skip)] = v.y * inv_n;
+    }
+    __syncthreads();
+  }
+}
+
 int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -228,6 +344,37 @@ void binaural_decode_dev(emagls_ctx* h, const double* in, long long num_samples,
     EM_CUDA(cudaGetLastError());
     EM_FFT(cufftExecD2Z(rp.filt, wp, reinterpret_cast<cufftDoubleComplex*>(Hw)));
     h->launches += 1;
+  }
+
+  // Fused route (EMAGLS_RENDER_FUSED=1; off by default): one kernel per call, the channel spectra stay in shared
+  // memory.  Needs the FFT and both accumulators in one CTA's shared memory (N <= 4096) and 16-byte aligned
+  // channels.  Measured on B200 (10 minutes, 32 channels, 512 taps; tools/gpu_render_ab.py,
+  // profiles/r01_v22_render_ab.txt): identical output to 8.5e-16, but 15.3 ms against 9.6 ms for the cuFFT route
+  // below -- the radix-4 shared-memory FFT makes six passes over 32 KB per channel with one 512-thread CTA per SM
+  // and is shared-memory bound; it needs a register-resident radix-16 transform before it can win.
+  if (env_int("EMAGLS_RENDER_FUSED", 0) != 0 && N <= 4096 && N >= 8 && (num_samples % 2 == 0) && (ov % 2 == 0) &&
+      (reinterpret_cast<uintptr_t>(in) % 16 == 0)) {
+    const int M2 = N / 2;
+    int logM = 0;
+    while ((1 << logM) < M2) ++logM;
+    cplx* WM = ar.get<cplx>((size_t)M2 / 2 + 1);
+    cplx* WN = ar.get<cplx>((size_t)M2 + 1);
+    render_twiddle_kernel<<<(M2 + 1 + 255) / 256, 256, 0, st>>>(M2, WM, WN);
+    EM_CUDA(cudaGetLastError());
+    const size_t smem = ((size_t)2 * M2 + 2 * (M2 + 1)) * sizeof(cplx);
+    static size_t set_to = 0;
+    if (smem > 48 * 1024 && smem > set_to) {
+      EM_CUDA(cudaFuncSetAttribute(fused_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      set_to = smem;
+    }
+    {
+      ProfSpan ps(h, EM_PROF_RENDER_MAC);
+      fused_render_kernel<<<(unsigned)nblk_total, 512, smem, st>>>(in, num_samples, num_ch, Hw, WM, WN, N, logM, L, ov, skip,
+                                                                  out_rows, out);
+      EM_CUDA(cudaGetLastError());
+    }
+    h->launches += 2;
+    return;
   }
 
   // Forward transforms.  Direct route (default when every channel of the caller's signal is 16-byte

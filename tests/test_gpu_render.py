@@ -104,3 +104,17 @@ def test_errors(em, h):
         em.binauralDecode(x, 48000, np.zeros((4, 2)), np.zeros((4, 2)), 48000, handle=h)
     with pytest.raises(NotImplementedError):
         em.binauralDecode(x, 48000, np.zeros((4, 3)), np.zeros((4, 3)), 44100, handle=h)
+
+
+@pytest.mark.parametrize("n,ch,ln,comp", [(30000, 32, 512, False), (7000, 25, 256, True), (20000, 8, 128, False)])
+def test_fused_overlap_save_route_matches_oracle(em, h, monkeypatch, n, ch, ln, comp):
+    """The optional single-kernel route (EMAGLS_RENDER_FUSED=1: shared-memory Stockham FFT, multiply-accumulate and
+    inverse transform per overlap-save block) against the oracle's convolution, 1e-9 relative as for the default."""
+    monkeypatch.setenv("EMAGLS_RENDER_FUSED", "1")
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((n, ch))
+    wL, wR = rng.standard_normal((ln, ch)), rng.standard_normal((ln, ch))
+    y = em.binauralDecode(x, 48000, wL, wR, 48000, comp, handle=h)
+    yo = oracle.binauralDecode(x, 48000, wL, wR, 48000, comp)
+    assert y.shape == yo.shape
+    assert np.abs(y - yo).max() / np.abs(yo).max() < 1e-9
