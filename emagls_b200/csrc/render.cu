@@ -180,15 +180,19 @@ __global__ void render_twiddle_kernel(int M, cplx* __restrict__ WM, cplx* __rest
   if (i <= M) { double s_, c_; sincospi(-(double)i / (double)M, &s_, &c_); WN[i] = mk(c_, s_); }
 }
 
-// in-place-free Stockham FFT of length M on the ping-pong buffers; returns the buffer holding the result
-template <bool INV>
-__device__ __forceinline__ cplx* stockham_fft(cplx* src, cplx* dst, int M, int logM, const cplx* __restrict__ WM,
-                                              int tid, int nt) {
+// Stockham FFT of length M on ping-pong buffers, NB independent transforms side by side (buffer pair q at
+// src + q * stride, dst + q * stride; the twiddles are shared); returns the offset-0 buffer holding the results
+template <bool INV, int NB>
+__device__ __forceinline__ cplx* stockham_fft(cplx* src, cplx* dst, long long stride, int M, int logM,
+                                              const cplx* __restrict__ WM, int tid, int nt) {
   int p = 1;
   if (logM & 1) {
     for (int j = tid; j < M / 2; j += nt) {
-      const cplx u0 = src[j], u1 = src[j + M / 2];
-      dst[2 * j] = cadd(u0, u1); dst[2 * j + 1] = csub(u0, u1);
+#pragma unroll
+      for (int q = 0; q < NB; ++q) {
+        const cplx u0 = src[q * stride + j], u1 = src[q * stride + j + M / 2];
+        dst[q * stride + 2 * j] = cadd(u0, u1); dst[q * stride + 2 * j + 1] = csub(u0, u1);
+      }
     }
     __syncthreads();
     cplx* t_ = src; src = dst; dst = t_;
@@ -202,12 +206,17 @@ __device__ __forceinline__ cplx* stockham_fft(cplx* src, cplx* dst, int M, int l
       cplx w1 = WM[k * tw], w2 = WM[2 * k * tw];
       if (INV) { w1.y = -w1.y; w2.y = -w2.y; }
       const cplx w3 = cmul(w1, w2);
-      const cplx u0 = src[t], u1 = cmul(src[t + T], w1), u2 = cmul(src[t + 2 * T], w2), u3 = cmul(src[t + 3 * T], w3);
-      const cplx v0 = cadd(u0, u2), v1 = csub(u0, u2), v2 = cadd(u1, u3);
-      cplx v3 = csub(u1, u3);
-      v3 = INV ? mk(-v3.y, v3.x) : mk(v3.y, -v3.x);          // * (+i) inverse, * (-i) forward
       const int j = ((t - k) << 2) + k;
-      dst[j] = cadd(v0, v2); dst[j + p] = cadd(v1, v3); dst[j + 2 * p] = csub(v0, v2); dst[j + 3 * p] = csub(v1, v3);
+#pragma unroll
+      for (int q = 0; q < NB; ++q) {
+        const cplx* sq = src + q * stride;
+        cplx* dq = dst + q * stride;
+        const cplx u0 = sq[t], u1 = cmul(sq[t + T], w1), u2 = cmul(sq[t + 2 * T], w2), u3 = cmul(sq[t + 3 * T], w3);
+        const cplx v0 = cadd(u0, u2), v1 = csub(u0, u2), v2 = cadd(u1, u3);
+        cplx v3 = csub(u1, u3);
+        v3 = INV ? mk(-v3.y, v3.x) : mk(v3.y, -v3.x);          // * (+i) inverse, * (-i) forward
+        dq[j] = cadd(v0, v2); dq[j + p] = cadd(v1, v3); dq[j + 2 * p] = csub(v0, v2); dq[j + 3 * p] = csub(v1, v3);
+      }
     }
     __syncthreads();
     cplx* t_ = src; src = dst; dst = t_;
@@ -216,66 +225,91 @@ __device__ __forceinline__ cplx* stockham_fft(cplx* src, cplx* dst, int M, int l
   return src;
 }
 
+// input block of one channel -> buffer (pairs x[2n], x[2n+1] as one complex value), asynchronously with zero fill
+// outside the signal (both samples of a pair are inside or outside: the block origin and num_samples are even)
+__device__ __forceinline__ void fused_load_async(cplx* buf, const double* __restrict__ x, long long s_first,
+                                                 long long num_samples, int M, int tid, int nt) {
+  for (int n = tid; n < M; n += nt) {
+    const long long i0 = s_first + 2LL * n;
+    const bool in_range = (i0 >= 0 && i0 < num_samples);
+    cp_async16(buf + n, x + (in_range ? i0 : 0), in_range);
+  }
+}
+
+// Two channels per pass (NB = 2): buffers [A0 | A1 | B0 | B1 | accL | accR].
 __global__ void __launch_bounds__(512, 1)
 fused_render_kernel(const double* __restrict__ in, long long num_samples, int num_ch, const cplx* __restrict__ Hw,
                     const cplx* __restrict__ WM, const cplx* __restrict__ WN, int N, int logM, int L, int ov,
                     long long skip, long long out_rows, double* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char fr_raw[];
   const int M = N / 2, F = M + 1, tid = threadIdx.x, nt = blockDim.x;
-  cplx* A = reinterpret_cast<cplx*>(fr_raw);
-  cplx* Bf = A + M;
-  cplx* accL = Bf + M;
+  cplx* A = reinterpret_cast<cplx*>(fr_raw);        // A0, A1
+  cplx* Bf = A + 2 * M;                             // B0, B1
+  cplx* accL = Bf + 2 * M;
   cplx* accR = accL + F;
   const long long b = blockIdx.x;
   const long long s_first = b * (long long)L - ov;          // even: L and ov are even
   for (int k = tid; k < F; k += nt) { accL[k] = mk(0.0, 0.0); accR[k] = mk(0.0, 0.0); }
-  for (int ch = 0; ch < num_ch; ++ch) {
-    const double* x = in + (long long)ch * num_samples;     // 16-byte aligned: num_samples is even
-    for (int n = tid; n < M; n += nt) {
-      const long long i0 = s_first + 2LL * n;
-      cplx v;
-      if (i0 >= 0 && i0 + 1 < num_samples) {
-        const double2 d = *reinterpret_cast<const double2*>(x + i0);
-        v = mk(d.x, d.y);
-      } else {
-        v = mk((i0 >= 0 && i0 < num_samples) ? x[i0] : 0.0, (i0 + 1 >= 0 && i0 + 1 < num_samples) ? x[i0 + 1] : 0.0);
+  // ping-pong roles: the transform of the pair in `cur` uses `oth` as scratch and leaves the spectra in one of
+  // the two; the other one is free while the spectra are unpacked and accumulated, so the next pair of channels
+  // is prefetched into it (cp.async) and becomes `cur` of the next iteration
+  cplx* cur = A;
+  cplx* oth = Bf;
+  fused_load_async(cur, in, s_first, num_samples, M, tid, nt);
+  if (num_ch > 1) fused_load_async(cur + M, in + num_samples, s_first, num_samples, M, tid, nt);
+  cp_async_commit();
+  for (int ch = 0; ch < num_ch; ch += 2) {
+    const int nb2 = (ch + 1 < num_ch) ? 2 : 1;
+    cp_async_wait<0>();
+    __syncthreads();
+    const cplx* Z = (nb2 == 2) ? stockham_fft<false, 2>(cur, oth, M, M, logM, WM, tid, nt)
+                               : stockham_fft<false, 1>(cur, oth, M, M, logM, WM, tid, nt);
+    cplx* freeb = (Z == cur) ? oth : cur;
+    if (ch + 2 < num_ch) {
+      fused_load_async(freeb, in + (long long)(ch + 2) * num_samples, s_first, num_samples, M, tid, nt);
+      if (ch + 3 < num_ch) fused_load_async(freeb + M, in + (long long)(ch + 3) * num_samples, s_first, num_samples, M, tid, nt);
+      cp_async_commit();
+    }
+    for (int q = 0; q < nb2; ++q) {
+      const cplx* Zq = Z + (long long)q * M;
+      const cplx* hl = Hw + (long long)(ch + q) * F;
+      const cplx* hr = Hw + ((long long)num_ch + ch + q) * F;
+      for (int k = tid; k < F; k += nt) {
+        const cplx zk = Zq[k & (M - 1)], zm = cconj(Zq[(M - k) & (M - 1)]);
+        const cplx sm_ = cadd(zk, zm), df = cmul(WN[k], csub(zk, zm));
+        const cplx X = mk(0.5 * (sm_.x + df.y), 0.5 * (sm_.y - df.x));     // sm/2 - (i/2) df
+        cfma(accL[k], X, hl[k]);
+        cfma(accR[k], X, hr[k]);
       }
-      A[n] = v;
     }
-    __syncthreads();
-    const cplx* Z = stockham_fft<false>(A, Bf, M, logM, WM, tid, nt);
-    const cplx* hl = Hw + (long long)ch * F;
-    const cplx* hr = Hw + ((long long)num_ch + ch) * F;
-    for (int k = tid; k < F; k += nt) {
-      const cplx zk = Z[k & (M - 1)], zm = cconj(Z[(M - k) & (M - 1)]);
-      const cplx sm_ = cadd(zk, zm), df = cmul(WN[k], csub(zk, zm));
-      // X = sm/2 - (i/2) df
-      const cplx X = mk(0.5 * (sm_.x + df.y), 0.5 * (sm_.y - df.x));
-      cfma(accL[k], X, hl[k]);
-      cfma(accR[k], X, hr[k]);
-    }
-    __syncthreads();
+    oth = (freeb == cur) ? oth : cur;
+    cur = freeb;
+    // the barrier at the top of the next iteration orders the reads of Z before the next transform's writes
   }
+  __syncthreads();
+  // both ears side by side
   const double inv_n = 1.0 / (double)N;
-  for (int ear = 0; ear < 2; ++ear) {
-    const cplx* acc = ear ? accR : accL;
-    for (int k = tid; k < M; k += nt) {
+  for (int k = tid; k < M; k += nt) {
+#pragma unroll
+    for (int ear = 0; ear < 2; ++ear) {
+      const cplx* acc = ear ? accR : accL;
       const cplx yk = acc[k], ym = cconj(acc[M - k]);
       const cplx sm_ = cadd(yk, ym), df = cmul(cconj(WN[k]), csub(yk, ym));
-      A[k] = mk(sm_.x - df.y, sm_.y + df.x);               // sm + i df
+      A[ear * M + k] = mk(sm_.x - df.y, sm_.y + df.x);               // sm + i df
     }
-    __syncthreads();
-    const cplx* zy = stockham_fft<true>(A, Bf, M, logM, WM, tid, nt);
-    for (int n = tid; n < M; n += nt) {
-      const int i = 2 * n;
-      if (i + 1 < ov) continue;
-      const cplx v = zy[n];
-      const long long s0 = b * (long long)L + (i - ov);
-      if (i >= ov && s0 < num_samples && s0 >= skip) out[(long long)ear * out_rows + (s0 - skip)] = v.x * inv_n;
-      const long long s1 = s0 + 1;
-      if (s1 >= 0 && s1 < num_samples && s1 >= skip) out[(long long)ear * out_rows + (s1 - skip)] = v.y * inv_n;
+  }
+  __syncthreads();
+  const cplx* zy = stockham_fft<true, 2>(A, Bf, M, M, logM, WM, tid, nt);
+  for (int n = tid; n < M; n += nt) {
+    const int i = 2 * n;
+    if (i < ov) continue;
+    const long long s0 = b * (long long)L + (i - ov);
+#pragma unroll
+    for (int ear = 0; ear < 2; ++ear) {
+      const cplx v = zy[ear * M + n];
+      if (s0 < num_samples && s0 >= skip) out[(long long)ear * out_rows + (s0 - skip)] = v.x * inv_n;
+      if (s0 + 1 < num_samples && s0 + 1 >= skip) out[(long long)ear * out_rows + (s0 + 1 - skip)] = v.y * inv_n;
     }
-    __syncthreads();
   }
 }
 
@@ -349,9 +383,10 @@ void binaural_decode_dev(emagls_ctx* h, const double* in, long long num_samples,
   // Fused route (EMAGLS_RENDER_FUSED=1; off by default): one kernel per call, the channel spectra stay in shared
   // memory.  Needs the FFT and both accumulators in one CTA's shared memory (N <= 4096) and 16-byte aligned
   // channels.  Measured on B200 (10 minutes, 32 channels, 512 taps; tools/gpu_render_ab.py,
-  // profiles/r01_v22_render_ab.txt): identical output to 8.5e-16, but 15.3 ms against 9.6 ms for the cuFFT route
-  // below -- the radix-4 shared-memory FFT makes six passes over 32 KB per channel with one 512-thread CTA per SM
-  // and is shared-memory bound; it needs a register-resident radix-16 transform before it can win.
+  // profiles/r01_v25_render_ab.txt): identical output to 8e-16, but 11.8 ms against 9.6 ms for the cuFFT route
+  // below (15.3 ms before two channels shared a pass and the next pair was prefetched with cp.async) -- the radix-4
+  // shared-memory FFT makes six barrier-separated passes per channel pair with one 512-thread CTA per SM; it needs
+  // register-resident radix-8/16 passes before it can win.
   if (env_int("EMAGLS_RENDER_FUSED", 0) != 0 && N <= 4096 && N >= 8 && (num_samples % 2 == 0) && (ov % 2 == 0) &&
       (reinterpret_cast<uintptr_t>(in) % 16 == 0)) {
     const int M2 = N / 2;
@@ -361,7 +396,7 @@ void binaural_decode_dev(emagls_ctx* h, const double* in, long long num_samples,
     cplx* WN = ar.get<cplx>((size_t)M2 + 1);
     render_twiddle_kernel<<<(M2 + 1 + 255) / 256, 256, 0, st>>>(M2, WM, WN);
     EM_CUDA(cudaGetLastError());
-    const size_t smem = ((size_t)2 * M2 + 2 * (M2 + 1)) * sizeof(cplx);
+    const size_t smem = ((size_t)4 * M2 + 2 * (M2 + 1)) * sizeof(cplx);   // two channels side by side
     static size_t set_to = 0;
     if (smem > 48 * 1024 && smem > set_to) {
       EM_CUDA(cudaFuncSetAttribute(fused_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -38,12 +38,15 @@ def run(reps=5):
 
 
 ref = None
-for fused in ("0", "1"):
+ffts = [int(v) for v in os.environ.get("AB_FFTS", "0").split(",")]
+for fused, fft in [(f, n_) for n_ in ffts for f in ("0", "1")]:
     os.environ["EMAGLS_RENDER_FUSED"] = fused
+    if fft:
+        os.environ["EMAGLS_RENDER_FFT"] = str(fft)
     ms = run()
     yy = y.clone()
     dev_ = 0.0 if ref is None else float((yy - ref).abs().max() / ref.abs().max())
     if ref is None:
         ref = yy
-    print(f"fused={fused}  {ms:8.3f} ms  {n / ms / 1e3:9.1f} Msamples/s  "
+    print(f"fft={fft or 'default'} fused={fused}  {ms:8.3f} ms  {n / ms / 1e3:9.1f} Msamples/s  "
           f"{(n * (ch + 2) * 8) / ms / 1e6:7.1f} GB/s algorithmic  max deviation from the cuFFT route {dev_:.1e}", flush=True)
