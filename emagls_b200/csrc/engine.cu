@@ -595,6 +595,7 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
             ProfSpan ps(h, EM_PROF_CHAIN_FWD);
             EM_CUDA(launch_fwd_small(st, Yc, Mc, S, d_roword, bk, pm, pj, Wsp, w_ear, K, kb - 1, Cv));
             if (use_oz) EM_CUDA(launch_slice_rows(st, Cv, S, 1, 4 * pj, S, KpS, oz_T, Cv_q, sCv));
+            h->launches += use_oz ? 2 : 1;
           }
           cv_ready = false;
           int nsplit = 1;
@@ -611,7 +612,6 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
               ProfSpan ps(h, EM_PROF_GEMM_BWD);
               EM_CUDA(launch_oz_bwd(st, Tt_q, sTt, 4 * pj, gram ? YhB_q : QB_q, gram ? sYhB : sQB, S, KpD, oz_T, tq));
             }
-            h->launches += 1;
           } else {
             {
               ProfSpan ps(h, EM_PROF_GEMM_FWD);
@@ -638,7 +638,7 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
               EM_CUDA(launch_chain_bwd(st, bp, ops, slot, slot_n, tq, 0, 0, 0, nsplit, split_stride, pm, Wsp, w_ear, K,
                                        kb, dc_fix, pj));
           }
-          h->launches += 4;
+          h->launches += 3;   // forward GEMM, backward GEMM, backward small / chain kernel
         }
       }
     }
