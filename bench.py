@@ -326,10 +326,11 @@ def main():
     # The largest single class of the step is the per-(orientation, bin) TSQR + Jacobi kernel of the clipped
     # bins (FP64 on the CUDA cores, neither an HBM nor a tensor-core roofline): reported beside the GEMM.
     # Algorithmic flops per problem: 8 (S M^2 - M^3 / 3) for the QR, ~1800 flops per rotated column pair
-    # x M (M - 1) / 2 pairs x the measured 9 sweeps, 8 M^3 for the projector.
+    # x M (M - 1) / 2 pairs x 8 sweeps (9 were measured with the earlier, stricter stop rule; the current rule
+    # saves one on most bins), 8 M^3 for the projector.
     fac = None
     if prof.get("factor", {}).get("n"):
-        fl = 8.0 * (S * M * M - M ** 3 / 3.0) + 9 * 1800.0 * M * (M - 1) / 2 + 8.0 * M ** 3
+        fl = 8.0 * (S * M * M - M ** 3 / 3.0) + 8 * 1800.0 * M * (M - 1) / 2 + 8.0 * M ** 3
         fac_ms = prof["factor"]["ms"] / args.steps
         fac = {"kernel": "factor_kernel (TSQR + one-sided Jacobi, FP64 CUDA cores)", "ms_per_step": fac_ms,
                "share": shares.get("factor"), "algorithmic_mflop_per_problem": fl / 1e6,
