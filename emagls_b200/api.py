@@ -313,11 +313,12 @@ def binauralDecode(inp, inFs, decodingFilterLeft, decodingFilterRight, decodingF
     -- dependencies/binauralDecode.m:1-2."""
     if decodingFilterFs != inFs or (signal is not None and signalFs is not None and signalFs != inFs):
         raise NotImplementedError("binauralDecode: resampling is outside the device path")
-    if horRotAngleRad is not None and horRotAngleRad != 0:
-        raise NotImplementedError("rotateHOA_N3D is not vendored by the reference (binauralDecode.m:26-30)")
     if signal is not None:
         raise NotImplementedError("mono-signal convolution (binauralDecode.m:45-48) is outside the device path")
     h = handle or default_handle()
+    if horRotAngleRad is not None and horRotAngleRad != 0:
+        # binauralDecode.m:26-30: in = rotateHOA_N3D(in, rad2deg(horRotAngleRad), 0, 0)  (emagls_rotate_sh)
+        inp = rotateSH(inp, float(horRotAngleRad), handle=h)
     x = _f(inp)
     wL, wR = _f(decodingFilterLeft), _f(decodingFilterRight)
     if x.ndim != 2 or wL.shape != wR.shape or wL.shape[1] != x.shape[1]:

@@ -921,7 +921,10 @@ def binauralDecode(inp, inFs, decodingFilterLeft, decodingFilterRight, decodingF
     if decodingFilterFs != inFs:
         raise NotImplementedError("resample path (binauralDecode.m:18-23) is not on the hot path")
     if horRotAngleRad is not None and horRotAngleRad != 0:
-        raise NotImplementedError("rotateHOA_N3D is not vendored by the reference (binauralDecode.m:26-30)")
+        # binauralDecode.m:26-30: in = rotateHOA_N3D(in, rad2deg(horRotAngleRad), 0, 0); the callee is not
+        # vendored by the reference -- its published body is restated in frontend_oracle.rotateSH
+        from .frontend_oracle import rotateSH
+        inp = rotateSH(inp, float(horRotAngleRad))
     n = inp.shape[0]
     cplx = np.iscomplexobj(inp) or np.iscomplexobj(wL) or np.iscomplexobj(wR)
     left = np.zeros(n, dtype=complex if cplx else float)

@@ -166,6 +166,20 @@ def test_rotate_sh_moves_a_plane_wave(em, h):
     assert np.abs(Yr[0] - oracle.getSH(5, np.array([[0.8, 1.1]]), "real")[0]).max() < 1e-13
 
 
+def test_binaural_decode_with_horizontal_rotation(em, h):
+    """binauralDecode(..., horRotAngleRad) (dependencies/binauralDecode.m:26-30): rotation of the SH-domain input
+    followed by the decode, against the oracle's composition of the same two reference steps."""
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((9000, 25))
+    wL, wR = rng.standard_normal((512, 25)), rng.standard_normal((512, 25))
+    y = em.binauralDecode(x, 48000, wL, wR, 48000, True, None, None, 0.6, handle=h)
+    yo = oracle.binauralDecode(x, 48000, wL, wR, 48000, True, None, None, 0.6)
+    assert y.shape == yo.shape and rel(y, yo) < 1e-9
+    y0 = em.binauralDecode(x, 48000, wL, wR, 48000, True, handle=h)
+    assert rel(y, y0) > 1e-2                       # the rotation does something
+    assert np.array_equal(em.binauralDecode(x, 48000, wL, wR, 48000, True, None, None, 0.0, handle=h), y0)
+
+
 def test_full_ls_render_chain(em, h, grids):
     """verifyEMagLs.m:235-257 end to end on the device: encode -> radial filter -> binauralDecode."""
     az, ze = grids["hrirGridAziRad"][::3], grids["hrirGridZenRad"][::3]
