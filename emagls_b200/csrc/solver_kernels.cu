@@ -302,8 +302,25 @@ factor_kernel(BlockPlan bp, RowSource src, OperatorSet ops, int kbase, int G, do
     // orders below the 1e-12 the projector is needed to, so no trailing check sweep is run after it.
     // (Offline study on the em32 bins, row-cyclic order: the same projector to every printed digit as with
     // a 1e-9 threshold, one sweep less on most bins: 9 -> 8, 8 -> 7.)
+#ifdef EMAGLS_JACOBI_INCR_NORMS
+    // Compile-time variant for the next round's A/B (not built by default, not yet measured on the GPU): the
+    // squared column norms are kept in shared memory, refreshed at the start of every sweep and updated by the
+    // rotation (a' = a - t |g|, b' = b + t |g|; de Rijk), so that only the inner product g is reduced per pair.
+    // Offline study (profiles/r01_jacobi_offline_study.txt): same sweeps and projector accuracy.
+    double* nrm = reinterpret_cast<double*>(bn_s) + 64;
+#endif
     for (sweeps = 1; sweeps <= 40; ++sweeps) {
       int big = 0;
+#ifdef EMAGLS_JACOBI_INCR_NORMS
+      for (int j = warp; j < Mc; j += FT / 32) {
+        double a_ = 0.0;
+#pragma unroll
+        for (int u = 0; u < MC / 32; ++u) a_ += cabs2(Xs[j * MC + lane + 32 * u]);
+        a_ = wsum(a_);
+        if (lane == 0) nrm[j] = a_;
+      }
+      __syncthreads();
+#endif
       for (int r = 0; r < ne - 1; ++r) {
         for (int pi = warp * 2 + half; pi < ne / 2; pi += FT / 16) {
           int p, q;
@@ -317,14 +334,21 @@ factor_kernel(BlockPlan bp, RowSource src, OperatorSet ops, int kbase, int G, do
           for (int u = 0; u < RPL; ++u) {
             int row = hl + 16 * u;
             xp[u] = Xs[p * MC + row]; xq[u] = Xs[q * MC + row];
+#ifndef EMAGLS_JACOBI_INCR_NORMS
             a += cabs2(xp[u]); b += cabs2(xq[u]);
+#endif
             cfmac(g, xp[u], xq[u]);
           }
 #pragma unroll
           for (int sft = 8; sft > 0; sft >>= 1) {
+#ifndef EMAGLS_JACOBI_INCR_NORMS
             a += __shfl_xor_sync(hmask, a, sft); b += __shfl_xor_sync(hmask, b, sft);
+#endif
             g.x += __shfl_xor_sync(hmask, g.x, sft); g.y += __shfl_xor_sync(hmask, g.y, sft);
           }
+#ifdef EMAGLS_JACOBI_INCR_NORMS
+          a = nrm[p]; b = nrm[q];
+#endif
           const double gg = cabs2(g), ab = a * b;
           if (gg > tol2 * ab && gg > 0.0) {
             if (gg > 1e-14 * ab) big = 1;
@@ -347,6 +371,9 @@ factor_kernel(BlockPlan bp, RowSource src, OperatorSet ops, int kbase, int G, do
               cplx njq = cscale(jq, cs); cfma(njq, sph, jp);
               Js[p * MC + row] = njp; Js[q * MC + row] = njq;
             }
+#ifdef EMAGLS_JACOBI_INCR_NORMS
+            if (hl == 0) { nrm[p] = fma(-tw, gg, a); nrm[q] = fma(tw, gg, b); }
+#endif
           }
         }
         __syncthreads();
