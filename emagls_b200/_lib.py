@@ -157,7 +157,7 @@ class Handle:
         return cfg
 
     PROF_CLASSES = ("setup", "factor", "chain_fwd", "gemm_fwd", "gemm_bwd", "chain_bwd", "tail",
-                    "render_mac", "render_fft", "render_stage", "gram")
+                    "render_mac", "render_fft", "render_stage", "gram", "jacobi")
 
     def profile(self, on: bool = True):
         self.check(self.lib.emagls_profile_enable(self._h, 1 if on else 0))

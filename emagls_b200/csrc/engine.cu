@@ -441,13 +441,20 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
 
   // ---------------- memory plan: orientation chunks of OC, Gram bin groups of NB, TSQR slots of G
   const int ne = Mc * (Mc + 1) / 2, ne_ld = (ne + 1) & ~1;
-  const BlockPlan bp = make_block_plan(S, Mc);
+  // Mc <= 32: register-resident TSQR / Jacobi / reflector kernels of tsqr_kernels.cu ("sep" block plan);
+  // EMAGLS_FACTOR_OLD=1 (A/B switch) and Mc > 32 use the shared-memory kernel of solver_kernels.cu.
+  const bool sep = (Mc <= 32) && getenv("EMAGLS_FACTOR_OLD") == nullptr;
+  const BlockPlan bp = sep ? make_block_plan_sep(S, Mc) : make_block_plan(S, Mc);
   const int NB = std::min(128, K - 1);
-  const int G = std::min(4, K - 1);
-  const long long v_stride = (long long)Mc * S, tau_stride = (long long)bp.nblk * bp.MC, pb_stride = (long long)Mc * Mc;
+  int g_slots = sep ? 8 : 4;   // bins factorised per launch; the Jacobi kernel warm-starts along them
+  if (const char* e = getenv("EMAGLS_FACTOR_SLOTS")) g_slots = std::max(1, atoi(e));
+  const int G = std::min(g_slots, K - 1);
+  const bool jacobi_warm = getenv("EMAGLS_JACOBI_COLD") == nullptr;
+  const long long v_stride = sep ? 32LL * S : (long long)Mc * S, tau_stride = (long long)bp.nblk * bp.MC,
+                  pb_stride = (long long)Mc * Mc;
   const size_t per_orient =
       (size_t)Etot * 8 + (size_t)(nqs + nqa) * ne_ld * 8 + (size_t)2 * NB * ne_ld * 8 + (size_t)NB * pb_stride * 16 +
-      (size_t)G * (v_stride + tau_stride + pb_stride) * 16 +
+      (size_t)G * (v_stride + tau_stride + pb_stride + (sep ? 1024 : 0)) * 16 +
       (size_t)a.num_sets * ((size_t)(1 + 6) * 4 * S * 8 + (size_t)4 * D * 8);
   size_t free_b = 0, total_b = 0;
   EM_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -484,6 +491,14 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
   ops.tau = ar.get<cplx>((size_t)OC * G * tau_stride);
   ops.Pb = ar.get<cplx>((size_t)OC * G * pb_stride);
   ops.info = ar.get<int>((size_t)OC * G);
+  cplx* Rbuf = sep ? ar.get<cplx>((size_t)OC * G * 1024) : nullptr;   // R_C of every (orientation, slot)
+  auto chain_bwd = [&](int slot, int slot_n, const double* rhs, long long set_stride, long long ear_stride, int shared,
+                       int nsplit, long long split_stride, const ProbMap& pm, int kb, int pj) {
+    return sep ? launch_chain_bwd_sep(st, bp, ops, slot, slot_n, rhs, set_stride, ear_stride, shared, nsplit, split_stride,
+                                      pm, Wsp, w_ear, K, kb, dc_fix, pj)
+               : launch_chain_bwd(st, bp, ops, slot, slot_n, rhs, set_stride, ear_stride, shared, nsplit, split_stride, pm,
+                                  Wsp, w_ear, K, kb, dc_fix, pj);
+  };
   double* Cv = ar.get<double>((size_t)4 * PJ * S);
   double* Tt = use_oz ? nullptr : ar.get<double>((size_t)D * 4 * PJ);
   int8_t* Cv_q = use_oz ? ar.get<int8_t>((size_t)oz_T * 4 * PJ * KpS) : nullptr;
@@ -560,12 +575,23 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
         if (!gram && !(kb >= slot_base && kb < slot_base + slot_n)) {
           int Gn = 0;
           while (Gn < G && kb + Gn < gb0 + nb && fail_h[1 + kb + Gn - gb0] != 0) ++Gn;
-          {
+          // bins refused by the Gram route skip the fast-path test (it cannot succeed there)
+          const int try_fast = gram_thr > 0.0 ? 0 : 1;
+          if (sep) {
+            {
+              ProfSpan ps(h, EM_PROF_FACTOR);
+              EM_CUDA(launch_tsqr_sep(st, bp, src, ops, Rbuf, oc, kb, Gn));
+            }
+            {
+              ProfSpan ps(h, EM_PROF_JACOBI);
+              EM_CUDA(launch_svdclip(st, Mc, Rbuf, ops, oc, Gn, cfg.svd_regul, try_fast, jacobi_warm ? 1 : 0));
+            }
+            h->launches += 2;
+          } else {
             ProfSpan ps(h, EM_PROF_FACTOR);
-            // bins refused by the Gram route skip the fast-path test (it cannot succeed there)
-            EM_CUDA(launch_factor(st, bp, src, ops, oc, kb, Gn, cfg.svd_regul, gram_thr > 0.0 ? 0 : 1));
+            EM_CUDA(launch_factor(st, bp, src, ops, oc, kb, Gn, cfg.svd_regul, try_fast));
+            h->launches += 1;
           }
-          h->launches += 1;
           slot_base = kb; slot_n = Gn;
           if (debug) {
             std::vector<int> info((size_t)oc * Gn);
@@ -587,8 +613,7 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
             EM_CUDA(launch_bwd_small(st, Yc, Mc, S, d_roword, bk, pbg, pm, pj, Zls + off, (long long)2 * nLS * 2 * S,
                                      (long long)nLS * 2 * S, 1, 1, 0, Wsp, w_ear, K, kb, dc_fix));
           else
-            EM_CUDA(launch_chain_bwd(st, bp, ops, slot, slot_n, Tls + off, (long long)2 * nLS * 2 * S,
-                                     (long long)nLS * 2 * S, 1, 1, 0, pm, Wsp, w_ear, K, kb, dc_fix, pj));
+            EM_CUDA(chain_bwd(slot, slot_n, Tls + off, (long long)2 * nLS * 2 * S, (long long)nLS * 2 * S, 1, 1, 0, pm, kb, pj));
           h->launches += 1;
         } else {
           if (!cv_ready) {   // else: the digits of u_kb were written by the fused tail of the previous Gram bin
@@ -635,8 +660,7 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
                                        KpS, oz_T));
               cv_ready = fuse;
             } else
-              EM_CUDA(launch_chain_bwd(st, bp, ops, slot, slot_n, tq, 0, 0, 0, nsplit, split_stride, pm, Wsp, w_ear, K,
-                                       kb, dc_fix, pj));
+              EM_CUDA(chain_bwd(slot, slot_n, tq, 0, 0, 0, nsplit, split_stride, pm, kb, pj));
           }
           h->launches += 3;   // forward GEMM, backward GEMM, backward small / chain kernel
         }

@@ -20,6 +20,7 @@ enum EmProfClass {
   EM_PROF_RENDER_FFT,     // cuFFT transforms of the render
   EM_PROF_RENDER_STAGE,   // staging copies of the render
   EM_PROF_GRAM,           // Gram route: F blocks, DMMA assembly of G_k, warp-per-matrix Cholesky
+  EM_PROF_JACOBI,         // clipped inverse of R_C (one-sided Jacobi), register-resident path
   EM_PROF_NUM
 };
 

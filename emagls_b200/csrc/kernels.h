@@ -65,7 +65,9 @@ struct OperatorSet {       // per-(problem, bin-slot) outputs of the factorisati
   cplx* Pb;   long long pb_stride;   // [Mc][Mc] row-major: W = g * Pb
   int* info;                         // [problem*G + slot]: jacobi sweeps (0 = fast path)
 };
-struct BlockPlan { int S, Mc, MC, RB, R0, nblk; };
+// sep == 0: rows [0, R0) form the first (dense) block and the triangle R_C lives in rows [0, Mc) of the vector
+// space (solver_kernels.cu).  sep == 1: 32-row blocks against a triangle in a separate R space (tsqr_kernels.cu).
+struct BlockPlan { int S, Mc, MC, RB, R0, nblk, sep; };
 BlockPlan make_block_plan(int S, int Mc);
 size_t factor_smem_bytes(const BlockPlan& bp);
 cudaError_t launch_factor(cudaStream_t st, const BlockPlan& bp, const RowSource& src,
@@ -77,6 +79,19 @@ cudaError_t launch_chain_bwd(cudaStream_t st, const BlockPlan& bp, const Operato
                              long long tq_ear_stride, int tq_shared, int nsplit, long long split_stride,
                              ProbMap pm, cplx* Wsp, long long w_ear_stride, int K, int k, int dc_fix,
                              int num_prob);
+// ---------------------------------------------------------------- tsqr_kernels.cu (Mc <= 32, factored model)
+// Register-resident TSQR (warp per (problem, bin)), Jacobi SVD-clip (CTA per problem, the G bins of a launch in
+// sequence with warm starts) and reflector application for the "sep" block plan.  V [S][32], tau [nblk][32],
+// R [problem*G + slot][32][32] row-major.
+BlockPlan make_block_plan_sep(int S, int Mc);
+cudaError_t launch_tsqr_sep(cudaStream_t st, const BlockPlan& bp, const RowSource& src, const OperatorSet& ops,
+                            cplx* Rout, int num_prob, int kbase, int G);
+cudaError_t launch_svdclip(cudaStream_t st, int Mc, const cplx* Rin, const OperatorSet& ops, int num_prob, int G,
+                           double regul, int try_fast, int warm);
+cudaError_t launch_chain_bwd_sep(cudaStream_t st, const BlockPlan& bp, const OperatorSet& ops, int slot, int G,
+                                 const double* tq, long long tq_set_stride, long long tq_ear_stride, int tq_shared,
+                                 int nsplit, long long split_stride, ProbMap pm, cplx* Wsp, long long w_ear_stride,
+                                 int K, int k, int dc_fix, int num_prob);
 // generic-path phase step on rows: t = absH * y/|y|
 cudaError_t launch_phase_rows(cudaStream_t st, const double* Y, double* T, int num_prob, int D,
                               const double* absH, long long abs_set_stride, long long abs_ear_stride,

@@ -20,7 +20,7 @@ constexpr int FT = 256;  // threads of the factorisation kernel
 
 BlockPlan make_block_plan(int S, int Mc) {
   BlockPlan bp;
-  bp.S = S; bp.Mc = Mc;
+  bp.S = S; bp.Mc = Mc; bp.sep = 0;
   bp.MC = (Mc <= 32) ? 32 : 64;
   // MC = 32: row blocks of 96 (three CTAs per SM).  EMAGLS_FACTOR_RB=64 selects blocks of 64 (52 KB working
   // set, four CTAs of <= 64 registers per thread per SM): measured on B200 the factor kernel gains 2.7 %

@@ -1,0 +1,520 @@
+// Register-resident factorisation kernels for the model-based designers with Mc <= 32 channels.
+//
+// Reference step (lib/getEMagLs2Filters.m:86-89), as in solver_kernels.cu:
+//     [U,s,V] = svd(pwGrid.','econ','vector'); s = 1 ./ max(s, c*max(s)); Y_reg_inv = conj(U) * (s .* V.');
+// with pwGrid.' = Q C_k, C_k = R diag(b_k) Y_o^T [S x Mc].  The CTA-per-problem kernel of
+// solver_kernels.cu keeps C_k in shared memory; every complex multiply-add then moves 40 B through a
+// 128 B/clk port, which caps it at a fifth of the FP64 rate (ncu: FP64 pipe 34 %).  Here the matrix
+// never sits in shared memory:
+//
+//   tsqr_sep_kernel   one warp per (orientation, bin).  Lane c owns column c of a 32-row block in
+//                     registers; the pivot column of a Householder step is broadcast through 512 B of
+//                     shared memory, every lane forms its own inner product and update without any
+//                     reduction or barrier.  Flat-tree TSQR over ceil(S/32) blocks against a 32 x 32
+//                     triangle R_C that lives in a separate "R space" (the stacked matrix is [R_C; block],
+//                     starting from R_C = 0), so all blocks are treated alike.
+//   svdclip_kernel    one CTA per orientation, bins of a group in sequence: one-sided Jacobi on
+//                     X = R_C^H (cold) or X = R_C^H J_prev (warm start from the previous bin where the
+//                     grading of R_C allows it), block round-robin order: a warp holds four columns of
+//                     [X; J] in registers and performs the four cross rotations (six in the first round)
+//                     per load/store, incrementally updated column norms (de Rijk).
+//   chain_bwd_sep_kernel  applies Q_C^H to the two ears' right-hand sides from the reflector tiles and
+//                     multiplies by Pb.
+//
+// Reflector storage ("sep" block plan): V [S][32] row-major (a block of 32 rows is one contiguous 16 KB
+// tile; entry (r, c) is the tail of reflector c of block r/32, scaled so that v = [1; tail] with the 1
+// at R-space row c), tau [nblk][32].
+#include <cstdlib>
+#include "kernels.h"
+#include "reflect.cuh"
+
+namespace emagls {
+
+BlockPlan make_block_plan_sep(int S, int Mc) {
+  BlockPlan bp;
+  bp.S = S; bp.Mc = Mc; bp.MC = 32; bp.RB = 32; bp.R0 = 0;
+  bp.nblk = (S + 31) / 32;
+  bp.sep = 1;
+  return bp;
+}
+
+namespace {
+
+constexpr int TQ_WARPS = 4;
+constexpr int TQ_TRI = 528;            // packed upper triangle of a 32 x 32 matrix
+constexpr int TQ_BN = 72;              // modal coefficients of one bin (orders 0..MAX_SH_ORDER)
+constexpr int TQ_WARP_CPLX = TQ_TRI + 32 + TQ_BN;
+
+__device__ __forceinline__ int tri_idx(int j, int c) { return j * 32 - ((j * (j - 1)) >> 1) + (c - j); }
+
+// LAPACK zlarfg conventions, as reflector_scalars() of solver_kernels.cu: beta real, H = I - tau v v^H,
+// v = [1; sc * x].
+__device__ __forceinline__ void hh_scalars(cplx alpha, double xn, double* beta_out, cplx* tau_out, cplx* sc_out) {
+  if (xn == 0.0 && alpha.y == 0.0) {
+    *beta_out = alpha.x; *tau_out = mk(0.0, 0.0); *sc_out = mk(0.0, 0.0);
+    return;
+  }
+  const double s2 = cabs2(alpha) + xn;
+  const double nrm = sqrt(s2);
+  const double beta = -copysign(nrm, alpha.x);
+  const double ib = 1.0 / beta;
+  const cplx d = mk(alpha.x - beta, alpha.y);
+  const double id2 = 1.0 / cabs2(d);
+  *beta_out = beta;
+  *tau_out = mk((beta - alpha.x) * ib, -alpha.y * ib);
+  *sc_out = mk(d.x * id2, -d.y * id2);
+}
+
+__global__ void __launch_bounds__(TQ_WARPS * 32, 3)
+tsqr_sep_kernel(BlockPlan bp, RowSource src, OperatorSet ops, cplx* __restrict__ Rout, int kbase, int G, int items) {
+  extern __shared__ __align__(16) unsigned char tq_raw[];
+  const int S = bp.S, Mc = bp.Mc;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int2* rowinfo = reinterpret_cast<int2*>(tq_raw);                 // (order, offset into E) per row
+  const int tab_bytes = ((S * (int)sizeof(int2) + 15) / 16) * 16;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) rowinfo[i] = make_int2(src.roword[i], src.rowoff[i]);
+  __syncthreads();
+  const int item = blockIdx.x * TQ_WARPS + warp;
+  if (item >= items) return;            // warp-uniform; only warp-level synchronisation below
+  cplx* Rt = reinterpret_cast<cplx*>(tq_raw + tab_bytes) + (size_t)warp * TQ_WARP_CPLX;
+  cplx* xbuf = Rt + TQ_TRI;
+  cplx* bn_s = xbuf + 32;
+  const int prob = item / G, slot = item - prob * G, k = kbase + slot;
+  const long long oidx = (long long)prob * G + slot;
+  const int N = src.N;
+  for (int n = lane; n <= N; n += 32) bn_s[n] = src.bn[(long long)k * (N + 1) + n];
+  for (int i = lane; i < TQ_TRI; i += 32) Rt[i] = mk(0.0, 0.0);
+  __syncwarp();
+  const double* Eo = src.E + (long long)prob * src.Etot + lane;
+  const bool col_ok = lane < Mc;
+  cplx* Vg = ops.V + oidx * ops.v_stride;
+  cplx* taug = ops.tau + oidx * ops.tau_stride;
+
+  for (int t = 0; t < bp.nblk; ++t) {
+    const int r0 = t * 32;
+    cplx b[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) b[i] = mk(0.0, 0.0);
+    // ---- rows r0 .. r0+31 of C_k: C[r][c] = sum_{n >= ord(r)} b_n E[off(r) + (n - ord(r)) Mc + c]
+    const int nlo = rowinfo[r0].x;      // orders below that of the first row contribute nothing
+    for (int n = nlo; n <= N; ++n) {
+      const cplx bnn = bn_s[n];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int r = r0 + i;
+        if (r < S) {
+          const int2 ri = rowinfo[r];
+          if (n >= ri.x && col_ok) {
+            const double ev = __ldg(Eo + ri.y + (n - ri.x) * Mc);
+            b[i].x = fma(bnn.x, ev, b[i].x);
+            b[i].y = fma(bnn.y, ev, b[i].y);
+          }
+        }
+      }
+    }
+    // ---- 32 Householder steps on [R_C; block]
+    cplx my_tau = mk(0.0, 0.0), my_sc = mk(0.0, 0.0);
+    for (int j = 0; j < Mc; ++j) {
+      if (lane == j) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) xbuf[i] = b[i];
+      }
+      __syncwarp();
+      cplx w0 = mk(0.0, 0.0), w1 = mk(0.0, 0.0);
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        cfmac(w0, xbuf[i], b[i]);
+        cfmac(w1, xbuf[i + 1], b[i + 1]);
+      }
+      const cplx w = cadd(w0, w1);                       // lane j: ||x||^2
+      const double xn = __shfl_sync(0xffffffffu, w.x, j);
+      const cplx alpha = Rt[tri_idx(j, j)];
+      double beta; cplx tau, sc;
+      hh_scalars(alpha, xn, &beta, &tau, &sc);           // redundantly on every lane (warp-uniform values)
+      __syncwarp();
+      if (lane == j) { my_tau = tau; my_sc = sc; Rt[tri_idx(j, j)] = mk(beta, 0.0); }
+      if (lane > j && (tau.x != 0.0 || tau.y != 0.0)) {
+        const int ti = tri_idx(j, lane);
+        const cplx rjc = Rt[ti];
+        const cplx wc = cadd(cmulc(w, sc), rjc);         // (sc x)^H a + a_j
+        const cplx f = cmul(cconj(tau), wc);             // H^H = I - conj(tau) v v^H
+        const cplx fs = cmul(f, sc);
+        Rt[ti] = csub(rjc, f);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cfms(b[i], fs, xbuf[i]);
+      }
+      __syncwarp();
+    }
+    // ---- flush the reflector tails of this block (scaled) and its tau row
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int r = r0 + i;
+      if (r < S) Vg[(long long)r * 32 + lane] = cmul(b[i], my_sc);
+    }
+    taug[t * 32 + lane] = my_tau;
+  }
+  // ---- R_C, full 32 x 32 row-major with zeros below the diagonal
+  cplx* Rg = Rout + oidx * 1024;
+  for (int j = 0; j < 32; ++j) Rg[j * 32 + lane] = (lane >= j && j < Mc && lane < Mc) ? Rt[tri_idx(j, lane)] : mk(0.0, 0.0);
+}
+
+// =============================================================================================
+// svdclip_kernel: Pb = conj(J) diag(1/(s max(s, c s_max))) X^T from R_C = J diag(s) (X/s)^H
+// =============================================================================================
+constexpr int SV_T = 256;
+
+// one rotation of the column pair (p, q) held by this warp: lane = row of X and of J
+__device__ __forceinline__ void rotate_pair(cplx& xp, cplx& xq, cplx& jp, cplx& jq, double& a, double& b,
+                                            double tol2, int& big) {
+  cplx g = mk(0.0, 0.0);
+  cfmac(g, xp, xq);
+  g = wsumc(g);
+  const double gg = cabs2(g), ab = a * b;
+  if (gg > tol2 * ab && gg > 0.0) {
+    if (gg > 1e-14 * ab) big = 1;
+    const double d = b - a;
+    const double s2 = fma(d, d, 4.0 * gg);
+    const double root = s2 * rsqrt(s2);
+    const double rden = __drcp_rn(fabs(d) + root);
+    const double tw = copysign(2.0 * rden, d);         // t / |g|, signed
+    const double cs = rsqrt(fma(tw * tw, gg, 1.0));    // 1 / sqrt(1 + t^2)
+    const cplx sph = cscale(g, cs * tw);               // s * ph
+    const cplx sphc = mk(sph.x, -sph.y);
+    cplx np_ = cscale(xp, cs); cfms(np_, sphc, xq);
+    cplx nq_ = cscale(xq, cs); cfma(nq_, sph, xp);
+    xp = np_; xq = nq_;
+    cplx njp = cscale(jp, cs); cfms(njp, sphc, jq);
+    cplx njq = cscale(jq, cs); cfma(njq, sph, jp);
+    jp = njp; jq = njq;
+    a = fma(-tw, gg, a); b = fma(tw, gg, b);           // de Rijk: norms follow the rotation
+  }
+}
+
+__global__ void __launch_bounds__(SV_T, 4)
+svdclip_kernel(int Mc, const cplx* __restrict__ Rin, OperatorSet ops, int G, double regul, int try_fast, int warm) {
+  extern __shared__ __align__(16) unsigned char sv_raw[];
+  cplx* Rs = reinterpret_cast<cplx*>(sv_raw);   // R_C row-major, later Pb
+  cplx* Xs = Rs + 1024;                         // column-major: X(i, c) = Xs[c*32 + i]
+  cplx* Js = Xs + 1024;                         // column-major
+  double* nrm = reinterpret_cast<double*>(Js + 1024);   // [32]
+  double* sv = nrm + 32;                                // [32]
+  double* red = sv + 32;                                // [20]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int prob = blockIdx.x;
+  bool have_j = false;                      // Js holds the converged J of the previous bin
+
+  for (int slot = 0; slot < G; ++slot) {
+    const long long oidx = (long long)prob * G + slot;
+    const cplx* Rg = Rin + oidx * 1024;
+    for (int idx = tid; idx < 1024; idx += SV_T) Rs[idx] = Rg[idx];
+    __syncthreads();
+    bool fast = false;
+    int sweeps = 0;
+    if (try_fast) {
+      // R^-1 (upper triangular) into Xs, row-major, row by row from the bottom; if
+      // ||R||_F ||R^-1||_F <= 1/c no singular value can be clipped and Pb = R^-T.
+      cplx* Ri = Xs;
+      for (int idx = tid; idx < 1024; idx += SV_T) Ri[idx] = mk(0.0, 0.0);
+      __syncthreads();
+      for (int i = Mc - 1; i >= 0; --i) {
+        const cplx rii = Rs[i * 32 + i];
+        // Rinv(i, m) = (delta_im - sum_{j=i+1..m} R(i, j) Rinv(j, m)) / R(i, i), one lane group of 8 per m
+        const int group = tid >> 3, rl = tid & 7;
+        const int m = group;                      // 32 groups of 8 lanes
+        const bool act = (m >= i && m < Mc);
+        cplx sum = mk(0.0, 0.0);
+        if (act)
+          for (int j = i + 1 + rl; j <= m; j += 8) cfma(sum, Rs[i * 32 + j], Ri[j * 32 + m]);
+        sum = group_sum<8>(sum);                  // every lane of the warp takes part
+        if (act && rl == 0) Ri[i * 32 + m] = cdiv(mk((m == i ? 1.0 : 0.0) - sum.x, -sum.y), rii);
+        __syncthreads();
+      }
+      double fr = 0.0, fi = 0.0;
+      for (int idx = tid; idx < 1024; idx += SV_T) { fr += cabs2(Rs[idx]); fi += cabs2(Ri[idx]); }
+      fr = wsum(fr); fi = wsum(fi);
+      if (lane == 0) { red[warp] = fr; red[8 + warp] = fi; }
+      __syncthreads();
+      if (tid == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < SV_T / 32; ++w) { a += red[w]; b += red[8 + w]; }
+        red[16] = sqrt(a) * sqrt(b);
+      }
+      __syncthreads();
+      const double condF = red[16];
+      fast = (regul > 0.0) ? (condF <= 1.0 / regul) : (condF < 1e300);   // NaN -> false
+      if (fast) {
+        // Pb(i, m) = Rinv(m, i)
+        cplx tmp[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const int idx = tid + q * SV_T; tmp[q] = Ri[(idx & 31) * 32 + (idx >> 5)]; }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) Rs[tid + q * SV_T] = tmp[q];
+        have_j = false;
+        __syncthreads();
+      }
+    }
+    if (!fast) {
+      // ---- starting matrix: warm (X = R^H J_prev) where the diagonal of R_C is graded by less than 1e4
+      // (the product loses eps * grading of relative accuracy in the small columns), else cold (X = R^H, J = I)
+      bool use_warm = false;
+      if (warm && have_j) {
+        if (tid < 32) {
+          double d = (tid < Mc) ? fabs(Rs[tid * 32 + tid].x) : 0.0;
+          double dmax = d, dmin = (tid < Mc) ? d : 1e300;
+#pragma unroll
+          for (int m = 16; m > 0; m >>= 1) {
+            dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, m));
+            dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, m));
+          }
+          if (tid == 0) red[17] = (dmin > 1e-4 * dmax) ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        use_warm = red[17] != 0.0;
+      }
+      if (use_warm) {
+        // X(i, c) = sum_{j <= i} conj(R(j, i)) J(j, c)
+        for (int idx = tid; idx < 1024; idx += SV_T) {
+          const int c = idx >> 5, i = idx & 31;
+          cplx acc = mk(0.0, 0.0);
+          for (int j = 0; j <= i; ++j) cfmac(acc, Rs[j * 32 + i], Js[c * 32 + j]);
+          Xs[idx] = acc;
+        }
+      } else {
+        for (int idx = tid; idx < 1024; idx += SV_T) {
+          const int c = idx >> 5, i = idx & 31;
+          const cplx r = Rs[c * 32 + i];      // R(c, i)
+          Xs[idx] = mk(r.x, -r.y);
+          Js[idx] = mk(c == i ? 1.0 : 0.0, 0.0);
+        }
+      }
+      __syncthreads();
+      const double tol2 = 4.930380657631324e-32 * (double)Mc;   // (eps sqrt(Mc))^2
+      for (sweeps = 1; sweeps <= 40; ++sweeps) {
+        int big = 0;
+        // refresh the squared column norms once per sweep
+        for (int c = warp; c < 32; c += SV_T / 32) {
+          const double a_ = wsum(cabs2(Xs[c * 32 + lane]));
+          if (lane == 0) nrm[c] = a_;
+        }
+        __syncthreads();
+        // block round-robin over 16 blocks of two columns; warp = one block pair
+        for (int r = 0; r < 15; ++r) {
+          int A, B;
+          if (warp == 0) { A = 15; B = r; }
+          else { A = (r + warp) % 15; B = (r - warp + 15) % 15; }
+          if (A > B) { const int t_ = A; A = B; B = t_; }
+          const int c0 = 2 * A, c1 = 2 * A + 1, c2 = 2 * B, c3 = 2 * B + 1;
+          cplx x0 = Xs[c0 * 32 + lane], x1 = Xs[c1 * 32 + lane], x2 = Xs[c2 * 32 + lane], x3 = Xs[c3 * 32 + lane];
+          cplx j0 = Js[c0 * 32 + lane], j1 = Js[c1 * 32 + lane], j2 = Js[c2 * 32 + lane], j3 = Js[c3 * 32 + lane];
+          double n0 = nrm[c0], n1 = nrm[c1], n2 = nrm[c2], n3 = nrm[c3];
+          if (r == 0) {   // pairs inside the two blocks: once per sweep
+            rotate_pair(x0, x1, j0, j1, n0, n1, tol2, big);
+            rotate_pair(x2, x3, j2, j3, n2, n3, tol2, big);
+          }
+          rotate_pair(x0, x2, j0, j2, n0, n2, tol2, big);
+          rotate_pair(x1, x3, j1, j3, n1, n3, tol2, big);
+          rotate_pair(x0, x3, j0, j3, n0, n3, tol2, big);
+          rotate_pair(x1, x2, j1, j2, n1, n2, tol2, big);
+          Xs[c0 * 32 + lane] = x0; Xs[c1 * 32 + lane] = x1; Xs[c2 * 32 + lane] = x2; Xs[c3 * 32 + lane] = x3;
+          Js[c0 * 32 + lane] = j0; Js[c1 * 32 + lane] = j1; Js[c2 * 32 + lane] = j2; Js[c3 * 32 + lane] = j3;
+          if (lane == 0) { nrm[c0] = n0; nrm[c1] = n1; nrm[c2] = n2; nrm[c3] = n3; }
+          __syncthreads();
+        }
+        if (!__syncthreads_or(big)) break;
+      }
+      // singular values = column norms of X; gains 1/(s * max(s, c*smax))
+      for (int c = warp; c < 32; c += SV_T / 32) {
+        const double a_ = wsum(cabs2(Xs[c * 32 + lane]));
+        if (lane == 0) sv[c] = sqrt(a_);
+      }
+      __syncthreads();
+      double smax = 0.0;
+      for (int c = 0; c < Mc; ++c) smax = fmax(smax, sv[c]);
+      __syncthreads();
+      if (tid < 32) {
+        const double s = sv[tid];
+        sv[tid] = (tid < Mc && s > 0.0) ? 1.0 / (s * fmax(s, regul * smax)) : 0.0;
+      }
+      __syncthreads();
+      // Pb(i, m) = sum_c conj(J(i, c)) gain_c X(m, c)
+      for (int idx = tid; idx < 1024; idx += SV_T) {
+        const int i = idx >> 5, m = idx & 31;
+        cplx acc = mk(0.0, 0.0);
+        if (i < Mc && m < Mc) {
+          for (int c = 0; c < Mc; ++c) cfmac(acc, Js[c * 32 + i], cscale(Xs[c * 32 + m], sv[c]));
+        }
+        Rs[idx] = acc;
+      }
+      have_j = true;
+      __syncthreads();
+    }
+    cplx* Pg = ops.Pb + oidx * ops.pb_stride;
+    for (int idx = tid; idx < Mc * Mc; idx += SV_T) {
+      const int i = idx / Mc, m = idx - i * Mc;
+      Pg[idx] = Rs[i * 32 + m];
+    }
+    if (tid == 0 && ops.info) ops.info[oidx] = fast ? 0 : sweeps;
+    __syncthreads();
+  }
+}
+
+// =============================================================================================
+// chain_bwd_sep_kernel: W_k = ((Q_C^H tq)[R space]) * Pb for both ears; one warp per problem.
+// Lane l holds row l of the current 32-row block of both right-hand sides and, in registers, row l of
+// the block's reflector tile (2 x 16 complex, each half fetched while the other is applied); entry c of
+// the R-space part of the right-hand sides lives in lane c.  No shared memory.
+// =============================================================================================
+constexpr int CS_WARPS = 4;
+
+__device__ __forceinline__ void load_half(const cplx* __restrict__ row, bool ok, cplx (&v)[16]) {
+#pragma unroll
+  for (int jj = 0; jj < 16; ++jj) {
+    if (ok) {
+      const double2 d = __ldg(reinterpret_cast<const double2*>(row + jj));
+      v[jj] = mk(d.x, d.y);
+    } else {
+      v[jj] = mk(0.0, 0.0);
+    }
+  }
+}
+
+// reflectors j0 .. j0+15 of one block (Q_C^H: in order, conj(tau))
+__device__ __forceinline__ void apply_half(const cplx (&v)[16], int j0, const cplx tau_l, cplx& xb0, cplx& xb1,
+                                           cplx& xr0, cplx& xr1, int lane) {
+#pragma unroll
+  for (int jj = 0; jj < 16; ++jj) {
+    const int j = j0 + jj;
+    cplx ta;
+    ta.x = __shfl_sync(0xffffffffu, tau_l.x, j);
+    ta.y = -__shfl_sync(0xffffffffu, tau_l.y, j);
+    cplx w0 = cmulc(xb0, v[jj]), w1 = cmulc(xb1, v[jj]);   // x * conj(v)
+    if (lane == j) { w0 = cadd(w0, xr0); w1 = cadd(w1, xr1); }
+    w0 = wsumc(w0); w1 = wsumc(w1);
+    const cplx f0 = cmul(ta, w0), f1 = cmul(ta, w1);
+    if (lane == j) { xr0 = csub(xr0, f0); xr1 = csub(xr1, f1); }
+    cfms(xb0, f0, v[jj]); cfms(xb1, f1, v[jj]);
+  }
+}
+
+__device__ __forceinline__ void load_rhs(const double* __restrict__ t0, const double* __restrict__ t1, int S, int r,
+                                         int nsplit, long long split_stride, cplx& x0, cplx& x1) {
+  if (r < S) {
+    double r0 = t0[r], i0 = t0[S + r], r1 = t1[r], i1 = t1[S + r];
+    for (int z = 1; z < nsplit; ++z) {   // split-K partials of the backward GEMM, fixed order
+      const long long o = (long long)z * split_stride;
+      r0 += t0[o + r]; i0 += t0[o + S + r]; r1 += t1[o + r]; i1 += t1[o + S + r];
+    }
+    x0 = mk(r0, i0); x1 = mk(r1, i1);
+  } else {
+    x0 = mk(0.0, 0.0); x1 = mk(0.0, 0.0);
+  }
+}
+
+__global__ void __launch_bounds__(CS_WARPS * 32, 3)
+chain_bwd_sep_kernel(BlockPlan bp, OperatorSet ops, int slot, int G, const double* __restrict__ tq,
+                     long long tq_set_stride, long long tq_ear_stride, int tq_shared, int nsplit,
+                     long long split_stride, ProbMap pm, cplx* __restrict__ Wsp, long long w_ear_stride, int K, int k,
+                     int dc_fix, int num_prob) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * CS_WARPS + warp;
+  if (j >= num_prob) return;
+  const long long p = pm.global(j);
+  const int S = bp.S, Mc = bp.Mc;
+  const long long oidx = (long long)(j % pm.oc) * G + slot;
+  const cplx* V = ops.V + oidx * ops.v_stride;
+  const cplx* tau = ops.tau + oidx * ops.tau_stride;
+  const cplx* Pb = ops.Pb + oidx * ops.pb_stride;
+  const double* t0 = tq_shared ? tq + (long long)(j / pm.oc) * tq_set_stride : tq + ((long long)(j * 2 + 0) * 2) * S;
+  const double* t1 = t0 + (tq_shared ? tq_ear_stride : 2 * (long long)S);
+
+  cplx xr0 = mk(0.0, 0.0), xr1 = mk(0.0, 0.0);   // R-space entry `lane` of the two right-hand sides
+  cplx va[16], vb[16];
+  cplx xb0, xb1;
+  load_half(V + (long long)lane * 32, lane < S, va);
+  load_rhs(t0, t1, S, lane, nsplit, split_stride, xb0, xb1);
+  for (int t = 0; t < bp.nblk; ++t) {
+    const int r = t * 32 + lane;
+    load_half(V + (long long)r * 32 + 16, r < S, vb);
+    const double2 tl = __ldg(reinterpret_cast<const double2*>(tau + t * 32 + lane));
+    const cplx tau_l = mk(tl.x, tl.y);
+    apply_half(va, 0, tau_l, xb0, xb1, xr0, xr1, lane);
+    cplx nx0 = mk(0.0, 0.0), nx1 = mk(0.0, 0.0);
+    if (t + 1 < bp.nblk) {
+      load_half(V + (long long)(r + 32) * 32, r + 32 < S, va);
+      load_rhs(t0, t1, S, r + 32, nsplit, split_stride, nx0, nx1);
+    }
+    apply_half(vb, 16, tau_l, xb0, xb1, xr0, xr1, lane);
+    xb0 = nx0; xb1 = nx1;
+  }
+  // W(m) = sum_i z(i) Pb(i, m)
+  cplx a0 = mk(0.0, 0.0), a1 = mk(0.0, 0.0);
+  for (int i = 0; i < Mc; ++i) {
+    cplx z0, z1;
+    z0.x = __shfl_sync(0xffffffffu, xr0.x, i); z0.y = __shfl_sync(0xffffffffu, xr0.y, i);
+    z1.x = __shfl_sync(0xffffffffu, xr1.x, i); z1.y = __shfl_sync(0xffffffffu, xr1.y, i);
+    if (lane < Mc) {
+      const cplx pb = Pb[i * Mc + lane];
+      cfma(a0, z0, pb);
+      cfma(a1, z1, pb);
+    }
+  }
+  if (lane < Mc) {
+    cplx* w0p = Wsp + (p * Mc + lane) * K + k;
+    cplx* w1p = w0p + w_ear_stride;
+    *w0p = a0;
+    *w1p = a1;
+    if (dc_fix && k == 1) {  // W(1,:) = real(W(2,:)), lib/getEMagLs2Filters.m:109-110
+      w0p[-1] = mk(a0.x, 0.0);
+      w1p[-1] = mk(a1.x, 0.0);
+    }
+  }
+}
+
+}  // namespace
+
+size_t tsqr_sep_smem_bytes(const BlockPlan& bp) {
+  return (size_t)(((bp.S * (int)sizeof(int2) + 15) / 16) * 16) + (size_t)TQ_WARPS * TQ_WARP_CPLX * sizeof(cplx);
+}
+
+cudaError_t launch_tsqr_sep(cudaStream_t st, const BlockPlan& bp, const RowSource& src, const OperatorSet& ops,
+                            cplx* Rout, int num_prob, int kbase, int G) {
+  if (!bp.sep || bp.Mc > 32 || src.E == nullptr || src.N + 1 > TQ_BN) return cudaErrorInvalidValue;
+  const size_t smem = tsqr_sep_smem_bytes(bp);
+  static size_t set_to = 0;
+  if (smem > 48 * 1024 && smem > set_to) {
+    cudaError_t e = cudaFuncSetAttribute(tsqr_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    set_to = smem;
+  }
+  const int items = num_prob * G;
+  tsqr_sep_kernel<<<(items + TQ_WARPS - 1) / TQ_WARPS, TQ_WARPS * 32, smem, st>>>(bp, src, ops, Rout, kbase, G, items);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_svdclip(cudaStream_t st, int Mc, const cplx* Rin, const OperatorSet& ops, int num_prob, int G,
+                           double regul, int try_fast, int warm) {
+  if (Mc > 32) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)3 * 1024 * sizeof(cplx) + (size_t)(32 + 32 + 20) * sizeof(double);
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(svdclip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    set = true;
+  }
+  svdclip_kernel<<<num_prob, SV_T, smem, st>>>(Mc, Rin, ops, G, regul, try_fast, warm);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_chain_bwd_sep(cudaStream_t st, const BlockPlan& bp, const OperatorSet& ops, int slot, int G,
+                                 const double* tq, long long tq_set_stride, long long tq_ear_stride, int tq_shared,
+                                 int nsplit, long long split_stride, ProbMap pm, cplx* Wsp, long long w_ear_stride,
+                                 int K, int k, int dc_fix, int num_prob) {
+  if (!bp.sep) return cudaErrorInvalidValue;
+  chain_bwd_sep_kernel<<<(num_prob + CS_WARPS - 1) / CS_WARPS, CS_WARPS * 32, 0, st>>>(
+      bp, ops, slot, G, tq, tq_set_stride, tq_ear_stride, tq_shared, nsplit, split_stride, pm, Wsp, w_ear_stride, K, k,
+      dc_fix, num_prob);
+  return cudaGetLastError();
+}
+
+}  // namespace emagls

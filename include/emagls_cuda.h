@@ -66,8 +66,8 @@ long long emagls_launch_count(emagls_handle h);
  * bracketed by an event pair on the handle's stream.  emagls_profile_read() synchronises, fills
  * ms[i] / counts[i] (accumulated milliseconds and spans per class, i < EMAGLS_PROF_CLASSES) and
  * returns the number of classes.  Class order: setup, factor, chain_fwd, gemm_fwd, gemm_bwd,
- * chain_bwd, tail, render_mac, render_fft, render_stage, gram.                                  */
-#define EMAGLS_PROF_CLASSES 11
+ * chain_bwd, tail, render_mac, render_fft, render_stage, gram, jacobi.                          */
+#define EMAGLS_PROF_CLASSES 12
 int emagls_profile_enable(emagls_handle h, int on);
 int emagls_profile_read(emagls_handle h, double* ms, long long* counts, int reset);
 /* Stream all work of this handle is enqueued on (cudaStream_t as void*), for event timing. */
