@@ -44,6 +44,7 @@ def parse():
                     help="length of the rendered 32-channel signal (SURVEY.md 8-d: 10 min)")
     ap.add_argument("--no-render", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-spot-check", action="store_true")
     return ap.parse_args()
 
 
@@ -206,6 +207,7 @@ def main():
     torch.cuda.synchronize()
     h.profile(True)
     h.profile_read()
+    h.stats_read()
     launches0 = h.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     emdist.barrier()
@@ -222,43 +224,88 @@ def main():
     ms = emdist.max_over_ranks(ms_local, dev)
     prof = h.profile_read()
     h.profile(False)
+    stats = h.stats_read()
     launches = h.launches - launches0
     value = world * B * args.steps / (ms * 1e-3)
 
-    # ---------------- end to end through the public API (pinned host buffers)
-    def pinned(shape):
-        t = torch.empty(shape[::-1], dtype=torch.float64, pin_memory=True)
-        return t, t.numpy().T  # Fortran-ordered view of the pinned block
+    # ---------------- end to end (pinned host buffers -> H2D -> design -> NCCL gather of the banks into rank 0's
+    # device bank -> D2H of every rank's shard), through the package's sharded designer (emagls_b200/dist.py).
+    # Weak scaling: rank r holds HRTF set r and the whole orientation grid, so the job is world x B filter sets.
+    sd = emdist.ShardedDesigner(h, pr["hL"], pr["hR"], pr["az"], pr["ze"], pr["r"], pr["maz"], pr["mze"], ORDER,
+                                pr["fs"], LEN, np.tile(pr["R"].reshape(-1, 9), (world, 1)), config=cfg)
+    assert sd.n_local == B
+    h2d, d2h = sd.h2d_bytes, sd.d2h_bytes
 
-    p_hL, hLv = pinned((T, D))
-    p_hR, hRv = pinned((T, D))
-    hLv[...] = pr["hL"]
-    hRv[...] = pr["hR"]
-    p_wL, wLv = pinned((LEN, M, B))
-    p_wR, wRv = pinned((LEN, M, B))
-    h2d = 2 * T * D * 8 + 2 * D * 8 + 2 * M * 8 + B * 9 * 8
-    d2h = 2 * LEN * M * B * 8
-    bank_total = None
+    def timed_e2e(designer, nsteps):
+        designer.step()
+        designer.wait()
+        emdist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(nsteps):
+            designer.step()
+            designer.wait()          # the host has its shard (and rank 0 the gathered device bank)
+        torch.cuda.synchronize()
+        return emdist.max_over_ranks(time.perf_counter() - t0, dev)
 
-    def step_e2e():
-        nonlocal bank_total
-        em.getEMagLs2Filters(hLv, hRv, pr["az"], pr["ze"], pr["r"], pr["maz"], pr["mze"], ORDER, pr["fs"], LEN,
-                             rotations=pr["R"], handle=h, out=(wLv, wRv))
-        if world > 1:  # NCCL gather of the finished banks onto rank 0 (the only collective)
-            bank = torch.stack([d_wL, d_wR], 1)          # device copy of the last device-resident banks
-            bank_total = emdist.gather_banks(bank, world * B, dst=0)
-            torch.cuda.synchronize()
-
-    step_e2e()
-    emdist.barrier()
-    torch.cuda.synchronize()
-    e2e_steps = max(1, min(args.steps, 2))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
-    torch.cuda.synchronize()
-    e2e_s = emdist.max_over_ranks(time.perf_counter() - t0, dev)
+    e2e_steps = max(5, min(args.steps, 10))
+    e2e_s = timed_e2e(sd, e2e_steps)
     e2e_value = world * B * e2e_steps / e2e_s
+    # the e2e path and the device-resident path must have produced the same banks (same inputs)
+    e2e_same = float(max((sd.bank[0] - d_wL).abs().max() / d_wL.abs().max(),
+                         (sd.bank[1] - d_wR).abs().max() / d_wR.abs().max()))
+    # and, through the reference-facing host call of the C ABI (one call, host buffers in and out; N = 1 only)
+    host_api = None
+    if world == 1:
+        wLh = np.zeros((LEN, M, B), order="F")
+        wRh = np.zeros((LEN, M, B), order="F")
+        t0 = time.perf_counter()
+        em.getEMagLs2Filters(pr["hL"], pr["hR"], pr["az"], pr["ze"], pr["r"], pr["maz"], pr["mze"], ORDER, pr["fs"], LEN,
+                             rotations=pr["R"], handle=h, out=(wLh, wRh))
+        host_api = {"value": B / (time.perf_counter() - t0), "unit": UNIT, "steps": 1,
+                    "call": "emagls_design_emagls2 (host pointers, pageable memory)"}
+        del wLh, wRh
+    del sd
+
+    # ---------------- the north-star batch: 3600 orientations of ONE HRTF set in total, sharded over the ranks
+    # (strong scaling: 3600 / world per GPU); time to solution for the whole bank on rank 0.
+    strong = None
+    if world > 1:
+        pr0 = problem(0, args.orient)
+        ss = emdist.ShardedDesigner(h, pr0["hL"], pr0["hR"], pr0["az"], pr0["ze"], pr0["r"], pr0["maz"], pr0["mze"],
+                                    ORDER, pr0["fs"], LEN, pr0["R"], config=cfg)
+        s_steps = max(5, min(args.steps, 10))
+        s_s = timed_e2e(ss, s_steps)
+        strong = {"orientations_total": int(ss.n_total), "orientations_per_gpu": int(ss.n_local),
+                  "ms_per_batch": s_s / s_steps * 1e3, "value": ss.n_total * s_steps / s_s, "unit": UNIT,
+                  "steps": s_steps, "scaling": "strong",
+                  "includes": "H2D of the inputs, design, NCCL gather into rank 0's bank, D2H of every shard"}
+        del ss
+
+    # ---------------- parity spot check of the timed batch (outside the timed regions): three orientations of the
+    # bank the device-resident steps produced against the oracle (NumPy restatement of the reference), rank 0
+    spot = None
+    if rank == 0 and not args.no_spot_check:
+        import oracle
+        from concurrent.futures import ThreadPoolExecutor
+        from emagls_b200 import synth
+        rng = np.random.default_rng(12345)
+        idx = sorted(int(i) for i in rng.choice(B, size=min(3, B), replace=False))
+
+        def ref(i):
+            raz, rze = synth.rotate_grid(pr["az"], pr["ze"], pr["R"][i])
+            return oracle.getEMagLs2Filters(pr["hL"], pr["hR"], raz, rze, pr["r"], pr["maz"], pr["mze"], ORDER, pr["fs"], LEN)
+        with ThreadPoolExecutor(max_workers=len(idx)) as ex:
+            refs = list(ex.map(ref, idx))
+        errs = []
+        for i, (rl, rr) in zip(idx, refs):
+            gl, gr = d_wL[i].cpu().numpy().T, d_wR[i].cpu().numpy().T       # [len, M]
+            sc = max(np.abs(rl).max(), np.abs(rr).max())
+            errs.append(float(max(np.abs(gl - rl).max(), np.abs(gr - rr).max()) / sc))
+        spot = {"orientations": idx, "max_rel_err_vs_oracle": max(errs), "per_orientation": errs,
+                "bound": 5e-9, "ok": bool(max(errs) <= 5e-9),
+                "note": "whole-filter max-norm error relative to the oracle; 5e-9 is the floor of two FP64 "
+                        "implementations on bins 1-7 (tests/test_gpu_design.py), north-star 1e-10 is per bin >= 16"}
 
     # ---------------- roofline of the dominant tensor kernel
     # The two direction-grid contractions run on the int8 tensor cores (tcgen05.mma kind::i8, FP64
@@ -323,42 +370,96 @@ def main():
                            " (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full launch)")
     except Exception:
         pass
-    # The largest single class of the step is the per-(orientation, bin) TSQR + Jacobi kernel of the clipped
-    # bins (FP64 on the CUDA cores, neither an HBM nor a tensor-core roofline): reported beside the GEMM.
-    # Algorithmic flops per problem: 8 (S M^2 - M^3 / 3) for the QR, ~1800 flops per rotated column pair
-    # x M (M - 1) / 2 pairs x 8 sweeps (9 were measured with the earlier, stricter stop rule; the current rule
-    # saves one on most bins), 8 M^3 for the projector.
-    fac = None
-    if prof.get("factor", {}).get("n"):
-        fl = 8.0 * (S * M * M - M ** 3 / 3.0) + 8 * 1800.0 * M * (M - 1) / 2 + 8.0 * M ** 3
-        fac_ms = prof["factor"]["ms"] / args.steps
-        fac = {"kernel": "factor_kernel (TSQR + one-sided Jacobi, FP64 CUDA cores)", "ms_per_step": fac_ms,
-               "share": shares.get("factor"), "algorithmic_mflop_per_problem": fl / 1e6,
-               "note": "problems per step = clipped bins x orientations (em32 @48 kHz: 87 x orientations); "
-                       "peak = the measured DGEMM figure (the FP64 pipe of this part)"}
-        if M == 32 and abs(pr["fs"] - 48000.0) < 1:
-            fac["achieved_tflops"] = fl * 87 * B / (fac_ms * 1e-3) / 1e12
-            fac["frac_of_dgemm_peak"] = (fac["achieved_tflops"] / dgemm_peak) if dgemm_peak else None
+    # ---------------- one roofline entry per kernel class of the step (work models: DESIGN.md section 5).
+    # FP64 CUDA-core classes are measured against the live cuBLAS DGEMM figure (the FP64 pipe of this part;
+    # MEASURED_PEAKS.json has no FP64 entry), HBM classes against MEASURED_PEAKS.json hbm_gbs.
+    hbm_peak = 6650.0
+    try:
+        hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    st = stats            # (problem, bin) counts of the timed steps, from the library
+    nblk = (S + 31) // 32
+    per_step = lambda k: prof[k]["ms"] / args.steps if prof.get(k, {}).get("n") else None   # noqa: E731
+    classes = {}
+
+    def add(name, kernel, bound, work, unit_scale, peak, unit, note):
+        ms_c = per_step(name)
+        if not ms_c or not work:
+            return
+        ach = work / (ms_c * 1e-3) / unit_scale
+        classes[name] = {"kernel": kernel, "ms_per_step": ms_c, "share": shares.get(name), "bound": bound,
+                         "achieved": ach, "peak": peak, "unit": unit, "frac": (ach / peak) if peak else None, "note": note}
+    tsqr_pb = st["tsqr_problem_bins"] / args.steps
+    gram_pb = st["gram_problem_bins"] / args.steps
+    jac_p = st["jacobi_problems"] / args.steps
+    jac_sw = st["jacobi_sweeps"] / args.steps
+    new_path = bool(prof.get("jacobi", {}).get("n"))
+    if new_path:
+        add("factor", "tsqr_sep_kernel (register-resident Householder TSQR, warp per (orientation, bin))", "fp64",
+            8.0 * (S * M * M - M ** 3 / 3.0) * tsqr_pb, 1e12, dgemm_peak, "TFLOP/s (FP64, algorithmic)",
+            f"8 (S M^2 - M^3/3) flops x {tsqr_pb:.0f} (orientation, bin) problems per step; the kernel executes "
+            f"{16.0 * 32 * 32 * 32 * nblk / 1e6:.2f} MFLOP per problem (full 32-lane steps of {nblk} blocks)")
+        add("jacobi", "svdclip_kernel (one-sided Jacobi, block round-robin, warm starts)", "fp64",
+            1800.0 * M * (M - 1) / 2 * jac_sw + 8.0 * M ** 3 * jac_p, 1e12, dgemm_peak, "TFLOP/s (FP64, algorithmic)",
+            f"1800 flops per rotated column pair x M (M - 1) / 2 pairs x {jac_sw / max(jac_p, 1):.2f} sweeps (measured mean) "
+            f"+ 8 M^3 for the projector, {jac_p:.0f} problems per step")
+    else:
+        add("factor", "factor_kernel (shared-memory TSQR + one-sided Jacobi, round-1 kernel)", "fp64",
+            (8.0 * (S * M * M - M ** 3 / 3.0) + 8 * 1800.0 * M * (M - 1) / 2 + 8.0 * M ** 3) * tsqr_pb, 1e12, dgemm_peak,
+            "TFLOP/s (FP64, algorithmic)", "QR + 8 Jacobi sweeps + projector per (orientation, bin) problem")
+    if use_oz:
+        for nm, lab in (("gemm_fwd", "forward y = Y_h c with fused phase continuation + digit slicing"),
+                        ("gemm_bwd", "backward t Y_h / t Q")):
+            n_l = max(prof[nm]["n"], 1) / args.steps
+            add(nm, f"ozaki_gemm_kernel<{oz_T}> ({lab}; tcgen05.mma kind::i8, TMEM accumulators, TMA operands)", "tensor",
+                i8_ops[nm] * n_l, 1e12, i8_peak, "TOP/s (int8, executed)",
+                f"{pairs} digit products per FP64 product; FP64-equivalent "
+                f"{fp64_flops[nm] * n_l / (per_step(nm) * 1e-3) / 1e12:.1f} TFLOP/s")
+    else:
+        for nm in ("gemm_fwd", "gemm_bwd"):
+            n_l = max(prof[nm]["n"], 1) / args.steps
+            add(nm, "gemm_f64_kernel (DMMA.8x8x4)", "tensor", fp64_flops[nm] * n_l, 1e12, dgemm_peak, "TFLOP/s (FP64)", "")
+    # backward small kernels: Gram bins read Y_o (Mc x S doubles), Pb, z, write digits; TSQR bins read the reflectors
+    bytes_bwd = gram_pb * (M * S * 8 + M * M * 16 + 4 * S * 8 + oz_T * 4 * KpS) + tsqr_pb * (S * 32 * 16 + M * M * 16 + 4 * S * 8)
+    add("chain_bwd", "bwd_small_kernel (Gram bins) + chain_bwd_sep_kernel (TSQR bins: 32-row reflector tiles)", "hbm",
+        bytes_bwd, 1e9, hbm_peak, "GB/s (algorithmic)", "operator bytes per (orientation, bin): Y_o 102 KB + Pb 16 KB "
+        "(Gram route, L2-resident in part) or reflectors 205 KB + Pb 16 KB (TSQR route)")
+    ne = M * (M + 1) // 2
+    add("gram", "gemm_f64_kernel (DMMA assembly of G_k from the F blocks) + gram_sweep_kernel (in-register inversion)", "fp64",
+        gram_pb * (2.0 * ne * S + 8.0 * M ** 3 / 2), 1e12, dgemm_peak, "TFLOP/s (FP64, algorithmic)",
+        "2 ne S flops of assembly + 4 M^3 of Hermitian inversion per (orientation, bin)")
+    dom_cls = max(classes, key=lambda k: classes[k]["ms_per_step"]) if classes else None
     if use_oz:
         achieved = i8_ops[dom] / (avg_ms * 1e-3) / 1e12
-        roofline = {"kernel": f"ozaki_gemm_kernel<{oz_T}> ({dom}: tcgen05.mma kind::i8, TMEM accumulators, TMA operands)",
-                    "bound": "tensor", "achieved": achieved, "peak": i8_peak, "unit": "TOP/s (int8, executed)",
-                    "frac": (achieved / i8_peak) if i8_peak else None, "traffic": traffic, "traffic_source": traffic_src,
-                    "peak_source": i8_src, "int8_ops_per_launch": i8_ops[dom], "slice_pairs": pairs,
-                    "fp64_equivalent_tflops": fp64_equiv, "fp64_flops_per_launch": fp64_flops[dom],
-                    "dgemm_peak_tflops": dgemm_peak, "fp64_equivalent_vs_dgemm_peak": (fp64_equiv / dgemm_peak) if dgemm_peak else None,
-                    "dgemm_peak_source": "live cuBLAS DGEMM 8192^3, best of 5 (MEASURED_PEAKS.json has no FP64 entry)",
-                    "avg_launch_ms": avg_ms, "class_time_share": shares,
-                    "algorithmic_tflops_whole_job": value / world * ALGO_GFLOP_PER_SET / 1e3}
+        gemm_roof = {"kernel": f"ozaki_gemm_kernel<{oz_T}> ({dom}: tcgen05.mma kind::i8, TMEM accumulators, TMA operands)",
+                     "bound": "tensor", "achieved": achieved, "peak": i8_peak, "unit": "TOP/s (int8, executed)",
+                     "frac": (achieved / i8_peak) if i8_peak else None, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": i8_src, "int8_ops_per_launch": i8_ops[dom], "slice_pairs": pairs,
+                     "fp64_equivalent_tflops": fp64_equiv, "fp64_flops_per_launch": fp64_flops[dom],
+                     "dgemm_peak_tflops": dgemm_peak,
+                     "fp64_equivalent_vs_dgemm_peak": (fp64_equiv / dgemm_peak) if dgemm_peak else None, "avg_launch_ms": avg_ms}
     else:
-        roofline = {"kernel": f"gemm_f64_kernel ({dom}, DMMA.8x8x4)", "bound": "tensor", "achieved": fp64_equiv,
-                    "peak": dgemm_peak, "unit": "TFLOP/s", "frac": (fp64_equiv / dgemm_peak) if dgemm_peak else None,
-                    "traffic": traffic, "traffic_source": traffic_src,
-                    "peak_source": "live cuBLAS DGEMM 8192^3, best of 5 (MEASURED_PEAKS.json has no FP64 entry)",
-                    "flops_per_launch": fp64_flops[dom], "avg_launch_ms": avg_ms, "class_time_share": shares,
-                    "algorithmic_tflops_whole_job": value / world * ALGO_GFLOP_PER_SET / 1e3}
-
-    roofline["largest_class"] = fac
+        gemm_roof = {"kernel": f"gemm_f64_kernel ({dom}, DMMA.8x8x4)", "bound": "tensor", "achieved": fp64_equiv,
+                     "peak": dgemm_peak, "unit": "TFLOP/s", "frac": (fp64_equiv / dgemm_peak) if dgemm_peak else None,
+                     "traffic": traffic, "traffic_source": traffic_src, "flops_per_launch": fp64_flops[dom],
+                     "avg_launch_ms": avg_ms}
+    # headline roofline = the class that takes the largest share of the step; the tensor-core GEMM beside it
+    if dom_cls in ("gemm_fwd", "gemm_bwd") or dom_cls is None:
+        roofline = dict(gemm_roof)
+    else:
+        c = classes[dom_cls]
+        roofline = {"kernel": c["kernel"], "bound": "tensor" if c["bound"] in ("tensor", "fp64") else "hbm",
+                    "pipe": c["bound"], "achieved": c["achieved"], "peak": c["peak"], "unit": c["unit"], "frac": c["frac"],
+                    "traffic": None, "note": c["note"], "ms_per_step": c["ms_per_step"], "share": c["share"]}
+    roofline["peak_source"] = ("int8: " + str(i8_src) + "; FP64: live cuBLAS DGEMM 8192^3, best of 5 (MEASURED_PEAKS.json "
+                               "has no FP64 entry); HBM: MEASURED_PEAKS.json hbm_gbs")
+    roofline["dominant_class"] = dom_cls
+    roofline["class_time_share"] = shares
+    roofline["classes"] = classes
+    roofline["tensor_gemm"] = gemm_roof
+    roofline["algorithmic_tflops_whole_job"] = value / world * ALGO_GFLOP_PER_SET / 1e3
+    roofline["jacobi_mean_sweeps"] = (jac_sw / jac_p) if jac_p else None
 
     # ---------------- render (secondary metric: Msamples/s of the 32 -> 2 channel, 512-tap FIR)
     render = None
@@ -416,8 +517,12 @@ def main():
                                        "2702-direction HRIR grid @48 kHz, head-orientation batch",
                            "orientations_per_gpu_per_step": B, "hrtf_sets_per_gpu": 1, "parallelism": f"shard{world}",
                            "l2": "flushed between steps (256 MiB write); per-step working set is several GB"},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": e2e_steps, "includes_nccl_gather": world > 1},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                        "steps": e2e_steps, "includes_nccl_gather": world > 1,
+                        "path": "emagls_b200.dist.ShardedDesigner: pinned host inputs -> H2D -> emagls_design_emagls2_dev "
+                                "-> NCCL send/recv of the shards into rank 0's device bank -> D2H of every shard (pinned)",
+                        "max_rel_diff_vs_device_resident_banks": e2e_same, "host_api_call": host_api},
+                "strong_scaling": strong, "parity_spot_check": spot,
                 "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline,
                 "cpu_baseline": cpu, "render": render}
         print(json.dumps(line), flush=True)

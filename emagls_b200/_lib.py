@@ -38,11 +38,15 @@ SIGNATURES = {
     "emagls_config_default": (None, [C.POINTER(Config)]),
     "emagls_launch_count": (C.c_longlong, [C.c_void_p]),
     "emagls_stream": (C.c_void_p, [C.c_void_p]),
+    "emagls_stats_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.c_int]),
     "emagls_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "emagls_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]),
     "emagls_design_emagls2": (C.c_int, _DESIGN_ARGS),
     "emagls_design_emagls2_dev": (C.c_int, _DESIGN_ARGS),
     "emagls_design_emagls": (C.c_int, _DESIGN_ARGS),
+    "emagls_design_sma_basis": (C.c_int, [C.c_void_p, C.POINTER(Config), C.c_int, c_dp, c_dp, C.c_int, C.c_int, c_dp,
+                                          C.c_int, C.c_double, c_dp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
+                                          C.c_int, c_dp, c_dp, c_dp]),
     "emagls_design_magls": (C.c_int, [C.c_void_p, C.POINTER(Config), c_dp, c_dp, C.c_int, C.c_int, c_dp, c_dp,
                                       C.c_int, C.c_double, C.c_int, c_dp, c_dp, c_dp]),
     "emagls_design_ls": (C.c_int, [C.c_void_p, C.POINTER(Config), c_dp, c_dp, C.c_int, C.c_int, c_dp, c_dp,
@@ -170,6 +174,12 @@ class Handle:
         if got != n:
             raise EmaglsError(got, "emagls_profile_read")
         return {k: dict(ms=ms[i], n=int(cnt[i])) for i, k in enumerate(self.PROF_CLASSES)}
+
+    def stats_read(self, reset: bool = True) -> dict:
+        out = (C.c_longlong * 4)()
+        self.check(self.lib.emagls_stats_read(self._h, out, 1 if reset else 0))
+        return dict(tsqr_problem_bins=int(out[0]), gram_problem_bins=int(out[1]), jacobi_problems=int(out[2]),
+                    jacobi_sweeps=int(out[3]))
 
     @property
     def launches(self) -> int:

@@ -29,7 +29,12 @@ __all__ = ["getEMagLs2Filters", "getEMagLsFilters", "getMagLsFilters", "getLsFil
 
 
 def _f(x):
-    return np.asfortranarray(np.asarray(x, dtype=np.float64))
+    x = np.asarray(x)
+    if np.iscomplexobj(x):
+        # never drop an imaginary part silently (numpy's cast only warns); callers that accept complex data
+        # split it explicitly (binauralDecode)
+        raise ValueError("complex input where the reference interface expects real data")
+    return np.asfortranarray(x, dtype=np.float64)
 
 
 def _p(a):
@@ -53,8 +58,46 @@ def _check_sh_function(shFunction):
         raise NotImplementedError("only the default shFunction (@getSH) is evaluated on the device")
 
 
+def _is_custom(shFunction):
+    return shFunction is not None and shFunction is not getSH
+
+
+def _rotated_angles(azi, zen, R):
+    """Angles of R^T u for the unit vectors u(azi, zen): microphone positions seen from head orientation R."""
+    u = np.stack([np.sin(zen) * np.cos(azi), np.sin(zen) * np.sin(azi), np.cos(zen)], 1)
+    v = u @ np.asarray(R, dtype=np.float64).reshape(3, 3)          # rows: (R^T u)^T = u^T R
+    return np.arctan2(v[:, 1], v[:, 0]), np.arccos(np.clip(v[:, 2], -1.0, 1.0))
+
+
+def _design_sma_custom(fn_name, h, cfg, shFunction, shDefinition, hL, hR, T, D, sets, az, ze, micRadius, maz, mze,
+                       order, fs, length, rot, B, Mc, return_spectra):
+    """Custom shFunction handle (lib/getEMagLs2Filters.m:32): evaluated here on the host, the two basis matrices
+    go down through emagls_design_sma_basis."""
+    if _basis(shDefinition) != 0:
+        raise NotImplementedError("custom shFunction handles are supported for shDefinition = 'real'")
+    simN = max(int(order), int(np.ceil(float(fs) * np.pi * float(micRadius) / cfg.speed_of_sound)))
+    S = (simN + 1) ** 2
+    Yh = np.asfortranarray(np.asarray(shFunction(simN, np.stack([az, ze], 1), "real"), dtype=np.float64))
+    if Yh.shape != (D, S):
+        raise ValueError("shFunction must return [directions, (order+1)^2]")
+    Ym = np.zeros((maz.size, S, B), order="F")
+    for o in range(B):
+        a_o, z_o = (maz, mze) if rot is None else _rotated_angles(maz, mze, rot[o])
+        Ym[:, :, o] = np.asarray(shFunction(simN, np.stack([a_o, z_o], 1), "real"), dtype=np.float64)
+    P = sets * B
+    K = min(cfg.nfft_max_len, 2 * length) // 2 + 1
+    wL = np.zeros((length, Mc, P), order="F")
+    wR = np.zeros((length, Mc, P), order="F")
+    sp = np.zeros((K, Mc, P, 2), dtype=np.complex128, order="F") if return_spectra else None
+    h.check(h.lib.emagls_design_sma_basis(h.ptr, C.byref(cfg), 0 if fn_name == "emagls_design_emagls2" else 1, _p(hL),
+                                          _p(hR), T, D, _p(Yh), S, float(micRadius), _p(Ym), maz.size, int(order),
+                                          float(fs), length, sets, B, _p(wL), _p(wR), _p(sp)))
+    return wL, wR, sp
+
+
 def _config(handle, config, shDefinition):
-    cfg = config if config is not None else handle.default_config()
+    # a private copy: the caller's Config is never written to
+    cfg = Config.from_buffer_copy(config) if config is not None else handle.default_config()
     cfg.basis = _basis(shDefinition)
     return cfg
 
@@ -75,7 +118,6 @@ def _prep_hrirs(hL, hR):
 def _design_sma(fn_name, channels_of, hL, hR, hrirGridAziRad, hrirGridZenRad, micRadius, micGridAziRad,
                 micGridZenRad, order, fs, length, shDefinition, shFunction, rotations, handle, config,
                 return_spectra, out=None):
-    _check_sh_function(shFunction)
     h = handle or default_handle()
     cfg = _config(h, config, shDefinition)
     hL, hR, T, D, sets = _prep_hrirs(hL, hR)
@@ -98,6 +140,17 @@ def _design_sma(fn_name, channels_of, hL, hR, hrirGridAziRad, hrirGridZenRad, mi
     K = nfft // 2 + 1
     cplx_out = cfg.basis == 1 and fn_name != "emagls_design_emagls2"
     odt = np.complex128 if cplx_out else np.float64
+    if _is_custom(shFunction):
+        if out is not None:
+            raise ValueError("out buffers are not supported together with a custom shFunction")
+        wL, wR, sp = _design_sma_custom(fn_name, h, cfg, shFunction, shDefinition, hL, hR, T, D, sets, az, ze, micRadius,
+                                        maz, mze, order, fs, length, None if rot is None else rot.reshape(-1, 3, 3), B,
+                                        Mc, return_spectra)
+        if P == 1 and rotations is None and sets == 1:
+            wL, wR = wL[:, :, 0], wR[:, :, 0]
+            if sp is not None:
+                sp = sp[:, :, 0, :]
+        return (wL, wR, sp) if return_spectra else (wL, wR)
     if out is not None:  # caller-provided (e.g. pinned) Fortran-ordered [len, Mc, P] buffers
         wL, wR = out
         for w in (wL, wR):
@@ -319,16 +372,26 @@ def binauralDecode(inp, inFs, decodingFilterLeft, decodingFilterRight, decodingF
     if horRotAngleRad is not None and horRotAngleRad != 0:
         # binauralDecode.m:26-30: in = rotateHOA_N3D(in, rad2deg(horRotAngleRad), 0, 0)  (emagls_rotate_sh)
         inp = rotateSH(inp, float(horRotAngleRad), handle=h)
-    x = _f(inp)
-    wL, wR = _f(decodingFilterLeft), _f(decodingFilterRight)
-    if x.ndim != 2 or wL.shape != wR.shape or wL.shape[1] != x.shape[1]:
+    x, wL, wR = np.asarray(inp), np.asarray(decodingFilterLeft), np.asarray(decodingFilterRight)
+    if x.ndim != 2 or wL.shape != wR.shape or wL.ndim != 2 or wL.shape[1] != x.shape[1]:
         raise ValueError("size mismatch between input channels and decoding filters")
     n, ch = x.shape
     ln = wL.shape[0]
     rows = n - (ln // 2 - 1) if compensateDelay else n
-    out = np.zeros((rows, 2), order="F")
-    h.check(h.lib.emagls_binaural_decode(h.ptr, _p(x), n, ch, _p(wL), _p(wR), ln, 1 if compensateDelay else 0,
-                                         _p(out)))
+
+    def dec(xr, wl, wr):
+        out = np.zeros((rows, 2), order="F")
+        h.check(h.lib.emagls_binaural_decode(h.ptr, _p(_f(xr)), n, ch, _p(_f(wl)), _p(_f(wr)), ln,
+                                             1 if compensateDelay else 0, _p(out)))
+        return out
+    if not (np.iscomplexobj(x) or np.iscomplexobj(wL) or np.iscomplexobj(wR)):
+        return dec(x, wL, wR)
+    # complex-basis signals and filters (shDefinition = 'complex'): the reference keeps real(sum_ch x * w)
+    # (binauralDecode.m:59-64) = sum_ch (Re x * Re w - Im x * Im w): two real renders on the device
+    out = dec(x.real, wL.real, wR.real)
+    xi, wli, wri = np.imag(x), np.imag(wL), np.imag(wR)
+    if np.any(xi) and (np.any(wli) or np.any(wri)):
+        out -= dec(xi, wli, wri)
     return out
 
 
@@ -421,6 +484,8 @@ def encodeCH(sig, micGridAziRad, order, chDefinition="real", *, handle=None):
 def rotateSH(sig, yawRad, pitchRad=0.0, rollRad=0.0, *, handle=None):
     """rotateHOA_N3D(sig, yaw, pitch, roll) as called at dependencies/binauralDecode.m:26-30 (radians)."""
     h = handle or default_handle()
+    if np.iscomplexobj(sig):
+        raise NotImplementedError("rotateSH: rotateHOA_N3D (binauralDecode.m:29) takes real N3D signals")
     x = _f(sig)
     N = int(round(np.sqrt(x.shape[1]))) - 1
     if x.ndim != 2 or (N + 1) ** 2 != x.shape[1]:

@@ -27,8 +27,28 @@ int emagls_create(int device, emagls_handle* out) {
     unsigned long long thr = ~0ull;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
+  if (cudaMalloc(&h->d_stats, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMemset(h->d_stats, 0, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return EMAGLS_ERR_CUDA;
+  }
   *out = h;
   return EMAGLS_OK;
+}
+
+int emagls_stats_read(emagls_handle h, long long* out, int reset) {
+  if (!h || !out) return EMAGLS_ERR_INVALID;
+  return guarded(h, [&] {
+    unsigned long long d[4] = {0, 0, 0, 0};
+    EM_CUDA(cudaStreamSynchronize(h->stream));
+    EM_CUDA(cudaMemcpy(d, h->d_stats, sizeof(d), cudaMemcpyDeviceToHost));
+    out[0] = h->stat_tsqr; out[1] = h->stat_gram; out[2] = (long long)d[1]; out[3] = (long long)d[0];
+    if (reset) {
+      h->stat_tsqr = h->stat_gram = 0;
+      EM_CUDA(cudaMemset(h->d_stats, 0, sizeof(d)));
+    }
+  });
 }
 
 int emagls_destroy(emagls_handle h) {
@@ -39,6 +59,7 @@ int emagls_destroy(emagls_handle h) {
   emagls::destroy_render_plans(h);
   emagls::destroy_fir_plans(h);
   cudaStreamDestroy(h->stream);
+  cudaFree(h->d_stats);
   delete h;
   return EMAGLS_OK;
 }
@@ -149,6 +170,49 @@ int emagls_design_emagls2_dev(emagls_handle h, const emagls_config* cfg, const d
     fill_args(a, Variant::EMAGLS2, hL, hR, num_samples, num_dirs, grid_azi, grid_zen, mic_radius, mic_azi,
               mic_zen, num_mics, order, fs, len, num_sets, num_orient, rotations, wL, wR, spectra);
     design_factored(h, *cfg, a);
+  });
+}
+
+// Custom shFunction: the host evaluates the handle, the bases come down as matrices.
+int emagls_design_sma_basis(emagls_handle h, const emagls_config* cfg, int sh_domain, const double* hL, const double* hR,
+                            int num_samples, int num_dirs, const double* Y_hrir, int num_harmonics, double mic_radius,
+                            const double* Y_mic, int num_mics, int order, double fs, int len, int num_sets,
+                            int num_orient, double* wL, double* wR, double* spectra) {
+  return guarded(h, [&] {
+    EM_REQUIRE(cfg && hL && hR && Y_hrir && Y_mic && wL && wR, "null argument");
+    const int T = num_samples, D = num_dirs, M = num_mics, S = num_harmonics, ns = num_sets, no = num_orient;
+    EM_REQUIRE(T > 0 && D > 0 && M > 0 && ns > 0 && no > 0 && len > 0 && S > 0, "empty input");
+    const int simN = std::max(order, (int)std::ceil(fs * M_PI * mic_radius / cfg->speed_of_sound));
+    EM_REQUIRE(S == (simN + 1) * (simN + 1),
+               "custom bases must be evaluated at the simulation order max(order, ceil(fs pi r / c)) (getSMAIRMatrix.m:95)");
+    EM_REQUIRE(cfg->basis == EMAGLS_BASIS_REAL || sh_domain == 0, "complex SH-domain output needs the default getSH");
+    const Variant v = sh_domain ? Variant::EMAGLS_SH : Variant::EMAGLS2;
+    cudaStream_t st = h->stream;
+    Arena ar(st);
+    const int Mc = sh_domain ? (order + 1) * (order + 1) : M;
+    const int K = std::min(cfg->nfft_max_len, 2 * len) / 2 + 1;
+    const size_t P = (size_t)ns * no;
+    const size_t wn = (size_t)len * Mc * P;
+    double* d_wL = ar.get<double>(wn);
+    double* d_wR = ar.get<double>(wn);
+    double* d_sp = spectra ? ar.get<double>((size_t)2 * K * Mc * P * 2) : nullptr;
+    // MATLAB [M x S] column-major per orientation -> [orientation][M][S] (S contiguous)
+    std::vector<double> ymt((size_t)no * M * S);
+    for (int o = 0; o < no; ++o)
+      for (int m = 0; m < M; ++m)
+        for (int s_ = 0; s_ < S; ++s_) ymt[((size_t)o * M + m) * S + s_] = Y_mic[((size_t)o * S + s_) * M + m];
+    DesignArgs a;
+    fill_args(a, v, ar.upload(hL, (size_t)T * D * ns), ar.upload(hR, (size_t)T * D * ns), T, D, nullptr, nullptr,
+              mic_radius, nullptr, nullptr, M, order, fs, len, ns, no, nullptr, d_wL, d_wR, d_sp);
+    a.Y_hrir = ar.upload(Y_hrir, (size_t)S * D);
+    a.Y_mic = ar.upload(ymt.data(), ymt.size());
+    EM_CUDA(cudaStreamSynchronize(st));   // ymt is a temporary
+    design_factored(h, *cfg, a);
+    EM_CUDA(cudaMemcpyAsync(wL, d_wL, wn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaMemcpyAsync(wR, d_wR, wn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (spectra)
+      EM_CUDA(cudaMemcpyAsync(spectra, d_sp, (size_t)2 * K * Mc * P * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaStreamSynchronize(st));
   });
 }
 

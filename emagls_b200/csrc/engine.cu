@@ -241,7 +241,7 @@ void regularized_apply_dev(emagls_ctx* h, Arena& ar, const cplx* At, int D, int 
                            int npair, double regul, cplx* W) {
   cudaStream_t st = h->stream;
   const BlockPlan bp = make_block_plan(D, Mc);
-  OperatorSet ops;
+  OperatorSet ops{};
   ops.v_stride = (long long)Mc * D; ops.tau_stride = (long long)bp.nblk * bp.MC;
   ops.pb_stride = (long long)Mc * Mc;
   ops.V = ar.get<cplx>(ops.v_stride); ops.tau = ar.get<cplx>(ops.tau_stride);
@@ -264,7 +264,8 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
   EM_REQUIRE(a.len >= a.T, "len too short");  // lib/getEMagLs2Filters.m:42
   EM_REQUIRE(a.len % 2 == 0, "len must be even");
   EM_REQUIRE(a.num_sets >= 1 && a.num_orient >= 1, "empty batch");
-  EM_REQUIRE(a.rotations != nullptr || a.num_orient == 1, "num_orient > 1 needs rotations");
+  EM_REQUIRE(a.rotations != nullptr || a.num_orient == 1 || a.Y_mic != nullptr, "num_orient > 1 needs rotations");
+  EM_REQUIRE((a.Y_hrir == nullptr) == (a.Y_mic == nullptr), "custom bases: Y_hrir and Y_mic must be given together");
   const int nfft = std::min(cfg.nfft_max_len, 2 * a.len);
   EM_REQUIRE(nfft % 2 == 0, "nfft must be even");  // getSMAIRMatrix.m:89
   EM_REQUIRE(nfft / 2 >= a.len / 2, "len exceeds NFFT_MAX_LEN (reference indexes out of range here)");
@@ -303,7 +304,10 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
   {
     double* work = ar.get<double>((size_t)S * D + 2 * S);
     double* Ytmp = ar.get<double>((size_t)S * D);
-    EM_CUDA(launch_sh_angles(st, simN, a.grid_azi, a.grid_zen, D, 0, Yh));
+    if (a.Y_hrir)
+      EM_CUDA(cudaMemcpyAsync(Yh, a.Y_hrir, (size_t)S * D * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    else
+      EM_CUDA(launch_sh_angles(st, simN, a.grid_azi, a.grid_zen, D, 0, Yh));
     EM_CUDA(cudaMemcpyAsync(Ytmp, Yh, (size_t)S * D * sizeof(double), cudaMemcpyDeviceToDevice, st));
     h->launches += 1;
     EM_CUDA(launch_householder_qr(st, Ytmp, D, S, Q, R, work, &h->launches));  // destroys its input
@@ -350,7 +354,10 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
       mic_zen = z;
       h->launches += 1;
     }
-    EM_CUDA(launch_sh_mics(st, simN, a.mic_azi, mic_zen, a.M, a.rotations, a.num_orient, Ym));
+    if (a.Y_mic)
+      EM_CUDA(cudaMemcpyAsync(Ym, a.Y_mic, (size_t)a.num_orient * a.M * S * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    else
+      EM_CUDA(launch_sh_mics(st, simN, a.mic_azi, mic_zen, a.M, a.rotations, a.num_orient, Ym));
     h->launches += 1;
     Yo = Ym;
     if (a.variant != Variant::EMAGLS2) {
@@ -360,7 +367,10 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
       cplx* At = ar.get<cplx>((size_t)a.M * Mc);
       if (a.variant == Variant::EMAGLS_SH) {
         double* Ym0 = ar.get<double>((size_t)a.M * S);
-        EM_CUDA(launch_sh_mics(st, simN, a.mic_azi, mic_zen, a.M, nullptr, 1, Ym0));
+        if (a.Y_mic)   // custom basis: Y_lo = the leading (order+1)^2 columns of the first orientation's matrix
+          EM_CUDA(cudaMemcpyAsync(Ym0, a.Y_mic, (size_t)a.M * S * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        else
+          EM_CUDA(launch_sh_mics(st, simN, a.mic_azi, mic_zen, a.M, nullptr, 1, Ym0));
         double* tmp = ar.get<double>((size_t)a.M * Mc);
         EM_CUDA(cudaMemcpy2DAsync(tmp, (size_t)Mc * sizeof(double), Ym0, (size_t)S * sizeof(double),
                                   (size_t)Mc * sizeof(double), a.M, cudaMemcpyDeviceToDevice, st));
@@ -485,12 +495,13 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
   double* Gim = ar.get<double>((size_t)NB * OC * ne_ld);
   cplx* PbG = ar.get<cplx>((size_t)NB * OC * pb_stride);
   int* d_fail = ar.get<int>(NB + 1);
-  OperatorSet ops;
+  OperatorSet ops{};
   ops.v_stride = v_stride; ops.tau_stride = tau_stride; ops.pb_stride = pb_stride;
   ops.V = ar.get<cplx>((size_t)OC * G * v_stride);
   ops.tau = ar.get<cplx>((size_t)OC * G * tau_stride);
   ops.Pb = ar.get<cplx>((size_t)OC * G * pb_stride);
   ops.info = ar.get<int>((size_t)OC * G);
+  ops.stats = h->d_stats;
   cplx* Rbuf = sep ? ar.get<cplx>((size_t)OC * G * 1024) : nullptr;   // R_C of every (orientation, slot)
   auto chain_bwd = [&](int slot, int slot_n, const double* rhs, long long set_stride, long long ear_stride, int shared,
                        int nsplit, long long split_stride, const ProbMap& pm, int kb, int pj) {
@@ -571,12 +582,14 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
       if (gb0 == 1) cv_ready = false;
       for (int kb = gb0; kb < gb0 + nb; ++kb) {
         const bool gram = fail_h[1 + kb - gb0] == 0;
+        if (gram) h->stat_gram += oc;
         const cplx* bk = bn + (size_t)kb * (simN + 1);
         if (!gram && !(kb >= slot_base && kb < slot_base + slot_n)) {
           int Gn = 0;
           while (Gn < G && kb + Gn < gb0 + nb && fail_h[1 + kb + Gn - gb0] != 0) ++Gn;
           // bins refused by the Gram route skip the fast-path test (it cannot succeed there)
           const int try_fast = gram_thr > 0.0 ? 0 : 1;
+          h->stat_tsqr += (long long)oc * Gn;   // factorisations are per orientation, shared by the HRTF sets
           if (sep) {
             {
               ProfSpan ps(h, EM_PROF_FACTOR);

@@ -29,6 +29,10 @@ struct emagls_ctx {
   cudaStream_t stream = nullptr;
   std::string err;
   long long launches = 0;
+  // work statistics of the design path (emagls_stats_read): (problem, bin) pairs on the TSQR + Jacobi route and
+  // on the Gram route; the Jacobi kernel adds {sweeps, problems} to the device counters d_stats[0..1]
+  long long stat_tsqr = 0, stat_gram = 0;
+  unsigned long long* d_stats = nullptr;
   // profiler
   bool profile = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -161,6 +165,11 @@ struct DesignArgs {
   const double* rotations;  // device [B x 9] or nullptr
   double *wL, *wR;          // device [len x Mc x P]
   double* spectra;          // device or nullptr: complex [K x Mc x P x 2]
+  // host-evaluated bases of a custom shFunction, device pointers or nullptr:
+  // Y_hrir [S][D] (= MATLAB [D x S] column-major) replaces getSH(simN, grid); Y_mic [num_orient][M][S]
+  // replaces getSH(simN, rotated microphones).  grid_* / mic_* / rotations are then not read.
+  const double* Y_hrir = nullptr;
+  const double* Y_mic = nullptr;
 };
 void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& a);
 void destroy_render_plans(emagls_ctx* h);  // render.cu

@@ -223,7 +223,7 @@ static void run_generic(emagls_ctx* h, Arena& ar, const GenericProblem& g) {
   EM_REQUIRE(g.D >= g.Mc, "fewer directions than channels");
   EM_REQUIRE(g.Mc <= 64, "more than 64 channels are not supported");
   const BlockPlan bp = make_block_plan(g.D, g.Mc);
-  OperatorSet ops;
+  OperatorSet ops{};
   ops.v_stride = (long long)g.Mc * g.D; ops.tau_stride = (long long)bp.nblk * bp.MC;
   ops.pb_stride = (long long)g.Mc * g.Mc;
   ops.V = ar.get<cplx>((size_t)g.num_ops * ops.v_stride);

@@ -64,6 +64,7 @@ struct OperatorSet {       // per-(problem, bin-slot) outputs of the factorisati
   cplx* tau;  long long tau_stride;  // [nblk][MC]
   cplx* Pb;   long long pb_stride;   // [Mc][Mc] row-major: W = g * Pb
   int* info;                         // [problem*G + slot]: jacobi sweeps (0 = fast path)
+  unsigned long long* stats;         // optional device counters: [0] += sweeps, [1] += 1 per Jacobi problem
 };
 // sep == 0: rows [0, R0) form the first (dense) block and the triangle R_C lives in rows [0, Mc) of the vector
 // space (solver_kernels.cu).  sep == 1: 32-row blocks against a triangle in a separate R space (tsqr_kernels.cu).

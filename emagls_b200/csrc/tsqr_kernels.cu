@@ -54,12 +54,21 @@ __device__ __forceinline__ void hh_scalars(cplx alpha, double xn, double* beta_o
     *beta_out = alpha.x; *tau_out = mk(0.0, 0.0); *sc_out = mk(0.0, 0.0);
     return;
   }
-  const double s2 = cabs2(alpha) + xn;
-  const double nrm = sqrt(s2);
-  const double beta = -copysign(nrm, alpha.x);
-  const double ib = 1.0 / beta;
+  // one reciprocal square root and one reciprocal instead of a square root and two divisions:
+  // nrm = s2 rsqrt(s2), 1/beta = -sign rsqrt(s2) (one Newton step each restores the last bits),
+  // |alpha - beta|^2 = |alpha|^2 + s2 + 2 |Re alpha| nrm (no cancellation: the signs agree)
+  const double a2 = cabs2(alpha);
+  const double s2 = a2 + xn;
+  double r = rsqrt(s2);
+  r = fma(r * 0.5, fma(-s2 * r, r, 1.0), r);            // Newton: r <- r + r/2 (1 - s2 r^2)
+  double nrm = s2 * r;
+  nrm = fma(fma(-nrm, nrm, s2), 0.5 * r, nrm);           // nrm <- nrm + (s2 - nrm^2) / (2 nrm)
+  const double sg = copysign(1.0, alpha.x);
+  const double beta = -sg * nrm;
+  const double ib = -sg * r;
   const cplx d = mk(alpha.x - beta, alpha.y);
-  const double id2 = 1.0 / cabs2(d);
+  const double d2 = fma(2.0 * fabs(alpha.x), nrm, a2 + s2);
+  const double id2 = __drcp_rn(d2);
   *beta_out = beta;
   *tau_out = mk((beta - alpha.x) * ib, -alpha.y * ib);
   *sc_out = mk(d.x * id2, -d.y * id2);
@@ -85,7 +94,7 @@ tsqr_sep_kernel(BlockPlan bp, RowSource src, OperatorSet ops, cplx* __restrict__
   for (int n = lane; n <= N; n += 32) bn_s[n] = src.bn[(long long)k * (N + 1) + n];
   for (int i = lane; i < TQ_TRI; i += 32) Rt[i] = mk(0.0, 0.0);
   __syncwarp();
-  const double* Eo = src.E + (long long)prob * src.Etot + lane;
+  const double* Eo = src.E + (long long)prob * src.Etot + (lane < Mc ? lane : 0);
   const bool col_ok = lane < Mc;
   cplx* Vg = ops.V + oidx * ops.v_stride;
   cplx* taug = ops.tau + oidx * ops.tau_stride;
@@ -95,21 +104,26 @@ tsqr_sep_kernel(BlockPlan bp, RowSource src, OperatorSet ops, cplx* __restrict__
     cplx b[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) b[i] = mk(0.0, 0.0);
-    // ---- rows r0 .. r0+31 of C_k: C[r][c] = sum_{n >= ord(r)} b_n E[off(r) + (n - ord(r)) Mc + c]
+    // ---- rows r0 .. r0+31 of C_k: C[r][c] = sum_{n >= ord(r)} b_n E[off(r) + (n - ord(r)) Mc + c].
+    // The loads are unconditional (invalid terms read E[0] and are multiplied by zero) so that the 32 loads
+    // of an order are in flight together instead of one per basic block.
     const int nlo = rowinfo[r0].x;      // orders below that of the first row contribute nothing
     for (int n = nlo; n <= N; ++n) {
       const cplx bnn = bn_s[n];
+      double ev[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const int r = r0 + i;
-        if (r < S) {
-          const int2 ri = rowinfo[r];
-          if (n >= ri.x && col_ok) {
-            const double ev = __ldg(Eo + ri.y + (n - ri.x) * Mc);
-            b[i].x = fma(bnn.x, ev, b[i].x);
-            b[i].y = fma(bnn.y, ev, b[i].y);
-          }
-        }
+        const int r = min(r0 + i, S - 1);
+        const int2 ri = rowinfo[r];
+        const bool ok = (r0 + i < S) && (n >= ri.x) && col_ok;
+        const int off = ok ? ri.y + (n - ri.x) * Mc : 0;
+        const double v = __ldg(Eo + off);
+        ev[i] = ok ? v : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        b[i].x = fma(bnn.x, ev[i], b[i].x);
+        b[i].y = fma(bnn.y, ev[i], b[i].y);
       }
     }
     // ---- 32 Householder steps on [R_C; block]
@@ -120,13 +134,15 @@ tsqr_sep_kernel(BlockPlan bp, RowSource src, OperatorSet ops, cplx* __restrict__
         for (int i = 0; i < 32; ++i) xbuf[i] = b[i];
       }
       __syncwarp();
-      cplx w0 = mk(0.0, 0.0), w1 = mk(0.0, 0.0);
+      cplx w0 = mk(0.0, 0.0), w1 = mk(0.0, 0.0), w2 = mk(0.0, 0.0), w3 = mk(0.0, 0.0);
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
+      for (int i = 0; i < 32; i += 4) {
         cfmac(w0, xbuf[i], b[i]);
         cfmac(w1, xbuf[i + 1], b[i + 1]);
+        cfmac(w2, xbuf[i + 2], b[i + 2]);
+        cfmac(w3, xbuf[i + 3], b[i + 3]);
       }
-      const cplx w = cadd(w0, w1);                       // lane j: ||x||^2
+      const cplx w = cadd(cadd(w0, w1), cadd(w2, w3));   // lane j: ||x||^2
       const double xn = __shfl_sync(0xffffffffu, w.x, j);
       const cplx alpha = Rt[tri_idx(j, j)];
       double beta; cplx tau, sc;
@@ -160,15 +176,23 @@ tsqr_sep_kernel(BlockPlan bp, RowSource src, OperatorSet ops, cplx* __restrict__
 
 // =============================================================================================
 // svdclip_kernel: Pb = conj(J) diag(1/(s max(s, c s_max))) X^T from R_C = J diag(s) (X/s)^H
+//
+// One CTA of 4 warps per orientation, the bins of a launch in sequence.  X and J (32 x 32 complex each,
+// column-major) live in shared memory.  Order: round-robin over 16 blocks of two columns; a half-warp
+// takes one block pair per round, holds its four columns of [X; J] in registers (lane = rows hl and
+// hl + 16 of X and of J) and performs the four cross rotations (plus the two inner ones in round 0) before
+// the columns go back, so a rotation moves 1 KB instead of 4 KB through the shared-memory port.  The two
+// independent rotations of a phase are reduced together (the halves of the 16-lane group end up with one
+// inner product each) and their parameters are computed once per 8-lane group, then exchanged.
 // =============================================================================================
-constexpr int SV_T = 256;
+constexpr int SV_T = 128;
 
-// one rotation of the column pair (p, q) held by this warp: lane = row of X and of J
-__device__ __forceinline__ void rotate_pair(cplx& xp, cplx& xq, cplx& jp, cplx& jq, double& a, double& b,
-                                            double tol2, int& big) {
-  cplx g = mk(0.0, 0.0);
-  cfmac(g, xp, xq);
-  g = wsumc(g);
+struct RotParam { double cs, sx, sy, na, nb; int rot; };
+
+// rotation parameters for the pair with inner product g and squared norms (a, b); de Rijk norm update
+__device__ __forceinline__ RotParam rot_param(cplx g, double a, double b, double tol2, int& big) {
+  RotParam p;
+  p.cs = 1.0; p.sx = 0.0; p.sy = 0.0; p.na = a; p.nb = b; p.rot = 0;
   const double gg = cabs2(g), ab = a * b;
   if (gg > tol2 * ab && gg > 0.0) {
     if (gg > 1e-14 * ab) big = 1;
@@ -178,55 +202,99 @@ __device__ __forceinline__ void rotate_pair(cplx& xp, cplx& xq, cplx& jp, cplx& 
     const double rden = __drcp_rn(fabs(d) + root);
     const double tw = copysign(2.0 * rden, d);         // t / |g|, signed
     const double cs = rsqrt(fma(tw * tw, gg, 1.0));    // 1 / sqrt(1 + t^2)
-    const cplx sph = cscale(g, cs * tw);               // s * ph
-    const cplx sphc = mk(sph.x, -sph.y);
-    cplx np_ = cscale(xp, cs); cfms(np_, sphc, xq);
-    cplx nq_ = cscale(xq, cs); cfma(nq_, sph, xp);
-    xp = np_; xq = nq_;
-    cplx njp = cscale(jp, cs); cfms(njp, sphc, jq);
-    cplx njq = cscale(jq, cs); cfma(njq, sph, jp);
-    jp = njp; jq = njq;
-    a = fma(-tw, gg, a); b = fma(tw, gg, b);           // de Rijk: norms follow the rotation
+    const double f = cs * tw;
+    p.cs = cs; p.sx = g.x * f; p.sy = g.y * f;         // s * ph
+    p.na = fma(-tw, gg, a); p.nb = fma(tw, gg, b);
+    p.rot = 1;
+  }
+  return p;
+}
+
+__device__ __forceinline__ void rot_apply(const RotParam& p, cplx (&xp)[2], cplx (&xq)[2], cplx (&jp)[2], cplx (&jq)[2]) {
+  const cplx sph = mk(p.sx, p.sy), sphc = mk(p.sx, -p.sy);
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    cplx np_ = cscale(xp[u], p.cs); cfms(np_, sphc, xq[u]);
+    cplx nq_ = cscale(xq[u], p.cs); cfma(nq_, sph, xp[u]);
+    xp[u] = np_; xq[u] = nq_;
+    cplx njp = cscale(jp[u], p.cs); cfms(njp, sphc, jq[u]);
+    cplx njq = cscale(jq[u], p.cs); cfma(njq, sph, jp[u]);
+    jp[u] = njp; jq[u] = njq;
   }
 }
 
-__global__ void __launch_bounds__(SV_T, 4)
+// one phase of a half-warp: the independent pairs (a, b) and (c, d)
+__device__ __forceinline__ void rot_phase(cplx (&xa)[2], cplx (&xb)[2], cplx (&ja)[2], cplx (&jb)[2], double& na, double& nb,
+                                          cplx (&xc)[2], cplx (&xd)[2], cplx (&jc)[2], cplx (&jd)[2], double& nc, double& nd,
+                                          bool hi8, double tol2, int& big) {
+  cplx g1 = mk(0.0, 0.0), g2 = mk(0.0, 0.0);
+#pragma unroll
+  for (int u = 0; u < 2; ++u) { cfmac(g1, xa[u], xb[u]); cfmac(g2, xc[u], xd[u]); }
+  __syncwarp();
+  // lanes 0-7 of the 16-lane group collect g1, lanes 8-15 collect g2
+  cplx keep = hi8 ? g2 : g1;
+  const cplx send = hi8 ? g1 : g2;
+  keep.x += __shfl_xor_sync(0xffffffffu, send.x, 8);
+  keep.y += __shfl_xor_sync(0xffffffffu, send.y, 8);
+#pragma unroll
+  for (int m = 4; m > 0; m >>= 1) {
+    keep.x += __shfl_xor_sync(0xffffffffu, keep.x, m);
+    keep.y += __shfl_xor_sync(0xffffffffu, keep.y, m);
+  }
+  const RotParam mine = rot_param(keep, hi8 ? nc : na, hi8 ? nd : nb, tol2, big);
+  RotParam oth;
+  oth.cs = __shfl_xor_sync(0xffffffffu, mine.cs, 8);
+  oth.sx = __shfl_xor_sync(0xffffffffu, mine.sx, 8);
+  oth.sy = __shfl_xor_sync(0xffffffffu, mine.sy, 8);
+  oth.na = __shfl_xor_sync(0xffffffffu, mine.na, 8);
+  oth.nb = __shfl_xor_sync(0xffffffffu, mine.nb, 8);
+  oth.rot = __shfl_xor_sync(0xffffffffu, mine.rot, 8);
+  const RotParam p1 = hi8 ? oth : mine, p2 = hi8 ? mine : oth;
+  if (p1.rot) { rot_apply(p1, xa, xb, ja, jb); na = p1.na; nb = p1.nb; }
+  if (p2.rot) { rot_apply(p2, xc, xd, jc, jd); nc = p2.na; nd = p2.nb; }
+}
+
+template <int OCC>
+__global__ void __launch_bounds__(SV_T, OCC)
 svdclip_kernel(int Mc, const cplx* __restrict__ Rin, OperatorSet ops, int G, double regul, int try_fast, int warm) {
   extern __shared__ __align__(16) unsigned char sv_raw[];
-  cplx* Rs = reinterpret_cast<cplx*>(sv_raw);   // R_C row-major, later Pb
-  cplx* Xs = Rs + 1024;                         // column-major: X(i, c) = Xs[c*32 + i]
-  cplx* Js = Xs + 1024;                         // column-major
+  cplx* Xs = reinterpret_cast<cplx*>(sv_raw);           // column-major: X(i, c) = Xs[c*32 + i]
+  cplx* Js = Xs + 1024;                                 // column-major
   double* nrm = reinterpret_cast<double*>(Js + 1024);   // [32]
   double* sv = nrm + 32;                                // [32]
   double* red = sv + 32;                                // [20]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int hw = tid >> 4, hl = tid & 15;
+  const bool hi8 = (hl & 8) != 0;
   const int prob = blockIdx.x;
   bool have_j = false;                      // Js holds the converged J of the previous bin
 
   for (int slot = 0; slot < G; ++slot) {
     const long long oidx = (long long)prob * G + slot;
-    const cplx* Rg = Rin + oidx * 1024;
-    for (int idx = tid; idx < 1024; idx += SV_T) Rs[idx] = Rg[idx];
-    __syncthreads();
+    const cplx* Rg = Rin + oidx * 1024;     // R_C row-major: R(j, i) = Rg[j*32 + i]
+    cplx* Pg = ops.Pb + oidx * ops.pb_stride;
     bool fast = false;
     int sweeps = 0;
     if (try_fast) {
-      // R^-1 (upper triangular) into Xs, row-major, row by row from the bottom; if
+      // R into Xs (row-major), R^-1 (upper triangular, row-major) into Js, row by row from the bottom; if
       // ||R||_F ||R^-1||_F <= 1/c no singular value can be clipped and Pb = R^-T.
-      cplx* Ri = Xs;
-      for (int idx = tid; idx < 1024; idx += SV_T) Ri[idx] = mk(0.0, 0.0);
+      cplx* Rs = Xs;
+      cplx* Ri = Js;
+      for (int idx = tid; idx < 1024; idx += SV_T) { Rs[idx] = Rg[idx]; Ri[idx] = mk(0.0, 0.0); }
       __syncthreads();
+      const int group = tid >> 3, rl = tid & 7;
       for (int i = Mc - 1; i >= 0; --i) {
         const cplx rii = Rs[i * 32 + i];
-        // Rinv(i, m) = (delta_im - sum_{j=i+1..m} R(i, j) Rinv(j, m)) / R(i, i), one lane group of 8 per m
-        const int group = tid >> 3, rl = tid & 7;
-        const int m = group;                      // 32 groups of 8 lanes
-        const bool act = (m >= i && m < Mc);
-        cplx sum = mk(0.0, 0.0);
-        if (act)
-          for (int j = i + 1 + rl; j <= m; j += 8) cfma(sum, Rs[i * 32 + j], Ri[j * 32 + m]);
-        sum = group_sum<8>(sum);                  // every lane of the warp takes part
-        if (act && rl == 0) Ri[i * 32 + m] = cdiv(mk((m == i ? 1.0 : 0.0) - sum.x, -sum.y), rii);
+        // Rinv(i, m) = (delta_im - sum_{j=i+1..m} R(i, j) Rinv(j, m)) / R(i, i), one group of 8 lanes per m
+        for (int m0 = 0; m0 < 32; m0 += SV_T / 8) {
+          const int m = m0 + group;
+          const bool act = (m >= i && m < Mc);
+          cplx sum = mk(0.0, 0.0);
+          if (act)
+            for (int j = i + 1 + rl; j <= m; j += 8) cfma(sum, Rs[i * 32 + j], Ri[j * 32 + m]);
+          sum = group_sum<8>(sum);                // every lane of the warp takes part
+          if (act && rl == 0) Ri[i * 32 + m] = cdiv(mk((m == i ? 1.0 : 0.0) - sum.x, -sum.y), rii);
+        }
         __syncthreads();
       }
       double fr = 0.0, fi = 0.0;
@@ -243,24 +311,21 @@ svdclip_kernel(int Mc, const cplx* __restrict__ Rin, OperatorSet ops, int G, dou
       const double condF = red[16];
       fast = (regul > 0.0) ? (condF <= 1.0 / regul) : (condF < 1e300);   // NaN -> false
       if (fast) {
-        // Pb(i, m) = Rinv(m, i)
-        cplx tmp[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { const int idx = tid + q * SV_T; tmp[q] = Ri[(idx & 31) * 32 + (idx >> 5)]; }
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) Rs[tid + q * SV_T] = tmp[q];
-        have_j = false;
-        __syncthreads();
+        for (int idx = tid; idx < Mc * Mc; idx += SV_T) {
+          const int i = idx / Mc, m = idx - i * Mc;
+          Pg[idx] = Ri[m * 32 + i];               // Pb(i, m) = Rinv(m, i)
+        }
       }
+      have_j = false;                             // Js was used as scratch: the next Jacobi start is cold
+      __syncthreads();
     }
     if (!fast) {
       // ---- starting matrix: warm (X = R^H J_prev) where the diagonal of R_C is graded by less than 1e4
-      // (the product loses eps * grading of relative accuracy in the small columns), else cold (X = R^H, J = I)
+      // (the product costs eps * grading of relative accuracy in the small columns), else cold (X = R^H, J = I)
       bool use_warm = false;
       if (warm && have_j) {
         if (tid < 32) {
-          double d = (tid < Mc) ? fabs(Rs[tid * 32 + tid].x) : 0.0;
+          const double d = (tid < Mc) ? fabs(Rg[tid * 32 + tid].x) : 0.0;
           double dmax = d, dmin = (tid < Mc) ? d : 1e300;
 #pragma unroll
           for (int m = 16; m > 0; m >>= 1) {
@@ -277,13 +342,13 @@ svdclip_kernel(int Mc, const cplx* __restrict__ Rin, OperatorSet ops, int G, dou
         for (int idx = tid; idx < 1024; idx += SV_T) {
           const int c = idx >> 5, i = idx & 31;
           cplx acc = mk(0.0, 0.0);
-          for (int j = 0; j <= i; ++j) cfmac(acc, Rs[j * 32 + i], Js[c * 32 + j]);
+          for (int j = 0; j <= i; ++j) cfmac(acc, Rg[j * 32 + i], Js[c * 32 + j]);
           Xs[idx] = acc;
         }
       } else {
         for (int idx = tid; idx < 1024; idx += SV_T) {
           const int c = idx >> 5, i = idx & 31;
-          const cplx r = Rs[c * 32 + i];      // R(c, i)
+          const cplx r = Rg[idx];               // R(c, i)
           Xs[idx] = mk(r.x, -r.y);
           Js[idx] = mk(c == i ? 1.0 : 0.0, 0.0);
         }
@@ -298,27 +363,31 @@ svdclip_kernel(int Mc, const cplx* __restrict__ Rin, OperatorSet ops, int G, dou
           if (lane == 0) nrm[c] = a_;
         }
         __syncthreads();
-        // block round-robin over 16 blocks of two columns; warp = one block pair
         for (int r = 0; r < 15; ++r) {
           int A, B;
-          if (warp == 0) { A = 15; B = r; }
-          else { A = (r + warp) % 15; B = (r - warp + 15) % 15; }
+          if (hw == 0) { A = 15; B = r; }
+          else { A = (r + hw) % 15; B = (r - hw + 15) % 15; }
           if (A > B) { const int t_ = A; A = B; B = t_; }
           const int c0 = 2 * A, c1 = 2 * A + 1, c2 = 2 * B, c3 = 2 * B + 1;
-          cplx x0 = Xs[c0 * 32 + lane], x1 = Xs[c1 * 32 + lane], x2 = Xs[c2 * 32 + lane], x3 = Xs[c3 * 32 + lane];
-          cplx j0 = Js[c0 * 32 + lane], j1 = Js[c1 * 32 + lane], j2 = Js[c2 * 32 + lane], j3 = Js[c3 * 32 + lane];
-          double n0 = nrm[c0], n1 = nrm[c1], n2 = nrm[c2], n3 = nrm[c3];
-          if (r == 0) {   // pairs inside the two blocks: once per sweep
-            rotate_pair(x0, x1, j0, j1, n0, n1, tol2, big);
-            rotate_pair(x2, x3, j2, j3, n2, n3, tol2, big);
+          cplx x0[2], x1[2], x2[2], x3[2], j0[2], j1[2], j2[2], j3[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int row = hl + 16 * u;
+            x0[u] = Xs[c0 * 32 + row]; x1[u] = Xs[c1 * 32 + row]; x2[u] = Xs[c2 * 32 + row]; x3[u] = Xs[c3 * 32 + row];
+            j0[u] = Js[c0 * 32 + row]; j1[u] = Js[c1 * 32 + row]; j2[u] = Js[c2 * 32 + row]; j3[u] = Js[c3 * 32 + row];
           }
-          rotate_pair(x0, x2, j0, j2, n0, n2, tol2, big);
-          rotate_pair(x1, x3, j1, j3, n1, n3, tol2, big);
-          rotate_pair(x0, x3, j0, j3, n0, n3, tol2, big);
-          rotate_pair(x1, x2, j1, j2, n1, n2, tol2, big);
-          Xs[c0 * 32 + lane] = x0; Xs[c1 * 32 + lane] = x1; Xs[c2 * 32 + lane] = x2; Xs[c3 * 32 + lane] = x3;
-          Js[c0 * 32 + lane] = j0; Js[c1 * 32 + lane] = j1; Js[c2 * 32 + lane] = j2; Js[c3 * 32 + lane] = j3;
-          if (lane == 0) { nrm[c0] = n0; nrm[c1] = n1; nrm[c2] = n2; nrm[c3] = n3; }
+          double n0 = nrm[c0], n1 = nrm[c1], n2 = nrm[c2], n3 = nrm[c3];
+          if (r == 0)   // pairs inside the two blocks: once per sweep
+            rot_phase(x0, x1, j0, j1, n0, n1, x2, x3, j2, j3, n2, n3, hi8, tol2, big);
+          rot_phase(x0, x2, j0, j2, n0, n2, x1, x3, j1, j3, n1, n3, hi8, tol2, big);
+          rot_phase(x0, x3, j0, j3, n0, n3, x1, x2, j1, j2, n1, n2, hi8, tol2, big);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int row = hl + 16 * u;
+            Xs[c0 * 32 + row] = x0[u]; Xs[c1 * 32 + row] = x1[u]; Xs[c2 * 32 + row] = x2[u]; Xs[c3 * 32 + row] = x3[u];
+            Js[c0 * 32 + row] = j0[u]; Js[c1 * 32 + row] = j1[u]; Js[c2 * 32 + row] = j2[u]; Js[c3 * 32 + row] = j3[u];
+          }
+          if (hl == 0) { nrm[c0] = n0; nrm[c1] = n1; nrm[c2] = n2; nrm[c3] = n3; }
           __syncthreads();
         }
         if (!__syncthreads_or(big)) break;
@@ -338,23 +407,18 @@ svdclip_kernel(int Mc, const cplx* __restrict__ Rin, OperatorSet ops, int G, dou
       }
       __syncthreads();
       // Pb(i, m) = sum_c conj(J(i, c)) gain_c X(m, c)
-      for (int idx = tid; idx < 1024; idx += SV_T) {
-        const int i = idx >> 5, m = idx & 31;
+      for (int idx = tid; idx < Mc * Mc; idx += SV_T) {
+        const int i = idx / Mc, m = idx - i * Mc;
         cplx acc = mk(0.0, 0.0);
-        if (i < Mc && m < Mc) {
-          for (int c = 0; c < Mc; ++c) cfmac(acc, Js[c * 32 + i], cscale(Xs[c * 32 + m], sv[c]));
-        }
-        Rs[idx] = acc;
+        for (int c = 0; c < Mc; ++c) cfmac(acc, Js[c * 32 + i], cscale(Xs[c * 32 + m], sv[c]));
+        Pg[idx] = acc;
       }
       have_j = true;
-      __syncthreads();
     }
-    cplx* Pg = ops.Pb + oidx * ops.pb_stride;
-    for (int idx = tid; idx < Mc * Mc; idx += SV_T) {
-      const int i = idx / Mc, m = idx - i * Mc;
-      Pg[idx] = Rs[i * 32 + m];
+    if (tid == 0) {
+      if (ops.info) ops.info[oidx] = fast ? 0 : sweeps;
+      if (ops.stats && !fast) { atomicAdd(ops.stats, (unsigned long long)sweeps); atomicAdd(ops.stats + 1, 1ull); }
     }
-    if (tid == 0 && ops.info) ops.info[oidx] = fast ? 0 : sweeps;
     __syncthreads();
   }
 }
@@ -495,14 +559,11 @@ cudaError_t launch_tsqr_sep(cudaStream_t st, const BlockPlan& bp, const RowSourc
 cudaError_t launch_svdclip(cudaStream_t st, int Mc, const cplx* Rin, const OperatorSet& ops, int num_prob, int G,
                            double regul, int try_fast, int warm) {
   if (Mc > 32) return cudaErrorInvalidValue;
-  const size_t smem = (size_t)3 * 1024 * sizeof(cplx) + (size_t)(32 + 32 + 20) * sizeof(double);
-  static bool set = false;
-  if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(svdclip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    set = true;
-  }
-  svdclip_kernel<<<num_prob, SV_T, smem, st>>>(Mc, Rin, ops, G, regul, try_fast, warm);
+  const size_t smem = (size_t)2 * 1024 * sizeof(cplx) + (size_t)(32 + 32 + 20) * sizeof(double);
+  // EMAGLS_JACOBI_OCC=5: five CTAs per SM under a 102-register cap (A/B switch; default four CTAs, 128 registers)
+  static const int occ = [] { const char* e = getenv("EMAGLS_JACOBI_OCC"); return (e && atoi(e) == 5) ? 5 : 4; }();
+  if (occ == 5) svdclip_kernel<5><<<num_prob, SV_T, smem, st>>>(Mc, Rin, ops, G, regul, try_fast, warm);
+  else svdclip_kernel<4><<<num_prob, SV_T, smem, st>>>(Mc, Rin, ops, G, regul, try_fast, warm);
   return cudaGetLastError();
 }
 

@@ -60,6 +60,97 @@ def gather_banks(local: torch.Tensor, n_total: int, dst: int = 0):
     return None
 
 
+def gather_into(local: torch.Tensor, total: torch.Tensor | None, n_total: int, dst: int = 0):
+    """Gather per-rank shards (unit index first) straight into the preallocated [n_total, ...] bank `total`
+    of rank `dst`: grouped send/recv, no staging copies.  On rank dst, `local` may be the view
+    total[lo:hi] of its own shard (then nothing is copied for it).  Returns `total` on dst, None elsewhere."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        if total is not None and total.data_ptr() != local.data_ptr():
+            total[: local.shape[0]].copy_(local)
+        return total if total is not None else local
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if rank == dst:
+        ops = []
+        for r in range(world):
+            lo, hi = shard_range(n_total, r, world)
+            if r == dst:
+                if total[lo:hi].data_ptr() != local.data_ptr():
+                    total[lo:hi].copy_(local)
+            elif hi > lo:
+                ops.append(dist.P2POp(dist.irecv, total[lo:hi], r))
+        for w in (dist.batch_isend_irecv(ops) if ops else []):
+            w.wait()
+        return total
+    if local.shape[0] > 0:
+        for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, local.contiguous(), dst)]):
+            w.wait()
+    return None
+
+
+class ShardedDesigner:
+    """End-to-end eMagLS2 design of one orientation batch sharded over the ranks: host inputs
+    in pinned memory -> H2D -> `emagls_design_emagls2_dev` on this rank's contiguous block of orientations ->
+    NCCL gather of the banks into rank 0's device bank -> D2H of this rank's shard into pinned host memory.
+    No data-path collective; the gather is the only exchange.  All buffers are allocated once."""
+
+    def __init__(self, handle, hL, hR, az, ze, mic_radius, maz, mze, order, fs, length, rotations_total, config=None):
+        import ctypes as C
+        import numpy as np
+        self.C, self.np, self.h = C, np, handle
+        rank, local_rank, world = env_world()
+        self.rank, self.world = rank, world
+        self.dev = torch.device("cuda", handle.device if hasattr(handle, "device") else local_rank)
+        self.cfg = config if config is not None else handle.default_config()
+        self.stream = torch.cuda.ExternalStream(handle.stream, device=self.dev)
+        R = np.ascontiguousarray(np.asarray(rotations_total, dtype=np.float64).reshape(-1, 9))
+        self.n_total = R.shape[0]
+        self.lo, self.hi = shard_range(self.n_total, rank, world)
+        self.n_local = self.hi - self.lo
+        self.T, self.D, self.M = hL.shape[0], hL.shape[1], int(np.asarray(maz).size)
+        self.order, self.fs, self.len, self.r = int(order), float(fs), int(length), float(mic_radius)
+
+        def pin(x):
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float64))).pin_memory()
+            return t, torch.empty_like(t, device=self.dev)
+        # [T, D] column-major == [D, T] row-major
+        self.host_in = [pin(np.asarray(hL).T), pin(np.asarray(hR).T), pin(az), pin(ze), pin(maz), pin(mze),
+                        pin(R[self.lo:self.hi])]
+        self.h2d_bytes = sum(h.numel() * 8 for h, _ in self.host_in)
+        shape = (max(self.n_local, 1), self.M, self.len)       # [len, M, B] column-major
+        # rank 0 designs straight into its slice of the total bank [2 ears][n_total]
+        self.total = (torch.empty((2, self.n_total, self.M, self.len), dtype=torch.float64, device=self.dev)
+                      if rank == 0 else None)
+        if rank == 0:
+            self.bank = [self.total[e, self.lo:self.hi] for e in range(2)]
+        else:
+            self.bank = [torch.empty(shape, dtype=torch.float64, device=self.dev)[: self.n_local] for _ in range(2)]
+        self.host_out = [torch.empty((self.n_local, self.M, self.len), dtype=torch.float64).pin_memory()
+                         for _ in range(2)]
+        self.d2h_bytes = 2 * self.n_local * self.M * self.len * 8
+
+    def step(self, gather: bool = True):
+        C, h = self.C, self.h
+        with torch.cuda.stream(self.stream):
+            for hbuf, dbuf in self.host_in:
+                dbuf.copy_(hbuf, non_blocking=True)
+            d = [db for _, db in self.host_in]
+            if self.n_local > 0:
+                rc = h.lib.emagls_design_emagls2_dev(
+                    h.ptr, C.byref(self.cfg), d[0].data_ptr(), d[1].data_ptr(), self.T, self.D, d[2].data_ptr(),
+                    d[3].data_ptr(), self.r, d[4].data_ptr(), d[5].data_ptr(), self.M, self.order, self.fs, self.len,
+                    1, self.n_local, d[6].data_ptr(), self.bank[0].data_ptr(), self.bank[1].data_ptr(), None)
+                h.check(rc)
+            for e in range(2):
+                self.host_out[e].copy_(self.bank[e], non_blocking=True)
+            if gather and self.world > 1:
+                for e in range(2):
+                    gather_into(self.bank[e], self.total[e] if self.total is not None else None, self.n_total, 0)
+        return self.total
+
+    def wait(self):
+        self.stream.synchronize()
+
+
 def max_over_ranks(value: float, device=None) -> float:
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return float(value)

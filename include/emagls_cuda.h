@@ -70,6 +70,10 @@ long long emagls_launch_count(emagls_handle h);
 #define EMAGLS_PROF_CLASSES 12
 int emagls_profile_enable(emagls_handle h, int on);
 int emagls_profile_read(emagls_handle h, double* ms, long long* counts, int reset);
+/* Work statistics of the design calls since creation / the last reset (bench.py's roofline accounting):
+ * out[0] = (problem, bin) pairs factorised on the TSQR + Jacobi route, out[1] = pairs solved on the Gram route,
+ * out[2] = Jacobi problems, out[3] = Jacobi sweeps summed over them.  Synchronises the handle's stream.      */
+int emagls_stats_read(emagls_handle h, long long* out, int reset);
 /* Stream all work of this handle is enqueued on (cudaStream_t as void*), for event timing. */
 void* emagls_stream(emagls_handle h);
 
@@ -98,6 +102,21 @@ int emagls_design_emagls2_dev(emagls_handle h, const emagls_config* cfg,
                               int num_mics, int order, double fs, int len,
                               int num_sets, int num_orient, const double* rotations,
                               double* wL, double* wR, double* spectra);
+
+/* ---- custom shFunction handles (lib/getEMagLs2Filters.m:32, lib/getEMagLsFilters.m:32; example at
+ * verifyEMagLs.m:356-368) ---------------------------------------------------------------------
+ * A CUDA library cannot call back into MATLAB: the MEX shim evaluates a non-default handle on the host and
+ * passes the two basis matrices down.  Both are evaluated at the SIMULATION order
+ * simN = max(order, ceil(fs pi micRadius / c)) (getSMAIRMatrix.m:95), num_harmonics = (simN+1)^2:
+ *   Y_hrir = shFunction(simN, [hrirGridAziRad hrirGridZenRad], 'real')       [num_dirs x num_harmonics], column-major
+ *   Y_mic  = shFunction(simN, [micGridAziRad  micGridZenRad ], 'real')       [num_mics x num_harmonics x num_orient]
+ * (one page of Y_mic per head orientation: the basis at the microphone positions seen from that orientation).
+ * sh_domain = 0: getEMagLs2Filters (outputs [len x num_mics x P]); 1: getEMagLsFilters (outputs
+ * [len x (order+1)^2 x P], Y_lo = the leading (order+1)^2 columns of the first page of Y_mic).  Real bases only. */
+int emagls_design_sma_basis(emagls_handle h, const emagls_config* cfg, int sh_domain, const double* hL, const double* hR,
+                            int num_samples, int num_dirs, const double* Y_hrir, int num_harmonics, double mic_radius,
+                            const double* Y_mic, int num_mics, int order, double fs, int len, int num_sets,
+                            int num_orient, double* wL, double* wR, double* spectra);
 
 /* ---- getEMagLsFilters (lib/getEMagLsFilters.m:1-2): SH-domain output, (order+1)^2 channels.
  * For cfg->basis == COMPLEX the outputs are interleaved complex [len x nsh x batch].           */

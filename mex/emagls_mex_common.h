@@ -36,6 +36,33 @@ static void emx_require_default_handle(int nrhs, const mxArray* prhs[], int idx,
   }
 }
 
+/* 1 if prhs[idx] is a function handle other than @<expected> (then the shim evaluates it on the host) */
+static int emx_is_custom_handle(int nrhs, const mxArray* prhs[], int idx, const char* expected) {
+  if (nrhs > idx && !mxIsEmpty(prhs[idx])) {
+    mxArray* name; char buf[64];
+    mexCallMATLAB(1, &name, 1, (mxArray**)&prhs[idx], "func2str");
+    mxGetString(name, buf, sizeof buf);
+    mxDestroyArray(name);
+    return strcmp(buf, expected) != 0;
+  }
+  return 0;
+}
+
+/* Y = shFunction(order, [azi zen], 'real') through feval: [numel(azi) x (order+1)^2] real */
+static mxArray* emx_eval_basis(const mxArray* fn, int order, const double* azi, const double* zen, mwSize n) {
+  mxArray* args[4]; mxArray* out = NULL;
+  mwSize i;
+  args[0] = (mxArray*)fn;
+  args[1] = mxCreateDoubleMatrix(1, 1, mxREAL); mxGetDoubles(args[1])[0] = (double)order;
+  args[2] = mxCreateDoubleMatrix(n, 2, mxREAL);
+  for (i = 0; i < n; ++i) { mxGetDoubles(args[2])[i] = azi[i]; mxGetDoubles(args[2])[n + i] = zen[i]; }
+  args[3] = mxCreateString("real");
+  if (mexCallMATLAB(1, &out, 4, args, "feval") != 0 || mxIsComplex(out))
+    mexErrMsgIdAndTxt("eMagLS:handle", "shFunction must return a real [directions x (order+1)^2] matrix");
+  mxDestroyArray(args[1]); mxDestroyArray(args[2]); mxDestroyArray(args[3]);
+  return out;
+}
+
 static mxArray* emx_out(mwSize rows, mwSize cols, int basis) {
   return mxCreateDoubleMatrix(rows, cols, basis == EMAGLS_BASIS_COMPLEX ? mxCOMPLEX : mxREAL);
 }

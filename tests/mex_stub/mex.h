@@ -26,6 +26,7 @@ mxArray* mxGetField(const mxArray*, mwSize, const char*);
 mxArray* mxCreateDoubleMatrix(mwSize, mwSize, mxComplexity);
 mxArray* mxCreateNumericArray(mwSize, const mwSize*, mxClassID, mxComplexity);
 mxArray* mxDuplicateArray(const mxArray*);
+mxArray* mxCreateString(const char*);
 void mxDestroyArray(mxArray*);
 int mexCallMATLAB(int, mxArray*[], int, mxArray*[], const char*);
 void mexErrMsgIdAndTxt(const char*, const char*, ...);

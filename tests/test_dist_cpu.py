@@ -31,15 +31,23 @@ WORKER = textwrap.dedent("""
     lo, hi = emdist.shard_range(n_total, rank, world)
     local = torch.arange(lo, hi, dtype=torch.float64).reshape(-1, 1, 1) * torch.ones(1, 3, 2, dtype=torch.float64)
     out = emdist.gather_banks(local, n_total, dst=0)
+    # gather straight into a preallocated bank; rank 0's own shard is a view of it (no staging copies)
+    total = torch.full((n_total, 3, 2), -1.0, dtype=torch.float64) if rank == 0 else None
+    mine = local
+    if rank == 0:
+        total[lo:hi] = local
+        mine = total[lo:hi]
+    out2 = emdist.gather_into(mine, total, n_total, dst=0)
     m = emdist.max_over_ranks(float(rank + 1))
     assert m == float(world)
     emdist.barrier()
     if rank == 0:
         assert out.shape == (n_total, 3, 2)
         assert torch.equal(out[:, 0, 0], torch.arange(n_total, dtype=torch.float64))
+        assert out2 is total and torch.equal(out2, out)
         print("GATHER_OK")
     else:
-        assert out is None
+        assert out is None and out2 is None
 """)
 
 

@@ -118,3 +118,27 @@ def test_fused_overlap_save_route_matches_oracle(em, h, monkeypatch, n, ch, ln, 
     yo = oracle.binauralDecode(x, 48000, wL, wR, 48000, comp)
     assert y.shape == yo.shape
     assert np.abs(y - yo).max() / np.abs(yo).max() < 1e-9
+
+
+def test_complex_basis_chain_keeps_the_real_part_of_the_complex_products(em, h, grids):
+    """shDefinition = 'complex': encodeSH and the designers return complex arrays; binauralDecode must render
+    real(sum_ch x * w) as the reference does (binauralDecode.m:39-42,59-64), not real(x) * real(w)."""
+    from emagls_b200 import synth
+    rng = np.random.default_rng(5)
+    maz, mze = grids["micGridAziRad"], grids["micGridZenRad"]
+    sig = rng.standard_normal((6000, maz.size))
+    x = em.encodeSH(sig, maz, mze, 4, "complex", handle=h)
+    assert np.iscomplexobj(x) and np.abs(x.imag).max() > 0
+    az, ze = grids["hrirGridAziRad"], grids["hrirGridZenRad"]
+    hL, hR = synth.synth_hrirs(az, ze)
+    wl, wr = em.getMagLsFilters(hL, hR, az, ze, 4, grids["fs"], 512, "complex", handle=h)
+    assert np.iscomplexobj(wl) and np.abs(wl.imag).max() > 0
+    for comp in (False, True):
+        y = em.binauralDecode(x, 48000, wl, wr, 48000, comp, handle=h)
+        yo = oracle.binauralDecode(x, 48000, wl, wr, 48000, comp)
+        assert y.shape == yo.shape and not np.iscomplexobj(y)
+        assert rel(y, yo) < 1e-9
+        # and it is not what dropping the imaginary parts gives
+        assert rel(em.binauralDecode(x.real, 48000, wl.real, wr.real, 48000, comp, handle=h), yo) > 1e-3
+    with pytest.raises(ValueError):
+        em.encodeSH(sig + 1j, maz, mze, 4, handle=h)

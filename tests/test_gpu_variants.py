@@ -209,3 +209,39 @@ def test_variant_errors(em, h, c1, ema):
     with pytest.raises(em.EmaglsError, match="fewer microphones"):
         em.getEMagLsFiltersEMAinCH(ema["hL"], ema["hR"], ema["az"], ema["ze"], 0.042, ema["maz"][:5], 4, 48000, 512,
                                    handle=h)
+
+
+# ------------------------------------------------------------------ custom shFunction handles
+def test_custom_sh_function_is_evaluated_on_the_host_and_passed_down(em, h, c1):
+    """A shFunction other than the default is evaluated on the host and reaches the device as the two basis
+    matrices (emagls_design_sma_basis).  With the oracle's getSH as the handle the result is the default one
+    (device getSH differs by rounding only) and equals the oracle called with the same handle
+    (lib/getEMagLs2Filters.m:32,52,61; example handle at verifyEMagLs.m:356-368)."""
+    calls = []
+
+    def my_sh(order, dirs, kind):
+        calls.append((order, dirs.shape[0], kind))
+        return oracle.getSH(order, dirs, kind)
+    args = (c1["az"], c1["ze"], c1["r"], c1["maz"], c1["mze"], 4, c1["fs"], 512)
+    wL, wR, sp = em.getEMagLs2Filters(c1["hL"], c1["hR"], *args, "real", my_sh, handle=h, return_spectra=True)
+    assert calls == [(19, c1["az"].size, "real"), (19, 32, "real")]
+    dL, dR, dsp = em.getEMagLs2Filters(c1["hL"], c1["hR"], *args, handle=h, return_spectra=True)
+    for e in range(2):
+        err = bin_err(sp[:, :, e], dsp[:, :, e])
+        assert err[16:].max() < 1e-10, err[16:].max()
+    assert rel(wL, dL) < 5e-9 and rel(wR, dR) < 5e-9
+    # batched over orientations: page 1 = the reference call with the rotated grid, handle evaluated per orientation
+    Rm = np.stack([np.eye(3), synth.rotation_yaw_pitch(75.0, -25.0)])
+    bL, bR = em.getEMagLs2Filters(c1["hL"], c1["hR"], *args, "real", my_sh, rotations=Rm, handle=h)
+    raz, rze = synth.rotate_grid(c1["az"], c1["ze"], Rm[1])
+    oL, oR = oracle.getEMagLs2Filters(c1["hL"], c1["hR"], raz, rze, *args[2:], shFunction=my_sh)
+    assert rel(bL[:, :, 0], wL) < 1e-12 and rel(bL[:, :, 1], oL) < 5e-9 and rel(bR[:, :, 1], oR) < 5e-9
+    # SH-domain variant
+    sL, sR = em.getEMagLsFilters(c1["hL"], c1["hR"], *args, "real", my_sh, handle=h)
+    oL, oR = oracle.getEMagLsFilters(c1["hL"], c1["hR"], *args, shFunction=my_sh)
+    assert sL.shape == (512, 25) and rel(sL, oL) < 1e-9 and rel(sR, oR) < 1e-9
+    # a different (scaled) basis really changes the design input: the handle is not ignored
+    xL, _ = em.getEMagLs2Filters(c1["hL"], c1["hR"], *args, "real", lambda n, d, k: 2.0 * oracle.getSH(n, d, k), handle=h)
+    assert rel(xL, wL) > 1e-3
+    with pytest.raises(NotImplementedError):
+        em.getEMagLs2Filters(c1["hL"], c1["hR"], *args, "complex", my_sh, handle=h)

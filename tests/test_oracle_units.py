@@ -1,4 +1,6 @@
 """Self-consistency tests of the oracle's building blocks (CPU only)."""
+import os
+
 import numpy as np
 import pytest
 from scipy.special import eval_legendre
@@ -152,3 +154,32 @@ def test_from_atf_runs_on_reference_fixture():
                                                   return_spectra=True)
     assert wL.shape == (256, 8) and wL[0].max() == 0 and np.all(np.isfinite(wR))
     assert info["meanGridDevDeg"] < 5.0
+
+
+def test_high_precision_oracle_agrees_with_fp64_on_a_well_conditioned_problem():
+    """oracle/hp_oracle.py (exact pwGrid + Gram in integers, mpmath eigendecomposition) against the LAPACK route
+    of oracle.regularized_inverse where both are accurate, including clipped singular values."""
+    from oracle import hp_oracle as hp
+    rng = np.random.default_rng(0)
+    S, D, M = 12, 40, 6
+    sm = rng.standard_normal((M, S)) + 1j * rng.standard_normal((M, S))
+    sm[-1] = sm[0] + 1e-3 * (rng.standard_normal(S) + 1j * rng.standard_normal(S))   # one singular value below the 1 % clip
+    Y = rng.standard_normal((S, D))
+    t = rng.standard_normal((2, D)) + 1j * rng.standard_normal((2, D))
+    W, sv = hp.exact_ls_rows(sm, Y, t, dps=60)
+    s64 = np.linalg.svd(sm @ Y, compute_uv=False)
+    assert s64[-1] < 0.01 * s64[0]
+    assert np.abs(sv - s64).max() <= 1e-12 * s64[0]
+    assert hp.rel_err(hp.fp64_ls_rows(sm, Y, t), W) <= 1e-10
+
+
+def test_high_precision_fixture_is_consistent():
+    """tests/golden/hp_goldens.npz: the stored FP64-oracle error is the distance of the stored oracle rows from
+    the stored exact rows, and it grows with the condition number as SURVEY.md section 0 reports."""
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hp_goldens.npz")
+    d = np.load(p)
+    ex, o64, err = d["c1_exact"], d["c1_oracle64"], d["c1_err_oracle64"]
+    assert ex.shape == o64.shape == (15, 2, 32)
+    for i in range(15):
+        assert abs(np.abs(o64[i] - ex[i]).max() / np.abs(ex[i]).max() - err[i]) <= 1e-3 * err[i] + 1e-18
+    assert err[0] > 1e-8 and err[-1] < 1e-11 and d["c1_cond"][0] > 1e12
