@@ -500,6 +500,65 @@ def main():
                                "class_ms": {k: v["ms"] / 3 for k, v in rp.items() if v["n"]}}}
         del x, y
 
+    # ---------------- BASELINE config 3 (secondary line): getEMagLsFiltersFromAtf on the measured glasses-on-HATS
+    # ATF set (1625 directions x 8 microphones), batched over the 3600-orientation grid, + the 10-minute 8-channel
+    # render that consumes one of the filter sets.  Rank 0, device-resident, CUDA events on the library's stream.
+    config3 = None
+    atf_path = os.path.join(ROOT, "tests", "golden", "atf_full.npz")
+    if not args.no_render and rank == 0 and world == 1 and os.path.exists(atf_path):
+        ad = np.load(atf_path)
+        atf = np.ascontiguousarray(ad["atfIrs"].astype(np.float64).transpose(2, 1, 0))     # [Da, M, Ta] = col-major [Ta, M, Da]
+        agd = np.deg2rad(ad["atfGridAziEleDeg"].astype(np.float64))
+        ag = np.stack([agd[:, 0], np.pi / 2 - agd[:, 1]], 0)                               # [2, Da] = col-major [Da, 2]
+        Da, M3, Ta = atf.shape
+        L3 = 256
+        d_atf, d_ag = dt64(atf), dt64(ag)
+        d_hg = dt64(np.stack([pr["az"], pr["ze"]], 0))
+        w3L = torch.empty((B, M3, L3), dtype=torch.float64, device=dev)
+        w3R = torch.empty_like(w3L)
+
+        def c3step():
+            h.check(h.lib.emagls_design_from_atf_batch_dev(
+                h.ptr, C.byref(cfg), d_hL.data_ptr(), d_hR.data_ptr(), T, D, d_hg.data_ptr(), d_atf.data_ptr(), Ta, M3, Da,
+                d_ag.data_ptr(), float(pr["fs"]), L3, 2000.0, B, d_R.data_ptr(), w3L.data_ptr(), w3R.data_ptr(), None))
+        for _ in range(2):
+            c3step()
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(3):
+            l2_flush()
+            c3step()
+        c1.record(stream)
+        torch.cuda.synchronize()
+        c3ms = c0.elapsed_time(c1) / 3
+        n3 = int(args.render_seconds * 48000)
+        x3 = torch.randn((M3, n3), dtype=torch.float64, device=dev)
+        y3 = torch.empty((2, n3), dtype=torch.float64, device=dev)
+        f3l, f3r = w3L[0].contiguous(), w3R[0].contiguous()
+
+        def r3step():
+            h.check(h.lib.emagls_binaural_decode_dev(h.ptr, x3.data_ptr(), n3, M3, f3l.data_ptr(), f3r.data_ptr(), L3, 0,
+                                                     y3.data_ptr()))
+        for _ in range(2):
+            r3step()
+        torch.cuda.synchronize()
+        c0.record(stream)
+        for _ in range(3):
+            r3step()
+        c1.record(stream)
+        torch.cuda.synchronize()
+        r3ms = c0.elapsed_time(c1) / 3
+        config3 = {"workload": "BASELINE config 3: getEMagLsFiltersFromAtf, glasses-on-HATS ATFs (1625 x 8, 192 taps), "
+                               "2702-direction HRIRs, filterLen 256, fTrans 2 kHz, 3600-orientation batch",
+                   "filter_sets_per_sec": B / (c3ms * 1e-3), "ms_per_batch": c3ms, "orientations": B,
+                   "render": {"frames": n3, "channels": M3, "taps": L3, "ms": r3ms,
+                              "msamples_per_sec": n3 / (r3ms * 1e-3) / 1e6,
+                              "hbm_frac": n3 * (M3 * 8 + 16.0) / (r3ms * 1e-3) / 1e9 / hbm_peak},
+                   "data": "measured ATF set (float32 copy of the reference's resource, tests/golden/atf_full.npz), "
+                           "synthetic rigid-sphere HRIRs"}
+        del x3, y3, d_atf
+
     # ---------------- CPU baseline (the reference algorithm restated, on this box's host cores)
     cpu = None
     if not args.no_cpu_baseline and rank == 0 and world == 1:
@@ -522,7 +581,7 @@ def main():
                         "path": "emagls_b200.dist.ShardedDesigner: pinned host inputs -> H2D -> emagls_design_emagls2_dev "
                                 "-> NCCL send/recv of the shards into rank 0's device bank -> D2H of every shard (pinned)",
                         "max_rel_diff_vs_device_resident_banks": e2e_same, "host_api_call": host_api},
-                "strong_scaling": strong, "parity_spot_check": spot,
+                "strong_scaling": strong, "parity_spot_check": spot, "config3": config3,
                 "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline,
                 "cpu_baseline": cpu, "render": render}
         print(json.dumps(line), flush=True)

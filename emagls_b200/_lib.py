@@ -54,6 +54,12 @@ SIGNATURES = {
     "emagls_design_from_atf": (C.c_int, [C.c_void_p, C.POINTER(Config), c_dp, c_dp, C.c_int, C.c_int, c_dp, c_dp,
                                          C.c_int, C.c_int, C.c_int, c_dp, C.c_double, C.c_int, C.c_double,
                                          c_dp, c_dp, c_dp, c_dp]),
+    "emagls_design_from_atf_batch": (C.c_int, [C.c_void_p, C.POINTER(Config), c_dp, c_dp, C.c_int, C.c_int, c_dp, c_dp,
+                                               C.c_int, C.c_int, C.c_int, c_dp, C.c_double, C.c_int, C.c_double,
+                                               C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    "emagls_design_from_atf_batch_dev": (C.c_int, [C.c_void_p, C.POINTER(Config), c_dp, c_dp, C.c_int, C.c_int, c_dp,
+                                                   c_dp, C.c_int, C.c_int, C.c_int, c_dp, C.c_double, C.c_int,
+                                                   C.c_double, C.c_int, c_dp, c_dp, c_dp, c_dp]),
     "emagls_design_ema_ch": (C.c_int, [C.c_void_p, C.POINTER(Config), c_dp, c_dp, C.c_int, C.c_int, c_dp, c_dp,
                                        C.c_double, c_dp, C.c_int, C.c_int, C.c_double, C.c_int, c_dp, c_dp, c_dp]),
     "emagls_design_ema_sh": (C.c_int, [C.c_void_p, C.POINTER(Config), c_dp, c_dp, C.c_int, C.c_int, c_dp, c_dp,

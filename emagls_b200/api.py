@@ -233,33 +233,46 @@ def getLsFilters(hL, hR, hrirGridAziRad, hrirGridZenRad, order, shDefinition="re
 
 
 def getEMagLsFiltersFromAtf(hL, hR, hrirGridAziZenRad, atfIrs, atfGridAziZenRad, fs, filterLen, fTrans, *,
-                            handle=None, config=None, return_spectra=False, return_info=False):
-    """[wMlsL, wMlsR] = getEMagLsFiltersFromAtf(...)  -- lib/getEMagLsFiltersFromAtf.m:1."""
+                            rotations=None, handle=None, config=None, return_spectra=False, return_info=False):
+    """[wMlsL, wMlsR] = getEMagLsFiltersFromAtf(...)  -- lib/getEMagLsFiltersFromAtf.m:1.
+
+    ``rotations`` ([B,3,3], keyword-only batch extension): page b of the ``[filterLen, numMics, B]`` outputs equals
+    one reference call with ``hrirGridAziZenRad`` rotated by ``rotations[b]``."""
     h = handle or default_handle()
     cfg = _config(h, config, "real")
     hL, hR, T, D, sets = _prep_hrirs(hL, hR)
     if sets != 1:
-        raise ValueError("getEMagLsFiltersFromAtf is not batched")
+        raise ValueError("getEMagLsFiltersFromAtf takes one HRTF set")
     hg = _f(np.asarray(hrirGridAziZenRad, dtype=np.float64).reshape(-1, 2))
     atf = _f(atfIrs)
     ag = _f(np.asarray(atfGridAziZenRad, dtype=np.float64).reshape(-1, 2))
     Ta, M, Da = atf.shape
     nfft = min(cfg.nfft_max_len, 2 * int(filterLen))
     K = nfft // 2 + 1
-    wL = np.zeros((int(filterLen), M), order="F")
-    wR = np.zeros((int(filterLen), M), order="F")
-    sp = np.zeros((K, M, 2), dtype=np.complex128, order="F") if return_spectra else None
-    dev = C.c_double(0.0)
-    h.check(h.lib.emagls_design_from_atf(h.ptr, C.byref(cfg), _p(hL), _p(hR), T, D, _p(hg), _p(atf), Ta, M, Da,
-                                         _p(ag), float(fs), int(filterLen), float(fTrans), _p(wL), _p(wR),
-                                         _p(sp), C.cast(C.byref(dev), C.c_void_p)))
+    if rotations is None:
+        rot, B = None, 1
+    else:
+        rot = np.ascontiguousarray(np.asarray(rotations, dtype=np.float64).reshape(-1, 9))
+        B = rot.shape[0]
+    wL = np.zeros((int(filterLen), M, B), order="F")
+    wR = np.zeros((int(filterLen), M, B), order="F")
+    sp = np.zeros((K, M, B, 2), dtype=np.complex128, order="F") if return_spectra else None
+    dev = np.zeros(B)
+    h.check(h.lib.emagls_design_from_atf_batch(h.ptr, C.byref(cfg), _p(hL), _p(hR), T, D, _p(hg), _p(atf), Ta, M, Da,
+                                               _p(ag), float(fs), int(filterLen), float(fTrans), B, _p(rot), _p(wL),
+                                               _p(wR), _p(sp), _p(dev)))
     # the reference prints this line (lib/getEMagLsFiltersFromAtf.m:96)
-    print(f"Matching HRTF and ATF grids, average grid deviation: {dev.value:.5g} deg")
+    for v in dev[: min(B, 3)]:
+        print(f"Matching HRTF and ATF grids, average grid deviation: {v:.5g} deg")
+    if rotations is None:
+        wL, wR = wL[:, :, 0], wR[:, :, 0]
+        if sp is not None:
+            sp = sp[:, :, 0, :]
     out = (wL, wR)
     if return_spectra:
         out += (sp,)
     if return_info:
-        out += (dict(meanGridDevDeg=dev.value),)
+        out += (dict(meanGridDevDeg=float(dev[0]) if rotations is None else dev),)
     return out
 
 

@@ -268,31 +268,59 @@ int emagls_design_ls(emagls_handle h, const emagls_config* cfg, const double* hL
     EM_CUDA(cudaStreamSynchronize(st));
   });
 }
+static int from_atf_host(emagls_handle h, const emagls_config* cfg, const double* hL, const double* hR,
+                         int num_samples, int num_dirs, const double* hrir_grid, const double* atf_irs,
+                         int atf_samples, int num_mics, int atf_dirs, const double* atf_grid, double fs,
+                         int filter_len, double f_trans, int num_orient, const double* rotations, double* wL,
+                         double* wR, double* spectra, double* mean_grid_dev_deg) {
+  return guarded(h, [&] {
+    EM_REQUIRE(cfg && hL && hR && hrir_grid && atf_irs && atf_grid && wL && wR, "null argument");
+    EM_REQUIRE(num_samples > 0 && num_dirs > 0 && atf_samples > 0 && num_mics > 0 && atf_dirs > 0 && filter_len > 0 &&
+                   num_orient > 0, "empty input");
+    cudaStream_t st = h->stream;
+    Arena ar(st);
+    const int T = num_samples, D = num_dirs, M = num_mics, B = num_orient;
+    const int K = std::min(cfg->nfft_max_len, 2 * filter_len) / 2 + 1;
+    const size_t wn = (size_t)filter_len * M * B;
+    double* d_wL = ar.get<double>(wn);
+    double* d_wR = ar.get<double>(wn);
+    double* d_sp = spectra ? ar.get<double>((size_t)2 * K * M * B * 2) : nullptr;
+    design_from_atf(h, *cfg, ar.upload(hL, (size_t)T * D), ar.upload(hR, (size_t)T * D), T, D,
+                    ar.upload(hrir_grid, (size_t)2 * D), ar.upload(atf_irs, (size_t)atf_samples * M * atf_dirs),
+                    atf_samples, M, atf_dirs, ar.upload(atf_grid, (size_t)2 * atf_dirs), fs, filter_len, f_trans, B,
+                    rotations ? ar.upload(rotations, (size_t)B * 9) : nullptr, d_wL, d_wR, d_sp, mean_grid_dev_deg);
+    EM_CUDA(cudaMemcpyAsync(wL, d_wL, wn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaMemcpyAsync(wR, d_wR, wn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (spectra)
+      EM_CUDA(cudaMemcpyAsync(spectra, d_sp, (size_t)2 * K * M * B * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaStreamSynchronize(st));
+  });
+}
 int emagls_design_from_atf(emagls_handle h, const emagls_config* cfg, const double* hL, const double* hR,
                            int num_samples, int num_dirs, const double* hrir_grid, const double* atf_irs,
                            int atf_samples, int num_mics, int atf_dirs, const double* atf_grid, double fs,
                            int filter_len, double f_trans, double* wL, double* wR, double* spectra,
                            double* mean_grid_dev_deg) {
+  return from_atf_host(h, cfg, hL, hR, num_samples, num_dirs, hrir_grid, atf_irs, atf_samples, num_mics, atf_dirs,
+                       atf_grid, fs, filter_len, f_trans, 1, nullptr, wL, wR, spectra, mean_grid_dev_deg);
+}
+int emagls_design_from_atf_batch(emagls_handle h, const emagls_config* cfg, const double* hL, const double* hR,
+                                 int num_samples, int num_dirs, const double* hrir_grid, const double* atf_irs,
+                                 int atf_samples, int num_mics, int atf_dirs, const double* atf_grid, double fs,
+                                 int filter_len, double f_trans, int num_orient, const double* rotations, double* wL,
+                                 double* wR, double* spectra, double* mean_grid_dev_deg) {
+  return from_atf_host(h, cfg, hL, hR, num_samples, num_dirs, hrir_grid, atf_irs, atf_samples, num_mics, atf_dirs,
+                       atf_grid, fs, filter_len, f_trans, num_orient, rotations, wL, wR, spectra, mean_grid_dev_deg);
+}
+int emagls_design_from_atf_batch_dev(emagls_handle h, const emagls_config* cfg, const double* hL, const double* hR,
+                                     int num_samples, int num_dirs, const double* hrir_grid, const double* atf_irs,
+                                     int atf_samples, int num_mics, int atf_dirs, const double* atf_grid, double fs,
+                                     int filter_len, double f_trans, int num_orient, const double* rotations,
+                                     double* wL, double* wR, double* spectra) {
   return guarded(h, [&] {
     EM_REQUIRE(cfg && hL && hR && hrir_grid && atf_irs && atf_grid && wL && wR, "null argument");
-    EM_REQUIRE(num_samples > 0 && num_dirs > 0 && atf_samples > 0 && num_mics > 0 && atf_dirs > 0 && filter_len > 0,
-               "empty input");
-    cudaStream_t st = h->stream;
-    Arena ar(st);
-    const int T = num_samples, D = num_dirs, M = num_mics;
-    const int K = std::min(cfg->nfft_max_len, 2 * filter_len) / 2 + 1;
-    const size_t wn = (size_t)filter_len * M;
-    double* d_wL = ar.get<double>(wn);
-    double* d_wR = ar.get<double>(wn);
-    double* d_sp = spectra ? ar.get<double>((size_t)2 * K * M * 2) : nullptr;
-    design_from_atf(h, *cfg, ar.upload(hL, (size_t)T * D), ar.upload(hR, (size_t)T * D), T, D,
-                    ar.upload(hrir_grid, (size_t)2 * D), ar.upload(atf_irs, (size_t)atf_samples * M * atf_dirs),
-                    atf_samples, M, atf_dirs, ar.upload(atf_grid, (size_t)2 * atf_dirs), fs, filter_len, f_trans,
-                    d_wL, d_wR, d_sp, mean_grid_dev_deg);
-    EM_CUDA(cudaMemcpyAsync(wL, d_wL, wn * sizeof(double), cudaMemcpyDeviceToHost, st));
-    EM_CUDA(cudaMemcpyAsync(wR, d_wR, wn * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (spectra) EM_CUDA(cudaMemcpyAsync(spectra, d_sp, (size_t)2 * K * M * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    EM_CUDA(cudaStreamSynchronize(st));
+    design_from_atf(h, *cfg, hL, hR, num_samples, num_dirs, hrir_grid, atf_irs, atf_samples, num_mics, atf_dirs,
+                    atf_grid, fs, filter_len, f_trans, num_orient, rotations, wL, wR, spectra, nullptr);
   });
 }
 int emagls_design_ema_ch(emagls_handle h, const emagls_config* cfg, const double* hL, const double* hR,

@@ -187,8 +187,8 @@ void design_magls(emagls_ctx* h, const emagls_config& cfg, const double* hL, con
                   double* wL, double* wR, double* spectra, int harmonics_kind = 0);
 void design_from_atf(emagls_ctx* h, const emagls_config& cfg, const double* hL, const double* hR, int T, int D,
                      const double* hrir_grid, const double* atf_irs, int Ta, int M, int Da, const double* atf_grid,
-                     double fs, int len, double f_trans, double* wL, double* wR, double* spectra,
-                     double* mean_dev_deg);
+                     double fs, int len, double f_trans, int num_orient, const double* rotations, double* wL,
+                     double* wR, double* spectra, double* mean_dev_deg);
 void design_ema_sh(emagls_ctx* h, const emagls_config& cfg, const double* hL, const double* hR, int T, int D,
                    const double* grid_azi, const double* grid_zen, double mic_radius, const double* mic_azi, int M,
                    int order, double fs, int len, double* wL, double* wR, double* spectra);

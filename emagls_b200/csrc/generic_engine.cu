@@ -56,9 +56,11 @@ form_q_kernel(BlockPlan bp, OperatorSet ops, cplx* __restrict__ QcT) {
 struct ChainArgs {
   const cplx* At; long long at_slot_stride;     // rows [slot][D][Mc]; stride 0: one operator for all bins
   const cplx* QcT; const cplx* Pb;              // [slot][Mc][D], [slot][Mc][Mc] (same slot stride rule)
-  const cplx* H; long long h_prob_stride, h_ear_stride;  // targets [prob][ear][K][D]
+  const cplx* H; long long h_prob_stride, h_ear_stride;  // targets [prob][ear][K][Dh]
   cplx* W; long long w_ear_stride, w_prob_stride;         // solutions [ear][prob][Mc][K]
   int D, Mc, K, first_bin, kls1, dc_fix, nyquist_real;
+  int Dh;                                                 // row length of H (= D unless columns are gathered)
+  const int* gidx; long long gidx_prob_stride;            // optional: target column of direction d is gidx[prob][d]
 };
 
 __global__ void __launch_bounds__(1024)
@@ -76,7 +78,8 @@ generic_chain_kernel(ChainArgs a) {
   cplx* Wp = a.W + (long long)ear * a.w_ear_stride + (long long)prob * a.w_prob_stride;
   for (int k = a.first_bin; k < K; ++k) {
     const long long slot = a.at_slot_stride ? (long long)(k - a.first_bin) : 0;
-    const cplx* Hk = Hp + (long long)k * D;
+    const cplx* Hk = Hp + (long long)k * a.Dh;
+    const int* gi = a.gidx ? a.gidx + (long long)prob * a.gidx_prob_stride : nullptr;
     if (k >= a.kls1) {  // with no LS bin before it the recursion starts from W = 0, i.e. phi = angle(0) = 0
       const cplx* Ak = a.At + slot * (long long)D * Mc;
       const bool nyq = a.nyquist_real && (k == K - 1);
@@ -84,7 +87,7 @@ generic_chain_kernel(ChainArgs a) {
         const cplx* row = Ak + (long long)d * Mc;
         cplx y = mk(0.0, 0.0);
         for (int c = 0; c < Mc; ++c) cfma(y, row[c], w[c]);
-        const cplx hv = Hk[d];
+        const cplx hv = Hk[gi ? gi[d] : d];
         const double mag = sqrt(cabs2(hv));
         const double a2 = cabs2(y);
         cplx tv;
@@ -94,7 +97,7 @@ generic_chain_kernel(ChainArgs a) {
         t[d] = tv;
       }
     } else {
-      for (int d = tid; d < D; d += nt) t[d] = Hk[d];
+      for (int d = tid; d < D; d += nt) t[d] = Hk[gi ? gi[d] : d];
     }
     __syncthreads();
     const cplx* Qk = a.QcT + slot * (long long)Mc * D;
@@ -166,11 +169,23 @@ __global__ void grid_cart_kernel(const double* __restrict__ grid, int n, double*
 
 // nearest neighbour of every direction of the smaller grid in the larger one
 // (lib/getEMagLsFiltersFromAtf.m:80-84: first minimum of the Euclidean distance)
+// Batched over head orientations (blockIdx.y): the HRIR-grid direction u points to R u.  rot_small != 0: the
+// smaller grid is the HRIR grid (x <- R x); else the larger one is, which is matched by x <- R^T x.
 __global__ void nn_match_kernel(const double* __restrict__ small_xyz, int ns, const double* __restrict__ large_xyz,
-                                int nl, int* __restrict__ idx, double* __restrict__ dev_deg) {
+                                int nl, const double* __restrict__ rot, int rot_small, int* __restrict__ idx,
+                                double* __restrict__ dev_deg) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ns) return;
-  const double x = small_xyz[3 * i], y = small_xyz[3 * i + 1], z = small_xyz[3 * i + 2];
+  double x = small_xyz[3 * i], y = small_xyz[3 * i + 1], z = small_xyz[3 * i + 2];
+  if (rot) {
+    const double* R = rot + 9 * blockIdx.y;
+    double rx, ry, rz;
+    if (rot_small) { rx = R[0] * x + R[1] * y + R[2] * z; ry = R[3] * x + R[4] * y + R[5] * z; rz = R[6] * x + R[7] * y + R[8] * z; }
+    else { rx = R[0] * x + R[3] * y + R[6] * z; ry = R[1] * x + R[4] * y + R[7] * z; rz = R[2] * x + R[5] * y + R[8] * z; }
+    x = rx; y = ry; z = rz;
+  }
+  idx += (long long)blockIdx.y * ns;
+  dev_deg += (long long)blockIdx.y * ns;
   double best = 1e300; int bi = 0;
   for (int j = 0; j < nl; ++j) {
     const double dx = large_xyz[3 * j] - x, dy = large_xyz[3 * j + 1] - y, dz = large_xyz[3 * j + 2] - z;
@@ -216,6 +231,8 @@ struct GenericProblem {
   const cplx* H; long long h_prob_stride, h_ear_stride;   // [prob][ear][K][D]
   int num_prob;
   cplx* W;  // [ear][prob][Mc][K]
+  long long w_ear_stride = 0;                             // 0: num_prob * Mc * K
+  int Dh = 0; const int* gidx = nullptr; long long gidx_prob_stride = 0;   // see ChainArgs
 };
 
 static void run_generic(emagls_ctx* h, Arena& ar, const GenericProblem& g) {
@@ -254,7 +271,9 @@ static void run_generic(emagls_ctx* h, Arena& ar, const GenericProblem& g) {
     c.At = g.At; c.at_slot_stride = g.num_ops > 1 ? 1 : 0;
     c.QcT = QcT; c.Pb = ops.Pb;
     c.H = g.H; c.h_prob_stride = g.h_prob_stride; c.h_ear_stride = g.h_ear_stride;
-    c.W = g.W; c.w_ear_stride = (long long)g.num_prob * g.Mc * g.K; c.w_prob_stride = (long long)g.Mc * g.K;
+    c.W = g.W; c.w_ear_stride = g.w_ear_stride ? g.w_ear_stride : (long long)g.num_prob * g.Mc * g.K;
+    c.w_prob_stride = (long long)g.Mc * g.K;
+    c.Dh = g.Dh ? g.Dh : g.D; c.gidx = g.gidx; c.gidx_prob_stride = g.gidx_prob_stride;
     c.D = g.D; c.Mc = g.Mc; c.K = g.K; c.first_bin = g.first_bin; c.kls1 = g.kls1; c.dc_fix = g.dc_fix;
     c.nyquist_real = g.nyquist_real;
     const size_t smem = ((size_t)g.D + 2 * g.Mc) * sizeof(cplx);
@@ -393,13 +412,20 @@ static double matlab_round(double x) { return (x < 0.0) ? -std::floor(-x + 0.5) 
 
 void design_from_atf(emagls_ctx* h, const emagls_config& cfg, const double* hL, const double* hR, int T, int D,
                      const double* hrir_grid, const double* atf_irs, int Ta, int M, int Da, const double* atf_grid,
-                     double fs, int len, double f_trans, double* wL, double* wR, double* spectra,
-                     double* mean_dev_deg) {
+                     double fs, int len, double f_trans, int num_orient, const double* rotations, double* wL,
+                     double* wR, double* spectra, double* mean_dev_deg) {
+  // Batch extension (not in the reference API): orientation b sees HRIR-grid direction u at R_b u, i.e. page b of
+  // the outputs equals one reference call with hrirGridAziZenRad rotated by R_b.  When the ATF grid is the smaller
+  // one (BASELINE config 3: 1625 < 2702) pwGrid is the whole ATF set for every orientation
+  // (lib/getEMagLsFiltersFromAtf.m:72-75): the per-bin factorisations are shared by the batch and only the
+  // nearest-neighbour-selected HRTF columns (:82-95) differ, which the chain kernel gathers on the fly.
   cudaStream_t st = h->stream;
   EM_REQUIRE(T > 0 && D > 0 && Ta > 0 && M > 0 && Da > 0 && len > 0, "empty input");
   EM_REQUIRE(len >= T, "len too short");
   EM_REQUIRE(len % 2 == 0, "filterLen must be even");
   EM_REQUIRE(M <= 64, "more than 64 channels are not supported");
+  EM_REQUIRE(num_orient >= 1 && (rotations != nullptr || num_orient == 1), "num_orient > 1 needs rotations");
+  const int B = num_orient;
   const int nfft = std::min(cfg.nfft_max_len, 2 * len);
   EM_REQUIRE(nfft % 2 == 0 && nfft / 2 >= len / 2, "len exceeds NFFT_MAX_LEN (reference indexes out of range here)");
   const int K = nfft / 2 + 1;
@@ -411,15 +437,19 @@ void design_from_atf(emagls_ctx* h, const emagls_config& cfg, const double* hL, 
   EM_REQUIRE(Dn >= M, "fewer directions than microphones");
   Arena ar(st);
   ProfSpan* setup_span = new ProfSpan(h, EM_PROF_SETUP);
-  // ---- grid matching (:56-96)
+  struct SpanGuard { ProfSpan*& p; ~SpanGuard() { delete p; p = nullptr; } } setup_guard{setup_span};
+  // ---- grid matching (:56-96), all orientations at once
   double* hx = ar.get<double>((size_t)3 * D);
   double* ax = ar.get<double>((size_t)3 * Da);
   grid_cart_kernel<<<(D + 127) / 128, 128, 0, st>>>(hrir_grid, D, hx);
   grid_cart_kernel<<<(Da + 127) / 128, 128, 0, st>>>(atf_grid, Da, ax);
-  int* d_idx = ar.get<int>(Dn);
-  double* d_dev = ar.get<double>(Dn);
-  nn_match_kernel<<<(Dn + 63) / 64, 64, 0, st>>>(hrtf_smaller ? hx : ax, Dn, hrtf_smaller ? ax : hx,
-                                                 hrtf_smaller ? Da : D, d_idx, d_dev);
+  int* d_idx = ar.get<int>((size_t)B * Dn);
+  double* d_dev = ar.get<double>((size_t)B * Dn);
+  {
+    dim3 grid((Dn + 63) / 64, B);
+    nn_match_kernel<<<grid, 64, 0, st>>>(hrtf_smaller ? hx : ax, Dn, hrtf_smaller ? ax : hx, hrtf_smaller ? Da : D,
+                                         rotations, hrtf_smaller ? 1 : 0, d_idx, d_dev);
+  }
   EM_CUDA(cudaGetLastError());
   h->launches += 3;
   // ---- HRIRs: integer group-delay removal (:42-49), spectra
@@ -437,52 +467,57 @@ void design_from_atf(emagls_ctx* h, const emagls_config& cfg, const double* hL, 
     }
     h->launches += 3;
   }
-  cplx* Hc = Hfull;
-  if (!hrtf_smaller) {
-    Hc = ar.get<cplx>((size_t)2 * K * Dn);
-    for (int e = 0; e < 2; ++e) {
-      long long n = (long long)K * Dn;
-      gather_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Hfull + (size_t)e * K * D, K, D, Dn, d_idx,
-                                                                      Hc + (size_t)e * K * Dn);
-    }
-    EM_CUDA(cudaGetLastError());
-    h->launches += 2;
-  }
-  // ---- ATF spectra (:54) and the matched steering rows
+  // ---- ATF spectra (:54)
   const int Tu = std::min(Ta, nfft);   // fft(x, nfft) truncates longer responses
   double* Ad = ar.get<double>((size_t)M * Da * 2 * K);
   {
     double* tw = ar.get<double>((size_t)2 * K * Tu);
     EM_CUDA(launch_dft_twiddle(st, K, Tu, nfft, tw));
-    GemmOperand A{atf_irs, Ta, 1}, B{tw, Tu, 1};
-    EM_CUDA(launch_gemm(st, A, B, GemmShape{M * Da, 2 * K, Tu}, EpiStore{Ad, 2LL * K, 1.0}));
+    GemmOperand A{atf_irs, Ta, 1}, Bm{tw, Tu, 1};
+    EM_CUDA(launch_gemm(st, A, Bm, GemmShape{M * Da, 2 * K, Tu}, EpiStore{Ad, 2LL * K, 1.0}));
     h->launches += 2;
   }
-  cplx* At = ar.get<cplx>((size_t)(K - 1) * Dn * M);
-  {
-    long long n = (long long)(K - 1) * Dn * M;
-    gather_atf_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Ad, M, K, Dn, hrtf_smaller ? d_idx : nullptr, At);
+  if (mean_dev_deg) {
+    std::vector<double> dev((size_t)B * Dn);
+    EM_CUDA(cudaMemcpyAsync(dev.data(), d_dev, dev.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaStreamSynchronize(st));
+    for (int b = 0; b < B; ++b) {
+      double acc = 0.0;
+      for (int i = 0; i < Dn; ++i) acc += dev[(size_t)b * Dn + i];
+      mean_dev_deg[b] = acc / (double)Dn;
+    }
+  }
+  delete setup_span; setup_span = nullptr;
+  cplx* Wsp = spectra ? reinterpret_cast<cplx*>(spectra) : ar.get<cplx>((size_t)2 * B * M * K);
+  EM_CUDA(cudaMemsetAsync(Wsp, 0, (size_t)2 * B * M * K * sizeof(cplx), st));
+  GenericProblem g{};
+  g.num_ops = K - 1; g.D = Dn; g.Mc = M; g.K = K; g.first_bin = 1; g.kls1 = kls1; g.dc_fix = 1;
+  g.nyquist_real = 1; g.regul = cfg.svd_regul;
+  g.H = Hfull; g.h_prob_stride = 0; g.h_ear_stride = (long long)K * D; g.Dh = D;
+  g.w_ear_stride = (long long)B * M * K;
+  const long long natf = (long long)(K - 1) * Dn * M;
+  if (!hrtf_smaller) {
+    // ATF grid smaller: one set of operators for the whole batch, HRTF columns gathered per orientation
+    cplx* At = ar.get<cplx>((size_t)natf);
+    gather_atf_kernel<<<(unsigned)((natf + 255) / 256), 256, 0, st>>>(Ad, M, K, Dn, nullptr, At);
     EM_CUDA(cudaGetLastError());
     h->launches += 1;
+    g.At = At; g.num_prob = B; g.W = Wsp; g.gidx = d_idx; g.gidx_prob_stride = Dn;
+    run_generic(h, ar, g);
+  } else {
+    // HRTF grid smaller: the matched ATF columns, hence the operators, differ per orientation
+    for (int b = 0; b < B; ++b) {
+      Arena ar_b(st);
+      cplx* At = ar_b.get<cplx>((size_t)natf);
+      gather_atf_kernel<<<(unsigned)((natf + 255) / 256), 256, 0, st>>>(Ad, M, K, Dn, d_idx + (size_t)b * Dn, At);
+      EM_CUDA(cudaGetLastError());
+      h->launches += 1;
+      g.At = At; g.num_prob = 1; g.W = Wsp + (size_t)b * M * K; g.gidx = nullptr;
+      run_generic(h, ar_b, g);
+    }
   }
-  if (mean_dev_deg) {
-    std::vector<double> dev(Dn);
-    EM_CUDA(cudaMemcpyAsync(dev.data(), d_dev, (size_t)Dn * sizeof(double), cudaMemcpyDeviceToHost, st));
-    EM_CUDA(cudaStreamSynchronize(st));
-    double acc = 0.0;
-    for (double v : dev) acc += v;
-    *mean_dev_deg = acc / (double)Dn;
-  }
-  delete setup_span;
-  cplx* Wsp = spectra ? reinterpret_cast<cplx*>(spectra) : ar.get<cplx>((size_t)2 * M * K);
-  EM_CUDA(cudaMemsetAsync(Wsp, 0, (size_t)2 * M * K * sizeof(cplx), st));
-  GenericProblem g{};
-  g.At = At; g.num_ops = K - 1; g.D = Dn; g.Mc = M; g.K = K; g.first_bin = 1; g.kls1 = kls1; g.dc_fix = 1;
-  g.nyquist_real = 1; g.regul = cfg.svd_regul; g.num_prob = 1;
-  g.H = Hc; g.h_prob_stride = 0; g.h_ear_stride = (long long)K * Dn; g.W = Wsp;
-  run_generic(h, ar, g);
   // integer shift by nfft/2, no restoration of the inter-aural delay difference (:136-138)
-  tail_real(h, ar, Wsp, 1, M, K, nfft, len, (double)(nfft / 2), (double)(nfft / 2), wL, wR);
+  tail_real(h, ar, Wsp, B, M, K, nfft, len, (double)(nfft / 2), (double)(nfft / 2), wL, wR);
 }
 
 // ------------------------------------------------------------------------------------------

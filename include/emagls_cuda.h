@@ -148,6 +148,24 @@ int emagls_design_from_atf(emagls_handle h, const emagls_config* cfg,
                            int num_mics, int atf_dirs, const double* atf_grid,
                            double fs, int filter_len, double f_trans,
                            double* wL, double* wR, double* spectra, double* mean_grid_dev_deg);
+/* Batched extension (not in the reference API): rotations [num_orient x 9] row-major; orientation b sees
+ * HRIR-grid direction u at R_b u, so page b equals one reference call with hrirGridAziZenRad rotated by R_b.
+ * wL, wR: [filter_len x num_mics x num_orient]; spectra (optional): [K x num_mics x num_orient x 2];
+ * mean_grid_dev_deg (optional): [num_orient].  When the ATF grid is the smaller one (BASELINE config 3) the
+ * per-bin factorisations are shared by the whole batch (lib/getEMagLsFiltersFromAtf.m:72-75,82-95).
+ * _dev: all pointers on the device, enqueued on the handle's stream.                                         */
+int emagls_design_from_atf_batch(emagls_handle h, const emagls_config* cfg,
+                                 const double* hL, const double* hR, int num_samples, int num_dirs,
+                                 const double* hrir_grid, const double* atf_irs, int atf_samples,
+                                 int num_mics, int atf_dirs, const double* atf_grid,
+                                 double fs, int filter_len, double f_trans, int num_orient, const double* rotations,
+                                 double* wL, double* wR, double* spectra, double* mean_grid_dev_deg);
+int emagls_design_from_atf_batch_dev(emagls_handle h, const emagls_config* cfg,
+                                     const double* hL, const double* hR, int num_samples, int num_dirs,
+                                     const double* hrir_grid, const double* atf_irs, int atf_samples,
+                                     int num_mics, int atf_dirs, const double* atf_grid,
+                                     double fs, int filter_len, double f_trans, int num_orient, const double* rotations,
+                                     double* wL, double* wR, double* spectra);
 
 /* ---- getEMagLsFiltersEMAinCH / EMAinSH (lib/getEMagLsFiltersEMAinCH.m:1-2, ...EMAinSH.m:1-2) */
 int emagls_design_ema_ch(emagls_handle h, const emagls_config* cfg,

@@ -5,7 +5,7 @@ Run in the build container only (needs /root/reference):
 Writes
     tests/golden/ref_goldens.npz        -- the woDC + LS golden filters (real & complex basis)
     emagls_b200/data/grids.npz          -- 2702-direction HRIR grid + em32 layout (input data)
-    tests/golden/atf_subset.npz         -- decimated glasses-on-HATS ATF set (input data)
+    tests/golden/atf_full.npz           -- glasses-on-HATS ATF set, float32 (input data; tests decimate it where needed)
 The em32 layout is the two degree lists of verifyEMagLs.m:30-31 (r = 0.042 m, :29).
 """
 import os
@@ -42,12 +42,13 @@ def main():
     np.savez_compressed(os.path.join(ROOT, "emagls_b200", "data", "grids.npz"), **grid)
 
     a = sio.loadmat(os.path.join(REF, "glasses_on_HATS_ATFs_sphere.mat"))
-    sel = np.arange(0, a["atfIrs"].shape[2], 4)  # every 4th direction -> 407 directions
-    np.savez_compressed(os.path.join(HERE, "atf_subset.npz"),
-                        atfIrs=a["atfIrs"][:, :, sel].astype(np.float32),
-                        atfGridAziEleDeg=a["atfGridAziEleDeg"][sel].astype(np.int16),
+    # the whole measured set (1625 directions x 8 microphones x 192 taps, BASELINE config 3), rounded to float32:
+    # it is INPUT data of the parity tests (the oracle and the CUDA path get the same rounded array)
+    np.savez_compressed(os.path.join(HERE, "atf_full.npz"),
+                        atfIrs=a["atfIrs"].astype(np.float32),
+                        atfGridAziEleDeg=a["atfGridAziEleDeg"].astype(np.int16),
                         fs=float(a["fs"].ravel()[0]))
-    for f in ("ref_goldens.npz", "atf_subset.npz"):
+    for f in ("ref_goldens.npz", "atf_full.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)))
 
 

@@ -146,8 +146,12 @@ def test_error_behaviour_mirrors_reference_asserts(em, h, c1):
         em.getEMagLs2Filters(c1["hL"], c1["hR"], *args, 64, handle=h)
     with pytest.raises(ValueError):
         em.getEMagLs2Filters(c1["hL"], c1["hR"][:, :100], *args, 512, handle=h)
+    # a custom shFunction is evaluated on the host: one that returns the wrong shape is refused
+    with pytest.raises(ValueError, match="shFunction must return"):
+        em.getEMagLs2Filters(c1["hL"], c1["hR"], *args, 512, "real", lambda n, d, k: np.zeros((3, 3)), handle=h)
+    # designers without the basis pass-through still refuse a non-default handle explicitly
     with pytest.raises(NotImplementedError):
-        em.getEMagLs2Filters(c1["hL"], c1["hR"], *args, 512, "real", lambda *a: None, handle=h)
+        em.getMagLsFilters(c1["hL"], c1["hR"], c1["az"], c1["ze"], 4, c1["fs"], 512, "real", lambda *a: None, handle=h)
 
 
 def test_other_filter_lengths_and_rates(em, h, grids):

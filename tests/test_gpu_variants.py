@@ -139,14 +139,14 @@ def test_magls_golden_pin_through_cabi(em, h, goldens):
 @pytest.fixture(scope="module")
 def atf():
     import os
-    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "atf_subset.npz"))
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "atf_full.npz"))
     ag = np.deg2rad(d["atfGridAziEleDeg"].astype(float))
     return d["atfIrs"].astype(float), np.stack([ag[:, 0], np.pi / 2 - ag[:, 1]], 1)
 
 
 @pytest.mark.parametrize("step", [3, 9])   # HRIR grid larger (901 > 407) and smaller (301 < 407) than the ATF grid
 def test_from_atf_matches_oracle(em, h, grids, atf, step, capsys):
-    atfIrs, ag = atf
+    atfIrs, ag = atf[0][:, :, ::4], atf[1][::4]          # every 4th direction of the measured set: 407
     az, ze = grids["hrirGridAziRad"][::step], grids["hrirGridZenRad"][::step]
     hL, hR = synth.synth_hrirs(az, ze)
     hg = np.stack([az, ze], 1)
@@ -161,6 +161,45 @@ def test_from_atf_matches_oracle(em, h, grids, atf, step, capsys):
         assert err[1:].max() <= 1e-10, err[1:].max()                     # measured ATFs are benign (cond < 200)
     assert rel(wL, oL) < 1e-10 and rel(wR, oR) < 1e-10
     assert np.all(wL[0] == 0) and np.all(sp[0].imag == 0)
+
+
+def test_from_atf_config3_full_size(em, h, grids, atf):
+    """BASELINE config 3 at its real size (testEMagLsFromAtfs.m:70-73): the whole glasses-on-HATS set (1625
+    directions x 8 microphones x 192 taps), the 2702-direction HRIR grid, filterLen 256, cut-on 2 kHz."""
+    atfIrs, ag = atf
+    assert atfIrs.shape == (192, 8, 1625)
+    az, ze = grids["hrirGridAziRad"], grids["hrirGridZenRad"]
+    hL, hR = synth.synth_hrirs(az, ze)
+    hg = np.stack([az, ze], 1)
+    wL, wR, sp = em.getEMagLsFiltersFromAtf(hL, hR, hg, atfIrs, ag, 48000, 256, 2000.0, handle=h, return_spectra=True)
+    oL, oR, osp = oracle.getEMagLsFiltersFromAtf(hL, hR, hg, atfIrs, ag, 48000, 256, 2000.0, return_spectra=True)
+    assert wL.shape == (256, 8)
+    for e, Wo in enumerate((osp["W_l"], osp["W_r"])):
+        err = bin_err(sp[:, :, e], Wo)
+        assert err[1:].max() <= 1e-10, err[1:].max()
+    assert rel(wL, oL) < 1e-10 and rel(wR, oR) < 1e-10
+
+
+@pytest.mark.parametrize("step", [1, 9])   # ATF grid smaller (operators shared by the batch) and HRIR grid smaller
+def test_from_atf_batched_over_orientations(em, h, grids, atf, step):
+    """Batch extension: page b equals one reference call with the HRIR grid rotated by R_b
+    (lib/getEMagLsFiltersFromAtf.m:62-95: only the nearest-neighbour matching sees the grid)."""
+    atfIrs, ag = (atf[0], atf[1]) if step == 1 else (atf[0][:, :, ::4], atf[1][::4])
+    az, ze = grids["hrirGridAziRad"][::step], grids["hrirGridZenRad"][::step]
+    hL, hR = synth.synth_hrirs(az, ze)
+    R = np.stack([np.eye(3), synth.rotation_yaw_pitch(33.0, 15.0), synth.rotation_yaw_pitch(250.0, -35.0)])
+    wL, wR, sp, info = em.getEMagLsFiltersFromAtf(hL, hR, np.stack([az, ze], 1), atfIrs, ag, 48000, 256, 2000.0,
+                                                  rotations=R, handle=h, return_spectra=True, return_info=True)
+    assert wL.shape == (256, 8, 3) and sp.shape == (129, 8, 3, 2)
+    for b in range(3):
+        raz, rze = synth.rotate_grid(az, ze, R[b])
+        oL, oR, osp = oracle.getEMagLsFiltersFromAtf(hL, hR, np.stack([raz, rze], 1), atfIrs, ag, 48000, 256, 2000.0,
+                                                     return_spectra=True)
+        assert abs(info["meanGridDevDeg"][b] - osp["meanGridDevDeg"]) < 1e-6
+        for e, Wo in enumerate((osp["W_l"], osp["W_r"])):
+            err = bin_err(sp[:, :, b, e], Wo)
+            assert err[1:].max() <= 1e-10, (b, err[1:].max())
+        assert rel(wL[:, :, b], oL) < 1e-10 and rel(wR[:, :, b], oR) < 1e-10
 
 
 # ------------------------------------------------------------------ EMA designers (config 4 shape at reduced radius)

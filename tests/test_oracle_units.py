@@ -143,7 +143,7 @@ def test_ema_variants_run_and_are_finite():
 
 def test_from_atf_runs_on_reference_fixture():
     import os
-    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "atf_subset.npz"))
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "atf_full.npz"))
     atf = d["atfIrs"].astype(float)
     ag = np.deg2rad(d["atfGridAziEleDeg"].astype(float))
     ag = np.stack([ag[:, 0], np.pi / 2 - ag[:, 1]], 1)

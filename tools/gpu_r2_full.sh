@@ -24,6 +24,8 @@ try:
     print("spot", j.get("parity_spot_check"))
     print("cpu", j.get("cpu_baseline"))
     print("render", (j.get("render") or {}).get("value"), ((j.get("render") or {}).get("roofline") or {}).get("frac"))
+    print("config3", j.get("config3"))
+    print("strong", j.get("strong_scaling"))
 except Exception as e:
     print("bench parse failed", repr(e)); print(open("gpurun_out/${TAG}_bench.err").read()[-3000:])
 PY
