@@ -301,20 +301,43 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
   double* Q = ar.get<double>((size_t)S * D);
   double* R = ar.get<double>((size_t)S * S);
   double* Gh = ar.get<double>((size_t)S * S);
+  int* d_qrflag = ar.get<int>(1);
+  bool chol_qr = S <= 2048 && getenv("EMAGLS_QR_HOUSEHOLDER") == nullptr;
   {
-    double* work = ar.get<double>((size_t)S * D + 2 * S);
-    double* Ytmp = ar.get<double>((size_t)S * D);
     if (a.Y_hrir)
       EM_CUDA(cudaMemcpyAsync(Yh, a.Y_hrir, (size_t)S * D * sizeof(double), cudaMemcpyDeviceToDevice, st));
     else
       EM_CUDA(launch_sh_angles(st, simN, a.grid_azi, a.grid_zen, D, 0, Yh));
-    EM_CUDA(cudaMemcpyAsync(Ytmp, Yh, (size_t)S * D * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    h->launches += 1;
-    EM_CUDA(launch_householder_qr(st, Ytmp, D, S, Q, R, work, &h->launches));  // destroys its input
     GemmOperand A0{Yh, D, 1}, B0{Yh, D, 1};
     EM_CUDA(launch_gemm(st, A0, B0, GemmShape{S, S, D}, EpiStore{Gh, S, 1.0}));
-    h->launches += 1;
+    h->launches += 2;
+    EM_CUDA(cudaMemsetAsync(d_qrflag, 0, sizeof(int), st));
+    if (chol_qr) {
+      // CholeskyQR2 (setup_kernels.cu): nine launches; the flag is read after the group-delay synchronisation below
+      double* R1 = ar.get<double>((size_t)S * S);
+      double* R2 = ar.get<double>((size_t)S * S);
+      double* Ri = ar.get<double>((size_t)S * S);
+      double* Q1 = ar.get<double>((size_t)S * D);
+      EM_CUDA(cudaMemcpyAsync(R1, Gh, (size_t)S * S * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      EM_CUDA(launch_chol_upper(st, R1, S, d_qrflag));
+      EM_CUDA(launch_tri_inverse(st, R1, S, Ri));
+      // Q1[i][d] = sum_j Rinv[j][i] Y_h[j][d]
+      EM_CUDA(launch_gemm(st, GemmOperand{Ri, S, 0}, GemmOperand{Yh, D, 0}, GemmShape{S, D, S}, EpiStore{Q1, D, 1.0}));
+      EM_CUDA(launch_gemm(st, GemmOperand{Q1, D, 1}, GemmOperand{Q1, D, 1}, GemmShape{S, S, D}, EpiStore{R2, S, 1.0}));
+      EM_CUDA(launch_chol_upper(st, R2, S, d_qrflag));
+      EM_CUDA(launch_tri_inverse(st, R2, S, Ri));
+      EM_CUDA(launch_gemm(st, GemmOperand{Ri, S, 0}, GemmOperand{Q1, D, 0}, GemmShape{S, D, S}, EpiStore{Q, D, 1.0}));
+      EM_CUDA(launch_tri_mul(st, R2, R1, S, R));
+      h->launches += 9;
+    }
   }
+  auto householder_qr = [&]() {
+    double* work = ar.get<double>((size_t)S * D + 2 * S);
+    double* Ytmp = ar.get<double>((size_t)S * D);
+    EM_CUDA(cudaMemcpyAsync(Ytmp, Yh, (size_t)S * D * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    EM_CUDA(launch_householder_qr(st, Ytmp, D, S, Q, R, work, &h->launches));  // destroys its input
+  };
+  if (!chol_qr) householder_qr();
   // ---------------- array: b_n table (minus sign, Nyquist real: getSMAIRMatrix.m:107,115-117)
   std::vector<double> kr(K);
   for (int k = 0; k < K; ++k) {
@@ -401,6 +424,11 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
 
   // ---------------- HRTF sets: group delay, H, |H|, H*Q, H*Y_h
   const std::vector<double> grpD = group_delays(h, ar, a.hL, a.hR, T, D, K, a.fs, a.num_sets);
+  if (chol_qr) {   // the stream is idle after the group-delay readback: the flag costs one 4-byte copy
+    int qrflag = 0;
+    EM_CUDA(cudaMemcpy(&qrflag, d_qrflag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (qrflag) householder_qr();   // badly conditioned direction grid: Householder route
+  }
   double* absH = ar.get<double>((size_t)a.num_sets * 2 * K * D);                     // [set][ear][K][D]
   const size_t ls_elems = (size_t)a.num_sets * 2 * std::max(nLS, 1) * 2 * S;         // [set][ear][kls][c][S]
   double* Tls = ar.get<double>(ls_elems);   // H * Q

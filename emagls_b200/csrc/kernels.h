@@ -26,6 +26,12 @@ cudaError_t launch_modal(cudaStream_t st, int N, const double* kr, int nk, int a
 // work: D*S doubles (reflectors) + 2*S doubles.
 cudaError_t launch_householder_qr(cudaStream_t st, double* A, int D, int S, double* Q, double* R,
                                   double* work, long long* launches);
+// CholeskyQR2 building blocks (setup_kernels.cu): in-place upper Cholesky factor of a symmetric [S][S] matrix
+// (*flag set on a non-positive pivot or a diagonal ratio beyond 1e6), upper-triangular inverse, product of two
+// upper-triangular matrices (all row-major).
+cudaError_t launch_chol_upper(cudaStream_t st, double* G, int S, int* flag);
+cudaError_t launch_tri_inverse(cudaStream_t st, const double* R, int S, double* Rinv);
+cudaError_t launch_tri_mul(cudaStream_t st, const double* R2, const double* R1, int S, double* R);
 // E rows for the factored steering model:  E[o][rowoff[i] + (n-ord(i))*Mc + c] =
 //   sum_{j in order-n block} R[i][j] * Ym[o][c][j]
 cudaError_t launch_build_E(cudaStream_t st, const double* R, int S, int N, const double* Ym,

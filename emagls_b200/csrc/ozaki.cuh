@@ -206,7 +206,51 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // Epilogue functor: operator()(m, n0, v[8], M, N) receives 8 consecutive columns n0..n0+7 of row m
-// (already scaled, FP64).  Called only for m < M; columns >= N hold zeros and must be skipped.
+// (already scaled, FP64).  Called only for m < M; columns >= N hold zeros and must be skipped.  A functor that
+// declares `static constexpr bool all_lanes = true` is entered by every lane of the warp (also m >= M) and
+// guards its own stores, so that it may use warp shuffles.
+template <class E, class = void> struct epi_all_lanes { static constexpr bool value = false; };
+template <class E> struct epi_all_lanes<E, decltype((void)E::all_lanes)> { static constexpr bool value = E::all_lanes; };
+
+// Balanced base-256 digits of eight values at once, packed per digit plane: word[s] holds digit s of values
+// 0..7 in its bytes (little endian), ready for one 8-byte store per plane.  Same arithmetic as slice_digits.
+__device__ __forceinline__ void transpose4x3(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t& r0, uint32_t& r1,
+                                             uint32_t& r2) {
+  const uint32_t ab_lo = __byte_perm(a, b, 0x5140), cd_lo = __byte_perm(c, d, 0x5140);   // [a0 b0 a1 b1]
+  const uint32_t ab_hi = __byte_perm(a, b, 0x7362), cd_hi = __byte_perm(c, d, 0x7362);   // [a2 b2 a3 b3]
+  r0 = __byte_perm(ab_lo, cd_lo, 0x5410);   // [a0 b0 c0 d0]
+  r1 = __byte_perm(ab_lo, cd_lo, 0x7632);   // [a1 b1 c1 d1]
+  r2 = __byte_perm(ab_hi, cd_hi, 0x5410);   // [a2 b2 c2 d2]
+}
+template <int T>
+__device__ __forceinline__ void slice_pack8(const double (&a)[8], uint2 (&word)[MAX_SLICES]) {
+  static_assert(T >= 4 && T <= 6, "hi limb: 1..3 digits, lo limb: 3 digits");
+  constexpr int nh = T - 3;
+  constexpr int bias_hi = (nh == 3) ? 0x808080 : (nh == 2 ? 0x8080 : 0x80);
+  uint32_t zl[8], zh[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const double ah = a[q] * (double)(1 << (8 * (nh - 1)));
+    int hi = __double2int_rn(ah);
+    const int lo = __double2int_rn((ah - (double)hi) * 16777216.0);
+    const int yl = lo + 0x808080;
+    hi += yl >> 24;
+    zl[q] = (uint32_t)(yl ^ 0x808080);          // bytes 0..2 = digits T-1, T-2, T-3
+    zh[q] = (uint32_t)((hi + bias_hi) ^ bias_hi);   // byte j = digit nh-1-j
+  }
+  uint32_t l0[2], l1[2], l2[2], h0[2], h1[2], h2[2];
+#pragma unroll
+  for (int g4 = 0; g4 < 2; ++g4) {
+    transpose4x3(zl[4 * g4], zl[4 * g4 + 1], zl[4 * g4 + 2], zl[4 * g4 + 3], l0[g4], l1[g4], l2[g4]);
+    transpose4x3(zh[4 * g4], zh[4 * g4 + 1], zh[4 * g4 + 2], zh[4 * g4 + 3], h0[g4], h1[g4], h2[g4]);
+  }
+  word[T - 1] = make_uint2(l0[0], l0[1]);
+  word[T - 2] = make_uint2(l1[0], l1[1]);
+  word[T - 3] = make_uint2(l2[0], l2[1]);
+  word[nh - 1] = make_uint2(h0[0], h0[1]);
+  if (nh >= 2) word[nh - 2] = make_uint2(h1[0], h1[1]);
+  if (nh >= 3) word[nh - 3] = make_uint2(h2[0], h2[1]);
+}
 struct EpiStoreF64 {
   double* C; long long ldc;
   __device__ __forceinline__ void operator()(int m, int n0, const double (&v)[8], int M, int N) const {
@@ -369,7 +413,12 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
       for (int ci = 0; ci < CH_PER_WARP; ++ci) {
         const int c0 = chunk0 + ci * chunk_step;
-        if (c0 < n_lim && m < g.M) epi(m, n0 + c0, v[ci], g.M, g.N);
+        if constexpr (epi_all_lanes<Epi>::value) {
+          // functors that exchange data between lanes are entered by the whole warp (c0 and n_lim are warp-uniform)
+          if (c0 < n_lim) epi(m, n0 + c0, v[ci], g.M, g.N);
+        } else {
+          if (c0 < n_lim && m < g.M) epi(m, n0 + c0, v[ci], g.M, g.N);
+        }
       }
       acc_phase ^= 1;
     }

@@ -52,6 +52,51 @@ struct EpiPhaseSlice {
   }
 };
 
+// Forward product with the operand roles swapped: rows m = (problem, ear, re/im) [4P], columns n = directions.
+// A thread owns eight consecutive directions of one row; the real and the imaginary row of a (problem, ear)
+// pair sit in neighbouring lanes and exchange their values by shuffle, every lane then forms t for its own
+// part and emits ONE 8-byte word per digit plane (six stores instead of 48 single bytes per 8 outputs).
+template <int T>
+struct EpiPhaseSliceRows {
+  static constexpr bool all_lanes = true;
+  int8_t* Tq; long long slice_stride; int Kpad;   // [T][rows][Kpad], element (m, n) at m * Kpad + n
+  double* sT;                                     // [rows] scale of row m (written by the n0 == 0 chunk)
+  const double* absH; long long abs_set_stride, abs_ear_stride;   // this bin: [set][ear][dir]
+  const double* up; const double* sc; int scale_stride;           // 2^(6-e), 2^(e-6) at [(set*2+ear)*scale_stride]
+  int orient_per_set; int nyquist;
+  __device__ __forceinline__ void operator()(int m, int n0, const double (&v)[8], int M, int N) const {
+    const bool valid = m < M;
+    const int mm = valid ? m : 0;
+    const int part = mm & 1, j = mm >> 1, ear = j & 1, prob = j >> 1;
+    const int set = prob / orient_per_set;
+    const double* mag = absH + (long long)set * abs_set_stride + (long long)ear * abs_ear_stride + n0;
+    const int si = (set * 2 + ear) * scale_stride;
+    const double u = up[si];
+    double a[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const double mine = v[q];
+      const double other = __shfl_xor_sync(0xffffffffu, mine, 1);
+      const double re = part ? other : mine, im = part ? mine : other;
+      const double a2 = fma(re, re, im * im);     // the same expression on both lanes (and as in EpiPhaseSlice)
+      double t;
+      const double mg = (n0 + q < N) ? mag[q] : 0.0;
+      if (a2 > 1e-290 && a2 < 1e290) t = mine * (mg * rsqrt(a2));
+      else if (a2 > 0.0) t = mine * (mg / sqrt(a2));
+      else t = part ? 0.0 : mg;                   // angle(0) = 0
+      if (nyquist && part) t = 0.0;
+      a[q] = t * u;                               // |t u| <= 64 (u = 2^(6-e), 2^e > max_d |H_k|)
+    }
+    if (!valid) return;
+    uint2 word[oz::MAX_SLICES];
+    oz::slice_pack8<T>(a, word);
+    int8_t* p = Tq + (long long)m * Kpad + n0;    // Kpad multiple of 32, n0 multiple of 8: 8-byte aligned
+#pragma unroll
+    for (int s = 0; s < T; ++s) *reinterpret_cast<uint2*>(p + (long long)s * slice_stride) = word[s];
+    if (n0 == 0) sT[m] = sc[si];
+  }
+};
+
 // one warp per row: 2^e > max_d |x(row, d)|  ->  up = 2^(6-e), sc = 2^(e-6)
 __global__ void row_scale_kernel(const double* __restrict__ x, long long rows, int D, double* __restrict__ up,
                                  double* __restrict__ sc) {
@@ -99,6 +144,19 @@ cudaError_t launch_row_scale(cudaStream_t st, const double* x, long long rows, i
 }
 
 template <int T>
+static cudaError_t oz_fwd_rows_t(cudaStream_t st, const OzFwdArgs& a) {
+  CUtensorMap tmA, tmB;
+  if (!oz::make_operand_map(&tmA, a.Cv_q, a.rows, a.KpS, T, oz::TILE_M) ||
+      !oz::make_operand_map(&tmB, a.YhA_q, a.D, a.KpS, T, oz::TILE_N))
+    return cudaErrorInvalidValue;
+  // n fastest: consecutive tiles (neighbouring SMs) share the rows of the large operand (the Cv digits)
+  oz::GemmArgs g{a.rows, a.D, a.KpS, a.sCv, a.sYhA, 0, 1, oz::TILE_N};
+  EpiPhaseSliceRows<T> epi{a.Tt_q, (long long)a.rows * a.KpD, a.KpD, a.sT, a.absH, a.abs_set_stride, a.abs_ear_stride,
+                           a.up, a.sc, a.scale_stride, a.orient_per_set, a.nyquist};
+  return oz::launch_ozaki_gemm_t<T>(st, tmA, tmB, g, epi, sm_count());
+}
+
+template <int T>
 static cudaError_t oz_fwd_t(cudaStream_t st, const OzFwdArgs& a) {
   CUtensorMap tmA, tmB;
   if (!oz::make_operand_map(&tmA, a.YhA_q, a.D, a.KpS, T, oz::TILE_M) ||
@@ -112,6 +170,16 @@ static cudaError_t oz_fwd_t(cudaStream_t st, const OzFwdArgs& a) {
 
 cudaError_t launch_oz_fwd(cudaStream_t st, const OzFwdArgs& a) {
   if (!oz::contraction_fits(a.KpS, a.T)) return cudaErrorInvalidValue;
+  // rows = 4 P is even, so the (re, im) rows of a pair share a warp; EMAGLS_OZ_FWD_COLS=1 selects the round-1
+  // orientation (rows = directions, byte stores) for A/B
+  static const bool by_rows = getenv("EMAGLS_OZ_FWD_COLS") == nullptr;
+  if (by_rows && (a.rows & 1) == 0) {
+    switch (a.T) {
+      case 4: return oz_fwd_rows_t<4>(st, a);
+      case 6: return oz_fwd_rows_t<6>(st, a);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   switch (a.T) {
     case 4: return oz_fwd_t<4>(st, a);
     case 6: return oz_fwd_t<6>(st, a);

@@ -229,6 +229,119 @@ cudaError_t launch_householder_qr(cudaStream_t st, double* A, int D, int S, doub
 }
 
 // ---------------------------------------------------------------------------------------------
+// CholeskyQR2 of the HRIR-grid basis matrix (nine launches instead of 2 S + 2 one-column Householder steps):
+//   G = Y^T Y,  R1 = chol(G),  Q1 = Y R1^-1,   G2 = Q1^T Q1,  R2 = chol(G2),  Q = Q1 R2^-1,  R = R2 R1.
+// One pass leaves ||Q^T Q - I|| ~ eps cond(Y)^2, the second restores eps for cond(Y) up to ~1e7 (the 2702-point
+// grid at order 19 has cond 1.5).  A non-positive pivot or a diagonal ratio beyond 1e6 raises *flag and the
+// caller falls back to the Householder route.
+// ---------------------------------------------------------------------------------------------
+// in place: upper triangle of the symmetric G [S][S] (row-major) -> R with G = R^T R; strictly lower part zeroed.
+// Single CTA, left-looking: step j computes row j from the finished rows k < j; column j of R (shared by every
+// thread of the step) is staged in shared memory, the other operand is a coalesced row read.
+__global__ void __launch_bounds__(1024)
+chol_upper_kernel(double* __restrict__ G, int S, int* __restrict__ flag) {
+  extern __shared__ double colj[];          // [S]
+  __shared__ double rjj_s;
+  __shared__ double dmin_s, dmax_s;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) { dmin_s = 1e300; dmax_s = 0.0; }
+  __syncthreads();
+  for (int j = 0; j < S; ++j) {
+    for (int k = tid; k < j; k += nt) colj[k] = G[(long long)k * S + j];
+    __syncthreads();
+    double acc[2] = {0.0, 0.0};
+    const int cols[2] = {j + tid, j + tid + nt};
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int i = cols[c];
+      if (i < S) {
+        const double* gi = G + i;
+        double a0 = G[(long long)j * S + i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int k = 0;
+        for (; k + 4 <= j; k += 4) {
+          a0 = fma(-colj[k], gi[(long long)k * S], a0);
+          a1 = fma(-colj[k + 1], gi[(long long)(k + 1) * S], a1);
+          a2 = fma(-colj[k + 2], gi[(long long)(k + 2) * S], a2);
+          a3 = fma(-colj[k + 3], gi[(long long)(k + 3) * S], a3);
+        }
+        for (; k < j; ++k) a0 = fma(-colj[k], gi[(long long)k * S], a0);
+        acc[c] = (a0 + a1) + (a2 + a3);
+      }
+    }
+    if (tid == 0) {
+      const double d = acc[0];
+      if (!(d > 0.0)) { atomicExch(flag, 1); rjj_s = 1.0; }
+      else rjj_s = sqrt(d);
+      dmin_s = fmin(dmin_s, rjj_s); dmax_s = fmax(dmax_s, rjj_s);
+    }
+    __syncthreads();
+    const double inv = 1.0 / rjj_s;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int i = cols[c];
+      if (i < S) G[(long long)j * S + i] = (i == j) ? rjj_s : acc[c] * inv;
+    }
+    __syncthreads();
+  }
+  for (long long idx = tid; idx < (long long)S * S; idx += nt)
+    if (idx / S > idx % S) G[idx] = 0.0;
+  if (tid == 0 && !(dmin_s > 1e-6 * dmax_s)) atomicExch(flag, 1);
+}
+
+// Rinv [S][S] row-major upper: column m by back substitution, one warp per column; the column under
+// construction stays in shared memory, the lanes split the inner products.
+constexpr int TI_WARPS = 4;
+__global__ void __launch_bounds__(TI_WARPS * 32)
+tri_inverse_kernel(const double* __restrict__ R, int S, double* __restrict__ Rinv) {
+  extern __shared__ double ti_x[];          // [TI_WARPS][S]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int m = blockIdx.x * TI_WARPS + warp;
+  if (m >= S) return;
+  double* x = ti_x + (size_t)warp * S;
+  for (int i = m; i >= 0; --i) {
+    const double* Ri = R + (long long)i * S;
+    double a = 0.0;
+    for (int j = i + 1 + lane; j <= m; j += 32) a = fma(Ri[j], x[j], a);
+    a = warp_sum_d(a);
+    const double v = (((i == m) ? 1.0 : 0.0) - a) / Ri[i];
+    if (lane == 0) x[i] = v;
+    __syncwarp();
+  }
+  for (int i = lane; i < S; i += 32) Rinv[(long long)i * S + m] = (i <= m) ? x[i] : 0.0;
+}
+
+// R = R2 * R1 (both upper, row-major)
+__global__ void tri_mul_kernel(const double* __restrict__ R2, const double* __restrict__ R1, int S, double* __restrict__ R) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S * S) return;
+  const int i = idx / S, j = idx % S;
+  double a = 0.0;
+  for (int k = i; k <= j; ++k) a = fma(R2[(long long)i * S + k], R1[(long long)k * S + j], a);
+  R[idx] = a;
+}
+
+cudaError_t launch_chol_upper(cudaStream_t st, double* G, int S, int* flag) {
+  if (S > 2048) return cudaErrorInvalidValue;
+  chol_upper_kernel<<<1, 1024, (size_t)S * sizeof(double), st>>>(G, S, flag);
+  return cudaGetLastError();
+}
+cudaError_t launch_tri_inverse(cudaStream_t st, const double* R, int S, double* Rinv) {
+  const size_t smem = (size_t)TI_WARPS * S * sizeof(double);
+  static size_t set_to = 0;
+  if (smem > 48 * 1024 && smem > set_to) {
+    cudaError_t e = cudaFuncSetAttribute(tri_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    set_to = smem;
+  }
+  tri_inverse_kernel<<<(S + TI_WARPS - 1) / TI_WARPS, TI_WARPS * 32, smem, st>>>(R, S, Rinv);
+  return cudaGetLastError();
+}
+cudaError_t launch_tri_mul(cudaStream_t st, const double* R2, const double* R1, int S, double* R) {
+  tri_mul_kernel<<<(S * S + 255) / 256, 256, 0, st>>>(R2, R1, S, R);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // E rows:  E[o][rowoff[i] + (n-ord(i))*Mc + c] = sum_{j in block n, j >= i} R[i][j] Ym[o][c][j]
 // ---------------------------------------------------------------------------------------------
 // One CTA per (order block n, orientation o): the block's columns of Ym[o] are staged in shared memory
