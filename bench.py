@@ -500,6 +500,31 @@ def main():
                                "class_ms": {k: v["ms"] / 3 for k, v in rp.items() if v["n"]}}}
         del x, y
 
+    # ---------------- render end to end: the 10-minute signal sharded by time blocks with a (taps - 1)-frame halo over
+    # all ranks, pinned host blocks -> H2D -> decode -> D2H of the block's two output channels
+    render_e2e = None
+    if not args.no_render:
+        n_all = int(args.render_seconds * 48000)
+        r_lo, r_hi, r_halo = emdist.render_shard(n_all, LEN, rank, world)
+        blk = np.random.default_rng(777 + rank).standard_normal((r_hi - r_lo + r_halo, 32))
+        wl_h, wr_h = d_wL[0].cpu().numpy().T, d_wR[0].cpu().numpy().T          # [len, M]
+        sr = emdist.ShardedRenderer(h, blk, wl_h, wr_h, r_halo)
+        del blk
+        sr.step(); sr.wait()
+        emdist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            sr.step()
+            sr.wait()
+        r_s = emdist.max_over_ranks(time.perf_counter() - t0, dev) / 3
+        render_e2e = {"value": n_all / r_s / 1e6, "unit": "Msamples/s", "ms": r_s * 1e3, "frames_total": n_all,
+                      "frames_per_gpu": r_hi - r_lo, "halo_frames": LEN - 1, "h2d_bytes_per_step": sr.h2d_bytes * world,
+                      "d2h_bytes_per_step": sr.d2h_bytes * world,
+                      "path": "emagls_b200.dist.ShardedRenderer (time blocks, no exchange between ranks)"}
+        del sr
+        if render is not None:
+            render["e2e"] = render_e2e
+
     # ---------------- BASELINE config 3 (secondary line): getEMagLsFiltersFromAtf on the measured glasses-on-HATS
     # ATF set (1625 directions x 8 microphones), batched over the 3600-orientation grid, + the 10-minute 8-channel
     # render that consumes one of the filter sets.  Rank 0, device-resident, CUDA events on the library's stream.
@@ -583,7 +608,7 @@ def main():
                         "max_rel_diff_vs_device_resident_banks": e2e_same, "host_api_call": host_api},
                 "strong_scaling": strong, "parity_spot_check": spot, "config3": config3,
                 "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline,
-                "cpu_baseline": cpu, "render": render}
+                "cpu_baseline": cpu, "render": render if render is not None else ({"e2e": render_e2e} if render_e2e else None)}
         print(json.dumps(line), flush=True)
     emdist.barrier()
 

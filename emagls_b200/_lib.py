@@ -62,6 +62,9 @@ SIGNATURES = {
                                                    C.c_double, C.c_int, c_dp, c_dp, c_dp, c_dp]),
     "emagls_design_ema_ch": (C.c_int, [C.c_void_p, C.POINTER(Config), c_dp, c_dp, C.c_int, C.c_int, c_dp, c_dp,
                                        C.c_double, c_dp, C.c_int, C.c_int, C.c_double, C.c_int, c_dp, c_dp, c_dp]),
+    "emagls_design_ema_ch_batch": (C.c_int, [C.c_void_p, C.POINTER(Config), c_dp, c_dp, C.c_int, C.c_int, c_dp, c_dp,
+                                             C.c_double, c_dp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
+                                             c_dp, c_dp, c_dp, c_dp]),
     "emagls_design_ema_sh": (C.c_int, [C.c_void_p, C.POINTER(Config), c_dp, c_dp, C.c_int, C.c_int, c_dp, c_dp,
                                        C.c_double, c_dp, C.c_int, C.c_int, C.c_double, C.c_int, c_dp, c_dp, c_dp]),
     "emagls_smair_matrix": (C.c_int, [C.c_void_p, C.POINTER(Config), c_dp, c_dp, C.c_int, C.c_int, C.c_double,

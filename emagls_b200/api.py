@@ -277,20 +277,32 @@ def getEMagLsFiltersFromAtf(hL, hR, hrirGridAziZenRad, atfIrs, atfGridAziZenRad,
 
 
 def _design_ema(fn_name, channels, hL, hR, hrirGridAziRad, hrirGridZenRad, micRadius, micGridAziRad, order,
-                fs, length, shDefinition, shFunction, chFunction, handle, config, return_spectra):
+                fs, length, shDefinition, shFunction, chFunction, handle, config, return_spectra, rotations=None):
     _check_sh_function(shFunction)
     if chFunction is not None:
         raise NotImplementedError("only the default chFunction (@getCH) is evaluated on the device")
     h = handle or default_handle()
     cfg = _config(h, config, shDefinition)
     hL, hR, T, D, sets = _prep_hrirs(hL, hR)
-    if sets != 1:
-        raise ValueError("EMA designs are not batched")
+    batched = fn_name == "emagls_design_ema_ch" and (sets != 1 or rotations is not None)
+    if sets != 1 and not batched:
+        raise ValueError("getEMagLsFiltersEMAinSH takes one HRTF set")
     az, ze, maz = _vec(hrirGridAziRad), _vec(hrirGridZenRad), _vec(micGridAziRad)
     Mc = channels(int(order))
     nfft = min(cfg.nfft_max_len, 2 * int(length))
     K = nfft // 2 + 1
     odt = np.complex128 if cfg.basis == 1 else np.float64
+    if batched:
+        rot = None if rotations is None else np.ascontiguousarray(np.asarray(rotations, dtype=np.float64).reshape(-1, 9))
+        B = 1 if rot is None else rot.shape[0]
+        P = sets * B
+        wL = np.zeros((int(length), Mc, P), dtype=odt, order="F")
+        wR = np.zeros((int(length), Mc, P), dtype=odt, order="F")
+        sp = np.zeros((K, Mc, P, 2), dtype=np.complex128, order="F") if return_spectra else None
+        h.check(h.lib.emagls_design_ema_ch_batch(h.ptr, C.byref(cfg), _p(hL), _p(hR), T, D, _p(az), _p(ze),
+                                                 float(micRadius), _p(maz), maz.size, int(order), float(fs),
+                                                 int(length), sets, B, _p(rot), _p(wL), _p(wR), _p(sp)))
+        return (wL, wR, sp) if return_spectra else (wL, wR)
     wL = np.zeros((int(length), Mc), dtype=odt, order="F")
     wR = np.zeros((int(length), Mc), dtype=odt, order="F")
     sp = np.zeros((K, Mc, 2), dtype=np.complex128, order="F") if return_spectra else None
@@ -301,12 +313,15 @@ def _design_ema(fn_name, channels, hL, hR, hrirGridAziRad, hrirGridZenRad, micRa
 
 
 def getEMagLsFiltersEMAinCH(hL, hR, hrirGridAziRad, hrirGridZenRad, micRadius, micGridAziRad, order, fs, len,
-                            shDefinition="real", shFunction=None, chFunction=None, *, handle=None, config=None,
-                            return_spectra=False):
-    """lib/getEMagLsFiltersEMAinCH.m:1-2 -> filters [len, 2*order+1]."""
+                            shDefinition="real", shFunction=None, chFunction=None, *, rotations=None, handle=None,
+                            config=None, return_spectra=False):
+    """lib/getEMagLsFiltersEMAinCH.m:1-2 -> filters [len, 2*order+1].
+
+    Keyword-only batch extension: ``rotations`` [B,3,3] and / or ``hL, hR`` [samples, dirs, sets] give
+    ``[len, 2*order+1, sets*B]`` (page b = one reference call with the HRIR grid rotated by ``rotations[b]``)."""
     return _design_ema("emagls_design_ema_ch", lambda N: 2 * N + 1, hL, hR, hrirGridAziRad, hrirGridZenRad,
                        micRadius, micGridAziRad, order, fs, len, shDefinition, shFunction, chFunction, handle,
-                       config, return_spectra)
+                       config, return_spectra, rotations)
 
 
 def getEMagLsFiltersEMAinSH(hL, hR, hrirGridAziRad, hrirGridZenRad, micRadius, micGridAziRad, order, fs, len,

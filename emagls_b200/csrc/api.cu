@@ -330,6 +330,14 @@ int emagls_design_ema_ch(emagls_handle h, const emagls_config* cfg, const double
   return design_host(h, cfg, Variant::EMA_CH, hL, hR, num_samples, num_dirs, grid_azi, grid_zen, mic_radius,
                      mic_azi, nullptr, num_mics, order, fs, len, 1, 1, nullptr, wL, wR, spectra);
 }
+int emagls_design_ema_ch_batch(emagls_handle h, const emagls_config* cfg, const double* hL, const double* hR,
+                               int num_samples, int num_dirs, const double* grid_azi, const double* grid_zen,
+                               double mic_radius, const double* mic_azi, int num_mics, int order, double fs, int len,
+                               int num_sets, int num_orient, const double* rotations, double* wL, double* wR,
+                               double* spectra) {
+  return design_host(h, cfg, Variant::EMA_CH, hL, hR, num_samples, num_dirs, grid_azi, grid_zen, mic_radius,
+                     mic_azi, nullptr, num_mics, order, fs, len, num_sets, num_orient, rotations, wL, wR, spectra);
+}
 int emagls_design_ema_sh(emagls_handle h, const emagls_config* cfg, const double* hL, const double* hR,
                          int num_samples, int num_dirs, const double* grid_azi, const double* grid_zen,
                          double mic_radius, const double* mic_azi, int num_mics, int order, double fs, int len,

@@ -302,7 +302,8 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
   double* R = ar.get<double>((size_t)S * S);
   double* Gh = ar.get<double>((size_t)S * S);
   int* d_qrflag = ar.get<int>(1);
-  bool chol_qr = S <= 2048 && getenv("EMAGLS_QR_HOUSEHOLDER") == nullptr;
+  // the single-CTA Cholesky kernel gives one column to a thread (S <= 1024); larger bases keep the Householder route
+  bool chol_qr = S <= 1024 && getenv("EMAGLS_QR_HOUSEHOLDER") == nullptr;
   {
     if (a.Y_hrir)
       EM_CUDA(cudaMemcpyAsync(Yh, a.Y_hrir, (size_t)S * D * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -484,7 +485,7 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
   const bool sep = (Mc <= 32) && getenv("EMAGLS_FACTOR_OLD") == nullptr;
   const BlockPlan bp = sep ? make_block_plan_sep(S, Mc) : make_block_plan(S, Mc);
   const int NB = std::min(128, K - 1);
-  int g_slots = sep ? 8 : 4;   // bins factorised per launch; the Jacobi kernel warm-starts along them
+  int g_slots = sep ? 16 : 4;  // bins factorised per launch; the Jacobi kernel warm-starts along them
   if (const char* e = getenv("EMAGLS_FACTOR_SLOTS")) g_slots = std::max(1, atoi(e));
   const int G = std::min(g_slots, K - 1);
   const bool jacobi_warm = getenv("EMAGLS_JACOBI_COLD") == nullptr;

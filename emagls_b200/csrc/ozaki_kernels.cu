@@ -170,9 +170,11 @@ static cudaError_t oz_fwd_t(cudaStream_t st, const OzFwdArgs& a) {
 
 cudaError_t launch_oz_fwd(cudaStream_t st, const OzFwdArgs& a) {
   if (!oz::contraction_fits(a.KpS, a.T)) return cudaErrorInvalidValue;
-  // rows = 4 P is even, so the (re, im) rows of a pair share a warp; EMAGLS_OZ_FWD_COLS=1 selects the round-1
-  // orientation (rows = directions, byte stores) for A/B
-  static const bool by_rows = getenv("EMAGLS_OZ_FWD_COLS") == nullptr;
+  // EMAGLS_OZ_FWD_ROWS=1 (A/B switch): operand roles swapped, a thread owns eight directions of one (problem, ear,
+  // re/im) row and stores 8-byte digit words.  Measured on B200 (profiles/r02_v7): 250 ms against 225 ms per step for
+  // the default orientation -- the 8-byte words of 32 different rows cost four times the L2 sectors of the byte
+  // stores, which a warp writes 32 at a time into one sector.
+  static const bool by_rows = getenv("EMAGLS_OZ_FWD_ROWS") != nullptr;
   if (by_rows && (a.rows & 1) == 0) {
     switch (a.T) {
       case 4: return oz_fwd_rows_t<4>(st, a);

@@ -236,55 +236,68 @@ cudaError_t launch_householder_qr(cudaStream_t st, double* A, int D, int S, doub
 // caller falls back to the Householder route.
 // ---------------------------------------------------------------------------------------------
 // in place: upper triangle of the symmetric G [S][S] (row-major) -> R with G = R^T R; strictly lower part zeroed.
-// Single CTA, left-looking: step j computes row j from the finished rows k < j; column j of R (shared by every
-// thread of the step) is staged in shared memory, the other operand is a coalesced row read.
+// Single CTA (S <= 1024 threads' worth of columns), left-looking by panels of 16 rows: thread i owns column i and
+// accumulates the 16 panel rows at once (one coalesced global load of R[k][i] feeds 16 FMAs against the panel's
+// columns of row k, staged in shared memory), then the panel is factorised row by row in shared memory.
+constexpr int CH_PB = 16;
 __global__ void __launch_bounds__(1024)
 chol_upper_kernel(double* __restrict__ G, int S, int* __restrict__ flag) {
-  extern __shared__ double colj[];          // [S]
-  __shared__ double rjj_s;
-  __shared__ double dmin_s, dmax_s;
+  extern __shared__ double ch_sm[];
+  double* rk = ch_sm;                       // [2][CH_PB]: R[k][j0 .. j0+15] of the row being applied (double buffered)
+  double* pan = ch_sm + 2 * CH_PB;          // [CH_PB][S]: the panel rows
+  __shared__ double dmin_s, dmax_s, piv_s;
   const int tid = threadIdx.x, nt = blockDim.x;
   if (tid == 0) { dmin_s = 1e300; dmax_s = 0.0; }
-  __syncthreads();
-  for (int j = 0; j < S; ++j) {
-    for (int k = tid; k < j; k += nt) colj[k] = G[(long long)k * S + j];
-    __syncthreads();
-    double acc[2] = {0.0, 0.0};
-    const int cols[2] = {j + tid, j + tid + nt};
+  for (int j0 = 0; j0 < S; j0 += CH_PB) {
+    const int pb = min(CH_PB, S - j0);
+    const int i = j0 + tid;                 // this thread's column (columns < j0 are finished)
+    // ---- A_panel = G[j0 + r][i] - sum_{k < j0} R[k][j0 + r] R[k][i]
+    double acc[CH_PB];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int i = cols[c];
+    for (int r = 0; r < CH_PB; ++r) acc[r] = (i < S && r < pb && i >= j0 + r) ? G[(long long)(j0 + r) * S + i] : 0.0;
+    for (int k = 0; k < j0; ++k) {
+      double* rkb = rk + (k & 1) * CH_PB;
+      if (tid < pb) rkb[tid] = G[(long long)k * S + j0 + tid];
+      __syncthreads();
       if (i < S) {
-        const double* gi = G + i;
-        double a0 = G[(long long)j * S + i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int k = 0;
-        for (; k + 4 <= j; k += 4) {
-          a0 = fma(-colj[k], gi[(long long)k * S], a0);
-          a1 = fma(-colj[k + 1], gi[(long long)(k + 1) * S], a1);
-          a2 = fma(-colj[k + 2], gi[(long long)(k + 2) * S], a2);
-          a3 = fma(-colj[k + 3], gi[(long long)(k + 3) * S], a3);
-        }
-        for (; k < j; ++k) a0 = fma(-colj[k], gi[(long long)k * S], a0);
-        acc[c] = (a0 + a1) + (a2 + a3);
+        const double v = G[(long long)k * S + i];
+#pragma unroll
+        for (int r = 0; r < CH_PB; ++r) acc[r] = fma(-rkb[r], v, acc[r]);
       }
     }
-    if (tid == 0) {
-      const double d = acc[0];
-      if (!(d > 0.0)) { atomicExch(flag, 1); rjj_s = 1.0; }
-      else rjj_s = sqrt(d);
-      dmin_s = fmin(dmin_s, rjj_s); dmax_s = fmax(dmax_s, rjj_s);
+    __syncthreads();
+    if (i < S) {
+#pragma unroll
+      for (int r = 0; r < CH_PB; ++r) pan[(size_t)r * S + i] = acc[r];
     }
     __syncthreads();
-    const double inv = 1.0 / rjj_s;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int i = cols[c];
-      if (i < S) G[(long long)j * S + i] = (i == j) ? rjj_s : acc[c] * inv;
+    // ---- factorise the panel in shared memory: row r from the panel rows q < r
+    for (int r = 0; r < pb; ++r) {
+      const int j = j0 + r;
+      double t = 0.0;
+      if (i < S && i >= j) {
+        t = pan[(size_t)r * S + i];
+        for (int q = 0; q < r; ++q) t = fma(-pan[(size_t)q * S + j], pan[(size_t)q * S + i], t);
+      }
+      if (i == j) {                         // the pivot
+        double d = t;
+        if (!(d > 0.0)) { atomicExch(flag, 1); d = 1.0; }
+        d = sqrt(d);
+        piv_s = d;
+        dmin_s = fmin(dmin_s, d); dmax_s = fmax(dmax_s, d);
+      }
+      __syncthreads();
+      const double rjj = piv_s;
+      if (i < S && i >= j) pan[(size_t)r * S + i] = (i == j) ? rjj : t / rjj;
+      __syncthreads();
+    }
+    // ---- write the finished rows back (zeros left of the diagonal)
+    for (int idx = tid; idx < pb * S; idx += nt) {
+      const int r = idx / S, c = idx - r * S;
+      G[(long long)(j0 + r) * S + c] = (c >= j0 + r) ? pan[(size_t)r * S + c] : 0.0;
     }
     __syncthreads();
   }
-  for (long long idx = tid; idx < (long long)S * S; idx += nt)
-    if (idx / S > idx % S) G[idx] = 0.0;
   if (tid == 0 && !(dmin_s > 1e-6 * dmax_s)) atomicExch(flag, 1);
 }
 
@@ -321,8 +334,16 @@ __global__ void tri_mul_kernel(const double* __restrict__ R2, const double* __re
 }
 
 cudaError_t launch_chol_upper(cudaStream_t st, double* G, int S, int* flag) {
-  if (S > 2048) return cudaErrorInvalidValue;
-  chol_upper_kernel<<<1, 1024, (size_t)S * sizeof(double), st>>>(G, S, flag);
+  if (S > 1024) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)(2 * CH_PB + (size_t)CH_PB * S) * sizeof(double);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  static size_t set_to = 0;
+  if (smem > 48 * 1024 && smem > set_to) {
+    cudaError_t e = cudaFuncSetAttribute(chol_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    set_to = smem;
+  }
+  chol_upper_kernel<<<1, 1024, smem, st>>>(G, S, flag);
   return cudaGetLastError();
 }
 cudaError_t launch_tri_inverse(cudaStream_t st, const double* R, int S, double* Rinv) {

@@ -151,6 +151,61 @@ class ShardedDesigner:
         self.stream.synchronize()
 
 
+def render_shard(n_frames: int, taps: int, rank: int, world: int) -> tuple[int, int, int]:
+    """Time-block sharding of the binaural render (dependencies/binauralDecode.m:39-42): rank r renders
+    the output frames [lo, hi); an FIR of `taps` taps needs the `taps - 1` input frames before lo as a halo (zeros
+    before frame 0).  Returns (lo, hi, halo) with halo = min(taps - 1, lo): the rank convolves in[lo - halo : hi] and
+    drops the first `halo` output frames.  No exchange between ranks."""
+    lo, hi = shard_range(n_frames, rank, world)
+    return lo, hi, min(max(taps - 1, 0), lo)
+
+
+class ShardedRenderer:
+    """binauralDecode of one long multichannel signal sharded over the ranks by time blocks with a (taps - 1)-frame
+    input halo: pinned host input block -> H2D -> emagls_binaural_decode_dev -> D2H of the block's two output
+    channels.  Every rank keeps its block of the output (gather with torch.distributed if one host needs it all)."""
+
+    def __init__(self, handle, block_host, wL, wR, halo: int):
+        """block_host: [halo + frames of this rank, channels], the rank's input block with its halo in front."""
+        import ctypes as C
+        import numpy as np
+        self.C, self.h = C, handle
+        self.dev = torch.device("cuda", handle.device)
+        self.stream = torch.cuda.ExternalStream(handle.stream, device=self.dev)
+        self.taps, self.ch = int(wL.shape[0]), int(wL.shape[1])
+        self.halo, self.n = int(halo), int(block_host.shape[0])
+        # [frames, channels] column-major == [channels, frames] row-major
+        blk = np.ascontiguousarray(np.asarray(block_host, dtype=np.float64).T)
+        self.x_h = torch.from_numpy(blk).pin_memory()
+        self.x_d = torch.empty_like(self.x_h, device=self.dev)
+        self.w = [torch.from_numpy(np.ascontiguousarray(np.asarray(w, dtype=np.float64).T)).to(self.dev) for w in (wL, wR)]
+        self.y_d = torch.empty((2, self.n), dtype=torch.float64, device=self.dev)
+        self.y_h = torch.empty((2, self.n - self.halo), dtype=torch.float64).pin_memory()
+        self.h2d_bytes = self.x_h.numel() * 8
+        self.d2h_bytes = self.y_h.numel() * 8
+
+    @classmethod
+    def for_signal(cls, handle, x_host, wL, wR):
+        """Shard the whole signal x_host [frames, channels] over the ranks of the process group."""
+        rank, _, world = env_world()
+        lo, hi, halo = render_shard(int(x_host.shape[0]), int(wL.shape[0]), rank, world)
+        r = cls(handle, x_host[lo - halo:hi], wL, wR, halo)
+        r.lo, r.hi = lo, hi
+        return r
+
+    def step(self):
+        h = self.h
+        with torch.cuda.stream(self.stream):
+            self.x_d.copy_(self.x_h, non_blocking=True)
+            h.check(h.lib.emagls_binaural_decode_dev(h.ptr, self.x_d.data_ptr(), self.n, self.ch, self.w[0].data_ptr(),
+                                                     self.w[1].data_ptr(), self.taps, 0, self.y_d.data_ptr()))
+            self.y_h.copy_(self.y_d[:, self.halo:], non_blocking=True)
+
+    def wait(self):
+        self.stream.synchronize()
+        return self.y_h.numpy().T        # [frames of this block, 2]
+
+
 def max_over_ranks(value: float, device=None) -> float:
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return float(value)

@@ -173,6 +173,15 @@ int emagls_design_ema_ch(emagls_handle h, const emagls_config* cfg,
                          const double* grid_azi, const double* grid_zen,
                          double mic_radius, const double* mic_azi, int num_mics,
                          int order, double fs, int len, double* wL, double* wR, double* spectra);
+/* Batched extension (not in the reference API), as for getEMagLs2Filters: hL, hR [num_samples x num_dirs x num_sets],
+ * rotations [num_orient x 9] row-major (page b = one reference call with the HRIR grid rotated by R_b),
+ * outputs [len x (2 order + 1) x (num_sets * num_orient)].                                                          */
+int emagls_design_ema_ch_batch(emagls_handle h, const emagls_config* cfg,
+                               const double* hL, const double* hR, int num_samples, int num_dirs,
+                               const double* grid_azi, const double* grid_zen,
+                               double mic_radius, const double* mic_azi, int num_mics,
+                               int order, double fs, int len, int num_sets, int num_orient, const double* rotations,
+                               double* wL, double* wR, double* spectra);
 int emagls_design_ema_sh(emagls_handle h, const emagls_config* cfg,
                          const double* hL, const double* hR, int num_samples, int num_dirs,
                          const double* grid_azi, const double* grid_zen,

@@ -142,3 +142,22 @@ def test_complex_basis_chain_keeps_the_real_part_of_the_complex_products(em, h, 
         assert rel(em.binauralDecode(x.real, 48000, wl.real, wr.real, 48000, comp, handle=h), yo) > 1e-3
     with pytest.raises(ValueError):
         em.encodeSH(sig + 1j, maz, mze, 4, handle=h)
+
+
+def test_time_block_sharded_render_with_halo(em, h):
+    """emagls_b200.dist.ShardedRenderer: every rank renders a time block with a (taps - 1)-frame input halo
+    (SURVEY.md 8-e); the concatenated blocks equal the unsharded oracle render."""
+    from emagls_b200 import dist as emdist
+    rng = np.random.default_rng(8)
+    n, taps, ch, world = 50000, 512, 32, 4
+    x = rng.standard_normal((n, ch))
+    wl, wr = rng.standard_normal((taps, ch)), rng.standard_normal((taps, ch))
+    ref = oracle.binauralDecode(x, 48000, wl, wr, 48000)
+    parts = []
+    for r in range(world):
+        lo, hi, halo = emdist.render_shard(n, taps, r, world)
+        sr = emdist.ShardedRenderer(h, x[lo - halo:hi], wl, wr, halo)
+        sr.step()
+        parts.append(sr.wait().copy())
+    got = np.concatenate(parts, 0)
+    assert got.shape == ref.shape and rel(got, ref) < 1e-9

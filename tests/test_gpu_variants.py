@@ -221,6 +221,22 @@ def ema(grids):
     return dict(az=az, ze=ze, hL=hL, hR=hR, maz=maz)
 
 
+def test_ema_ch_batched_over_sets_and_orientations(em, h, ema):
+    """Batch extension of getEMagLsFiltersEMAinCH: page (set, b) equals one reference call with that HRTF set and
+    the HRIR grid rotated by R_b (lib/getEMagLsFiltersEMAinCH.m:57-75: the steering model sees only the angles)."""
+    hL2, hR2 = synth.synth_hrirs(ema["az"], ema["ze"], head_radius=0.09, ear_azi_deg=88.0, seed=5)
+    HL, HR = np.stack([ema["hL"], hL2], 2), np.stack([ema["hR"], hR2], 2)
+    R = np.stack([np.eye(3), synth.rotation_yaw_pitch(40.0, 0.0), synth.rotation_yaw_pitch(200.0, 20.0)])
+    args = (0.042, ema["maz"], 4, 48000, 512)
+    wL, wR = em.getEMagLsFiltersEMAinCH(HL, HR, ema["az"], ema["ze"], *args, rotations=R, handle=h)
+    assert wL.shape == (512, 9, 6)
+    for s_, (hl, hr) in enumerate(((ema["hL"], ema["hR"]), (hL2, hR2))):
+        for b in (0, 2):
+            raz, rze = synth.rotate_grid(ema["az"], ema["ze"], R[b])
+            oL, oR = oracle.getEMagLsFiltersEMAinCH(hl, hr, raz, rze, *args)
+            assert rel(wL[:, :, s_ * 3 + b], oL) < 1e-8 and rel(wR[:, :, s_ * 3 + b], oR) < 1e-8, (s_, b)
+
+
 @pytest.mark.parametrize("basis", ["real", "complex"])
 @pytest.mark.parametrize("radius,order", [(0.042, 4), (0.08, 6)])
 def test_ema_ch_matches_oracle(em, h, ema, basis, radius, order):
