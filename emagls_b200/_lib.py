@@ -49,6 +49,8 @@ SIGNATURES = {
                                           C.c_int, c_dp, c_dp, c_dp]),
     "emagls_design_magls": (C.c_int, [C.c_void_p, C.POINTER(Config), c_dp, c_dp, C.c_int, C.c_int, c_dp, c_dp,
                                       C.c_int, C.c_double, C.c_int, c_dp, c_dp, c_dp]),
+    "emagls_design_magls_batch": (C.c_int, [C.c_void_p, C.POINTER(Config), c_dp, c_dp, C.c_int, C.c_int, c_dp, c_dp,
+                                            C.c_int, C.c_double, C.c_int, C.c_int, c_dp, c_dp, c_dp]),
     "emagls_design_ls": (C.c_int, [C.c_void_p, C.POINTER(Config), c_dp, c_dp, C.c_int, C.c_int, c_dp, c_dp,
                                    C.c_int, c_dp, c_dp]),
     "emagls_design_from_atf": (C.c_int, [C.c_void_p, C.POINTER(Config), c_dp, c_dp, C.c_int, C.c_int, c_dp, c_dp,

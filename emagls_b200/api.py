@@ -200,18 +200,21 @@ def getMagLsFilters(hL, hR, hrirGridAziRad, hrirGridZenRad, order, fs, len, shDe
     h = handle or default_handle()
     cfg = _config(h, config, shDefinition)
     hL, hR, T, D, sets = _prep_hrirs(hL, hR)
-    if sets != 1:
-        raise ValueError("getMagLsFilters is not batched")
     az, ze = _vec(hrirGridAziRad), _vec(hrirGridZenRad)
     H = (int(order) + 1) ** 2
     nfft = min(cfg.nfft_max_len, 2 * int(len))
     K = nfft // 2 + 1
     odt = np.complex128 if cfg.basis == 1 else np.float64
-    wL = np.zeros((int(len), H), dtype=odt, order="F")
-    wR = np.zeros((int(len), H), dtype=odt, order="F")
-    sp = np.zeros((K, H, 2), dtype=np.complex128, order="F") if return_spectra else None
-    h.check(h.lib.emagls_design_magls(h.ptr, C.byref(cfg), _p(hL), _p(hR), T, D, _p(az), _p(ze), int(order),
-                                      float(fs), int(len), _p(wL), _p(wR), _p(sp)))
+    batched = hL.ndim == 3          # [samples, dirs, sets]: keyword-free batch extension over HRTF sets
+    wL = np.zeros((int(len), H, sets), dtype=odt, order="F")
+    wR = np.zeros((int(len), H, sets), dtype=odt, order="F")
+    sp = np.zeros((K, H, sets, 2), dtype=np.complex128, order="F") if return_spectra else None
+    h.check(h.lib.emagls_design_magls_batch(h.ptr, C.byref(cfg), _p(hL), _p(hR), T, D, _p(az), _p(ze), int(order),
+                                            float(fs), int(len), sets, _p(wL), _p(wR), _p(sp)))
+    if not batched:
+        wL, wR = wL[:, :, 0], wR[:, :, 0]
+        if sp is not None:
+            sp = sp[:, :, 0, :]
     return (wL, wR, sp) if return_spectra else (wL, wR)
 
 

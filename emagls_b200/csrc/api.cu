@@ -226,27 +226,38 @@ int emagls_design_emagls(emagls_handle h, const emagls_config* cfg, const double
 }
 
 
+static int magls_host(emagls_handle h, const emagls_config* cfg, const double* hL, const double* hR,
+                      int num_samples, int num_dirs, const double* grid_azi, const double* grid_zen, int order,
+                      double fs, int len, int num_sets, double* wL, double* wR, double* spectra) {
+  return guarded(h, [&] {
+    EM_REQUIRE(cfg && hL && hR && grid_azi && grid_zen && wL && wR, "null argument");
+    EM_REQUIRE(num_samples > 0 && num_dirs > 0 && len > 0 && order >= 0 && num_sets > 0, "empty input");
+    cudaStream_t st = h->stream;
+    Arena ar(st);
+    const int T = num_samples, D = num_dirs, Mc = (order + 1) * (order + 1), NS = num_sets;
+    const int K = std::min(cfg->nfft_max_len, 2 * len) / 2 + 1;
+    const size_t wn = (size_t)len * Mc * NS * (cfg->basis == EMAGLS_BASIS_COMPLEX ? 2 : 1);
+    double* d_wL = ar.get<double>(wn);
+    double* d_wR = ar.get<double>(wn);
+    double* d_sp = spectra ? ar.get<double>((size_t)2 * K * Mc * NS * 2) : nullptr;
+    design_magls(h, *cfg, ar.upload(hL, (size_t)T * D * NS), ar.upload(hR, (size_t)T * D * NS), T, D,
+                 ar.upload(grid_azi, D), ar.upload(grid_zen, D), order, fs, len, false, d_wL, d_wR, d_sp, 0, NS);
+    EM_CUDA(cudaMemcpyAsync(wL, d_wL, wn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaMemcpyAsync(wR, d_wR, wn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (spectra)
+      EM_CUDA(cudaMemcpyAsync(spectra, d_sp, (size_t)2 * K * Mc * NS * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaStreamSynchronize(st));
+  });
+}
 int emagls_design_magls(emagls_handle h, const emagls_config* cfg, const double* hL, const double* hR,
                         int num_samples, int num_dirs, const double* grid_azi, const double* grid_zen, int order,
                         double fs, int len, double* wL, double* wR, double* spectra) {
-  return guarded(h, [&] {
-    EM_REQUIRE(cfg && hL && hR && grid_azi && grid_zen && wL && wR, "null argument");
-    EM_REQUIRE(num_samples > 0 && num_dirs > 0 && len > 0 && order >= 0, "empty input");
-    cudaStream_t st = h->stream;
-    Arena ar(st);
-    const int T = num_samples, D = num_dirs, Mc = (order + 1) * (order + 1);
-    const int K = std::min(cfg->nfft_max_len, 2 * len) / 2 + 1;
-    const size_t wn = (size_t)len * Mc * (cfg->basis == EMAGLS_BASIS_COMPLEX ? 2 : 1);
-    double* d_wL = ar.get<double>(wn);
-    double* d_wR = ar.get<double>(wn);
-    double* d_sp = spectra ? ar.get<double>((size_t)2 * K * Mc * 2) : nullptr;
-    design_magls(h, *cfg, ar.upload(hL, (size_t)T * D), ar.upload(hR, (size_t)T * D), T, D, ar.upload(grid_azi, D),
-                 ar.upload(grid_zen, D), order, fs, len, false, d_wL, d_wR, d_sp);
-    EM_CUDA(cudaMemcpyAsync(wL, d_wL, wn * sizeof(double), cudaMemcpyDeviceToHost, st));
-    EM_CUDA(cudaMemcpyAsync(wR, d_wR, wn * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (spectra) EM_CUDA(cudaMemcpyAsync(spectra, d_sp, (size_t)2 * K * Mc * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    EM_CUDA(cudaStreamSynchronize(st));
-  });
+  return magls_host(h, cfg, hL, hR, num_samples, num_dirs, grid_azi, grid_zen, order, fs, len, 1, wL, wR, spectra);
+}
+int emagls_design_magls_batch(emagls_handle h, const emagls_config* cfg, const double* hL, const double* hR,
+                              int num_samples, int num_dirs, const double* grid_azi, const double* grid_zen, int order,
+                              double fs, int len, int num_sets, double* wL, double* wR, double* spectra) {
+  return magls_host(h, cfg, hL, hR, num_samples, num_dirs, grid_azi, grid_zen, order, fs, len, num_sets, wL, wR, spectra);
 }
 
 int emagls_design_ls(emagls_handle h, const emagls_config* cfg, const double* hL, const double* hR,

@@ -184,7 +184,7 @@ cudaError_t launch_basis_change_spectra(cudaStream_t st, cplx* Wsp, int kind, in
                                         int dc_quirk);
 void design_magls(emagls_ctx* h, const emagls_config& cfg, const double* hL, const double* hR, int T, int D,
                   const double* grid_azi, const double* grid_zen, int order, double fs, int len, bool ls_only,
-                  double* wL, double* wR, double* spectra, int harmonics_kind = 0);
+                  double* wL, double* wR, double* spectra, int harmonics_kind = 0, int num_sets = 1);
 void design_from_atf(emagls_ctx* h, const emagls_config& cfg, const double* hL, const double* hR, int T, int D,
                      const double* hrir_grid, const double* atf_irs, int Ta, int M, int Da, const double* atf_grid,
                      double fs, int len, double f_trans, int num_orient, const double* rotations, double* wL,

@@ -308,11 +308,12 @@ static void tail_real(emagls_ctx* h, Arena& ar, const cplx* Wsp, int P, int Mc, 
 // ------------------------------------------------------------------------------------------
 void design_magls(emagls_ctx* h, const emagls_config& cfg, const double* hL, const double* hR, int T, int D,
                   const double* grid_azi, const double* grid_zen, int order, double fs, int len, bool ls_only,
-                  double* wL, double* wR, double* spectra, int harmonics_kind) {
+                  double* wL, double* wR, double* spectra, int harmonics_kind, int num_sets) {
   // harmonics_kind 0: spherical harmonics (getMagLsFilters / getLsFilters); 1: circular harmonics of the
   // azimuth only (lib/getMagLsFilters2D.m:44-45), channels ordered [0,-1,+1,...]
   cudaStream_t st = h->stream;
-  EM_REQUIRE(T > 0 && D > 0, "empty input");
+  EM_REQUIRE(T > 0 && D > 0 && num_sets >= 1, "empty input");
+  EM_REQUIRE(num_sets == 1 || !ls_only, "getLsFilters takes one HRTF set");
   EM_REQUIRE(order >= 0 && order <= MAX_SH_ORDER, "order out of range");
   const int Mc = harmonics_kind == 1 ? 2 * order + 1 : (order + 1) * (order + 1);
   EM_REQUIRE(Mc <= 64, "more than 64 channels are not supported");
@@ -371,37 +372,59 @@ void design_magls(emagls_ctx* h, const emagls_config& cfg, const double* hL, con
   const double df = (fs / 2.0) / (double)(K - 1);
   const int k_cut = (int)std::ceil(std::max(cfg.f_cut_min, 500.0 * order) / df);
   const int kls1 = std::min(std::max(k_cut - 1, 1), K);
-  const std::vector<double> grpD = group_delays(h, ar, hL, hR, T, D, K, fs, 1);
-  cplx* Hc = ar.get<cplx>((size_t)2 * K * D);
+  // HRTF-set batch (extension, not in the reference API): the one pinv(Y) operator serves every set, the sets are
+  // independent problems of the chain kernel (lib/getMagLsFilters.m:48,64-72)
+  const int NS = num_sets;
+  const std::vector<double> grpD = group_delays(h, ar, hL, hR, T, D, K, fs, NS);
+  cplx* Hc = ar.get<cplx>((size_t)NS * 2 * K * D);
   {
     double* tw = ar.get<double>((size_t)2 * K * T);
     EM_CUDA(launch_dft_twiddle(st, K, T, nfft, tw));
     double* Hd = ar.get<double>((size_t)D * 2 * K);
-    for (int e = 0; e < 2; ++e) {
-      hrir_spectrum(h, ar, e ? hR : hL, T, D, K, tw, grpD[e], Hd);
-      dim3 grid((K + 31) / 32, (D + 31) / 32), block(32, 8);
-      spectrum_rows_kernel<<<grid, block, 0, st>>>(Hd, D, K, Hc + (size_t)e * K * D);
-      EM_CUDA(cudaGetLastError());
-      h->launches += 1;
-    }
+    for (int s_ = 0; s_ < NS; ++s_)
+      for (int e = 0; e < 2; ++e) {
+        hrir_spectrum(h, ar, (e ? hR : hL) + (size_t)s_ * T * D, T, D, K, tw, grpD[(size_t)s_ * 2 + e], Hd);
+        dim3 grid((K + 31) / 32, (D + 31) / 32), block(32, 8);
+        spectrum_rows_kernel<<<grid, block, 0, st>>>(Hd, D, K, Hc + ((size_t)s_ * 2 + e) * K * D);
+        EM_CUDA(cudaGetLastError());
+        h->launches += 1;
+      }
     h->launches += 1;
   }
   delete setup_span;
-  cplx* Wsp = spectra ? reinterpret_cast<cplx*>(spectra) : ar.get<cplx>((size_t)2 * Mc * K);
+  cplx* Wsp = spectra ? reinterpret_cast<cplx*>(spectra) : ar.get<cplx>((size_t)2 * NS * Mc * K);
   g.K = K; g.first_bin = 0; g.kls1 = kls1; g.dc_fix = 0; g.nyquist_real = 1;   // lib/getMagLsFilters.m:64-72
-  g.H = Hc; g.h_prob_stride = 0; g.h_ear_stride = (long long)K * D; g.W = Wsp;
+  g.num_prob = NS;
+  g.H = Hc; g.h_prob_stride = 2LL * K * D; g.h_ear_stride = (long long)K * D; g.W = Wsp;
   run_generic(h, ar, g);
-  const double dl = (double)(nfft / 2), dr = dl + (grpD[1] - grpD[0]);
-  if (!cplx_out) {
-    tail_real(h, ar, Wsp, 1, Mc, K, nfft, len, dl, dr, wL, wR);
-  } else {
-    double* tmp = ar.get<double>((size_t)2 * Mc * len);
-    tail_real(h, ar, Wsp, 1, Mc, K, nfft, len, dl, dr, tmp, tmp + (size_t)Mc * len);
-    EM_CUDA(launch_basis_change_filters(st, tmp, harmonics_kind, Mc, len, 1, nullptr, 0, 1, reinterpret_cast<cplx*>(wL)));
-    EM_CUDA(launch_basis_change_filters(st, tmp + (size_t)Mc * len, harmonics_kind, Mc, len, 1, nullptr, 0, 1,
-                                        reinterpret_cast<cplx*>(wR)));
-    if (spectra) EM_CUDA(launch_basis_change_spectra(st, Wsp, harmonics_kind, Mc, K, 2, 0));
-    h->launches += 3;
+  // tail per set: the right ear's shift restores that set's inter-aural group-delay difference
+  double* tmp = cplx_out ? ar.get<double>((size_t)2 * Mc * len) : nullptr;
+  cplx* Wset = ar.get<cplx>((size_t)2 * Mc * K);
+  for (int s_ = 0; s_ < NS; ++s_) {
+    const double dl = (double)(nfft / 2), dr = dl + (grpD[(size_t)s_ * 2 + 1] - grpD[(size_t)s_ * 2]);
+    const cplx* Ws = Wsp;
+    if (NS > 1) {   // gather this set's two ear blocks [ear][set][Mc][K] -> [ear][Mc][K]
+      for (int e = 0; e < 2; ++e)
+        EM_CUDA(cudaMemcpyAsync(Wset + (size_t)e * Mc * K, Wsp + ((size_t)e * NS + s_) * Mc * K,
+                                (size_t)Mc * K * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+      Ws = Wset;
+    }
+    const size_t esz = (size_t)Mc * len * (cplx_out ? 2 : 1);
+    double* oL = wL + (size_t)s_ * esz;
+    double* oR = wR + (size_t)s_ * esz;
+    if (!cplx_out) {
+      tail_real(h, ar, Ws, 1, Mc, K, nfft, len, dl, dr, oL, oR);
+    } else {
+      tail_real(h, ar, Ws, 1, Mc, K, nfft, len, dl, dr, tmp, tmp + (size_t)Mc * len);
+      EM_CUDA(launch_basis_change_filters(st, tmp, harmonics_kind, Mc, len, 1, nullptr, 0, 1, reinterpret_cast<cplx*>(oL)));
+      EM_CUDA(launch_basis_change_filters(st, tmp + (size_t)Mc * len, harmonics_kind, Mc, len, 1, nullptr, 0, 1,
+                                          reinterpret_cast<cplx*>(oR)));
+      h->launches += 2;
+    }
+  }
+  if (cplx_out && spectra) {
+    EM_CUDA(launch_basis_change_spectra(st, Wsp, harmonics_kind, Mc, K, 2LL * NS, 0));
+    h->launches += 1;
   }
 }
 

@@ -133,6 +133,12 @@ int emagls_design_magls(emagls_handle h, const emagls_config* cfg,
                         const double* hL, const double* hR, int num_samples, int num_dirs,
                         const double* grid_azi, const double* grid_zen,
                         int order, double fs, int len, double* wL, double* wR, double* spectra);
+/* Batched extension (not in the reference API): hL, hR [num_samples x num_dirs x num_sets]; the one pinv(Y)
+ * serves every HRTF set; outputs [len x (order+1)^2 x num_sets], spectra [K x (order+1)^2 x num_sets x 2].   */
+int emagls_design_magls_batch(emagls_handle h, const emagls_config* cfg,
+                              const double* hL, const double* hR, int num_samples, int num_dirs,
+                              const double* grid_azi, const double* grid_zen,
+                              int order, double fs, int len, int num_sets, double* wL, double* wR, double* spectra);
 int emagls_design_ls(emagls_handle h, const emagls_config* cfg,
                      const double* hL, const double* hR, int num_samples, int num_dirs,
                      const double* grid_azi, const double* grid_zen, int order,

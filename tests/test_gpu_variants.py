@@ -109,6 +109,21 @@ def test_magls_matches_oracle(em, h, c1, basis):
 
 
 @pytest.mark.parametrize("basis", ["real", "complex"])
+def test_magls_batched_over_hrtf_sets(em, h, c1, basis):
+    """Batch extension: hL, hR [samples, dirs, sets] -> [len, (N+1)^2, sets]; the one pinv(Y) serves every set
+    (lib/getMagLsFilters.m:48), each page equals the single call."""
+    hL2, hR2 = synth.synth_hrirs(c1["az"], c1["ze"], head_radius=0.09, ear_azi_deg=88.0, seed=5)
+    HL, HR = np.stack([c1["hL"], hL2, c1["hL"]], 2), np.stack([c1["hR"], hR2, c1["hR"]], 2)
+    wL, wR, sp = em.getMagLsFilters(HL, HR, c1["az"], c1["ze"], 4, c1["fs"], 512, basis, handle=h, return_spectra=True)
+    assert wL.shape == (512, 25, 3) and sp.shape == (513, 25, 3, 2)
+    for s_, (hl, hr) in enumerate(((c1["hL"], c1["hR"]), (hL2, hR2), (c1["hL"], c1["hR"]))):
+        oL, oR, osp = oracle.getMagLsFilters(hl, hr, c1["az"], c1["ze"], 4, c1["fs"], 512, basis, return_spectra=True)
+        for e in range(2):
+            assert bin_err(sp[:, :, s_, e], osp["W"][:, :, e]).max() <= 1e-10
+        assert rel(wL[:, :, s_], oL) < 1e-11 and rel(wR[:, :, s_], oR) < 1e-11
+
+
+@pytest.mark.parametrize("basis", ["real", "complex"])
 def test_ls_matches_oracle(em, h, c1, basis):
     wL, wR = em.getLsFilters(c1["hL"], c1["hR"], c1["az"], c1["ze"], 4, basis, handle=h)
     oL, oR = oracle.getLsFilters(c1["hL"], c1["hR"], c1["az"], c1["ze"], 4, basis)
