@@ -67,15 +67,51 @@ def problem(rank: int, n_orient: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / power / throttle reasons during the timed region (B200_PROFILING.md recipe), sampled every 0.2 s
+    through NVML (nvidia_ml_py) in a background thread; falls back to spawning nvidia-smi when NVML is not importable.
+    NVML queries do not take the driver lock a whole `nvidia-smi` process start does, so they do not stall the
+    kernel launches of the step being timed."""
 
     def __init__(self, index: int):
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._dev = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+        except Exception:
+            self._nvml = None
+
+    @staticmethod
+    def _physical_index(index: int) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                return int(ids[index])
+        return index
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
         return self
+
+    def _sample_nvml(self):
+        n, d = self._nvml, self._dev
+        sm = n.nvmlDeviceGetClockInfo(d, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(d, n.NVML_CLOCK_SM)
+        try:
+            pw = n.nvmlDeviceGetPowerUsage(d) / 1000.0
+        except Exception:
+            pw = 0.0
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(d) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(d)
+        def flag(suffix):
+            bit = getattr(n, "nvmlClocksEventReason" + suffix, None) or getattr(n, "nvmlClocksThrottleReason" + suffix, 0)
+            return "Active" if r & bit else "Not Active"
+        return [str(sm), str(mx), f"{pw:.1f}", flag("HwSlowdown"), flag("HwThermalSlowdown"), flag("SwThermalSlowdown"),
+                flag("SwPowerCap")]
 
     def _run(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -83,10 +119,13 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                if out.returncode == 0 and out.stdout.strip():
-                    self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+                if self._nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                    if out.returncode == 0 and out.stdout.strip():
+                        self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
             except Exception:
                 pass
             self._stop.wait(0.2)
@@ -101,7 +140,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 def cpu_port_round(pr, first, workers):

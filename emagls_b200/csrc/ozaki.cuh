@@ -209,6 +209,15 @@ __device__ __forceinline__ bool elect_one() {
 // (already scaled, FP64).  Called only for m < M; columns >= N hold zeros and must be skipped.  A functor that
 // declares `static constexpr bool all_lanes = true` is entered by every lane of the warp (also m >= M) and
 // guards its own stores, so that it may use warp shuffles.
+// A functor that declares `static constexpr bool staged = true` provides stage() / flush(): the four warps of a
+// TMEM lane group (32 rows x NT columns of the tile) write their results into a shared-memory tile, meet at a
+// named barrier and store the tile with row-contiguous 8-byte words (STG_ROW bytes per staged row).
+constexpr int STG_ROW = 72;
+template <class E, class = void> struct epi_staged { static constexpr bool value = false; };
+template <class E> struct epi_staged<E, decltype((void)E::staged)> { static constexpr bool value = E::staged; };
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 template <class E, class = void> struct epi_all_lanes { static constexpr bool value = false; };
 template <class E> struct epi_all_lanes<E, decltype((void)E::all_lanes)> { static constexpr bool value = E::all_lanes; };
 
@@ -272,6 +281,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int NT = Cfg::NT, ST = Cfg::ST, B_SLICE_BYTES = NT * TILE_K;
   constexpr int stage_bytes = T * (A_SLICE_BYTES + B_SLICE_BYTES);
+  uint8_t* epi_stage_area = base + (size_t)ST * stage_bytes;   // only for staged functors (see launch: extra smem)
   __shared__ __align__(8) uint64_t full_bar[ST], empty_bar[ST], tmem_full_bar, tmem_empty_bar;
   __shared__ uint32_t tmem_base_s;
 
@@ -410,6 +420,18 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar);
+      if constexpr (epi_staged<Epi>::value) {
+        static_assert(EPI_WARPS == 16 && NT == 64, "staged epilogue: four warps per lane group, 64-column tiles");
+        uint8_t* stg = epi_stage_area + (size_t)lg * (T * 32 * STG_ROW);
+#pragma unroll
+        for (int ci = 0; ci < CH_PER_WARP; ++ci) {
+          const int c0 = chunk0 + ci * chunk_step;
+          if (c0 < n_lim) epi.stage(stg, lane, c0, m, n0 + c0, v[ci], g.M, g.N);
+        }
+        named_bar_sync(1 + lg, 128);
+        if (n_lim > 0) epi.flush(stg, ((warp - 2) >> 2) * 32 + lane, m0 + lg * 32, n0, n_lim, g.M);
+        named_bar_sync(1 + lg, 128);      // the tile is free again for the next one
+      } else
 #pragma unroll
       for (int ci = 0; ci < CH_PER_WARP; ++ci) {
         const int c0 = chunk0 + ci * chunk_step;
@@ -474,7 +496,7 @@ template <int T, class Epi, class Cfg = TileDefault>
 cudaError_t launch_ozaki_gemm_t(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs g,
                                 Epi epi, int num_sms) {
   static_assert(T * Cfg::NT <= 512 && Cfg::NT % 16 == 0, "TMEM holds 512 columns; UMMA N is a multiple of 16");
-  const size_t smem = gemm_smem_bytes<Cfg>(T);
+  const size_t smem = gemm_smem_bytes<Cfg>(T) + (epi_staged<Epi>::value ? (size_t)4 * T * 32 * STG_ROW : 0);
   cudaError_t e = cudaFuncSetAttribute(ozaki_gemm_kernel<T, Epi, Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   g.tile_n = Cfg::NT;

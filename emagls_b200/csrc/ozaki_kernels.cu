@@ -58,13 +58,15 @@ struct EpiPhaseSlice {
 // part and emits ONE 8-byte word per digit plane (six stores instead of 48 single bytes per 8 outputs).
 template <int T>
 struct EpiPhaseSliceRows {
-  static constexpr bool all_lanes = true;
+  static constexpr bool staged = true;            // stage() by every lane of the warp, then flush() by the lane group
   int8_t* Tq; long long slice_stride; int Kpad;   // [T][rows][Kpad], element (m, n) at m * Kpad + n
-  double* sT;                                     // [rows] scale of row m (written by the n0 == 0 chunk)
+  double* sT;                                     // [rows] scale of row m (written by the n == 0 chunk)
   const double* absH; long long abs_set_stride, abs_ear_stride;   // this bin: [set][ear][dir]
   const double* up; const double* sc; int scale_stride;           // 2^(6-e), 2^(e-6) at [(set*2+ear)*scale_stride]
   int orient_per_set; int nyquist;
-  __device__ __forceinline__ void operator()(int m, int n0, const double (&v)[8], int M, int N) const {
+  // row `row` of the lane group's tile, columns c0 .. c0+7 (absolute: m, n0 .. n0+7)
+  __device__ __forceinline__ void stage(uint8_t* stg, int row, int c0, int m, int n0, const double (&v)[8], int M,
+                                        int N) const {
     const bool valid = m < M;
     const int mm = valid ? m : 0;
     const int part = mm & 1, j = mm >> 1, ear = j & 1, prob = j >> 1;
@@ -90,10 +92,23 @@ struct EpiPhaseSliceRows {
     if (!valid) return;
     uint2 word[oz::MAX_SLICES];
     oz::slice_pack8<T>(a, word);
-    int8_t* p = Tq + (long long)m * Kpad + n0;    // Kpad multiple of 32, n0 multiple of 8: 8-byte aligned
 #pragma unroll
-    for (int s = 0; s < T; ++s) *reinterpret_cast<uint2*>(p + (long long)s * slice_stride) = word[s];
+    for (int s = 0; s < T; ++s) *reinterpret_cast<uint2*>(stg + (s * 32 + row) * oz::STG_ROW + c0) = word[s];
     if (n0 == 0) sT[m] = sc[si];
+  }
+  // t = 0 .. 127 within the lane group; rows m_base .. m_base+31, columns n0 .. n0+n_lim-1 of the tile
+  __device__ __forceinline__ void flush(const uint8_t* stg, int t, int m_base, int n0, int n_lim, int M) const {
+#pragma unroll
+    for (int s = 0; s < T; ++s) {
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int idx = it * 128 + t, row = idx >> 3, piece = (idx & 7) * 8;
+        if (piece < n_lim && m_base + row < M) {
+          const uint2 w = *reinterpret_cast<const uint2*>(stg + (s * 32 + row) * oz::STG_ROW + piece);
+          *reinterpret_cast<uint2*>(Tq + (long long)s * slice_stride + (long long)(m_base + row) * Kpad + n0 + piece) = w;
+        }
+      }
+    }
   }
 };
 
@@ -153,7 +168,7 @@ static cudaError_t oz_fwd_rows_t(cudaStream_t st, const OzFwdArgs& a) {
   oz::GemmArgs g{a.rows, a.D, a.KpS, a.sCv, a.sYhA, 0, 1, oz::TILE_N};
   EpiPhaseSliceRows<T> epi{a.Tt_q, (long long)a.rows * a.KpD, a.KpD, a.sT, a.absH, a.abs_set_stride, a.abs_ear_stride,
                            a.up, a.sc, a.scale_stride, a.orient_per_set, a.nyquist};
-  return oz::launch_ozaki_gemm_t<T>(st, tmA, tmB, g, epi, sm_count());
+  return oz::launch_ozaki_gemm_t<T, EpiPhaseSliceRows<T>, oz::TileCfg<64, 2>>(st, tmA, tmB, g, epi, sm_count());
 }
 
 template <int T>
@@ -171,9 +186,9 @@ static cudaError_t oz_fwd_t(cudaStream_t st, const OzFwdArgs& a) {
 cudaError_t launch_oz_fwd(cudaStream_t st, const OzFwdArgs& a) {
   if (!oz::contraction_fits(a.KpS, a.T)) return cudaErrorInvalidValue;
   // EMAGLS_OZ_FWD_ROWS=1 (A/B switch): operand roles swapped, a thread owns eight directions of one (problem, ear,
-  // re/im) row and stores 8-byte digit words.  Measured on B200 (profiles/r02_v7): 250 ms against 225 ms per step for
-  // the default orientation -- the 8-byte words of 32 different rows cost four times the L2 sectors of the byte
-  // stores, which a warp writes 32 at a time into one sector.
+  // re/im) row, packs 8-byte digit words, and the lane group stores its 32 x 64 tile row-contiguously through a
+  // shared-memory stage.  (Without the stage the 8-byte words of 32 different rows cost four times the L2 sectors of
+  // the default orientation's byte stores: 250 ms against 225 ms per step, profiles/r02_v7.)
   static const bool by_rows = getenv("EMAGLS_OZ_FWD_ROWS") != nullptr;
   if (by_rows && (a.rows & 1) == 0) {
     switch (a.T) {

@@ -74,58 +74,104 @@ __device__ __forceinline__ void hh_scalars(cplx alpha, double xn, double* beta_o
   *sc_out = mk(d.x * id2, -d.y * id2);
 }
 
+// E tiles: for block t (rows 32 t ..) and order n the 32 x Mc doubles E[off(r) + (n - ord(r)) Mc + c], zero where
+// n < ord(r).  The four warps of a CTA factorise four bins of the SAME orientation, so a tile is fetched once
+// (cp.async, three-stage ring, two tiles in flight -- also across the Householder phase of a block) and consumed
+// by all of them: b[i] += b_n(bin) * tile[i][lane].
+constexpr int TQ_STAGES = 3;
+constexpr int TQ_TILE = 32 * 32;       // doubles per stage
+
+__device__ __forceinline__ void tq_issue_tile(double* tile, const double* __restrict__ Eo, const int2* rowinfo, int S,
+                                              int Mc, int t, int n, bool any) {
+  // one commit group per call, empty when the tile stream is exhausted (any == false)
+  if (any) {
+    const int r0 = t * 32;
+    if ((Mc & 1) == 0) {
+      const int per_row = Mc >> 1;     // 16-byte chunks per row
+      for (int idx = threadIdx.x; idx < 32 * per_row; idx += TQ_WARPS * 32) {
+        const int i = idx / per_row, c2 = idx - i * per_row;
+        const int r = min(r0 + i, S - 1);
+        const int2 ri = rowinfo[r];
+        const bool ok = (r0 + i < S) && (n >= ri.x);
+        cp_async16(tile + i * 32 + 2 * c2, Eo + (ok ? ri.y + (n - ri.x) * Mc + 2 * c2 : 0), ok);
+      }
+    } else {
+      for (int idx = threadIdx.x; idx < 32 * Mc; idx += TQ_WARPS * 32) {
+        const int i = idx / Mc, c = idx - i * Mc;
+        const int r = min(r0 + i, S - 1);
+        const int2 ri = rowinfo[r];
+        const bool ok = (r0 + i < S) && (n >= ri.x);
+        cp_async8(tile + i * 32 + c, Eo + (ok ? ri.y + (n - ri.x) * Mc + c : 0), ok);
+      }
+    }
+  }
+  cp_async_commit();
+}
+
 __global__ void __launch_bounds__(TQ_WARPS * 32, 3)
-tsqr_sep_kernel(BlockPlan bp, RowSource src, OperatorSet ops, cplx* __restrict__ Rout, int kbase, int G, int items) {
+tsqr_sep_kernel(BlockPlan bp, RowSource src, OperatorSet ops, cplx* __restrict__ Rout, int kbase, int G, int sgroups) {
   extern __shared__ __align__(16) unsigned char tq_raw[];
   const int S = bp.S, Mc = bp.Mc;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int2* rowinfo = reinterpret_cast<int2*>(tq_raw);                 // (order, offset into E) per row
   const int tab_bytes = ((S * (int)sizeof(int2) + 15) / 16) * 16;
   for (int i = threadIdx.x; i < S; i += blockDim.x) rowinfo[i] = make_int2(src.roword[i], src.rowoff[i]);
-  __syncthreads();
-  const int item = blockIdx.x * TQ_WARPS + warp;
-  if (item >= items) return;            // warp-uniform; only warp-level synchronisation below
-  cplx* Rt = reinterpret_cast<cplx*>(tq_raw + tab_bytes) + (size_t)warp * TQ_WARP_CPLX;
+  double* tiles = reinterpret_cast<double*>(tq_raw + tab_bytes);
+  cplx* Rt = reinterpret_cast<cplx*>(tiles + TQ_STAGES * TQ_TILE) + (size_t)warp * TQ_WARP_CPLX;
   cplx* xbuf = Rt + TQ_TRI;
   cplx* bn_s = xbuf + 32;
-  const int prob = item / G, slot = item - prob * G, k = kbase + slot;
-  const long long oidx = (long long)prob * G + slot;
+  // CTA = one orientation x four consecutive bins of the launch; a warp without a bin only helps with the tiles
+  const int prob = blockIdx.x / sgroups, slot = (blockIdx.x - prob * sgroups) * TQ_WARPS + warp;
+  const bool active = slot < G;
+  const int k = kbase + min(slot, G - 1);
+  const long long oidx = (long long)prob * G + min(slot, G - 1);
   const int N = src.N;
   for (int n = lane; n <= N; n += 32) bn_s[n] = src.bn[(long long)k * (N + 1) + n];
   for (int i = lane; i < TQ_TRI; i += 32) Rt[i] = mk(0.0, 0.0);
-  __syncwarp();
-  const double* Eo = src.E + (long long)prob * src.Etot + (lane < Mc ? lane : 0);
+  __syncthreads();
+  const double* Eo = src.E + (long long)prob * src.Etot;
   const bool col_ok = lane < Mc;
   cplx* Vg = ops.V + oidx * ops.v_stride;
   cplx* taug = ops.tau + oidx * ops.tau_stride;
+
+  // tile stream over (block, order): iterator of the next tile to issue
+  int it_t = 0, it_n = rowinfo[0].x, q_issue = 0;
+  auto issue_next = [&]() {
+    const bool any = it_t < bp.nblk;
+    tq_issue_tile(tiles + (q_issue % TQ_STAGES) * TQ_TILE, Eo, rowinfo, S, Mc, it_t, it_n, any);
+    ++q_issue;
+    if (any) {
+      if (it_n < N) ++it_n;
+      else { ++it_t; it_n = (it_t < bp.nblk) ? rowinfo[it_t * 32].x : 0; }
+    }
+  };
+  issue_next();
+  issue_next();
+  int q = 0;   // tiles consumed so far
 
   for (int t = 0; t < bp.nblk; ++t) {
     const int r0 = t * 32;
     cplx b[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) b[i] = mk(0.0, 0.0);
-    // ---- rows r0 .. r0+31 of C_k: C[r][c] = sum_{n >= ord(r)} b_n E[off(r) + (n - ord(r)) Mc + c].
-    // The loads are unconditional (invalid terms read E[0] and are multiplied by zero) so that the 32 loads
-    // of an order are in flight together instead of one per basic block.
+    // ---- rows r0 .. r0+31 of C_k: C[r][c] = sum_{n >= ord(r)} b_n E[off(r) + (n - ord(r)) Mc + c]
     const int nlo = rowinfo[r0].x;      // orders below that of the first row contribute nothing
-    for (int n = nlo; n <= N; ++n) {
-      const cplx bnn = bn_s[n];
-      double ev[32];
+    for (int n = nlo; n <= N; ++n, ++q) {
+      cp_async_wait<TQ_STAGES - 2>();   // tile q has landed (this thread's copies; the barrier covers the others)
+      __syncthreads();                  // ... and every warp is done with the stage tile q + 2 goes into
+      issue_next();
+      if (active && col_ok) {
+        const double* tile = tiles + (q % TQ_STAGES) * TQ_TILE + lane;
+        const cplx bnn = bn_s[n];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int r = min(r0 + i, S - 1);
-        const int2 ri = rowinfo[r];
-        const bool ok = (r0 + i < S) && (n >= ri.x) && col_ok;
-        const int off = ok ? ri.y + (n - ri.x) * Mc : 0;
-        const double v = __ldg(Eo + off);
-        ev[i] = ok ? v : 0.0;
-      }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        b[i].x = fma(bnn.x, ev[i], b[i].x);
-        b[i].y = fma(bnn.y, ev[i], b[i].y);
+        for (int i = 0; i < 32; ++i) {
+          const double ev = tile[i * 32];
+          b[i].x = fma(bnn.x, ev, b[i].x);
+          b[i].y = fma(bnn.y, ev, b[i].y);
+        }
       }
     }
+    if (!active) continue;
     // ---- 32 Householder steps on [R_C; block]
     cplx my_tau = mk(0.0, 0.0), my_sc = mk(0.0, 0.0);
     for (int j = 0; j < Mc; ++j) {
@@ -169,6 +215,7 @@ tsqr_sep_kernel(BlockPlan bp, RowSource src, OperatorSet ops, cplx* __restrict__
     }
     taug[t * 32 + lane] = my_tau;
   }
+  if (!active) return;
   // ---- R_C, full 32 x 32 row-major with zeros below the diagonal
   cplx* Rg = Rout + oidx * 1024;
   for (int j = 0; j < 32; ++j) Rg[j * 32 + lane] = (lane >= j && j < Mc && lane < Mc) ? Rt[tri_idx(j, lane)] : mk(0.0, 0.0);
@@ -538,7 +585,8 @@ chain_bwd_sep_kernel(BlockPlan bp, OperatorSet ops, int slot, int G, const doubl
 }  // namespace
 
 size_t tsqr_sep_smem_bytes(const BlockPlan& bp) {
-  return (size_t)(((bp.S * (int)sizeof(int2) + 15) / 16) * 16) + (size_t)TQ_WARPS * TQ_WARP_CPLX * sizeof(cplx);
+  return (size_t)(((bp.S * (int)sizeof(int2) + 15) / 16) * 16) + (size_t)TQ_STAGES * TQ_TILE * sizeof(double) +
+         (size_t)TQ_WARPS * TQ_WARP_CPLX * sizeof(cplx);
 }
 
 cudaError_t launch_tsqr_sep(cudaStream_t st, const BlockPlan& bp, const RowSource& src, const OperatorSet& ops,
@@ -551,8 +599,8 @@ cudaError_t launch_tsqr_sep(cudaStream_t st, const BlockPlan& bp, const RowSourc
     if (e != cudaSuccess) return e;
     set_to = smem;
   }
-  const int items = num_prob * G;
-  tsqr_sep_kernel<<<(items + TQ_WARPS - 1) / TQ_WARPS, TQ_WARPS * 32, smem, st>>>(bp, src, ops, Rout, kbase, G, items);
+  const int sgroups = (G + TQ_WARPS - 1) / TQ_WARPS;
+  tsqr_sep_kernel<<<num_prob * sgroups, TQ_WARPS * 32, smem, st>>>(bp, src, ops, Rout, kbase, G, sgroups);
   return cudaGetLastError();
 }
 
