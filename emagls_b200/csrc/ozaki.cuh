@@ -63,10 +63,14 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // bounded wait: a protocol error becomes a trap (launch failure) instead of a hung GPU
+#ifndef EMAGLS_OZ_SPIN_SLEEP
+#define EMAGLS_OZ_SPIN_SLEEP 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try(bar, parity)) {
+    if (EMAGLS_OZ_SPIN_SLEEP > 0) __nanosleep(EMAGLS_OZ_SPIN_SLEEP);   // leave the issue slots to the working warps
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
@@ -80,6 +84,17 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, ui
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// shared-memory tile -> global tensor (bulk async group of the issuing thread)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy writes to shared memory become visible to the async proxy (TMA)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
@@ -130,6 +145,49 @@ __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr) {
 // n_dim = N >> 3 @17, m_dim = M >> 4 @24
 __device__ __forceinline__ uint32_t instr_desc_i8(int m, int n) {
   return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------- conversions without the XU pipe
+// I2F / F2I on FP64 values run on the conversion (XU) pipe, 16 lanes per clock and SM; the epilogues below need
+// eight to twelve of them per output value, so they use the classic mantissa tricks on the FP64 / integer pipes:
+//   int32 -> double : the word (a ^ 0x80000000) placed in the low mantissa of 2^52 is 2^52 + 2^31 + a exactly
+//   double -> int32 : x + 1.5 * 2^52 holds rn(x) (ties to even, |x| < 2^31) in its low word
+constexpr double RN_MAGIC = 6755399441055744.0;   // 1.5 * 2^52
+__device__ __forceinline__ double i2d_exact(int a) {
+  return __hiloint2double(0x43300000, a ^ (int)0x80000000) - 4503601774854144.0;   // 2^52 + 2^31
+}
+// Exact integer value of one output element from its T diagonal accumulators, rounded once to FP64:
+//   v = rn(sum_d acc_d 256^(T-1-d)) = rn(H 256^(T-3) + L),  H = digits 0..2 (|H| < 2^38), L = digits 3..T-1 (|L| < 2^42)
+template <int T>
+__device__ __forceinline__ double combine_diagonals(const int32_t (&a)[MAX_SLICES][8], int q) {
+  double H = i2d_exact(a[0][q]);
+#pragma unroll
+  for (int d = 1; d < 3; ++d)
+    if (d < T) H = fma(H, 256.0, i2d_exact(a[d][q]));
+  if (T <= 3) return H;
+  double L = i2d_exact(a[3][q]);
+#pragma unroll
+  for (int d = 4; d < MAX_SLICES; ++d)
+    if (d < T) L = fma(L, 256.0, i2d_exact(a[d][q]));
+  return fma(H, (double)(1 << (8 * (T - 3))), L);
+}
+// weight of the integer above: C = sA sB 256^-(T-1) v
+template <int T> __device__ __forceinline__ double diagonal_weight() { return 1.0 / (double)(1ull << (8 * (T - 1))); }
+
+// Balanced base-256 digits (see slice_digits) of ah = a * 256^(T-4), |a| <= 64, as two words: byte j of zl is
+// digit T-1-j (j < 3), byte j of zh is digit T-4-j (j < T-3).  Same results as slice_digits, no F2I / I2F.
+template <int T>
+__device__ __forceinline__ void slice_words(double ah, uint32_t& zl, uint32_t& zh) {
+  static_assert(T >= 4 && T <= 6, "hi limb: 1..3 digits, lo limb: 3 digits");
+  constexpr int nh = T - 3;
+  constexpr int bias_hi = (nh == 3) ? 0x808080 : (nh == 2 ? 0x8080 : 0x80);
+  const double th = ah + RN_MAGIC;
+  int hi = __double2loint(th);                                         // rn(ah), |hi| <= 2^22
+  const double tl = fma(ah - (th - RN_MAGIC), 16777216.0, RN_MAGIC);   // the remainder is exact, |.| <= 1/2
+  const int yl = __double2loint(tl) + 0x808080;                        // in (0, 2^25)
+  hi += yl >> 24;                                                      // carry (0 or 1)
+  zl = (uint32_t)(yl ^ 0x808080);
+  zh = (uint32_t)((hi + bias_hi) ^ bias_hi);                           // |hi| <= 2^22 + 1: no carry out
 }
 
 // ------------------------------------------------------------------------------------- slicing
@@ -186,7 +244,7 @@ struct GemmArgs {
   int M, N, Kpad;           // C is M x N; Kpad multiple of 32 (bytes per slice row of both operands)
   const double* sA;         // [M] row scales of A
   const double* sB;         // [N] row scales of B
-  int dbg;                  // microbenchmark switches: 1 = skip the epilogue work, 2 = skip the MMAs
+  int dbg;                  // microbenchmark switches: 1 = skip the epilogue work, 2 = skip the MMAs, 4 = drain only (raw functors)
   int n_fastest;            // tile order: consecutive tiles share the A rows (1) or the B rows (0)
   int tile_n;               // Cfg::NT of the launched instance (tile_origin)
 };
@@ -218,6 +276,19 @@ template <class E> struct epi_staged<E, decltype((void)E::staged)> { static cons
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// A functor that declares `static constexpr bool raw = true` works on the unscaled integers (combine_diagonals):
+//   begin_tile(m, n, M, N) -> TileState   loads that do not depend on the accumulators, issued before the wait
+//   apply(state, m, n0, v[8], M, N)       called for m < M
+// (the forward product only needs the direction of y, so the operand scales cancel).
+template <class E, class = void> struct epi_raw { static constexpr bool value = false; };
+template <class E> struct epi_raw<E, decltype((void)E::raw)> { static constexpr bool value = E::raw; };
+// A raw functor that declares `static constexpr int tma_stage_bytes` (= T * NT * 128) writes its int8 results into a
+// shared-memory tile [T][NT columns][128 rows] with apply_staged(); the epilogue warps meet at a named barrier and one
+// thread stores the tile through the third tensor map (cp.async.bulk.tensor, clipped at the tensor's extent -- in
+// 4-byte granules along the inner dimension (measured: with an inner extent of 2702 bytes the columns 2702 and 2703
+// are written), so apply_staged() is also entered for rows m >= M and must stage zeros there).
+template <class E, class = void> struct epi_tma_stage { static constexpr int value = 0; };
+template <class E> struct epi_tma_stage<E, decltype((void)E::tma_stage_bytes)> { static constexpr int value = E::tma_stage_bytes; };
 template <class E, class = void> struct epi_all_lanes { static constexpr bool value = false; };
 template <class E> struct epi_all_lanes<E, decltype((void)E::all_lanes)> { static constexpr bool value = E::all_lanes; };
 
@@ -275,7 +346,8 @@ struct EpiStoreF64 {
 
 template <int T, class Epi, class Cfg = TileDefault>
 __global__ void __launch_bounds__(THREADS, 1)
-ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g, Epi epi) {
+ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmC, GemmArgs g, Epi epi) {
   extern __shared__ uint8_t oz_smem_raw[];
   // 1024-byte aligned carve-up: [stage][A slices | B slices]
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -295,6 +367,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (epi_tma_stage<Epi>::value) tma_prefetch_desc(&tmC);
     for (int s = 0; s < ST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tmem_full_bar, 1);
     mbar_init(&tmem_empty_bar, EPI_WARPS);   // one arrival per epilogue warp
@@ -379,71 +452,104 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     constexpr int chunk_step = 8 * (EPI_WARPS / 4);
     constexpr int CH_PER_WARP = (NT + chunk_step - 1) / chunk_step;
     uint32_t acc_phase = 0;
-    const double w_hi = scalbn(1.0, -8 * ((T < 3 ? T : 3) - 1)), w_lo = scalbn(1.0, -8 * (T - 1));
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m0, n0;
       tile_origin(g, tile, m_tiles, n_tiles, m0, n0);
       const int n_mma = min(NT, ((g.N - n0) + 15) & ~15);
       const int m = m0 + lg * 32 + lane;
-      mbar_wait(&tmem_full_bar, acc_phase);
-      tc_fence_after();
-      const double sa = (m < g.M) ? g.sA[m] : 0.0;
       const int n_lim = (g.dbg & 1) ? 0 : n_mma;
-      // Phase 1 (drain): this warp's chunks go TMEM -> registers -> FP64; the accumulators are then
-      // handed back, so the MMA warp starts the next tile while phase 2 (the functor: phase
-      // continuation, slicing, global stores) runs from registers.
+      // Phase 1 (drain): this warp's chunks go TMEM -> registers -> FP64 (exact integers, one rounding); the
+      // accumulators are then handed back, so the MMA warp starts the next tile while phase 2 (the functor:
+      // phase continuation, slicing, global stores) runs from registers.
       double v[CH_PER_WARP][8];
-#pragma unroll
-      for (int ci = 0; ci < CH_PER_WARP; ++ci) {
-        const int c0 = chunk0 + ci * chunk_step;
-        if (c0 < n_lim) {
-          int32_t a[MAX_SLICES][8];
-#pragma unroll
-          for (int d = 0; d < MAX_SLICES; ++d)
-            if (d < T) tmem_ld8(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(d * NT + c0), a[d]);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            long long hi = 0, lo = 0;
-#pragma unroll
-            for (int d = 0; d < 3; ++d)
-              if (d < T) hi = hi * 256 + a[d][q];
-#pragma unroll
-            for (int d = 3; d < MAX_SLICES; ++d)
-              if (d < T) lo = lo * 256 + a[d][q];
-            const int n = n0 + c0 + q;
-            const double sb = (n < g.N) ? g.sB[n] : 0.0;
-            v[ci][q] = fma((double)lo, w_lo, (double)hi * w_hi) * (sa * sb);
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar);
-      if constexpr (epi_staged<Epi>::value) {
-        static_assert(EPI_WARPS == 16 && NT == 64, "staged epilogue: four warps per lane group, 64-column tiles");
-        uint8_t* stg = epi_stage_area + (size_t)lg * (T * 32 * STG_ROW);
+      auto drain = [&]() {
 #pragma unroll
         for (int ci = 0; ci < CH_PER_WARP; ++ci) {
           const int c0 = chunk0 + ci * chunk_step;
-          if (c0 < n_lim) epi.stage(stg, lane, c0, m, n0 + c0, v[ci], g.M, g.N);
-        }
-        named_bar_sync(1 + lg, 128);
-        if (n_lim > 0) epi.flush(stg, ((warp - 2) >> 2) * 32 + lane, m0 + lg * 32, n0, n_lim, g.M);
-        named_bar_sync(1 + lg, 128);      // the tile is free again for the next one
-      } else
+          if (c0 < n_lim) {
+            int32_t a[MAX_SLICES][8];
 #pragma unroll
-      for (int ci = 0; ci < CH_PER_WARP; ++ci) {
-        const int c0 = chunk0 + ci * chunk_step;
-        if constexpr (epi_all_lanes<Epi>::value) {
-          // functors that exchange data between lanes are entered by the whole warp (c0 and n_lim are warp-uniform)
-          if (c0 < n_lim) epi(m, n0 + c0, v[ci], g.M, g.N);
+            for (int d = 0; d < MAX_SLICES; ++d)
+              if (d < T) tmem_ld8(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(d * NT + c0), a[d]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[ci][q] = combine_diagonals<T>(a, q);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar);
+      };
+      if constexpr (epi_raw<Epi>::value) {
+        auto ts = epi.begin_tile(m < g.M ? m : g.M - 1, n0 + chunk0, g.M, g.N);
+        mbar_wait(&tmem_full_bar, acc_phase);
+        tc_fence_after();
+        drain();
+        if (g.dbg & 4) { acc_phase ^= 1; continue; }
+        if constexpr (epi_tma_stage<Epi>::value != 0) {
+          static_assert(epi_tma_stage<Epi>::value == T * NT * TILE_M, "staging tile: [T][NT][128] bytes");
+          const bool issuer = (warp == 2 && lane == 0);
+          if (issuer) bulk_wait_read0();                  // the previous tile's store has read the staging tile
+          named_bar_sync(1, 32 * EPI_WARPS);
+          uint8_t* stg = epi_stage_area + lg * 32 + lane;
+#pragma unroll
+          for (int ci = 0; ci < CH_PER_WARP; ++ci) {
+            const int c0 = chunk0 + ci * chunk_step;
+            if (c0 < n_lim) epi.apply_staged(ts, stg + c0 * TILE_M, m, n0 + c0, v[ci], g.M, g.N);   // m >= M: zeros
+          }
+          fence_proxy_async();
+          named_bar_sync(1, 32 * EPI_WARPS);
+          if (issuer && n_lim > 0) { tma_store_3d(&tmC, epi_stage_area, m0, n0, 0); bulk_commit(); }
         } else {
-          if (c0 < n_lim && m < g.M) epi(m, n0 + c0, v[ci], g.M, g.N);
+#pragma unroll
+          for (int ci = 0; ci < CH_PER_WARP; ++ci) {
+            const int c0 = chunk0 + ci * chunk_step;
+            if (c0 < n_lim && m < g.M) epi.apply(ts, m, n0 + c0, v[ci], g.M, g.N);
+          }
+        }
+      } else {
+        mbar_wait(&tmem_full_bar, acc_phase);
+        tc_fence_after();
+        const double sa = (m < g.M) ? g.sA[m] * diagonal_weight<T>() : 0.0;
+        drain();
+#pragma unroll
+        for (int ci = 0; ci < CH_PER_WARP; ++ci) {
+          const int c0 = chunk0 + ci * chunk_step;
+          if (c0 < n_lim) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int n = n0 + c0 + q;
+              v[ci][q] *= sa * ((n < g.N) ? g.sB[n] : 0.0);
+            }
+          }
+        }
+        if constexpr (epi_staged<Epi>::value) {
+          static_assert(EPI_WARPS == 16 && NT == 64, "staged epilogue: four warps per lane group, 64-column tiles");
+          uint8_t* stg = epi_stage_area + (size_t)lg * (T * 32 * STG_ROW);
+#pragma unroll
+          for (int ci = 0; ci < CH_PER_WARP; ++ci) {
+            const int c0 = chunk0 + ci * chunk_step;
+            if (c0 < n_lim) epi.stage(stg, lane, c0, m, n0 + c0, v[ci], g.M, g.N);
+          }
+          named_bar_sync(1 + lg, 128);
+          if (n_lim > 0) epi.flush(stg, ((warp - 2) >> 2) * 32 + lane, m0 + lg * 32, n0, n_lim, g.M);
+          named_bar_sync(1 + lg, 128);      // the tile is free again for the next one
+        } else {
+#pragma unroll
+          for (int ci = 0; ci < CH_PER_WARP; ++ci) {
+            const int c0 = chunk0 + ci * chunk_step;
+            if constexpr (epi_all_lanes<Epi>::value) {
+              // functors that exchange data between lanes are entered by the whole warp (c0 and n_lim are warp-uniform)
+              if (c0 < n_lim) epi(m, n0 + c0, v[ci], g.M, g.N);
+            } else {
+              if (c0 < n_lim && m < g.M) epi(m, n0 + c0, v[ci], g.M, g.N);
+            }
+          }
         }
       }
       acc_phase ^= 1;
     }
+    if (epi_tma_stage<Epi>::value != 0 && warp == 2 && lane == 0) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -486,6 +592,20 @@ inline bool make_operand_map(CUtensorMap* tm, const int8_t* ptr, int rows, int K
   return r == CUDA_SUCCESS;
 }
 
+// int8 output [T][rows][Kpad] written by TMA from a staging tile [T][box_rows][128]: the tensor's inner extent is the
+// number of valid columns, so the padding columns (and the rows past the end) are never written.
+inline bool make_output_map(CUtensorMap* tm, int8_t* ptr, int rows, int cols_valid, int Kpad, int T, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)cols_valid, (cuuint64_t)rows, (cuuint64_t)T};
+  cuuint64_t strides[2] = {(cuuint64_t)Kpad, (cuuint64_t)Kpad * (cuuint64_t)rows};
+  cuuint32_t box[3] = {(cuuint32_t)TILE_M, (cuuint32_t)box_rows, (cuuint32_t)T};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 // int32 accumulators: a diagonal holds at most T pairs of products bounded by 2^14 each
 inline bool contraction_fits(int Kpad, int T) { return (long long)T * 16384LL * Kpad < (1LL << 31); }
 
@@ -494,14 +614,16 @@ inline size_t gemm_smem_bytes(int T) { return (size_t)Cfg::ST * T * (A_SLICE_BYT
 
 template <int T, class Epi, class Cfg = TileDefault>
 cudaError_t launch_ozaki_gemm_t(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs g,
-                                Epi epi, int num_sms) {
+                                Epi epi, int num_sms, const CUtensorMap* tmC = nullptr) {
   static_assert(T * Cfg::NT <= 512 && Cfg::NT % 16 == 0, "TMEM holds 512 columns; UMMA N is a multiple of 16");
-  const size_t smem = gemm_smem_bytes<Cfg>(T) + (epi_staged<Epi>::value ? (size_t)4 * T * 32 * STG_ROW : 0);
+  const size_t smem = gemm_smem_bytes<Cfg>(T) + (epi_staged<Epi>::value ? (size_t)4 * T * 32 * STG_ROW : 0) +
+                      (size_t)epi_tma_stage<Epi>::value;
+  if (epi_tma_stage<Epi>::value != 0 && !tmC) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(ozaki_gemm_kernel<T, Epi, Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   g.tile_n = Cfg::NT;
   const int tiles = ((g.M + TILE_M - 1) / TILE_M) * ((g.N + Cfg::NT - 1) / Cfg::NT);
-  ozaki_gemm_kernel<T, Epi, Cfg><<<tiles < num_sms ? tiles : num_sms, THREADS, smem, st>>>(tmA, tmB, g, epi);
+  ozaki_gemm_kernel<T, Epi, Cfg><<<tiles < num_sms ? tiles : num_sms, THREADS, smem, st>>>(tmA, tmB, tmC ? *tmC : tmA, g, epi);
   return cudaGetLastError();
 }
 

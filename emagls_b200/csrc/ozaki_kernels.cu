@@ -4,6 +4,7 @@
 //             which also slices t into the int8 digits the backward product consumes;
 //   backward: t^T Y_h (or t^T Q)  (4P x S, contraction over the D directions), FP64 out.
 #include <cstdlib>
+#include <string>
 #include "kernels.h"
 #include "ozaki.cuh"
 
@@ -49,6 +50,108 @@ struct EpiPhaseSlice {
       if (m == 0) { const double s_ = sc[si]; sT[n] = s_; sT[n + 1] = s_; }
       if (ear == 1 && --left == 0) { ++set; left = orient_per_set; }   // next pair belongs to the next problem
     }
+  }
+};
+
+// The same epilogue on the unscaled integer results (oz::epi_raw): y / |y| does not depend on a common scale, so
+// the row scale of Y_h and the weight of the digit planes are not applied (only the scales of the re and the im
+// row of c, which differ); |H_k|, its power-of-two scale and the 256^(T-4) of the digit split are one factor per
+// (set, ear, direction), fetched before the accumulators are waited for; the digits come out of the FP64 / integer
+// pipes (oz::slice_words) instead of F2I / I2F.  Bitwise the same digits as EpiPhaseSlice (every factor that moved
+// is a power of two).
+template <int T>
+struct EpiPhaseSliceRaw {
+  static constexpr bool raw = true;
+  int8_t* Tq; long long slice_stride; int Kpad;   // [T][rows][Kpad], element (n, m) at n * Kpad + m
+  double* sT;                                     // [rows] scale of row n (written by the m == 0 lanes)
+  const double* absH; long long abs_set_stride, abs_ear_stride;   // this bin: [set][ear][dir]
+  const double* up; const double* sc; int scale_stride;           // 2^(6-e), 2^(e-6) at [(set*2+ear)*scale_stride]
+  int orient_per_set; int nyquist;
+  const double* sB;                               // [rows] scales of the rows of c (the B operand)
+  struct TileState { double mu[2]; int set; };
+  __device__ __forceinline__ void load_set(TileState& ts, int set, int m) const {
+    constexpr double split = (double)(1 << (8 * (T - 4)));
+    ts.set = set;
+#pragma unroll
+    for (int ear = 0; ear < 2; ++ear)
+      ts.mu[ear] = absH[(long long)set * abs_set_stride + (long long)ear * abs_ear_stride + m] *
+                   (up[(set * 2 + ear) * scale_stride] * split);
+  }
+  __device__ __forceinline__ TileState begin_tile(int m, int n, int M, int N) const {
+    TileState ts;
+    load_set(ts, (min(n, N - 1) >> 2) / orient_per_set, m);   // a chunk past the last column is never applied
+    return ts;
+  }
+  // columns n0..n0+7 are the (re, im) pairs of four consecutive (problem, ear) indices j = n / 2 (n0 is a multiple
+  // of 8, so the ear is (q >> 1) & 1); the HRTF set of a problem is found with one division per call and then
+  // tracked incrementally.  store(q, zl, zh) receives the digit words of column n0 + q.
+  template <class Store>
+  __device__ __forceinline__ void phase_slice(TileState& ts, int m, int n0, const double (&v)[8], int N, Store&& store) const {
+    const int prob = n0 >> 2;
+    int set = prob / orient_per_set;
+    int left = (set + 1) * orient_per_set - prob;     // problems left in this set, >= 1
+    if (m == 0) {                                     // scale of the output rows (one writer per row)
+      int s2 = set, l2 = left;
+      for (int q = 0; q < 8 && n0 + q < N; q += 2) {
+        const int e = (q >> 1) & 1;
+        const double s_ = sc[(s2 * 2 + e) * scale_stride];
+        sT[n0 + q] = s_; sT[n0 + q + 1] = s_;
+        if (e == 1 && --l2 == 0) { ++s2; l2 = orient_per_set; }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q += 2) {
+      if (n0 + q >= N) break;
+      const int e = (q >> 1) & 1;
+      if (set != ts.set) load_set(ts, set, m);        // warp-uniform: a tile rarely straddles two HRTF sets
+      const double mu = ts.mu[e];
+      const double2 sb = *reinterpret_cast<const double2*>(sB + n0 + q);   // warp-uniform, 16-byte aligned
+      const double re = v[q] * sb.x, im = v[q + 1] * sb.y;
+      const double a2 = fma(re, re, im * im);         // zero only if y == 0
+      double tr = mu, ti = 0.0;                       // angle(0) = 0
+      if (a2 > 0.0) {
+        const double inv = mu * rsqrt(a2);
+        tr = re * inv; ti = im * inv;
+      }
+      if (nyquist) ti = 0.0;
+      uint32_t zl, zh;                                // |tr|, |ti| <= 64 * 256^(T-4)
+      oz::slice_words<T>(tr, zl, zh);
+      store(q, zl, zh);
+      oz::slice_words<T>(ti, zl, zh);
+      store(q + 1, zl, zh);
+      if (e == 1 && --left == 0) { ++set; left = orient_per_set; }   // next pair belongs to the next problem
+    }
+  }
+  template <class P>
+  static __device__ __forceinline__ void put_digits(P* p, long long plane, uint32_t zl, uint32_t zh) {
+    p[(T - 1) * plane] = (P)zl;
+    p[(T - 2) * plane] = (P)(zl >> 8);
+    p[(T - 3) * plane] = (P)(zl >> 16);
+    p[(T - 4) * plane] = (P)zh;
+    if (T >= 5) p[(T - 5) * plane] = (P)(zh >> 8);
+    if (T >= 6) p[(T - 6) * plane] = (P)(zh >> 16);
+  }
+  __device__ __forceinline__ void apply(TileState& ts, int m, int n0, const double (&v)[8], int M, int N) const {
+    int8_t* p = Tq + (long long)n0 * Kpad + m;
+    phase_slice(ts, m, n0, v, N, [&](int q, uint32_t zl, uint32_t zh) { put_digits(p + (long long)q * Kpad, slice_stride, zl, zh); });
+  }
+};
+// ... with the digits staged in shared memory and stored by TMA (oz::epi_tma_stage): the byte stores go to
+// compile-time offsets of one shared-memory address, and the tile leaves as 128-byte rows.
+template <int T>
+struct EpiPhaseSliceTma : EpiPhaseSliceRaw<T> {
+  static constexpr int tma_stage_bytes = T * oz::TILE_N * oz::TILE_M;
+  // stg: the staging byte of (this thread's row, first column of the chunk) in plane 0
+  __device__ __forceinline__ void apply_staged(typename EpiPhaseSliceRaw<T>::TileState& ts, uint8_t* stg, int m, int n0,
+                                               const double (&v)[8], int M, int N) const {
+    if (m >= M) {   // rows past the tensor's extent: the store may reach up to three of them (padding columns, zero)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) EpiPhaseSliceRaw<T>::put_digits(stg + q * oz::TILE_M, (long long)(oz::TILE_N * oz::TILE_M), 0u, 0u);
+      return;
+    }
+    this->phase_slice(ts, m, n0, v, N, [&](int q, uint32_t zl, uint32_t zh) {
+      EpiPhaseSliceRaw<T>::put_digits(stg + q * oz::TILE_M, (long long)(oz::TILE_N * oz::TILE_M), zl, zh);
+    });
   }
 };
 
@@ -171,16 +274,21 @@ static cudaError_t oz_fwd_rows_t(cudaStream_t st, const OzFwdArgs& a) {
   return oz::launch_ozaki_gemm_t<T, EpiPhaseSliceRows<T>, oz::TileCfg<64, 2>>(st, tmA, tmB, g, epi, sm_count());
 }
 
-template <int T>
+int oz_fwd_debug = 0;   // GemmArgs::dbg of the forward launches (tools/microbench/oz_fwd_bench.cu)
+
+template <int T, class Epi, class Cfg = oz::TileDefault>
 static cudaError_t oz_fwd_t(cudaStream_t st, const OzFwdArgs& a) {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;
   if (!oz::make_operand_map(&tmA, a.YhA_q, a.D, a.KpS, T, oz::TILE_M) ||
       !oz::make_operand_map(&tmB, a.Cv_q, a.rows, a.KpS, T, oz::TILE_N))
     return cudaErrorInvalidValue;
-  oz::GemmArgs g{a.D, a.rows, a.KpS, a.sYhA, a.sCv, 0, 0, oz::TILE_N};   // m fastest: the 42 MB of Cv digits are the shared operand
-  EpiPhaseSlice<T> epi{a.Tt_q, (long long)a.rows * a.KpD, a.KpD, a.sT, a.absH, a.abs_set_stride, a.abs_ear_stride,
-                       a.up, a.sc, a.scale_stride, a.orient_per_set, a.nyquist};
-  return oz::launch_ozaki_gemm_t<T>(st, tmA, tmB, g, epi, sm_count());
+  const bool tma_out = oz::epi_tma_stage<Epi>::value != 0;
+  if (tma_out && !oz::make_output_map(&tmC, a.Tt_q, a.rows, a.D, a.KpD, T, oz::TILE_N)) return cudaErrorInvalidValue;
+  oz::GemmArgs g{a.D, a.rows, a.KpS, a.sYhA, a.sCv, oz_fwd_debug, 0, oz::TILE_N};   // m fastest: the 42 MB of Cv digits are the shared operand
+  Epi epi{a.Tt_q, (long long)a.rows * a.KpD, a.KpD, a.sT, a.absH, a.abs_set_stride, a.abs_ear_stride,
+          a.up, a.sc, a.scale_stride, a.orient_per_set, a.nyquist};
+  if constexpr (oz::epi_raw<Epi>::value) epi.sB = a.sCv;
+  return oz::launch_ozaki_gemm_t<T, Epi, Cfg>(st, tmA, tmB, g, epi, sm_count(), tma_out ? &tmC : nullptr);
 }
 
 cudaError_t launch_oz_fwd(cudaStream_t st, const OzFwdArgs& a) {
@@ -197,9 +305,22 @@ cudaError_t launch_oz_fwd(cudaStream_t st, const OzFwdArgs& a) {
       default: return cudaErrorInvalidValue;
     }
   }
-  switch (a.T) {
-    case 4: return oz_fwd_t<4>(st, a);
-    case 6: return oz_fwd_t<6>(st, a);
+  // A/B switches: EMAGLS_OZ_FWD=scaled is the epilogue of round 1 on the scaled FP64 values (F2I / I2F slicing),
+  // =tma the integer epilogue with the digits staged in shared memory and stored by TMA (two-stage operand ring to
+  // make room; 0.44 against 0.425 ms per launch, profiles/r02_v16_fwd_microbench.txt); default: the integer epilogue
+  // with byte stores to global memory.  All three produce the same bytes.
+  static const int mode = [] {
+    const char* e = getenv("EMAGLS_OZ_FWD");
+    return !e ? 1 : (std::string(e) == "scaled" ? 2 : (std::string(e) == "tma" ? 0 : 1));
+  }();
+  using Ring2 = oz::TileCfg<oz::TILE_N, 2>;
+  switch (a.T * 4 + mode) {
+    case 4 * 4 + 0: return oz_fwd_t<4, EpiPhaseSliceTma<4>, Ring2>(st, a);
+    case 6 * 4 + 0: return oz_fwd_t<6, EpiPhaseSliceTma<6>, Ring2>(st, a);
+    case 4 * 4 + 1: return oz_fwd_t<4, EpiPhaseSliceRaw<4>>(st, a);
+    case 6 * 4 + 1: return oz_fwd_t<6, EpiPhaseSliceRaw<6>>(st, a);
+    case 4 * 4 + 2: return oz_fwd_t<4, EpiPhaseSlice<4>>(st, a);
+    case 6 * 4 + 2: return oz_fwd_t<6, EpiPhaseSlice<6>>(st, a);
     default: return cudaErrorInvalidValue;
   }
 }
