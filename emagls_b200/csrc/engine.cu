@@ -535,7 +535,7 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
   auto chain_bwd = [&](int slot, int slot_n, const double* rhs, long long set_stride, long long ear_stride, int shared,
                        int nsplit, long long split_stride, const ProbMap& pm, int kb, int pj) {
     return sep ? launch_chain_bwd_sep(st, bp, ops, slot, slot_n, rhs, set_stride, ear_stride, shared, nsplit, split_stride,
-                                      pm, Wsp, w_ear, K, kb, dc_fix, pj)
+                                      pm, Wsp, w_ear, K, kb, dc_fix, pj, bn + (size_t)kb * (simN + 1), simN, d_roword)
                : launch_chain_bwd(st, bp, ops, slot, slot_n, rhs, set_stride, ear_stride, shared, nsplit, split_stride, pm,
                                   Wsp, w_ear, K, kb, dc_fix, pj);
   };

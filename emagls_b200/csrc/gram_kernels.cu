@@ -386,7 +386,6 @@ cudaError_t launch_fwd_small(cudaStream_t st, const double* Y, int Mc, int S, co
 struct FwdFuse {
   const cplx* bk_next;     // b_n(k+1) [N+1]; nullptr: no fused tail
   int8_t* Cv_q; double* sCv; int KpS; long long rows;   // digits [T][rows][KpS], rows = 4 * num_prob
-  int stage_y, stage_row0;                              // rows stage_row0 .. Mc-1 of Y_o staged in shared memory
 };
 
 template <int T>
@@ -400,21 +399,10 @@ bwd_small_kernel(const double* __restrict__ Y, int Mc, int S, const int* __restr
   cplx* zb = reinterpret_cast<cplx*>(bsm_raw);   // [2][S]
   cplx* v = zb + 2 * (size_t)S;                  // [2][Mc]
   cplx* wk = v + 2 * Mc;                         // [2][Mc]: W_k for the fused tail
-  double* Ys = reinterpret_cast<double*>(wk + 2 * Mc);   // [Mc][S]: this orientation's Y_o (ff.stage_y)
   const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const int ol = j % pm.oc;
   const long long p = pm.global(j);
   const double* Yg = Y + (long long)ol * Mc * S;
-  const int ys0 = ff.stage_y ? ff.stage_row0 : Mc;   // rows ys0 .. Mc-1 of Y_o are staged in shared memory
-  if (ff.stage_y) {
-    // Y_o (Mc x S doubles, 102 KB for em32) is read twice below; fetch it once, asynchronously, while the
-    // right-hand sides are prepared (cp.async, 16-byte chunks).  Two CTAs must fit an SM, so the first
-    // stage_row0 rows stay in global memory / L2.
-    const double* src = Yg + (long long)ys0 * S;
-    const int n16 = ((Mc - ys0) * S) >> 1;
-    for (int c = tid; c < n16; c += blockDim.x) cp_async16(Ys + 2 * c, src + 2 * c, true);
-    cp_async_commit();
-  }
   const double* z0 = z_shared ? z + (long long)(j / pm.oc) * z_set_stride : z + ((long long)(j * 2) * 2) * S;
   const double* z1 = z0 + (z_shared ? z_ear_stride : 2LL * S);
   for (int s = tid; s < S; s += blockDim.x) {
@@ -428,10 +416,9 @@ bwd_small_kernel(const double* __restrict__ Y, int Mc, int S, const int* __restr
     zb[s] = mk(fma(b.x, r0, b.y * i0), fma(b.x, i0, -b.y * r0));
     zb[S + s] = mk(fma(b.x, r1, b.y * i1), fma(b.x, i1, -b.y * r1));
   }
-  if (ff.stage_y) cp_async_wait<0>();
   __syncthreads();
   for (int i = warp; i < Mc; i += nw) {
-    const double* y = (i >= ys0) ? Ys + (long long)(i - ys0) * S : Yg + (long long)i * S;
+    const double* y = Yg + (long long)i * S;
     double a0r = 0.0, a0i = 0.0, a1r = 0.0, a1i = 0.0;
 #pragma unroll 4
     for (int s = lane; s < S; s += 32) {
@@ -469,7 +456,7 @@ bwd_small_kernel(const double* __restrict__ Y, int Mc, int S, const int* __restr
       double a0r = 0.0, a0i = 0.0, a1r = 0.0, a1i = 0.0;
 #pragma unroll 8
       for (int m = 0; m < Mc; ++m) {
-        const double y = (m >= ys0) ? Ys[(long long)(m - ys0) * S + s2] : Yg[(long long)m * S + s2];
+        const double y = Yg[(long long)m * S + s2];
         a0r = fma(y, wk[m].x, a0r); a0i = fma(y, wk[m].y, a0i);
         a1r = fma(y, wk[Mc + m].x, a1r); a1i = fma(y, wk[Mc + m].y, a1i);
       }
@@ -527,16 +514,11 @@ cudaError_t launch_bwd_small(cudaStream_t st, const double* Y, int Mc, int S, co
                              long long z_set_stride, long long z_ear_stride, int z_shared, int nsplit,
                              long long split_stride, cplx* Wsp, long long w_ear_stride, int K, int k, int dc_fix,
                              const cplx* bk_next, int8_t* Cv_q, double* sCv, int KpS, int T) {
-  size_t smem = ((size_t)2 * S + 4 * Mc) * sizeof(cplx);
-  // stage Y_o in shared memory when two CTAs still fit an SM (EMAGLS_BWD_NO_STAGE=1: A/B switch)
-  static const bool no_stage = getenv("EMAGLS_BWD_NO_STAGE") != nullptr;
-  // as many rows of Y_o as leave room for two CTAs per SM (2 x 112 KB); the rows must start 16-byte aligned
-  const size_t budget = 112 * 1024;
-  int row0 = 0;
-  while (row0 < Mc && (smem + (size_t)(Mc - row0) * S * sizeof(double) > budget || ((row0 * S) & 1))) ++row0;
-  const int stage_y = (!no_stage && row0 < Mc && (((Mc - row0) * S) & 1) == 0 && Mc - row0 >= Mc / 2) ? 1 : 0;
-  if (stage_y) smem += (size_t)(Mc - row0) * S * sizeof(double);
-  FwdFuse ff{bk_next, Cv_q, sCv, KpS, 4LL * num_prob, stage_y, row0};
+  // Y_o (102 KB per problem for em32) is read twice from global memory / L2.  Staging part of it in shared memory
+  // was measured and removed: with two CTAs per SM only some rows fit, and the per-row choice between the two
+  // address spaces turns the inner loads into generic ones (chain_bwd 138 -> 167 ms per step, profiles/README r02).
+  const size_t smem = ((size_t)2 * S + 4 * Mc) * sizeof(cplx);
+  FwdFuse ff{bk_next, Cv_q, sCv, KpS, 4LL * num_prob};
   const int Tf = bk_next ? T : 0;
 #define EM_BWD_ARGS st, smem, num_prob, Y, Mc, S, roword, bk, Pb, pm, z, z_set_stride, z_ear_stride, z_shared, nsplit, \
                     split_stride, Wsp, w_ear_stride, K, k, dc_fix, ff

@@ -98,7 +98,7 @@ cudaError_t launch_svdclip(cudaStream_t st, int Mc, const cplx* Rin, const Opera
 cudaError_t launch_chain_bwd_sep(cudaStream_t st, const BlockPlan& bp, const OperatorSet& ops, int slot, int G,
                                  const double* tq, long long tq_set_stride, long long tq_ear_stride, int tq_shared,
                                  int nsplit, long long split_stride, ProbMap pm, cplx* Wsp, long long w_ear_stride,
-                                 int K, int k, int dc_fix, int num_prob);
+                                 int K, int k, int dc_fix, int num_prob, const cplx* bn_k, int N, const int* roword);
 // generic-path phase step on rows: t = absH * y/|y|
 cudaError_t launch_phase_rows(cudaStream_t st, const double* Y, double* T, int num_prob, int D,
                               const double* absH, long long abs_set_stride, long long abs_ear_stride,

@@ -43,9 +43,30 @@ namespace {
 constexpr int TQ_WARPS = 4;
 constexpr int TQ_TRI = 528;            // packed upper triangle of a 32 x 32 matrix
 constexpr int TQ_BN = 72;              // modal coefficients of one bin (orders 0..MAX_SH_ORDER)
-constexpr int TQ_WARP_CPLX = TQ_TRI + 32 + TQ_BN;
+constexpr int TQ_XBUF = 40;             // pivot column; the folded steps keep its two halves 17 entries apart
+constexpr int TQ_WARP_CPLX = TQ_TRI + TQ_XBUF + TQ_BN;
 
 __device__ __forceinline__ int tri_idx(int j, int c) { return j * 32 - ((j * (j - 1)) >> 1) + (c - j); }
+
+// Rows of C_k = R diag(b_k) Y_o^T that belong to order n carry the factor sum_{n' >= n} |b_n'| (R is upper
+// triangular).  At low frequencies the modal coefficients of the high orders fall below 2^-60 of the largest one
+// (b_n ~ (kr)^n / (2n + 1)!!), i.e. far below the rounding of the rows that matter, so the 32-row blocks made of
+// such rows are left out of the factorisation and of the reflector chain (bin 1 of the em32 configuration: 2 of
+// 13 blocks; from bin 55 on all of them).  The count depends on the bin only, so both kernels recompute it.
+__device__ __forceinline__ int significant_blocks(const cplx* bn, int N, const int* __restrict__ roword, int S, int nblk) {
+  double mx = 0.0;
+  for (int n = 0; n <= N; ++n) mx = fmax(mx, cabs2(bn[n]));
+  const double thr = sqrt(mx) * 8.673617379884035e-19;   // 2^-60
+  int ncut = N + 1;
+  double tail = 0.0;
+  for (int n = N; n >= 0; --n) {
+    tail += sqrt(cabs2(bn[n]));
+    if (tail < thr) ncut = n; else break;
+  }
+  int nb = 0;
+  while (nb < nblk && roword[min(nb * 32, S - 1)] < ncut) ++nb;   // orders are non-decreasing along the rows
+  return max(nb, 1);
+}
 
 // LAPACK zlarfg conventions, as reflector_scalars() of solver_kernels.cu: beta real, H = I - tau v v^H,
 // v = [1; sc * x].
@@ -119,7 +140,7 @@ tsqr_sep_kernel(BlockPlan bp, RowSource src, OperatorSet ops, cplx* __restrict__
   double* tiles = reinterpret_cast<double*>(tq_raw + tab_bytes);
   cplx* Rt = reinterpret_cast<cplx*>(tiles + TQ_STAGES * TQ_TILE) + (size_t)warp * TQ_WARP_CPLX;
   cplx* xbuf = Rt + TQ_TRI;
-  cplx* bn_s = xbuf + 32;
+  cplx* bn_s = xbuf + TQ_XBUF;
   // CTA = one orientation x four consecutive bins of the launch; a warp without a bin only helps with the tiles
   const int prob = blockIdx.x / sgroups, slot = (blockIdx.x - prob * sgroups) * TQ_WARPS + warp;
   const bool active = slot < G;
@@ -128,7 +149,14 @@ tsqr_sep_kernel(BlockPlan bp, RowSource src, OperatorSet ops, cplx* __restrict__
   const int N = src.N;
   for (int n = lane; n <= N; n += 32) bn_s[n] = src.bn[(long long)k * (N + 1) + n];
   for (int i = lane; i < TQ_TRI; i += 32) Rt[i] = mk(0.0, 0.0);
+  __shared__ int nblk_s[TQ_WARPS];
+  __syncwarp();
+  const int my_nblk = significant_blocks(bn_s, N, src.roword, S, bp.nblk);   // warp-uniform
+  if (lane == 0) nblk_s[warp] = active ? my_nblk : 0;
   __syncthreads();
+  int cta_nblk = 0;
+#pragma unroll
+  for (int w = 0; w < TQ_WARPS; ++w) cta_nblk = max(cta_nblk, nblk_s[w]);
   const double* Eo = src.E + (long long)prob * src.Etot;
   const bool col_ok = lane < Mc;
   cplx* Vg = ops.V + oidx * ops.v_stride;
@@ -137,20 +165,26 @@ tsqr_sep_kernel(BlockPlan bp, RowSource src, OperatorSet ops, cplx* __restrict__
   // tile stream over (block, order): iterator of the next tile to issue
   int it_t = 0, it_n = rowinfo[0].x, q_issue = 0;
   auto issue_next = [&]() {
-    const bool any = it_t < bp.nblk;
+    const bool any = it_t < cta_nblk;
     tq_issue_tile(tiles + (q_issue % TQ_STAGES) * TQ_TILE, Eo, rowinfo, S, Mc, it_t, it_n, any);
     ++q_issue;
     if (any) {
       if (it_n < N) ++it_n;
-      else { ++it_t; it_n = (it_t < bp.nblk) ? rowinfo[it_t * 32].x : 0; }
+      else { ++it_t; it_n = (it_t < cta_nblk) ? rowinfo[it_t * 32].x : 0; }
     }
   };
   issue_next();
   issue_next();
   int q = 0;   // tiles consumed so far
+  // Mc == 32: after 16 steps the finished lanes take over the lower half of the rows of the remaining columns,
+  // so that steps 16..31 cost half (the lane = column mapping otherwise idles lane c from step c on)
+  const bool fold = (Mc == 32);
+  const int hoff = lane < 16 ? 17 : 0;        // this lane's half of the pivot column in xbuf (folded steps)
+  const int fcol = 16 + (lane & 15);          // ... and its column
 
-  for (int t = 0; t < bp.nblk; ++t) {
+  for (int t = 0; t < cta_nblk; ++t) {
     const int r0 = t * 32;
+    const bool mine = active && t < my_nblk;
     cplx b[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) b[i] = mk(0.0, 0.0);
@@ -160,7 +194,7 @@ tsqr_sep_kernel(BlockPlan bp, RowSource src, OperatorSet ops, cplx* __restrict__
       cp_async_wait<TQ_STAGES - 2>();   // tile q has landed (this thread's copies; the barrier covers the others)
       __syncthreads();                  // ... and every warp is done with the stage tile q + 2 goes into
       issue_next();
-      if (active && col_ok) {
+      if (mine && col_ok) {
         const double* tile = tiles + (q % TQ_STAGES) * TQ_TILE + lane;
         const cplx bnn = bn_s[n];
 #pragma unroll
@@ -171,10 +205,11 @@ tsqr_sep_kernel(BlockPlan bp, RowSource src, OperatorSet ops, cplx* __restrict__
         }
       }
     }
-    if (!active) continue;
-    // ---- 32 Householder steps on [R_C; block]
+    if (!mine) continue;
+    // ---- Householder steps on [R_C; block]: lane = column, all 32 rows
     cplx my_tau = mk(0.0, 0.0), my_sc = mk(0.0, 0.0);
-    for (int j = 0; j < Mc; ++j) {
+    const int jsplit = fold ? 16 : Mc;
+    for (int j = 0; j < jsplit; ++j) {
       if (lane == j) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) xbuf[i] = b[i];
@@ -207,13 +242,76 @@ tsqr_sep_kernel(BlockPlan bp, RowSource src, OperatorSet ops, cplx* __restrict__
       }
       __syncwarp();
     }
-    // ---- flush the reflector tails of this block (scaled) and its tau row
+    if (!fold) {
+      // ---- flush the reflector tails of this block (scaled) and its tau row
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int r = r0 + i;
-      if (r < S) Vg[(long long)r * 32 + lane] = cmul(b[i], my_sc);
+      for (int i = 0; i < 32; ++i) {
+        const int r = r0 + i;
+        if (r < S) Vg[(long long)r * 32 + lane] = cmul(b[i], my_sc);
+      }
+      taug[t * 32 + lane] = my_tau;
+      continue;
     }
-    taug[t * 32 + lane] = my_tau;
+    // ---- fold: columns 0..15 are finished; their lanes store the tails and take rows 16..31 of columns 16..31
+    if (lane < 16) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int r = r0 + i;
+        if (r < S) Vg[(long long)r * 32 + lane] = cmul(b[i], my_sc);
+      }
+      taug[t * 32 + lane] = my_tau;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const double ux = __shfl_down_sync(0xffffffffu, b[16 + i].x, 16);
+      const double uy = __shfl_down_sync(0xffffffffu, b[16 + i].y, 16);
+      if (lane < 16) b[i] = mk(ux, uy);
+    }
+    for (int j = 16; j < 32; ++j) {
+      if (fcol == j) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) xbuf[hoff + i] = b[i];
+      }
+      __syncwarp();
+      cplx w0 = mk(0.0, 0.0), w1 = mk(0.0, 0.0), w2 = mk(0.0, 0.0), w3 = mk(0.0, 0.0);
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        cfmac(w0, xbuf[hoff + i], b[i]);
+        cfmac(w1, xbuf[hoff + i + 1], b[i + 1]);
+        cfmac(w2, xbuf[hoff + i + 2], b[i + 2]);
+        cfmac(w3, xbuf[hoff + i + 3], b[i + 3]);
+      }
+      cplx w = cadd(cadd(w0, w1), cadd(w2, w3));
+      w.x += __shfl_xor_sync(0xffffffffu, w.x, 16);      // the two halves of a column (same sum on both lanes)
+      w.y += __shfl_xor_sync(0xffffffffu, w.y, 16);
+      const double xn = __shfl_sync(0xffffffffu, w.x, j);
+      const cplx alpha = Rt[tri_idx(j, j)];
+      const bool upd = fcol > j;
+      const int ti = tri_idx(j, upd ? fcol : j);
+      const cplx rjc = Rt[ti];                           // read by both lanes of a column before one of them writes
+      double beta; cplx tau, sc;
+      hh_scalars(alpha, xn, &beta, &tau, &sc);
+      __syncwarp();
+      if (fcol == j) { my_tau = tau; my_sc = sc; if (lane >= 16) Rt[ti] = mk(beta, 0.0); }
+      if (upd && (tau.x != 0.0 || tau.y != 0.0)) {
+        const cplx wc = cadd(cmulc(w, sc), rjc);
+        const cplx f = cmul(cconj(tau), wc);
+        const cplx fs = cmul(f, sc);
+        if (lane >= 16) Rt[ti] = csub(rjc, f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cfms(b[i], fs, xbuf[hoff + i]);
+      }
+      __syncwarp();
+    }
+    {
+      const int rh = r0 + (lane < 16 ? 16 : 0);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int r = rh + i;
+        if (r < S) Vg[(long long)r * 32 + fcol] = cmul(b[i], my_sc);
+      }
+      if (lane >= 16) taug[t * 32 + lane] = my_tau;
+    }
   }
   if (!active) return;
   // ---- R_C, full 32 x 32 row-major with zeros below the diagonal
@@ -526,10 +624,11 @@ __global__ void __launch_bounds__(CS_WARPS * 32, 3)
 chain_bwd_sep_kernel(BlockPlan bp, OperatorSet ops, int slot, int G, const double* __restrict__ tq,
                      long long tq_set_stride, long long tq_ear_stride, int tq_shared, int nsplit,
                      long long split_stride, ProbMap pm, cplx* __restrict__ Wsp, long long w_ear_stride, int K, int k,
-                     int dc_fix, int num_prob) {
+                     int dc_fix, int num_prob, const cplx* __restrict__ bn_k, int N, const int* __restrict__ roword) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j = blockIdx.x * CS_WARPS + warp;
   if (j >= num_prob) return;
+  const int nblk = significant_blocks(bn_k, N, roword, bp.S, bp.nblk);   // the blocks tsqr_sep_kernel factorised
   const long long p = pm.global(j);
   const int S = bp.S, Mc = bp.Mc;
   const long long oidx = (long long)(j % pm.oc) * G + slot;
@@ -544,14 +643,14 @@ chain_bwd_sep_kernel(BlockPlan bp, OperatorSet ops, int slot, int G, const doubl
   cplx xb0, xb1;
   load_half(V + (long long)lane * 32, lane < S, va);
   load_rhs(t0, t1, S, lane, nsplit, split_stride, xb0, xb1);
-  for (int t = 0; t < bp.nblk; ++t) {
+  for (int t = 0; t < nblk; ++t) {
     const int r = t * 32 + lane;
     load_half(V + (long long)r * 32 + 16, r < S, vb);
     const double2 tl = __ldg(reinterpret_cast<const double2*>(tau + t * 32 + lane));
     const cplx tau_l = mk(tl.x, tl.y);
     apply_half(va, 0, tau_l, xb0, xb1, xr0, xr1, lane);
     cplx nx0 = mk(0.0, 0.0), nx1 = mk(0.0, 0.0);
-    if (t + 1 < bp.nblk) {
+    if (t + 1 < nblk) {
       load_half(V + (long long)(r + 32) * 32, r + 32 < S, va);
       load_rhs(t0, t1, S, r + 32, nsplit, split_stride, nx0, nx1);
     }
@@ -618,11 +717,11 @@ cudaError_t launch_svdclip(cudaStream_t st, int Mc, const cplx* Rin, const Opera
 cudaError_t launch_chain_bwd_sep(cudaStream_t st, const BlockPlan& bp, const OperatorSet& ops, int slot, int G,
                                  const double* tq, long long tq_set_stride, long long tq_ear_stride, int tq_shared,
                                  int nsplit, long long split_stride, ProbMap pm, cplx* Wsp, long long w_ear_stride,
-                                 int K, int k, int dc_fix, int num_prob) {
+                                 int K, int k, int dc_fix, int num_prob, const cplx* bn_k, int N, const int* roword) {
   if (!bp.sep) return cudaErrorInvalidValue;
   chain_bwd_sep_kernel<<<(num_prob + CS_WARPS - 1) / CS_WARPS, CS_WARPS * 32, 0, st>>>(
       bp, ops, slot, G, tq, tq_set_stride, tq_ear_stride, tq_shared, nsplit, split_stride, pm, Wsp, w_ear_stride, K, k,
-      dc_fix, num_prob);
+      dc_fix, num_prob, bn_k, N, roword);
   return cudaGetLastError();
 }
 
