@@ -653,7 +653,7 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
           const size_t off = (size_t)(kb - 1) * 2 * S;
           if (gram)
             EM_CUDA(launch_bwd_small(st, Yc, Mc, S, d_roword, bk, pbg, pm, pj, Zls + off, (long long)2 * nLS * 2 * S,
-                                     (long long)nLS * 2 * S, 1, 1, 0, Wsp, w_ear, K, kb, dc_fix));
+                                     (long long)nLS * 2 * S, 1, 1, 0, Wsp, w_ear, K, kb, dc_fix, nullptr, nullptr, nullptr, 0, 0, simN));
           else
             EM_CUDA(chain_bwd(slot, slot_n, Tls + off, (long long)2 * nLS * 2 * S, (long long)nLS * 2 * S, 1, 1, 0, pm, kb, pj));
           h->launches += 1;
@@ -699,7 +699,7 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
               const bool fuse = use_oz && fuse_fwd && kb + 1 < K;
               EM_CUDA(launch_bwd_small(st, Yc, Mc, S, d_roword, bk, pbg, pm, pj, tq, 0, 0, 0, nsplit, split_stride, Wsp,
                                        w_ear, K, kb, dc_fix, fuse ? bn + (size_t)(kb + 1) * (simN + 1) : nullptr, Cv_q, sCv,
-                                       KpS, oz_T));
+                                       KpS, oz_T, simN));
               cv_ready = fuse;
             } else
               EM_CUDA(chain_bwd(slot, slot_n, tq, 0, 0, 0, nsplit, split_stride, pm, kb, pj));

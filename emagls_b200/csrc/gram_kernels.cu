@@ -492,6 +492,256 @@ bwd_small_kernel(const double* __restrict__ Y, int Mc, int S, const int* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// bwd_fused_kernel: the same step (and the same fused tail) for Mc <= 32, S <= 512, organised around ONE pass
+// over Y_o.  The matrix (102 KB for em32) arrives in shared memory by a single bulk copy (cp.async.bulk +
+// mbarrier) while the right-hand sides are prepared; two CTAs per SM, so one computes while the other loads.
+// Lane = harmonic s in both contractions (consecutive lanes read consecutive doubles of a row of Y_o: no bank
+// conflicts), the right-hand sides and the results of the tail stay in registers:
+//   v = Y_o zb      : per lane 8 rows x 4 components of partial sums over its harmonics, then a warp
+//                     reduce-scatter (31 shuffle-adds per 32 values: lane l ends with value l), warps summed through
+//                     shared memory
+//   W = v Pb        : thread = (m, eight rows i), partial sums through shared memory
+//   u = Y_o^T W     : W broadcast from shared memory, one accumulator set per harmonic of the lane
+// 10 k warp instructions per problem instead of 27 k, Y_o read from HBM / L2 once.
+// ---------------------------------------------------------------------------------------------
+constexpr int BF_WARPS = 8;      // v = Y_o zb: warp = (chunk set w & 3: chunks (w & 3) + 4 c, rows 16 (w >> 2) .. + 15)
+constexpr int BF_CH = 4;         // S <= 512;  tail: warp w owns the chunks w and w + 8
+
+template <int n>
+__device__ __forceinline__ void reduce_scatter_step(double (&v)[32], int lane, int off) {
+  const bool upper = (lane & off) != 0;
+#pragma unroll
+  for (int i = 0; i < n; ++i) {
+    const double keep = upper ? v[i + n] : v[i];
+    const double send = upper ? v[i] : v[i + n];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+  }
+}
+
+template <int T>
+__global__ void __launch_bounds__(BF_WARPS * 32, 2)
+bwd_fused_kernel(const double* __restrict__ Y, int Mc, int S, const int* __restrict__ roword,
+                 const cplx* __restrict__ bk, const cplx* __restrict__ Pb, ProbMap pm,
+                 const double* __restrict__ z, long long z_set_stride, long long z_ear_stride,
+                 int z_shared, int nsplit, long long split_stride, cplx* __restrict__ Wsp, long long w_ear_stride, int K, int k, int dc_fix,
+                 FwdFuse ff, int N) {
+  extern __shared__ __align__(128) unsigned char bf_raw[];
+  double* Ys = reinterpret_cast<double*>(bf_raw);                    // [Mc][S]
+  double* vpart = Ys + (((size_t)Mc * S + 1) & ~(size_t)1);          // [4 chunk sets][32 rows][4]: partial v, then
+  cplx* wpart = reinterpret_cast<cplx*>(vpart);                      // [BF_WARPS][2][32]: partial W (same 8 KB)
+  cplx* vfin = wpart + BF_WARPS * 64;                                // [2][32]
+  cplx* wfin = vfin + 64;                                            // [2][32]
+  cplx* bks = wfin + 64;                                             // [2][40]: b_n(k), b_n(k+1)
+  double* red = reinterpret_cast<double*>(bks + 80);                 // [4][BF_WARPS] row maxima, [4] scales
+  __shared__ __align__(8) uint64_t bar;
+  const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ol = j % pm.oc;
+  const long long p = pm.global(j);
+  const double* Yg = Y + (long long)ol * Mc * S;
+  if (tid == 0) { oz::mbar_init(&bar, 1); oz::fence_barrier_init(); }
+  if (tid <= N) { bks[tid] = bk[tid]; if (T > 0) bks[40 + tid] = ff.bk_next[tid]; }
+  // Pb rows of this thread (m = lane, rows 4 warp .. 4 warp + 3): issued first, consumed after the contraction
+  cplx pbr[4];
+  {
+    const cplx* pb = Pb + (long long)ol * Mc * Mc;
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+      const int i = 4 * warp + ii;
+      pbr[ii] = (i < Mc && lane < Mc) ? pb[i * Mc + lane] : mk(0.0, 0.0);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t bytes = (uint32_t)((size_t)Mc * S * sizeof(double));
+    oz::mbar_expect_tx(&bar, bytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(oz::smem_u32(Ys)), "l"(Yg), "r"(bytes), "r"(oz::smem_u32(&bar)) : "memory");
+  }
+  // ---- conj(b_k) .* z for this lane's harmonics (both ears), while Y_o is in flight
+  const double* z0 = z_shared ? z + (long long)(j / pm.oc) * z_set_stride : z + ((long long)(j * 2) * 2) * S;
+  const double* z1 = z0 + (z_shared ? z_ear_stride : 2LL * S);
+  const int cset = warp & 3, rhalf = warp >> 2;
+  double zq[BF_CH][4];
+  int sidx[BF_CH];
+#pragma unroll
+  for (int c = 0; c < BF_CH; ++c) {
+    const int s = (cset + 4 * c) * 32 + lane;
+    sidx[c] = min(s, S - 1);             // lanes past the end carry zero right-hand sides
+    zq[c][0] = zq[c][1] = zq[c][2] = zq[c][3] = 0.0;
+    if (s < S) {
+      const cplx b = bks[roword[s]];
+      double r0 = z0[s], i0 = z0[S + s], r1 = z1[s], i1 = z1[S + s];
+      for (int q = 1; q < nsplit; ++q) {   // split-K partials of the backward GEMM, fixed order
+        const long long o = (long long)q * split_stride;
+        r0 += z0[o + s]; i0 += z0[o + S + s]; r1 += z1[o + s]; i1 += z1[o + S + s];
+      }
+      zq[c][0] = fma(b.x, r0, b.y * i0); zq[c][1] = fma(b.x, i0, -b.y * r0);
+      zq[c][2] = fma(b.x, r1, b.y * i1); zq[c][3] = fma(b.x, i1, -b.y * r1);
+    }
+  }
+  oz::mbar_wait(&bar, 0);
+  // ---- v = Y_o zb: rows 16 rhalf + 8 g + r
+#pragma unroll 1
+  for (int g = 0; g < 2; ++g) {
+    double acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.0;
+    int rowoff[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) rowoff[r] = min(16 * rhalf + 8 * g + r, Mc - 1) * S;   // rows >= Mc: duplicates, never used
+#pragma unroll
+    for (int c = 0; c < BF_CH; ++c) {
+      if ((cset + 4 * c) * 32 < S) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const double y = Ys[rowoff[r] + sidx[c]];
+          acc[4 * r + 0] = fma(y, zq[c][0], acc[4 * r + 0]); acc[4 * r + 1] = fma(y, zq[c][1], acc[4 * r + 1]);
+          acc[4 * r + 2] = fma(y, zq[c][2], acc[4 * r + 2]); acc[4 * r + 3] = fma(y, zq[c][3], acc[4 * r + 3]);
+        }
+      }
+    }
+    reduce_scatter_step<16>(acc, lane, 16);
+    reduce_scatter_step<8>(acc, lane, 8);
+    reduce_scatter_step<4>(acc, lane, 4);
+    reduce_scatter_step<2>(acc, lane, 2);
+    reduce_scatter_step<1>(acc, lane, 1);
+    // value (row 16 rhalf + 8 g + lane / 4, component lane % 4) of chunk set cset
+    vpart[cset * 128 + (16 * rhalf + 8 * g) * 4 + lane] = acc[0];
+  }
+  __syncthreads();
+  if (tid < 128) {
+    const double sum = (vpart[tid] + vpart[128 + tid]) + (vpart[256 + tid] + vpart[384 + tid]);
+    const int i = tid >> 2, q = tid & 3;                 // q: ear * 2 + {re, im}
+    reinterpret_cast<double*>(vfin)[((q >> 1) * 32 + i) * 2 + (q & 1)] = sum;
+  }
+  __syncthreads();
+  // ---- W_k = v Pb: thread (m = lane, rows 4 warp .. 4 warp + 3)
+  {
+    cplx a0 = mk(0.0, 0.0), a1 = mk(0.0, 0.0);
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+      const int i = 4 * warp + ii;
+      cfma(a0, vfin[i], pbr[ii]);
+      cfma(a1, vfin[32 + i], pbr[ii]);
+    }
+    wpart[(warp * 2 + 0) * 32 + lane] = a0;
+    wpart[(warp * 2 + 1) * 32 + lane] = a1;
+  }
+  __syncthreads();
+  if (tid < 64) {
+    const int e = tid >> 5, m = tid & 31;
+    cplx acc = wpart[e * 32 + m];
+#pragma unroll
+    for (int w = 1; w < BF_WARPS; ++w) acc = cadd(acc, wpart[(w * 2 + e) * 32 + m]);
+    wfin[e * 32 + m] = acc;
+    if (m < Mc) {
+      cplx* wp = Wsp + (long long)e * w_ear_stride + (p * Mc + m) * K + k;
+      *wp = acc;
+      if (dc_fix && k == 1) wp[-1] = mk(acc.x, 0.0);  // W(1,:) = real(W(2,:)), lib/getEMagLs2Filters.m:109-110
+    }
+  }
+  if constexpr (T > 0) {
+    __syncthreads();
+    // ---- fused tail: u = b_{k+1} .* (Y_o^T W_k) for the harmonics of chunks warp and warp + 8, then the digits of u
+    constexpr int TC = 2;
+    double u[TC][4];
+    int ts[TC];
+#pragma unroll
+    for (int c = 0; c < TC; ++c) {
+      u[c][0] = u[c][1] = u[c][2] = u[c][3] = 0.0;
+      ts[c] = min((warp + BF_WARPS * c) * 32 + lane, S - 1);
+    }
+    const bool two = (warp + BF_WARPS) * 32 < S;          // warp-uniform: second chunk exists
+    if ((warp * 32) < S) {
+#pragma unroll 4
+      for (int m = 0; m < Mc; ++m) {
+        const cplx w0 = wfin[m], w1 = wfin[32 + m];
+        const int ro = m * S;
+        const double y0 = Ys[ro + ts[0]];
+        u[0][0] = fma(y0, w0.x, u[0][0]); u[0][1] = fma(y0, w0.y, u[0][1]);
+        u[0][2] = fma(y0, w1.x, u[0][2]); u[0][3] = fma(y0, w1.y, u[0][3]);
+        if (two) {
+          const double y1 = Ys[ro + ts[1]];
+          u[1][0] = fma(y1, w0.x, u[1][0]); u[1][1] = fma(y1, w0.y, u[1][1]);
+          u[1][2] = fma(y1, w1.x, u[1][2]); u[1][3] = fma(y1, w1.y, u[1][3]);
+        }
+      }
+    }
+    double mx[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int c = 0; c < TC; ++c) {
+      const int s = (warp + BF_WARPS * c) * 32 + lane;
+      if (s < S) {
+        const cplx b = bks[40 + roword[s]];
+        const double c0 = fma(b.x, u[c][0], -b.y * u[c][1]), c1 = fma(b.x, u[c][1], b.y * u[c][0]);
+        const double c2 = fma(b.x, u[c][2], -b.y * u[c][3]), c3 = fma(b.x, u[c][3], b.y * u[c][2]);
+        u[c][0] = c0; u[c][1] = c1; u[c][2] = c2; u[c][3] = c3;
+        mx[0] = fmax(mx[0], fabs(c0)); mx[1] = fmax(mx[1], fabs(c1));
+        mx[2] = fmax(mx[2], fabs(c2)); mx[3] = fmax(mx[3], fabs(c3));
+      } else {
+        u[c][0] = u[c][1] = u[c][2] = u[c][3] = 0.0;     // padding columns of the digit rows
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) mx[r] = fmax(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], sh));
+      if (lane == 0) red[r * BF_WARPS + warp] = mx[r];
+    }
+    __syncthreads();
+    if (tid < 4) {
+      double m4 = red[tid * BF_WARPS];
+#pragma unroll
+      for (int w = 1; w < BF_WARPS; ++w) m4 = fmax(m4, red[tid * BF_WARPS + w]);
+      int e = 0;
+      if (m4 > 0.0 && m4 < 1e300) frexp(m4, &e);           // slice_rows_kernel: 2^e > max |x|
+      ff.sCv[(long long)j * 4 + tid] = scalbn(1.0, e - 6);
+      red[4 * BF_WARPS + tid] = scalbn(1.0, 6 - e + 8 * (T - 4));   // with the 256^(T-4) of oz::slice_words
+    }
+    __syncthreads();
+    double up[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) up[r] = red[4 * BF_WARPS + r];
+    const long long plane = ff.rows * ff.KpS;
+#pragma unroll
+    for (int c = 0; c < TC; ++c) {
+      const int s = (warp + BF_WARPS * c) * 32 + lane;
+      if (s < ff.KpS) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          uint32_t zl, zh;
+          oz::slice_words<T>(u[c][r] * up[r], zl, zh);
+          int8_t* o = ff.Cv_q + ((long long)j * 4 + r) * ff.KpS + s;
+          o[(T - 1) * plane] = (int8_t)zl;
+          o[(T - 2) * plane] = (int8_t)(zl >> 8);
+          o[(T - 3) * plane] = (int8_t)(zl >> 16);
+          o[(T - 4) * plane] = (int8_t)zh;
+          if (T >= 5) o[(T - 5) * plane] = (int8_t)(zh >> 8);
+          if (T >= 6) o[(T - 6) * plane] = (int8_t)(zh >> 16);
+        }
+      }
+    }
+  }
+}
+
+template <int T>
+static cudaError_t launch_bwd_fused_t(cudaStream_t st, size_t smem, int num_prob, const double* Y, int Mc, int S,
+                                      const int* roword, const cplx* bk, const cplx* Pb, ProbMap pm, const double* z,
+                                      long long z_set_stride, long long z_ear_stride, int z_shared, int nsplit,
+                                      long long split_stride, cplx* Wsp, long long w_ear_stride, int K, int k, int dc_fix,
+                                      FwdFuse ff, int N) {
+  static size_t set_to = 0;
+  if (smem > set_to) {
+    cudaError_t e = cudaFuncSetAttribute(bwd_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    set_to = smem;
+  }
+  bwd_fused_kernel<T><<<num_prob, BF_WARPS * 32, smem, st>>>(Y, Mc, S, roword, bk, Pb, pm, z, z_set_stride, z_ear_stride,
+                                                              z_shared, nsplit, split_stride, Wsp, w_ear_stride, K, k, dc_fix, ff, N);
+  return cudaGetLastError();
+}
+
 template <int T>
 static cudaError_t launch_bwd_small_t(cudaStream_t st, size_t smem, int num_prob, const double* Y, int Mc, int S,
                                       const int* roword, const cplx* bk, const cplx* Pb, ProbMap pm, const double* z,
@@ -513,19 +763,30 @@ cudaError_t launch_bwd_small(cudaStream_t st, const double* Y, int Mc, int S, co
                              const cplx* bk, const cplx* Pb, ProbMap pm, int num_prob, const double* z,
                              long long z_set_stride, long long z_ear_stride, int z_shared, int nsplit,
                              long long split_stride, cplx* Wsp, long long w_ear_stride, int K, int k, int dc_fix,
-                             const cplx* bk_next, int8_t* Cv_q, double* sCv, int KpS, int T) {
-  // Y_o (102 KB per problem for em32) is read twice from global memory / L2.  Staging part of it in shared memory
-  // was measured and removed: with two CTAs per SM only some rows fit, and the per-row choice between the two
-  // address spaces turns the inner loads into generic ones (chain_bwd 138 -> 167 ms per step, profiles/README r02).
-  const size_t smem = ((size_t)2 * S + 4 * Mc) * sizeof(cplx);
+                             const cplx* bk_next, int8_t* Cv_q, double* sCv, int KpS, int T, int N) {
   FwdFuse ff{bk_next, Cv_q, sCv, KpS, 4LL * num_prob};
   const int Tf = bk_next ? T : 0;
-#define EM_BWD_ARGS st, smem, num_prob, Y, Mc, S, roword, bk, Pb, pm, z, z_set_stride, z_ear_stride, z_shared, nsplit, \
+#define EM_BWD_ARGS num_prob, Y, Mc, S, roword, bk, Pb, pm, z, z_set_stride, z_ear_stride, z_shared, nsplit, \
                     split_stride, Wsp, w_ear_stride, K, k, dc_fix, ff
+  // bwd_fused_kernel: Y_o staged once in shared memory (two CTAs per SM must fit; the bulk copy moves multiples of
+  // 16 bytes); EMAGLS_BWD_OLD=1 (A/B switch) and larger problems: bwd_small_kernel, which reads Y_o twice through L2.
+  static const bool old_kernel = getenv("EMAGLS_BWD_OLD") != nullptr;
+  const size_t fused_smem = (((size_t)Mc * S + 1) & ~(size_t)1) * sizeof(double) +
+                            (size_t)(BF_WARPS * 64 + 64 + 64 + 80) * sizeof(cplx) + (4 * BF_WARPS + 4) * sizeof(double);
+  if (!old_kernel && N >= 0 && N < 40 && Mc <= 32 && S <= 128 * BF_CH && ((Mc * S) & 1) == 0 &&
+      fused_smem <= 113 * 1024 && (!bk_next || KpS <= 64 * BF_WARPS)) {
+    switch (Tf) {
+      case 0: return launch_bwd_fused_t<0>(st, fused_smem, EM_BWD_ARGS, N);
+      case 4: return launch_bwd_fused_t<4>(st, fused_smem, EM_BWD_ARGS, N);
+      case 6: return launch_bwd_fused_t<6>(st, fused_smem, EM_BWD_ARGS, N);
+      default: return cudaErrorInvalidValue;
+    }
+  }
+  const size_t smem = ((size_t)2 * S + 4 * Mc) * sizeof(cplx);
   switch (Tf) {
-    case 0: return launch_bwd_small_t<0>(EM_BWD_ARGS);
-    case 4: return launch_bwd_small_t<4>(EM_BWD_ARGS);
-    case 6: return launch_bwd_small_t<6>(EM_BWD_ARGS);
+    case 0: return launch_bwd_small_t<0>(st, smem, EM_BWD_ARGS);
+    case 4: return launch_bwd_small_t<4>(st, smem, EM_BWD_ARGS);
+    case 6: return launch_bwd_small_t<6>(st, smem, EM_BWD_ARGS);
     default: return cudaErrorInvalidValue;
   }
 #undef EM_BWD_ARGS

@@ -135,7 +135,7 @@ cudaError_t launch_bwd_small(cudaStream_t st, const double* Y, int Mc, int S, co
                              long long split_stride, cplx* Wsp, long long w_ear_stride, int K, int k, int dc_fix,
                              // fused forward of the next bin + slicing (bk_next != nullptr): see gram_kernels.cu
                              const cplx* bk_next = nullptr, int8_t* Cv_q = nullptr, double* sCv = nullptr,
-                             int KpS = 0, int T = 0);
+                             int KpS = 0, int T = 0, int N = -1);
 
 // ---------------------------------------------------------------- ozaki_kernels.cu
 // FP64-accurate GEMMs on the int8 tensor cores (tcgen05 + TMEM + TMA); see ozaki.cuh.
