@@ -23,7 +23,7 @@ from ._lib import Config, EmaglsError, Handle, RadialParams, default_handle  # n
 
 __all__ = ["getEMagLs2Filters", "getEMagLsFilters", "getMagLsFilters", "getLsFilters",
            "getEMagLsFiltersFromAtf", "getEMagLsFiltersEMAinCH", "getEMagLsFiltersEMAinSH",
-           "getSMAIRMatrix", "binauralDecode", "getSH", "sphModalCoeffs", "regularizedApply",
+           "getSMAIRMatrix", "binauralDecode", "getSH", "sphModalCoeffs", "regularizedApply", "grpdelay",
            "getRadialFilter", "applyRadialFilter", "encodeSH", "encodeCH", "rotateSH", "getMagLsFilters2D",
            "getMagLsSphericalHeadFilter", "getMagLsArrayDiffuseFilter", "Handle", "EmaglsError"]
 
@@ -598,6 +598,25 @@ def sphModalCoeffs(N, kr, arrayType="rigid", dirCoeff=0.0, *, handle=None):
     h.check(h.lib.emagls_sph_modal_coeffs(h.ptr, int(N), _p(kr), kr.size, 0 if arrayType == "rigid" else 1,
                                           _p(out)))
     return out
+
+
+def grpdelay(h_sum_or_set, f, fs, *, handle=None):
+    """``grpdelay(sum(h, 2), 1, f, fs)`` and its median as the designers use it (lib/getEMagLs2Filters.m:72-75).
+
+    ``h_sum_or_set``: [taps] or [taps x dirs] (summed over the directions on the device); ``f`` must be
+    ``linspace(0, fs/2, numPosFreqs)`` as in the reference.  Returns (gd [numPosFreqs], median)."""
+    hnd = handle or default_handle()
+    x = np.asarray(h_sum_or_set, dtype=np.float64)
+    if x.ndim == 1:
+        x = x[:, None]
+    x = np.asfortranarray(x)
+    f = _vec(f)
+    if f.size < 2 or not np.allclose(f, np.linspace(0.0, fs / 2.0, f.size)):
+        raise ValueError("f must be linspace(0, fs/2, numPosFreqs)")
+    gd = np.zeros(f.size)
+    med = np.zeros(1)
+    hnd.check(hnd.lib.emagls_group_delay(hnd.ptr, _p(x), x.shape[0], x.shape[1], f.size, float(fs), _p(gd), _p(med)))
+    return gd, float(med[0])
 
 
 def regularizedApply(pwGrid, targets, svd_regul=0.01, *, handle=None):

@@ -1,11 +1,28 @@
 // C ABI of libemagls_cuda (see include/emagls_cuda.h).
+#include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <vector>
 #include "engine.h"
 #include "special.cuh"
 
 using namespace emagls;
+
+namespace emagls {
+namespace {
+std::mutex g_pool_mu;
+std::map<cudaStream_t, cudaMemPool_t> g_pools;
+}  // namespace
+void register_stream_pool(cudaStream_t st, cudaMemPool_t pool) { std::lock_guard<std::mutex> l(g_pool_mu); g_pools[st] = pool; }
+void unregister_stream_pool(cudaStream_t st) { std::lock_guard<std::mutex> l(g_pool_mu); g_pools.erase(st); }
+cudaMemPool_t pool_of_stream(cudaStream_t st) {
+  std::lock_guard<std::mutex> l(g_pool_mu);
+  auto it = g_pools.find(st);
+  return it == g_pools.end() ? nullptr : it->second;
+}
+}  // namespace emagls
 
 extern "C" {
 
@@ -21,15 +38,28 @@ int emagls_create(int device, emagls_handle* out) {
     delete h;
     return EMAGLS_ERR_CUDA;
   }
-  // keep freed scratch in the stream-ordered pool between calls
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-    unsigned long long thr = ~0ull;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  // A private stream-ordered pool keeps freed scratch cached between calls without touching the device's default
+  // pool (which other users of the process share); it is destroyed, and its memory returned, with the handle.
+  {
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    if (cudaMemPoolCreate(&h->pool, &props) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &thr);
+      register_stream_pool(h->stream, h->pool);
+    } else {
+      h->pool = nullptr;   // fall back to the default pool with its default release threshold
+      cudaGetLastError();
+    }
   }
   if (cudaMalloc(&h->d_stats, 4 * sizeof(unsigned long long)) != cudaSuccess ||
       cudaMemset(h->d_stats, 0, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+    unregister_stream_pool(h->stream);
     cudaStreamDestroy(h->stream);
+    if (h->pool) cudaMemPoolDestroy(h->pool);
     delete h;
     return EMAGLS_ERR_CUDA;
   }
@@ -58,7 +88,9 @@ int emagls_destroy(emagls_handle h) {
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   emagls::destroy_render_plans(h);
   emagls::destroy_fir_plans(h);
+  unregister_stream_pool(h->stream);
   cudaStreamDestroy(h->stream);
+  if (h->pool) cudaMemPoolDestroy(h->pool);
   cudaFree(h->d_stats);
   delete h;
   return EMAGLS_OK;
@@ -559,6 +591,32 @@ int emagls_get_sh(emagls_handle h, int order, const double* azi, const double* z
     h->launches += 1;
     EM_CUDA(cudaMemcpyAsync(out, d_out, n * sizeof(double), cudaMemcpyDeviceToHost, st));
     EM_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+int emagls_group_delay(emagls_handle h, const double* hrir, int taps, int num_dirs, int num_freqs, double fs,
+                       double* gd, double* median_out) {
+  return guarded(h, [&] {
+    EM_REQUIRE(hrir && taps > 0 && num_dirs > 0 && num_freqs > 1 && fs > 0.0, "invalid argument");
+    cudaStream_t st = h->stream;
+    Arena ar(st);
+    const int nchunk = 32;
+    const double* d_h = ar.upload(hrir, (size_t)taps * num_dirs);
+    double* partial = ar.get<double>((size_t)nchunk * taps);
+    double* hsum = ar.get<double>((size_t)taps);
+    double* d_gd = ar.get<double>((size_t)num_freqs);
+    EM_CUDA(launch_colsum(st, d_h, taps, num_dirs, partial, nchunk, hsum));
+    EM_CUDA(launch_grpdelay(st, hsum, taps, num_freqs, fs, d_gd));
+    h->launches += 3;
+    std::vector<double> g((size_t)num_freqs);
+    EM_CUDA(cudaMemcpyAsync(g.data(), d_gd, g.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EM_CUDA(cudaStreamSynchronize(st));
+    if (gd) std::copy(g.begin(), g.end(), gd);
+    if (median_out) {
+      std::sort(g.begin(), g.end());
+      const size_t n = g.size();
+      *median_out = (n & 1) ? g[n / 2] : 0.5 * (g[n / 2 - 1] + g[n / 2]);
+    }
   });
 }
 

@@ -499,9 +499,9 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
   EM_CUDA(cudaMemGetInfo(&free_b, &total_b));
   // memory still cached in the stream-ordered pool is reusable: plan against the larger figure
   {
-    cudaMemPool_t pool;
+    cudaMemPool_t pool = h->pool;
     unsigned long long reserved = 0, used = 0;
-    if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess &&
+    if ((pool || cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) &&
         cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
         cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
       free_b += (size_t)(reserved - used);

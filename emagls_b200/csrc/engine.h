@@ -27,6 +27,7 @@ enum EmProfClass {
 struct emagls_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaMemPool_t pool = nullptr;   // private stream-ordered pool of this handle (scratch stays cached between calls)
   std::string err;
   long long launches = 0;
   // work statistics of the design path (emagls_stats_read): (problem, bin) pairs on the TSQR + Jacobi route and
@@ -71,10 +72,16 @@ struct Fail {
     if (!(cond)) throw ::emagls::Fail{EMAGLS_ERR_INVALID, std::string(msg)};    \
   } while (0)
 
+// Handles register their private memory pool under their stream, so that every Arena built on that stream draws
+// from it (api.cu); a stream without an entry uses the device's default pool.
+void register_stream_pool(cudaStream_t st, cudaMemPool_t pool);
+void unregister_stream_pool(cudaStream_t st);
+cudaMemPool_t pool_of_stream(cudaStream_t st);
+
 // Stream-ordered scratch arena: everything allocated through it is released when it dies.
 class Arena {
  public:
-  explicit Arena(cudaStream_t st) : st_(st) {}
+  explicit Arena(cudaStream_t st) : st_(st), pool_(pool_of_stream(st)) {}
   ~Arena() {
     for (void* p : ptrs_) cudaFreeAsync(p, st_);
   }
@@ -82,7 +89,7 @@ class Arena {
   T* get(size_t n) {
     void* p = nullptr;
     if (n == 0) n = 1;
-    cudaError_t e = cudaMallocAsync(&p, n * sizeof(T), st_);
+    cudaError_t e = pool_ ? cudaMallocFromPoolAsync(&p, n * sizeof(T), pool_, st_) : cudaMallocAsync(&p, n * sizeof(T), st_);
     if (e != cudaSuccess)
       throw Fail{EMAGLS_ERR_CUDA, std::string("cudaMallocAsync(") + std::to_string(n * sizeof(T)) + " B): " +
                                       cudaGetErrorString(e)};
@@ -99,6 +106,7 @@ class Arena {
 
  private:
   cudaStream_t st_;
+  cudaMemPool_t pool_;
   std::vector<void*> ptrs_;
 };
 

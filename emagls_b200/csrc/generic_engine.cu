@@ -321,6 +321,7 @@ void design_magls(emagls_ctx* h, const emagls_config& cfg, const double* hL, con
   const bool cplx_out = cfg.basis == EMAGLS_BASIS_COMPLEX;
   Arena ar(st);
   ProfSpan* setup_span = new ProfSpan(h, EM_PROF_SETUP);
+  struct SetupSpanGuard { ProfSpan*& p; ~SetupSpanGuard() { delete p; p = nullptr; } } setup_span_guard{setup_span};   // also on a thrown Fail
   // Y_conj.' rows in the real basis; a complex basis is a unitary change of the output (engine.cu)
   cplx* At = ar.get<cplx>((size_t)D * Mc);
   if (harmonics_kind == 1) {
@@ -345,7 +346,7 @@ void design_magls(emagls_ctx* h, const emagls_config& cfg, const double* hL, con
       EM_CUDA(cudaGetLastError());
     }
     h->launches += 2;
-    delete setup_span;
+    delete setup_span; setup_span = nullptr;
     cplx* W = ar.get<cplx>((size_t)2 * Mc * T);
     g.K = T; g.first_bin = 0; g.kls1 = T; g.dc_fix = 0; g.nyquist_real = 0;
     g.H = Hc; g.h_prob_stride = 0; g.h_ear_stride = (long long)T * D; g.W = W;
@@ -391,7 +392,7 @@ void design_magls(emagls_ctx* h, const emagls_config& cfg, const double* hL, con
       }
     h->launches += 1;
   }
-  delete setup_span;
+  delete setup_span; setup_span = nullptr;
   cplx* Wsp = spectra ? reinterpret_cast<cplx*>(spectra) : ar.get<cplx>((size_t)2 * NS * Mc * K);
   g.K = K; g.first_bin = 0; g.kls1 = kls1; g.dc_fix = 0; g.nyquist_real = 1;   // lib/getMagLsFilters.m:64-72
   g.num_prob = NS;
@@ -460,7 +461,7 @@ void design_from_atf(emagls_ctx* h, const emagls_config& cfg, const double* hL, 
   EM_REQUIRE(Dn >= M, "fewer directions than microphones");
   Arena ar(st);
   ProfSpan* setup_span = new ProfSpan(h, EM_PROF_SETUP);
-  struct SpanGuard { ProfSpan*& p; ~SpanGuard() { delete p; p = nullptr; } } setup_guard{setup_span};
+  struct SetupSpanGuard { ProfSpan*& p; ~SetupSpanGuard() { delete p; p = nullptr; } } setup_span_guard{setup_span};   // also on a thrown Fail
   // ---- grid matching (:56-96), all orientations at once
   double* hx = ar.get<double>((size_t)3 * D);
   double* ax = ar.get<double>((size_t)3 * Da);
@@ -581,6 +582,7 @@ void design_ema_sh(emagls_ctx* h, const emagls_config& cfg, const double* hL, co
   const bool cplx_out = cfg.basis == EMAGLS_BASIS_COMPLEX;
   Arena ar(st);
   ProfSpan* setup_span = new ProfSpan(h, EM_PROF_SETUP);
+  struct SetupSpanGuard { ProfSpan*& p; ~SetupSpanGuard() { delete p; p = nullptr; } } setup_span_guard{setup_span};   // also on a thrown Fail
   // ---- array model pieces
   std::vector<double> kr(K);
   for (int k = 0; k < K; ++k) kr[k] = 2.0 * M_PI * ((double)k * df) / cfg.speed_of_sound * mic_radius;
@@ -630,7 +632,7 @@ void design_ema_sh(emagls_ctx* h, const emagls_config& cfg, const double* hL, co
     }
     h->launches += 3;
   }
-  delete setup_span;
+  delete setup_span; setup_span = nullptr;
   cplx* Wsp = spectra ? reinterpret_cast<cplx*>(spectra) : ar.get<cplx>((size_t)2 * nsh * K);
   EM_CUDA(cudaMemsetAsync(Wsp, 0, (size_t)2 * nsh * K * sizeof(cplx), st));
   GenericProblem g{};

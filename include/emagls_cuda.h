@@ -56,6 +56,10 @@ typedef struct {
   int reserved[5];
 } emagls_config;
 
+/* A handle owns one CUDA stream and one private stream-ordered memory pool on `device` (scratch stays cached in
+ * it between calls and is returned to the device by emagls_destroy; the device's default pool is not touched).
+ * A handle is NOT thread-safe: calls on one handle must not overlap (error text, plans and profiler state are per
+ * handle).  Different handles may be used from different host threads concurrently.                          */
 int emagls_create(int device, emagls_handle* out);
 int emagls_destroy(emagls_handle h);
 const char* emagls_last_error(emagls_handle h);
@@ -300,6 +304,11 @@ int emagls_array_diffuse_filter(emagls_handle h, const emagls_config* cfg, doubl
  * out [num_dirs x (N+1)^2] column-major; interleaved complex for COMPLEX.                      */
 int emagls_get_sh(emagls_handle h, int order, const double* azi, const double* zen, int num_dirs,
                   int basis, double* out);
+/* grpdelay(sum(h, 2), 1, f, fs) with f = linspace(0, fs/2, num_freqs), and its median: the group delay the
+ * designers remove from an HRIR set (lib/getEMagLs2Filters.m:72-75).  hrir [taps x num_dirs] column-major
+ * on the host; gd [num_freqs] and median_out may be NULL.                                          */
+int emagls_group_delay(emagls_handle h, const double* hrir, int taps, int num_dirs, int num_freqs,
+                       double fs, double* gd, double* median_out);
 /* sphModalCoeffs(N, kr, arrayType) (dependencies/Array-Response-Simulator/sphModalCoeffs.m:1):
  * out interleaved complex [num_kr x (N+1)] column-major.                                       */
 int emagls_sph_modal_coeffs(emagls_handle h, int order, const double* kr, int num_kr,

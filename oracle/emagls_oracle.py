@@ -29,7 +29,7 @@ __all__ = [
     "getSHrotMtx", "complex2realSHMtx",
     "getLsFilters", "getMagLsFilters", "getEMagLsFilters", "getEMagLs2Filters",
     "getEMagLsFiltersEMAinCH", "getEMagLsFiltersEMAinSH", "getEMagLsFiltersFromAtf",
-    "binauralDecode", "fftfilt", "regularized_inverse", "matlab_round",
+    "binauralDecode", "fftfilt", "regularized_inverse", "diffuseness_matrix", "matlab_round",
     "DEFAULTS",
 ]
 
@@ -504,8 +504,25 @@ def regularized_inverse(pwGrid, svd_regul=DEFAULTS["SVD_REGUL_CONST"]):
     return np.conj(U) @ (s[:, None] * np.conj(Vh))
 
 
+def diffuseness_matrix(R, Rhat):
+    """2 x 2 mixing matrix A with A Rhat A^H = R that changes the rendered ear signals least (EXTENSION).
+
+    The diffuse-field covariance constraint ("wDC") was removed from the reference before the surveyed commit
+    (CHANGELOG.md:10-18; only its outputs resources/*_wDC.mat remain), so there is no reference code to follow and
+    this part is "parity unpinned".  It restates the published formulation the CHANGELOG names (Zaunschirm,
+    Schoerkhuber, Hoeldrich 2018, eqs. 12-15): with Cholesky factors R = X^H X, Rhat = Xh^H Xh every
+    A = X^H Q Xh^-H with unitary Q matches the covariance; Q = V U^H from Xh X^H = U S V^H (orthogonal Procrustes)
+    minimises || (A - I) Xh^H ||_F.
+    """
+    X = np.linalg.cholesky(R).conj().T          # upper, R = X^H X
+    Xh = np.linalg.cholesky(Rhat).conj().T
+    U, _, Vh = np.linalg.svd(Xh @ X.conj().T)
+    Q = Vh.conj().T @ U.conj().T
+    return X.conj().T @ Q @ np.linalg.inv(Xh.conj().T)
+
+
 def _magls_loop(pw_of_k, HL, HR, numPosFreqs, numCh, k_cut, svd_regul, nyquist_real=True,
-                diag=None):
+                diag=None, diffuseness=False):
     """Hot loop shared by the five eMagLS variants (lib/getEMagLs2Filters.m:85-106).
 
     ``pw_of_k(k)`` returns the ``[channels, D]`` steering matrix of MATLAB bin
@@ -533,6 +550,25 @@ def _magls_loop(pw_of_k, HL, HR, numPosFreqs, numCh, k_cut, svd_regul, nyquist_r
                 tr = tr.real
             W_l[i] = tl @ Yri
             W_r[i] = tr @ Yri
+    if diffuseness:
+        # EXTENSION (see diffuseness_matrix): after the loop and before the DC bin is set, as the CHANGELOG describes
+        # the removed code (CHANGELOG.md:7,20-22).  Target covariance from the HRTF set, rendered covariance from the
+        # plane-wave responses of the array through the filters; at a real Nyquist bin the real parts, so that the
+        # filters stay real.
+        for k in range(2, numPosFreqs + 1):
+            i = k - 1
+            pw = pw_of_k(k)
+            D = pw.shape[1]
+            H = np.stack([HL[i], HR[i]])
+            Wk = np.stack([W_l[i], W_r[i]])
+            Hhat = Wk @ pw
+            R = H @ H.conj().T / D
+            Rhat = Hhat @ Hhat.conj().T / D
+            if k == numPosFreqs and nyquist_real:
+                R, Rhat = R.real.astype(complex), Rhat.real.astype(complex)
+            A = diffuseness_matrix(R, Rhat)
+            Wk = A @ Wk
+            W_l[i], W_r[i] = Wk[0], Wk[1]
     # DC fix, lib/getEMagLs2Filters.m:109-110
     W_l[0] = W_l[1].real
     W_r[0] = W_r[1].real
@@ -622,7 +658,8 @@ def getEMagLs2Filters(hL, hR, hrirGridAziRad, hrirGridZenRad, micRadius, micGrid
     HL, HR, grpDL, grpDR = _prep_hrirs(hL, hR, nfft, f, fs)
     diag = kw.get("diag")
     W_l, W_r = _magls_loop(lambda k: smairMat[:, :, k - 1] @ Y_conj, HL, HR, K, numMics,
-                           k_cut, cfg["SVD_REGUL_CONST"], diag=diag)
+                           k_cut, cfg["SVD_REGUL_CONST"], diag=diag,
+                           diffuseness=bool(kw.get("applyDiffusenessConst", False)))
     wL, wR = _tail(W_l, W_r, K, nfft, length, grpDL, grpDR, _real_extend)
     wL, wR = _finish_real(wL, wR, np.isrealobj(Y_conj))
     if return_spectra:
@@ -655,7 +692,8 @@ def getEMagLsFilters(hL, hR, hrirGridAziRad, hrirGridZenRad, micRadius, micGridA
     Y_Hi_conj = np.conj(shFunction(simN, np.stack([az, ze], 1), shDefinition)).T
     HL, HR, grpDL, grpDR = _prep_hrirs(hL, hR, nfft, f, fs)
     W_l, W_r = _magls_loop(lambda k: smairMat[:, :, k - 1] @ Y_Hi_conj, HL, HR, K, numHarm,
-                           k_cut, cfg["SVD_REGUL_CONST"])
+                           k_cut, cfg["SVD_REGUL_CONST"],
+                           diffuseness=bool(kw.get("applyDiffusenessConst", False)))
     is_real = np.isrealobj(Y_Hi_conj)
     extend = _real_extend if is_real else getShFreqDomainConjugate
     wL, wR = _tail(W_l, W_r, K, nfft, length, grpDL, grpDR, extend)

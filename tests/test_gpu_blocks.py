@@ -3,6 +3,7 @@ import numpy as np
 import pytest
 
 import oracle
+from emagls_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
@@ -95,3 +96,22 @@ def test_regularized_apply_rank_deficient(em, h):
     Wo = t @ oracle.regularized_inverse(A, 0.01)
     # the clipped direction carries gain 1/(c*smax); compare the well-determined part only
     assert rel(W @ A, Wo @ A) < 1e-10
+
+
+def test_group_delay_matches_oracle(em):
+    """a14: median(grpdelay(sum(h, 2), 1, f, fs)) (lib/getEMagLs2Filters.m:72-75) on the device against the oracle."""
+    g = synth.load_grids()
+    az, ze = g["hrirGridAziRad"][::7], g["hrirGridZenRad"][::7]
+    for taps, delay, fs in ((128, 30, 48000.0), (96, 17, 44100.0)):
+        hL, hR = synth.synth_hrirs(az, ze, taps=taps, delay=delay)
+        K = taps + 1
+        f = np.linspace(0.0, fs / 2.0, K)
+        for h in (hL, hR):
+            gd, med = em.grpdelay(h, f, fs)
+            ref = oracle.grpdelay(h.sum(1), f, fs)
+            assert np.abs(gd - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max())
+            assert abs(med - np.median(ref)) <= 1e-9 * max(1.0, abs(np.median(ref)))
+    # pure delay: the group delay is the delay
+    x = np.zeros(64); x[11] = 1.0
+    gd, med = em.grpdelay(x, np.linspace(0, 24000.0, 33), 48000.0)
+    assert np.abs(gd - 11.0).max() < 1e-9 and abs(med - 11.0) < 1e-9
