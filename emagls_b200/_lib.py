@@ -19,7 +19,7 @@ class Config(C.Structure):
     """struct emagls_config (include/emagls_cuda.h)."""
     _fields_ = [("nfft_max_len", C.c_int), ("f_cut_min", C.c_double), ("svd_regul", C.c_double),
                 ("speed_of_sound", C.c_double), ("array_type", C.c_int), ("basis", C.c_int),
-                ("precision", C.c_int), ("reserved", C.c_int * 5)]
+                ("precision", C.c_int), ("diffuseness_const", C.c_int), ("reserved", C.c_int * 4)]
 
 
 class RadialParams(C.Structure):

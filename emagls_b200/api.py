@@ -95,10 +95,14 @@ def _design_sma_custom(fn_name, h, cfg, shFunction, shDefinition, hL, hR, T, D, 
     return wL, wR, sp
 
 
-def _config(handle, config, shDefinition):
+def _config(handle, config, shDefinition, applyDiffusenessConst=False):
     # a private copy: the caller's Config is never written to
     cfg = Config.from_buffer_copy(config) if config is not None else handle.default_config()
     cfg.basis = _basis(shDefinition)
+    if applyDiffusenessConst:
+        if cfg.basis != 0:   # as the reference did (CHANGELOG.md:18)
+            raise NotImplementedError('the diffuseness constraint is not implemented for "complex" SH conventions')
+        cfg.diffuseness_const = 1
     return cfg
 
 
@@ -117,9 +121,9 @@ def _prep_hrirs(hL, hR):
 
 def _design_sma(fn_name, channels_of, hL, hR, hrirGridAziRad, hrirGridZenRad, micRadius, micGridAziRad,
                 micGridZenRad, order, fs, length, shDefinition, shFunction, rotations, handle, config,
-                return_spectra, out=None):
+                return_spectra, out=None, applyDiffusenessConst=False):
     h = handle or default_handle()
-    cfg = _config(h, config, shDefinition)
+    cfg = _config(h, config, shDefinition, applyDiffusenessConst)
     hL, hR, T, D, sets = _prep_hrirs(hL, hR)
     az, ze = _vec(hrirGridAziRad), _vec(hrirGridZenRad)
     maz, mze = _vec(micGridAziRad), _vec(micGridZenRad)
@@ -173,24 +177,26 @@ def _design_sma(fn_name, channels_of, hL, hR, hrirGridAziRad, hrirGridZenRad, mi
 
 def getEMagLs2Filters(hL, hR, hrirGridAziRad, hrirGridZenRad, micRadius, micGridAziRad, micGridZenRad,
                       order, fs, len, shDefinition="real", shFunction=None, *, rotations=None,
-                      handle=None, config=None, return_spectra=False, out=None):
+                      handle=None, config=None, return_spectra=False, out=None, applyDiffusenessConst=False):
     """[wMlsL, wMlsR] = getEMagLs2Filters(...)  -- lib/getEMagLs2Filters.m:1-2.
 
     Returns filters ``[len, numMics]`` (``[len, numMics, batch]`` when batched).  With
     ``return_spectra`` also the positive-frequency solutions ``[K, numMics, (batch,) 2]``.
+    ``applyDiffusenessConst`` (extension, default off): the diffuse-field covariance constraint of earlier
+    reference versions (CHANGELOG.md:10-18), see include/emagls_cuda.h ``diffuseness_const``.
     """
     return _design_sma("emagls_design_emagls2", lambda M, N: M, hL, hR, hrirGridAziRad, hrirGridZenRad,
                        micRadius, micGridAziRad, micGridZenRad, order, fs, len, shDefinition, shFunction,
-                       rotations, handle, config, return_spectra, out)
+                       rotations, handle, config, return_spectra, out, applyDiffusenessConst)
 
 
 def getEMagLsFilters(hL, hR, hrirGridAziRad, hrirGridZenRad, micRadius, micGridAziRad, micGridZenRad,
                      order, fs, len, shDefinition="real", shFunction=None, *, rotations=None,
-                     handle=None, config=None, return_spectra=False):
+                     handle=None, config=None, return_spectra=False, applyDiffusenessConst=False):
     """[wMlsL, wMlsR] = getEMagLsFilters(...)  -- lib/getEMagLsFilters.m:1-2 ([len, (order+1)^2])."""
     return _design_sma("emagls_design_emagls", lambda M, N: (N + 1) ** 2, hL, hR, hrirGridAziRad,
                        hrirGridZenRad, micRadius, micGridAziRad, micGridZenRad, order, fs, len, shDefinition,
-                       shFunction, rotations, handle, config, return_spectra)
+                       shFunction, rotations, handle, config, return_spectra, None, applyDiffusenessConst)
 
 
 def getMagLsFilters(hL, hR, hrirGridAziRad, hrirGridZenRad, order, fs, len, shDefinition="real",

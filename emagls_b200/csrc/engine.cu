@@ -430,6 +430,11 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
     EM_CUDA(cudaMemcpy(&qrflag, d_qrflag, sizeof(int), cudaMemcpyDeviceToHost));
     if (qrflag) householder_qr();   // badly conditioned direction grid: Householder route
   }
+  // EXTENSION (default off): diffuse-field covariance constraint, see gram_kernels.cu
+  const bool wdc = cfg.diffuseness_const != 0;
+  EM_REQUIRE(!wdc || (cfg.basis == EMAGLS_BASIS_REAL && Mc <= 32),
+             "the diffuseness constraint is implemented for the real SH basis and up to 32 channels");
+  double* Rt = wdc ? ar.get<double>((size_t)a.num_sets * K * 4) : nullptr;           // target covariance [set][K][4]
   double* absH = ar.get<double>((size_t)a.num_sets * 2 * K * D);                     // [set][ear][K][D]
   const size_t ls_elems = (size_t)a.num_sets * 2 * std::max(nLS, 1) * 2 * S;         // [set][ear][kls][c][S]
   double* Tls = ar.get<double>(ls_elems);   // H * Q
@@ -438,9 +443,11 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
     double* tw = ar.get<double>((size_t)2 * K * T);
     EM_CUDA(launch_dft_twiddle(st, K, T, nfft, tw));
     h->launches += 1;
-    double* Hd = ar.get<double>((size_t)D * 2 * K);
+    double* Hd0 = ar.get<double>((size_t)D * 2 * K);
+    double* Hd1 = wdc ? ar.get<double>((size_t)D * 2 * K) : Hd0;   // the constraint needs both ears' spectra at once
     for (int s = 0; s < a.num_sets; ++s)
       for (int e = 0; e < 2; ++e) {
+        double* Hd = e == 0 ? Hd0 : Hd1;
         const double* hp = (e == 0 ? a.hL : a.hR) + (size_t)s * T * D;
         hrir_spectrum(h, ar, hp, T, D, K, tw, grpD[(size_t)s * 2 + e], Hd);
         EM_CUDA(launch_abs_transpose(st, Hd, D, K, absH + ((size_t)s * 2 + e) * K * D));
@@ -451,6 +458,10 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
           EM_CUDA(launch_gemm(st, A2, B2, GemmShape{2 * nLS, S, D}, EpiStore{Tls + off, S, 1.0}));
           EM_CUDA(launch_gemm(st, A2, B3, GemmShape{2 * nLS, S, D}, EpiStore{Zls + off, S, 1.0}));
           h->launches += 2;
+        }
+        if (wdc && e == 1) {
+          EM_CUDA(launch_target_cov(st, Hd0, Hd1, D, K, Rt + (size_t)s * K * 4));
+          h->launches += 1;
         }
       }
   }
@@ -554,6 +565,20 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
   const bool debug = getenv("EMAGLS_DEBUG_INFO") != nullptr;
   std::vector<int> fail_h(NB + 1);
 
+  // G_k of the bins gb0 .. gb0 + nb - 1 for every orientation of the chunk (packed lower triangles in Gre / Gim)
+  auto assemble_gram = [&](int gb0, int nb, int oc) {
+    const int ncol = oc * ne_ld;
+    GemmOperand A1{bre + (size_t)gb0 * nqs, nqs, 1}, B1{Fs, (long long)ncol, 0};
+    EM_CUDA(launch_gemm(st, A1, B1, GemmShape{nb, ncol, nqs}, EpiStore{Gre, (long long)ncol, 1.0}));
+    if (simN > 0) {
+      GemmOperand A2{bim + (size_t)gb0 * nqa, nqa, 1}, B2{Fa, (long long)ncol, 0};
+      EM_CUDA(launch_gemm(st, A2, B2, GemmShape{nb, ncol, simN * (simN + 1) / 2}, EpiStore{Gim, (long long)ncol, 1.0}));
+    } else {
+      EM_CUDA(cudaMemsetAsync(Gim, 0, (size_t)nb * ncol * sizeof(double), st));
+    }
+    h->launches += 2;
+  };
+
   for (int o0 = 0; o0 < a.num_orient; o0 += OC) {
     const int oc = std::min(OC, a.num_orient - o0);
     const int pj = a.num_sets * oc;
@@ -570,7 +595,7 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
         h->launches += 1;
       }
     }
-    if (gram_thr > 0.0) {
+    if (gram_thr > 0.0 || wdc) {
       ProfSpan ps(h, EM_PROF_GRAM);
       // build_F addresses (q*P + o) with P = oc: one launch per <= 32768 orientations is not possible
       // with that layout, so the grid's y dimension limits a chunk to 65535 orientations (OC <= 8192).
@@ -587,18 +612,10 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
       std::fill(fail_h.begin(), fail_h.end(), 1);
       if (gram_thr > 0.0) {
         ProfSpan ps(h, EM_PROF_GRAM);
-        const int ncol = oc * ne_ld;
         EM_CUDA(cudaMemsetAsync(d_fail, 0, (size_t)(NB + 1) * sizeof(int), st));
-        GemmOperand A1{bre + (size_t)gb0 * nqs, nqs, 1}, B1{Fs, (long long)ncol, 0};
-        EM_CUDA(launch_gemm(st, A1, B1, GemmShape{nb, ncol, nqs}, EpiStore{Gre, (long long)ncol, 1.0}));
-        if (simN > 0) {
-          GemmOperand A2{bim + (size_t)gb0 * nqa, nqa, 1}, B2{Fa, (long long)ncol, 0};
-          EM_CUDA(launch_gemm(st, A2, B2, GemmShape{nb, ncol, simN * (simN + 1) / 2}, EpiStore{Gim, (long long)ncol, 1.0}));
-        } else {
-          EM_CUDA(cudaMemsetAsync(Gim, 0, (size_t)nb * ncol * sizeof(double), st));
-        }
+        assemble_gram(gb0, nb, oc);
         EM_CUDA(launch_gram_chol(st, Gre, Gim, Mc, oc, ne_ld, nb, gram_thr, PbG, d_fail));
-        h->launches += 3;
+        h->launches += 1;
         EM_CUDA(cudaMemcpyAsync(fail_h.data(), d_fail, (size_t)(nb + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
         EM_CUDA(cudaStreamSynchronize(st));
       }
@@ -706,6 +723,17 @@ void design_factored(emagls_ctx* h, const emagls_config& cfg, const DesignArgs& 
           }
           h->launches += 3;   // forward GEMM, backward GEMM, backward small / chain kernel
         }
+      }
+    }
+    if (wdc) {
+      // after the recursion (the phase continuation runs on the unconstrained solutions, as in the removed reference
+      // code) and before the tail; the DC bin is set again from the constrained bin 1
+      ProfSpan ps(h, EM_PROF_GRAM);
+      for (int gb0 = 1; gb0 < K; gb0 += NB) {
+        const int nb = std::min(NB, K - gb0);
+        assemble_gram(gb0, nb, oc);
+        EM_CUDA(launch_diffuseness_apply(st, Gre, Gim, Mc, oc, ne_ld, nb, gb0, D, Rt, pm, pj, Wsp, w_ear, K, dc_fix ? 1 : 0, 1));
+        h->launches += 1;
       }
     }
   }

@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include "kernels.h"
 #include "ozaki.cuh"
+#include "reflect.cuh"
 
 namespace emagls {
 
@@ -329,6 +330,143 @@ cudaError_t launch_gram_chol(cudaStream_t st, const double* Gre, const double* G
   }
   gram_chol_kernel<<<(unsigned)((nmat + wpc - 1) / wpc), wpc * 32, smem, st>>>(Gre, Gim, Mc, P, ne_ld, nmat, thr,
                                                                                     Pb, fail);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// EXTENSION (config.diffuseness_const, default off): diffuse-field covariance constraint.  The reference removed
+// this step before the surveyed commit (CHANGELOG.md:10-18; outputs resources/*_wDC.mat remain), so it follows the
+// published formulation the CHANGELOG names (Zaunschirm, Schoerkhuber, Hoeldrich 2018) as restated in
+// oracle.diffuseness_matrix: per bin, with the target covariance R = H H^H / D of the HRTF set and the covariance
+// Rhat = (W pw)(W pw)^H / D = W (pw pw^H) W^H / D of the rendered plane-wave responses,
+//     W <- A W,   A = X^H Q Xh^-H,   R = X^H X, Rhat = Xh^H Xh (Cholesky),   Q^H = polar factor of Xh X^H.
+// pw pw^H = conj(G_k) is the Gram matrix the Gram route assembles anyway.
+// ---------------------------------------------------------------------------------------------
+// R[k] = {sum |HL|^2, sum |HR|^2, Re sum HL conj(HR), Im ...} / D from the two ears' spectra Hd [D][2K]
+__global__ void __launch_bounds__(256)
+target_cov_kernel(const double* __restrict__ HdL, const double* __restrict__ HdR, int D, int K, double* __restrict__ out) {
+  const int k = blockIdx.x, tid = threadIdx.x;
+  double a = 0.0, b = 0.0, cr = 0.0, ci = 0.0;
+  for (int d = tid; d < D; d += blockDim.x) {
+    const double2 l = *reinterpret_cast<const double2*>(HdL + ((long long)d * K + k) * 2);
+    const double2 r = *reinterpret_cast<const double2*>(HdR + ((long long)d * K + k) * 2);
+    a = fma(l.x, l.x, fma(l.y, l.y, a));
+    b = fma(r.x, r.x, fma(r.y, r.y, b));
+    cr += l.x * r.x + l.y * r.y;          // l conj(r)
+    ci += l.y * r.x - l.x * r.y;
+  }
+  __shared__ double red[4][8];
+  a = wsum(a); b = wsum(b); cr = wsum(cr); ci = wsum(ci);
+  if ((tid & 31) == 0) { red[0][tid >> 5] = a; red[1][tid >> 5] = b; red[2][tid >> 5] = cr; red[3][tid >> 5] = ci; }
+  __syncthreads();
+  if (tid < 4) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[tid][w];
+    out[(long long)k * 4 + tid] = s / (double)D;
+  }
+}
+
+cudaError_t launch_target_cov(cudaStream_t st, const double* HdL, const double* HdR, int D, int K, double* out) {
+  target_cov_kernel<<<K, 256, 0, st>>>(HdL, HdR, D, K, out);
+  return cudaGetLastError();
+}
+
+// 2 x 2 mixing matrix (row-major a[0..3]); false when a covariance is not positive definite
+__device__ bool diffuseness_mix(double r11, double r22, cplx r12, double h11r, double h22r, cplx h12r, cplx (&a)[4]) {
+  // Cholesky factors (upper): R = X^H X, Rhat = Xh^H Xh
+  if (!(r11 > 0.0) || !(h11r > 0.0)) return false;
+  const double x11 = sqrt(r11), g11 = sqrt(h11r);
+  const cplx x12 = mk(r12.x / x11, r12.y / x11), g12 = mk(h12r.x / g11, h12r.y / g11);
+  const double x22s = r22 - cabs2(x12), g22s = h22r - cabs2(g12);
+  if (!(x22s > 0.0) || !(g22s > 0.0) || !(x22s < 1e300) || !(g22s < 1e300)) return false;
+  const double x22 = sqrt(x22s), g22 = sqrt(g22s);
+  // B = Xh X^H
+  const cplx b00 = cadd(mk(g11 * x11, 0.0), cmulc(g12, x12));   // g11 x11 + g12 conj(x12)   (cmulc(a, b) = a conj(b))
+  const cplx b01 = mk(g12.x * x22, g12.y * x22);
+  const cplx b10 = mk(g22 * x12.x, -g22 * x12.y);
+  const cplx b11 = mk(g22 * x22, 0.0);
+  // P = B^H B, polar factor Pm = c B (P + s I)^-1 with s = |det B|, c = sqrt(tr P + 2 s)
+  const double p00 = cabs2(b00) + cabs2(b10), p11 = cabs2(b01) + cabs2(b11);
+  const cplx p01 = cadd(cmulc(b01, b00), cmulc(b11, b10));      // conj(b00) b01 + conj(b10) b11
+  const cplx det = csub(cmul(b00, b11), cmul(b01, b10));
+  const double sdet = sqrt(cabs2(det));
+  const double c = sqrt(p00 + p11 + 2.0 * sdet);
+  const double m00 = p00 + sdet, m11 = p11 + sdet;
+  const double dm = m00 * m11 - cabs2(p01);
+  if (!(dm > 0.0)) return false;
+  const double f = c / dm;
+  // inv(M) = [[m11, -p01], [-conj(p01), m00]] / dm
+  const cplx i00 = mk(m11 * f, 0.0), i01 = mk(-p01.x * f, -p01.y * f), i10 = mk(-p01.x * f, p01.y * f), i11 = mk(m00 * f, 0.0);
+  const cplx q00 = cadd(cmul(b00, i00), cmul(b01, i10)), q01 = cadd(cmul(b00, i01), cmul(b01, i11));
+  const cplx q10 = cadd(cmul(b10, i00), cmul(b11, i10)), q11 = cadd(cmul(b10, i01), cmul(b11, i11));
+  // T = X^H Pm^H:  X^H = [[x11, 0], [conj(x12), x22]],  Pm^H = [[conj q00, conj q10], [conj q01, conj q11]]
+  const cplx t00 = mk(x11 * q00.x, -x11 * q00.y), t01 = mk(x11 * q10.x, -x11 * q10.y);
+  const cplx t10 = cadd(cmulc(cconj(x12), q00), mk(x22 * q01.x, -x22 * q01.y));   // conj(x12) conj(q00) + x22 conj(q01)
+  const cplx t11 = cadd(cmulc(cconj(x12), q10), mk(x22 * q11.x, -x22 * q11.y));
+  // A = T Xh^-H,  Xh^-H = [[1/g11, 0], [-conj(g12)/(g11 g22), 1/g22]]
+  const double ig11 = 1.0 / g11, ig22 = 1.0 / g22;
+  const cplx l10 = mk(-g12.x * ig11 * ig22, g12.y * ig11 * ig22);
+  a[0] = cadd(mk(t00.x * ig11, t00.y * ig11), cmul(t01, l10));
+  a[1] = mk(t01.x * ig22, t01.y * ig22);
+  a[2] = cadd(mk(t10.x * ig11, t10.y * ig11), cmul(t11, l10));
+  a[3] = mk(t11.x * ig22, t11.y * ig22);
+  return true;
+}
+
+// one warp per (bin of the group, chunk-local problem): lane m holds W_l(m), W_r(m)
+__global__ void __launch_bounds__(128)
+diffuseness_apply_kernel(const double* __restrict__ Gre, const double* __restrict__ Gim, int Mc, int oc, int ne_ld, int nb,
+                         int gb0, int D, const double* __restrict__ Rt, ProbMap pm, int pj, cplx* __restrict__ Wsp,
+                         long long w_ear_stride, int K, int dc_fix, int nyquist_real) {
+  const int lane = threadIdx.x & 31;
+  const long long id = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (id >= (long long)nb * pj) return;
+  const int b = (int)(id / pj), j = (int)(id - (long long)b * pj);
+  const int k = gb0 + b, ol = j % oc, set = j / oc;
+  const long long p = pm.global(j);
+  const double* gr = Gre + ((long long)b * oc + ol) * ne_ld;
+  const double* gi = Gim + ((long long)b * oc + ol) * ne_ld;
+  cplx* w0p = Wsp + (p * Mc + lane) * K + k;
+  cplx* w1p = w0p + w_ear_stride;
+  const bool act = lane < Mc;
+  const cplx w0 = act ? *w0p : mk(0.0, 0.0), w1 = act ? *w1p : mk(0.0, 0.0);
+  // t_b(m) = sum_m' conj(G(m, m')) conj(W_b(m'))  (pw pw^H = conj(G)); packed entry (hi, lo) holds G(hi, lo)
+  cplx t0 = mk(0.0, 0.0), t1 = mk(0.0, 0.0);
+  for (int mp = 0; mp < Mc; ++mp) {
+    cplx v0, v1;
+    v0.x = __shfl_sync(0xffffffffu, w0.x, mp); v0.y = __shfl_sync(0xffffffffu, w0.y, mp);
+    v1.x = __shfl_sync(0xffffffffu, w1.x, mp); v1.y = __shfl_sync(0xffffffffu, w1.y, mp);
+    if (act) {
+      const int hi = max(lane, mp), lo = min(lane, mp);
+      const int e = hi * (hi + 1) / 2 + lo;
+      double im = (hi == lo) ? 0.0 : gi[e];
+      if (mp > lane) im = -im;                       // G(lane, mp), upper triangle: conj of the stored entry
+      const cplx gc = mk(gr[e], -im);                // conj(G(lane, mp))
+      cfma(t0, gc, cconj(v0));
+      cfma(t1, gc, cconj(v1));
+    }
+  }
+  // Rhat_ab = sum_m W_a(m) t_b(m) / D
+  const cplx h00 = wsumc(cmul(w0, t0)), h01 = wsumc(cmul(w0, t1)), h11 = wsumc(cmul(w1, t1));
+  const double* rt = Rt + ((long long)set * K + k) * 4;
+  cplx r12 = mk(rt[2], rt[3]), g12 = mk(h01.x / D, h01.y / D);
+  if (nyquist_real && k == K - 1) { r12.y = 0.0; g12.y = 0.0; }
+  cplx a[4];
+  if (!diffuseness_mix(rt[0], rt[1], r12, h00.x / D, h11.x / D, g12, a)) return;   // warp-uniform
+  if (act) {
+    const cplx n0 = cadd(cmul(a[0], w0), cmul(a[1], w1)), n1 = cadd(cmul(a[2], w0), cmul(a[3], w1));
+    *w0p = n0; *w1p = n1;
+    if (dc_fix && k == 1) { w0p[-1] = mk(n0.x, 0.0); w1p[-1] = mk(n1.x, 0.0); }   // lib/getEMagLs2Filters.m:109-110
+  }
+}
+
+cudaError_t launch_diffuseness_apply(cudaStream_t st, const double* Gre, const double* Gim, int Mc, int oc, int ne_ld, int nb,
+                                     int gb0, int D, const double* Rt, ProbMap pm, int pj, cplx* Wsp, long long w_ear_stride,
+                                     int K, int dc_fix, int nyquist_real) {
+  if (Mc > 32) return cudaErrorInvalidValue;
+  const long long n = (long long)nb * pj;
+  diffuseness_apply_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(Gre, Gim, Mc, oc, ne_ld, nb, gb0, D, Rt, pm, pj, Wsp,
+                                                                    w_ear_stride, K, dc_fix, nyquist_real);
   return cudaGetLastError();
 }
 

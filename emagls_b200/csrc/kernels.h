@@ -125,6 +125,11 @@ cudaError_t launch_gram_beta(cudaStream_t st, const cplx* bn, int N, int K, doub
 cudaError_t launch_gram_chol(cudaStream_t st, const double* Gre, const double* Gim, int Mc, int P,
                              int ne_ld, int nbins, double thr, cplx* Pb, int* fail);
 // forward of every bin: Cv rows (j*2+ear)*2+{re,im} = b_k .* (Y_o^T W_{k-1})
+// EXTENSION: diffuse-field covariance constraint (gram_kernels.cu)
+cudaError_t launch_target_cov(cudaStream_t st, const double* HdL, const double* HdR, int D, int K, double* out);
+cudaError_t launch_diffuseness_apply(cudaStream_t st, const double* Gre, const double* Gim, int Mc, int oc, int ne_ld, int nb,
+                                     int gb0, int D, const double* Rt, ProbMap pm, int pj, cplx* Wsp, long long w_ear_stride,
+                                     int K, int dc_fix, int nyquist_real);
 cudaError_t launch_fwd_small(cudaStream_t st, const double* Y, int Mc, int S, const int* roword,
                              const cplx* bk, ProbMap pm, int num_prob, const cplx* Wsp,
                              long long w_ear_stride, int K, int kprev, double* Cv);

@@ -53,7 +53,11 @@ typedef struct {
   int array_type;        /* SIMULATION_ARRAY_TYPE = 'rigid' */
   int basis;             /* shDefinition: 'real' (default) or 'complex' */
   int precision;         /* emagls_precision (default FP64) */
-  int reserved[5];
+  int diffuseness_const; /* EXTENSION, default 0: diffuse-field covariance constraint ("applyDiffusenessConst" of
+                          * earlier reference versions, removed before the surveyed commit: CHANGELOG.md:10-18) applied
+                          * to the per-bin solutions of getEMagLsFilters / getEMagLs2Filters before the DC bin is set;
+                          * real SH basis only, as in the reference (CHANGELOG.md:18) */
+  int reserved[4];
 } emagls_config;
 
 /* A handle owns one CUDA stream and one private stream-ordered memory pool on `device` (scratch stays cached in

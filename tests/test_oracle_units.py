@@ -183,3 +183,15 @@ def test_high_precision_fixture_is_consistent():
     for i in range(15):
         assert abs(np.abs(o64[i] - ex[i]).max() / np.abs(ex[i]).max() - err[i]) <= 1e-3 * err[i] + 1e-18
     assert err[0] > 1e-8 and err[-1] < 1e-11 and d["c1_cond"][0] > 1e12
+
+
+def test_diffuseness_matrix_matches_the_target_covariance():
+    """EXTENSION (oracle.diffuseness_matrix): A Rhat A^H = R, and A = I when the covariances already agree."""
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        X = rng.standard_normal((2, 7)) + 1j * rng.standard_normal((2, 7))
+        Y = rng.standard_normal((2, 7)) + 1j * rng.standard_normal((2, 7))
+        R, Rh = X @ X.conj().T / 7, Y @ Y.conj().T / 7
+        A = oracle.diffuseness_matrix(R, Rh)
+        assert np.abs(A @ Rh @ A.conj().T - R).max() <= 1e-12 * np.abs(R).max()
+        assert np.abs(oracle.diffuseness_matrix(R, R) - np.eye(2)).max() <= 1e-12
