@@ -401,11 +401,11 @@ def main():
     fp64_equiv = fp64_flops[dom] / (avg_ms * 1e-3) / 1e12
     traffic, traffic_src = None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_oz_traffic.json" if use_oz else "r01_gemm_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_oz_traffic.json" if use_oz else "r01_gemm_traffic.json")))
         want = ("EpiPhase" if dom == "gemm_fwd" else "EpiStore")
         if B == 3600:
             traffic = next(x["traffic_bytes"] for x in tj["launches"] if want in x["kernel"])
-            traffic_src = ("profiles/" + ("r01_oz_traffic.json" if use_oz else "r01_gemm_traffic.json") +
+            traffic_src = ("profiles/" + ("r02_oz_traffic.json" if use_oz else "r01_gemm_traffic.json") +
                            " (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full launch)")
     except Exception:
         pass
@@ -437,8 +437,9 @@ def main():
     if new_path:
         add("factor", "tsqr_sep_kernel (register-resident Householder TSQR, warp per (orientation, bin))", "fp64",
             8.0 * (S * M * M - M ** 3 / 3.0) * tsqr_pb, 1e12, dgemm_peak, "TFLOP/s (FP64, algorithmic)",
-            f"8 (S M^2 - M^3/3) flops x {tsqr_pb:.0f} (orientation, bin) problems per step; the kernel executes "
-            f"{16.0 * 32 * 32 * 32 * nblk / 1e6:.2f} MFLOP per problem (full 32-lane steps of {nblk} blocks)")
+            f"8 (S M^2 - M^3/3) flops x {tsqr_pb:.0f} (orientation, bin) problems per step (algorithmic: all {nblk} row "
+            f"blocks); the kernel skips row blocks whose modal coefficients are below 2^-60 of the largest and folds the "
+            f"last 16 Householder steps of a block onto all 32 lanes (12 k instead of 16 k FP64 lane-FMAs per block)")
         add("jacobi", "svdclip_kernel (one-sided Jacobi, block round-robin, warm starts)", "fp64",
             1800.0 * M * (M - 1) / 2 * jac_sw + 8.0 * M ** 3 * jac_p, 1e12, dgemm_peak, "TFLOP/s (FP64, algorithmic)",
             f"1800 flops per rotated column pair x M (M - 1) / 2 pairs x {jac_sw / max(jac_p, 1):.2f} sweeps (measured mean) "
@@ -461,9 +462,10 @@ def main():
             add(nm, "gemm_f64_kernel (DMMA.8x8x4)", "tensor", fp64_flops[nm] * n_l, 1e12, dgemm_peak, "TFLOP/s (FP64)", "")
     # backward small kernels: Gram bins read Y_o (Mc x S doubles), Pb, z, write digits; TSQR bins read the reflectors
     bytes_bwd = gram_pb * (M * S * 8 + M * M * 16 + 4 * S * 8 + oz_T * 4 * KpS) + tsqr_pb * (S * 32 * 16 + M * M * 16 + 4 * S * 8)
-    add("chain_bwd", "bwd_small_kernel (Gram bins) + chain_bwd_sep_kernel (TSQR bins: 32-row reflector tiles)", "hbm",
-        bytes_bwd, 1e9, hbm_peak, "GB/s (algorithmic)", "operator bytes per (orientation, bin): Y_o 102 KB + Pb 16 KB "
-        "(Gram route, L2-resident in part) or reflectors 205 KB + Pb 16 KB (TSQR route)")
+    add("chain_bwd", "bwd_fused_kernel (Gram bins: Y_o staged once in shared memory by cp.async.bulk) + chain_bwd_sep_kernel "
+        "(TSQR bins: 32-row reflector tiles)", "hbm",
+        bytes_bwd, 1e9, hbm_peak, "GB/s (algorithmic)", "operator bytes per (orientation, bin): Y_o 102 KB + Pb 16 KB + "
+        "right-hand sides 13 KB + digits 10 KB (Gram route) or reflectors 205 KB + Pb 16 KB (TSQR route, all row blocks)")
     ne = M * (M + 1) // 2
     add("gram", "gemm_f64_kernel (DMMA assembly of G_k from the F blocks) + gram_sweep_kernel (in-register inversion)", "fp64",
         gram_pb * (2.0 * ne * S + 8.0 * M ** 3 / 2), 1e12, dgemm_peak, "TFLOP/s (FP64, algorithmic)",

@@ -313,6 +313,294 @@ fused_render_kernel(const double* __restrict__ in, long long num_samples, int nu
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fused_render16_kernel (N = 4096, EMAGLS_RENDER_FUSED=2): the same overlap-save block per CTA with
+// register-resident radix-16 / radix-8 Stockham passes (2048 = 16 x 16 x 8).  Four channels at a time, one
+// radix-16 butterfly per thread and pass: the first pass reads its sixteen 16-byte sample pairs straight from
+// global memory (coalesced over the butterfly index; they are issued before the previous group's spectra are
+// accumulated, so the loads fly during that phase), the other two passes run in place in shared memory
+// (read - barrier - write - barrier) on buffers padded by one element per sixteen (the stride-16 writes of the
+// first pass would otherwise hit one bank).  Six barriers per FOUR transforms instead of six per two, sixteen
+// independent loads per thread instead of four.
+// ---------------------------------------------------------------------------------------------
+constexpr int FR_M = 2048, FR_T = 512, FR_LD = FR_M + FR_M / 16;   // complex points, threads, padded buffer length
+__device__ __forceinline__ int fr_pad(int i) { return i + (i >> 4); }
+
+// Twiddles of the two in-place passes in the order the lanes read them (consecutive lanes -> consecutive entries):
+// P2[ji][k] = exp(-2 pi i k 2^ji / 256) (stride-16 pass, k < 16, ji < 4) at ji * 16 + k, then
+// P3[ji][tt] = exp(-2 pi i tt 2^ji / 2048) (last pass, tt < 256, ji < 3) at 64 + ji * 256 + tt.
+constexpr int FR_TW = 4 * 16 + 3 * 256;
+#ifndef EMAGLS_FR_TW_SMEM
+#define EMAGLS_FR_TW_SMEM 0     // 1: the kernel copies the table into shared memory (A/B: slower, it shrinks the L1)
+#endif
+__global__ void render_twiddle_full_kernel(cplx* __restrict__ TW) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= FR_TW) return;
+  const int j = (i < 64) ? ((i & 15) * 8) << (i >> 4) : ((i - 64) & 255) << ((i - 64) >> 8);
+  double s_, c_;
+  sincospi(-2.0 * (double)j / (double)FR_M, &s_, &c_);
+  TW[i] = mk(c_, s_);
+}
+
+template <bool INV>
+__device__ __forceinline__ void fr_dft4(cplx& a0, cplx& a1, cplx& a2, cplx& a3) {
+  const cplx s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = csub(a1, a3);
+  const cplx jd = INV ? mk(-d13.y, d13.x) : mk(d13.y, -d13.x);      // (+i) d13 inverse, (-i) d13 forward
+  a0 = cadd(s02, s13); a1 = cadd(d02, jd); a2 = csub(s02, s13); a3 = csub(d02, jd);
+}
+// multiply by W16^e (forward) or its conjugate (inverse), e a compile-time exponent
+template <bool INV, int E>
+__device__ __forceinline__ cplx fr_w16(cplx a) {
+  constexpr double c1 = 0.92387953251128673848, s1 = 0.38268343236508977173, r2 = 0.70710678118654752440;
+  constexpr int e = E & 15;
+  if (e == 0) return a;
+  if (e == 4) return INV ? mk(-a.y, a.x) : mk(a.y, -a.x);                         // -i / +i
+  if (e == 8) return mk(-a.x, -a.y);
+  double c = 1.0, sn = 0.0;                                                        // W16^e = c - i sn (forward)
+  if (e == 1) { c = c1; sn = s1; } else if (e == 2) { c = r2; sn = r2; } else if (e == 3) { c = s1; sn = c1; }
+  else if (e == 6) { c = -r2; sn = r2; } else if (e == 9) { c = -c1; sn = -s1; }
+  const double si = INV ? sn : -sn;                                                // imaginary part of the factor
+  return mk(fma(a.x, c, -a.y * si), fma(a.x, si, a.y * c));
+}
+// in: v[4 n1 + n2] = x[4 n1 + n2]; out: X[m1 + 4 m2] at v[4 m1 + m2]
+template <bool INV>
+__device__ __forceinline__ void fr_dft16(cplx (&v)[16]) {
+#pragma unroll
+  for (int n2 = 0; n2 < 4; ++n2) fr_dft4<INV>(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
+  v[5] = fr_w16<INV, 1>(v[5]);   v[6] = fr_w16<INV, 2>(v[6]);   v[7] = fr_w16<INV, 3>(v[7]);
+  v[9] = fr_w16<INV, 2>(v[9]);   v[10] = fr_w16<INV, 4>(v[10]); v[11] = fr_w16<INV, 6>(v[11]);
+  v[13] = fr_w16<INV, 3>(v[13]); v[14] = fr_w16<INV, 6>(v[14]); v[15] = fr_w16<INV, 9>(v[15]);
+#pragma unroll
+  for (int m1 = 0; m1 < 4; ++m1) fr_dft4<INV>(v[4 * m1], v[4 * m1 + 1], v[4 * m1 + 2], v[4 * m1 + 3]);
+}
+// in: v[n]; out: X[m] at o[m]
+template <bool INV>
+__device__ __forceinline__ void fr_dft8(cplx (&v)[8], cplx (&o)[8]) {
+  fr_dft4<INV>(v[0], v[2], v[4], v[6]);     // y[m1][0] at v[2 m1]
+  fr_dft4<INV>(v[1], v[3], v[5], v[7]);     // y[m1][1] at v[2 m1 + 1]
+  const cplx t0 = v[1], t1 = fr_w16<INV, 2>(v[3]), t2 = fr_w16<INV, 4>(v[5]), t3 = fr_w16<INV, 6>(v[7]);
+  o[0] = cadd(v[0], t0); o[4] = csub(v[0], t0);
+  o[1] = cadd(v[2], t1); o[5] = csub(v[2], t1);
+  o[2] = cadd(v[4], t2); o[6] = csub(v[4], t2);
+  o[3] = cadd(v[6], t3); o[7] = csub(v[6], t3);
+}
+template <bool INV> __device__ __forceinline__ cplx fr_tw(const cplx* tab, int idx) {
+  const cplx w = tab[idx];
+  return INV ? mk(w.x, -w.y) : w;
+}
+// X[q'] of fr_dft16 sits at v[4 (q' & 3) + (q' >> 2)]
+#define FR_OUT16(v, qp) (v)[4 * ((qp) & 3) + ((qp) >> 2)]
+
+// radix-16 pass with stride p (1 or 16) in place on the padded buffer Z; every thread of the CTA calls it (barriers)
+template <bool INV>
+__device__ __forceinline__ void fr_pass16(cplx* Z, int t, int p, bool active, const cplx* TW) {
+  cplx v[16];
+  const int k = t & (p - 1), a = t / p;
+  if (active) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = Z[fr_pad(t + 128 * q)];
+    if (p > 1) {
+      // twiddle w^q, w = exp(-+2 pi i k / (16 p)); only p = 16 has twiddles
+      const cplx w1 = fr_tw<INV>(TW, k), w2 = fr_tw<INV>(TW, 16 + k), w4 = fr_tw<INV>(TW, 32 + k), w8 = fr_tw<INV>(TW, 48 + k);
+      const cplx w3 = cmul(w1, w2), w5 = cmul(w4, w1), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
+      v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3); v[4] = cmul(v[4], w4);
+      v[5] = cmul(v[5], w5); v[6] = cmul(v[6], w6); v[7] = cmul(v[7], w7); v[8] = cmul(v[8], w8);
+      v[9] = cmul(v[9], cmul(w8, w1)); v[10] = cmul(v[10], cmul(w8, w2)); v[11] = cmul(v[11], cmul(w8, w3));
+      v[12] = cmul(v[12], cmul(w8, w4)); v[13] = cmul(v[13], cmul(w8, w5)); v[14] = cmul(v[14], cmul(w8, w6));
+      v[15] = cmul(v[15], cmul(w8, w7));
+    }
+    fr_dft16<INV>(v);
+  }
+  __syncthreads();
+  if (active) {
+    const int base = a * p * 16 + k;
+#pragma unroll
+    for (int qp = 0; qp < 16; ++qp) Z[fr_pad(base + qp * p)] = FR_OUT16(v, qp);
+  }
+  __syncthreads();
+}
+// last pass (radix 8, stride 256): butterflies t and t + 128 of the transform
+template <bool INV>
+__device__ __forceinline__ void fr_pass8(cplx* Z, int t, bool active, const cplx* TW) {
+  cplx o[2][8];
+  if (active) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int tt = t + 128 * u;
+      cplx v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = Z[fr_pad(tt + 256 * q)];
+      const cplx w1 = fr_tw<INV>(TW, 64 + tt), w2 = fr_tw<INV>(TW, 64 + 256 + tt), w4 = fr_tw<INV>(TW, 64 + 512 + tt);
+      const cplx w3 = cmul(w1, w2);
+      v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3); v[4] = cmul(v[4], w4);
+      v[5] = cmul(v[5], cmul(w4, w1)); v[6] = cmul(v[6], cmul(w4, w2)); v[7] = cmul(v[7], cmul(w4, w3));
+      fr_dft8<INV>(v, o[u]);
+    }
+  }
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int qp = 0; qp < 8; ++qp) Z[fr_pad(t + 128 * u + 256 * qp)] = o[u][qp];
+  }
+  __syncthreads();
+}
+
+// first forward pass of channel `ch` from global memory: pairs (x[2n], x[2n+1]) at n = t + 128 q, zero outside the signal
+__device__ __forceinline__ void fr_load_first(cplx (&v)[16], const double* __restrict__ in, long long num_samples, int ch,
+                                              bool valid, long long s_first, int t) {
+  const double* x = in + (long long)ch * num_samples;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const long long i0 = s_first + 2LL * (t + 128 * q);
+    if (valid && i0 >= 0 && i0 < num_samples) {
+      const double2 d = *reinterpret_cast<const double2*>(x + i0);
+      v[q] = mk(d.x, d.y);
+    } else {
+      v[q] = mk(0.0, 0.0);
+    }
+  }
+}
+
+__device__ __forceinline__ void fr_prefetch_first(const double* __restrict__ in, long long num_samples, int ch, bool valid,
+                                                  long long s_first, int t) {
+  if (!valid || (t & 7) != 0) return;          // one prefetch per 128-byte line (eight 16-byte pairs)
+  const double* x = in + (long long)ch * num_samples;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const long long i0 = s_first + 2LL * (t + 128 * q);
+    if (i0 >= 0 && i0 < num_samples) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + i0));
+  }
+}
+
+// bin k of the spectra of channels cg .. cg + nc - 1 (packed transforms in Zb) into the two ears' accumulators; the
+// filter spectra of all CU channels are requested before anything is computed (CU = 4: full group, CU = 1: tail)
+template <int CU>
+__device__ __forceinline__ void fr_accumulate(const cplx* Zb, cplx* accL, cplx* accR, const cplx* __restrict__ Hw,
+                                              const cplx* __restrict__ WN, int num_ch, int cg, int k, int nc) {
+  constexpr int M = FR_M, F = FR_M + 1;
+  const cplx wn = WN[k];
+  cplx aL = accL[k], aR = accR[k];
+  const int ik = fr_pad(k & (M - 1)), im = fr_pad((M - k) & (M - 1));
+  for (int c0 = 0; c0 < nc; c0 += CU) {
+    cplx hl[CU], hr[CU];
+#pragma unroll
+    for (int u = 0; u < CU; ++u) {
+      const int c = min(c0 + u, nc - 1);           // a channel past the end: loaded again, not used
+      hl[u] = Hw[(long long)(cg + c) * F + k];
+      hr[u] = Hw[((long long)num_ch + cg + c) * F + k];
+    }
+#pragma unroll
+    for (int u = 0; u < CU; ++u) {
+      if (c0 + u >= nc) break;
+      const cplx zk = Zb[(c0 + u) * FR_LD + ik], zm = cconj(Zb[(c0 + u) * FR_LD + im]);
+      const cplx sm_ = cadd(zk, zm), df = cmul(wn, csub(zk, zm));
+      const cplx X = mk(0.5 * (sm_.x + df.y), 0.5 * (sm_.y - df.x));     // sm/2 - (i/2) df
+      cfma(aL, X, hl[u]);
+      cfma(aR, X, hr[u]);
+    }
+  }
+  accL[k] = aL; accR[k] = aR;
+}
+
+// PRE = 1: the next group's samples are loaded into registers before the accumulation (they fly during it);
+// PRE = 0: they are only pulled into L2 there and loaded afterwards (more registers for the filter spectra in flight)
+template <int PRE>
+__global__ void __launch_bounds__(FR_T, 1)
+fused_render16_kernel(const double* __restrict__ in, long long num_samples, int num_ch, const cplx* __restrict__ Hw,
+                      const cplx* __restrict__ TWg, const cplx* __restrict__ WN, int L, int ov, long long skip,
+                      long long out_rows, double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char fr16_raw[];
+  constexpr int M = FR_M, F = FR_M + 1, N = 2 * FR_M;
+  cplx* Zb = reinterpret_cast<cplx*>(fr16_raw);        // [4][FR_LD]
+  cplx* accL = Zb + 4 * FR_LD;                         // [F]
+  cplx* accR = accL + F;
+#if EMAGLS_FR_TW_SMEM
+  cplx* TW = accR + F;                                 // [FR_TW]
+#else
+  const cplx* TW = TWg;
+#endif
+  const int tid = threadIdx.x, g4 = tid >> 7, t = tid & 127;
+  cplx* Z = Zb + g4 * FR_LD;
+  const long long b = blockIdx.x;
+  const long long s_first = b * (long long)L - ov;     // even: L and ov are even
+  cplx v[16];
+  fr_load_first(v, in, num_samples, g4, g4 < num_ch, s_first, t);
+  for (int k = tid; k < F; k += FR_T) { accL[k] = mk(0.0, 0.0); accR[k] = mk(0.0, 0.0); }
+#if EMAGLS_FR_TW_SMEM
+  for (int i = tid; i < FR_TW; i += FR_T) TW[i] = TWg[i];
+#endif
+  for (int cg = 0; cg < num_ch; cg += 4) {
+    // ---- pass 1 (stride 1, no twiddles) from the registers loaded ahead
+    fr_dft16<false>(v);
+    __syncthreads();                                   // the previous group's spectra have been accumulated
+    {
+      const int base = 16 * t;
+#pragma unroll
+      for (int qp = 0; qp < 16; ++qp) Z[fr_pad(base + qp)] = FR_OUT16(v, qp);
+    }
+    __syncthreads();
+    fr_pass16<false>(Z, t, 16, true, TW);
+    fr_pass8<false>(Z, t, true, TW);
+    // ---- this group's spectra are unpacked and accumulated while the next group's samples are on their way
+    const bool more = cg + 4 < num_ch;
+    const int nc = min(4, num_ch - cg);
+    if (PRE) {
+      if (more) fr_load_first(v, in, num_samples, cg + 4 + g4, cg + 4 + g4 < num_ch, s_first, t);
+      for (int j = 0; j < 5; ++j) {
+        const int k = tid + FR_T * j;
+        if (k > M) break;                              // bin M (Nyquist) belongs to thread 0
+        const cplx wn = WN[k];
+        cplx aL = accL[k], aR = accR[k];
+        const int ik = fr_pad(k & (M - 1)), im = fr_pad((M - k) & (M - 1));
+        for (int c = 0; c < nc; ++c) {
+          const cplx zk = Zb[c * FR_LD + ik], zm = cconj(Zb[c * FR_LD + im]);
+          const cplx sm_ = cadd(zk, zm), df = cmul(wn, csub(zk, zm));
+          const cplx X = mk(0.5 * (sm_.x + df.y), 0.5 * (sm_.y - df.x));     // sm/2 - (i/2) df
+          cfma(aL, X, Hw[(long long)(cg + c) * F + k]);
+          cfma(aR, X, Hw[((long long)num_ch + cg + c) * F + k]);
+        }
+        accL[k] = aL; accR[k] = aR;
+      }
+    } else {
+      if (more) fr_prefetch_first(in, num_samples, cg + 4 + g4, cg + 4 + g4 < num_ch, s_first, t);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) fr_accumulate<4>(Zb, accL, accR, Hw, WN, num_ch, cg, tid + FR_T * j, nc);
+      if (tid == 0) fr_accumulate<4>(Zb, accL, accR, Hw, WN, num_ch, cg, M, nc);
+      if (more) fr_load_first(v, in, num_samples, cg + 4 + g4, cg + 4 + g4 < num_ch, s_first, t);
+    }
+  }
+  __syncthreads();
+  // ---- both ears: Hermitian spectrum -> packed half-length sequence, inverse transform (transforms 0 and 1)
+  for (int k = tid; k < M; k += FR_T) {
+#pragma unroll
+    for (int ear = 0; ear < 2; ++ear) {
+      const cplx* acc = ear ? accR : accL;
+      const cplx yk = acc[k], ym = cconj(acc[M - k]);
+      const cplx sm_ = cadd(yk, ym), df = cmul(cconj(WN[k]), csub(yk, ym));
+      Zb[ear * FR_LD + fr_pad(k)] = mk(sm_.x - df.y, sm_.y + df.x);               // sm + i df
+    }
+  }
+  __syncthreads();
+  const bool act = g4 < 2;
+  fr_pass16<true>(Z, t, 1, act, TW);
+  fr_pass16<true>(Z, t, 16, act, TW);
+  fr_pass8<true>(Z, t, act, TW);
+  const double inv_n = 1.0 / (double)N;
+  for (int n = tid; n < M; n += FR_T) {
+    const int i = 2 * n;
+    if (i < ov) continue;
+    const long long s0 = b * (long long)L + (i - ov);
+#pragma unroll
+    for (int ear = 0; ear < 2; ++ear) {
+      const cplx y = Zb[ear * FR_LD + fr_pad(n)];
+      if (s0 < num_samples && s0 >= skip) out[(long long)ear * out_rows + (s0 - skip)] = y.x * inv_n;
+      if (s0 + 1 < num_samples && s0 + 1 >= skip) out[(long long)ear * out_rows + (s0 + 1 - skip)] = y.y * inv_n;
+    }
+  }
+}
+
 int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -387,6 +675,36 @@ void binaural_decode_dev(emagls_ctx* h, const double* in, long long num_samples,
   // below (15.3 ms before two channels shared a pass and the next pair was prefetched with cp.async) -- the radix-4
   // shared-memory FFT makes six barrier-separated passes per channel pair with one 512-thread CTA per SM; it needs
   // register-resident radix-8/16 passes before it can win.
+  // EMAGLS_RENDER_FUSED=2 / 3: register-resident radix-16 version of the fused route (N = 4096 only)
+  const int fused_mode = env_int("EMAGLS_RENDER_FUSED", 0);
+  if ((fused_mode == 2 || fused_mode == 3) && N == 2 * FR_M && (num_samples % 2 == 0) && (ov % 2 == 0) &&
+      (reinterpret_cast<uintptr_t>(in) % 16 == 0)) {
+    cplx* TW = ar.get<cplx>((size_t)FR_TW);
+    cplx* WMu = ar.get<cplx>((size_t)FR_M / 2 + 1);
+    cplx* WN = ar.get<cplx>((size_t)FR_M + 1);
+    render_twiddle_full_kernel<<<(FR_TW + 255) / 256, 256, 0, st>>>(TW);
+    render_twiddle_kernel<<<(FR_M + 1 + 255) / 256, 256, 0, st>>>(FR_M, WMu, WN);
+    EM_CUDA(cudaGetLastError());
+    const size_t smem = ((size_t)4 * FR_LD + 2 * (FR_M + 1) + (EMAGLS_FR_TW_SMEM ? FR_TW : 0)) * sizeof(cplx);
+    static bool attr_set = false;
+    if (!attr_set) {
+      EM_CUDA(cudaFuncSetAttribute(fused_render16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      EM_CUDA(cudaFuncSetAttribute(fused_render16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    {
+      ProfSpan ps(h, EM_PROF_RENDER_MAC);
+      if (fused_mode == 2)
+        fused_render16_kernel<1><<<(unsigned)nblk_total, FR_T, smem, st>>>(in, num_samples, num_ch, Hw, TW, WN, L, ov, skip,
+                                                                         out_rows, out);
+      else
+        fused_render16_kernel<0><<<(unsigned)nblk_total, FR_T, smem, st>>>(in, num_samples, num_ch, Hw, TW, WN, L, ov, skip,
+                                                                         out_rows, out);
+      EM_CUDA(cudaGetLastError());
+    }
+    h->launches += 3;
+    return;
+  }
   if (env_int("EMAGLS_RENDER_FUSED", 0) != 0 && N <= 4096 && N >= 8 && (num_samples % 2 == 0) && (ov % 2 == 0) &&
       (reinterpret_cast<uintptr_t>(in) % 16 == 0)) {
     const int M2 = N / 2;

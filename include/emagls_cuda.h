@@ -101,8 +101,11 @@ int emagls_design_emagls2(emagls_handle h, const emagls_config* cfg,
                           int num_sets, int num_orient, const double* rotations,
                           double* wL, double* wR, double* spectra);
 
-/* Same, but every array argument is a device pointer on the handle's device and the call only
- * enqueues work on emagls_stream(h) (bench.py's device-resident `value`).                      */
+/* Same, but every array argument is a device pointer on the handle's device: no bulk host <-> device
+ * copies; all kernels run on emagls_stream(h) (bench.py's device-resident `value`).  The call is NOT
+ * fully asynchronous: it waits on the stream for four small read-backs that decide what is launched next
+ * (the group delays, whose median is taken on the host; the conditioning flag of the grid basis; per
+ * 128-bin group the bins admitted to the Gram route) and returns with the remaining work enqueued.       */
 int emagls_design_emagls2_dev(emagls_handle h, const emagls_config* cfg,
                               const double* hL, const double* hR, int num_samples, int num_dirs,
                               const double* grid_azi, const double* grid_zen,
