@@ -536,6 +536,9 @@ def main():
         algo_bytes = n * 272.0                                              # 272 B / frame
         render = {"metric": "render_msamples_per_sec", "value": n / (rms * 1e-3) / 1e6, "unit": "Msamples/s",
                   "frames": n, "channels": 32, "taps": LEN, "ms": rms,
+                  "kernel": "fused_render16_kernel (overlap-save block per CTA: radix 16 x 16 x 8 Stockham passes in "
+                            "registers / shared memory, multiply-accumulate over the channels, inverse transform; the "
+                            "channel spectra never reach HBM)",
                   "roofline": {"bound": "hbm", "achieved": algo_bytes / (rms * 1e-3) / 1e9, "peak": hbm,
                                "unit": "GB/s", "frac": algo_bytes / (rms * 1e-3) / 1e9 / hbm,
                                "class_ms": {k: v["ms"] / 3 for k, v in rp.items() if v["n"]}}}

@@ -675,8 +675,11 @@ void binaural_decode_dev(emagls_ctx* h, const double* in, long long num_samples,
   // below (15.3 ms before two channels shared a pass and the next pair was prefetched with cp.async) -- the radix-4
   // shared-memory FFT makes six barrier-separated passes per channel pair with one 512-thread CTA per SM; it needs
   // register-resident radix-8/16 passes before it can win.
-  // EMAGLS_RENDER_FUSED=2 / 3: register-resident radix-16 version of the fused route (N = 4096 only)
-  const int fused_mode = env_int("EMAGLS_RENDER_FUSED", 0);
+  // Default route for N = 4096 (filters of 257 .. 512 taps): the register-resident fused kernel (radix 16 x 16 x 8),
+  // 6.7 ms against 9.7 ms for the cuFFT route on 10 minutes x 32 channels (profiles/r02_v27_render_reps.txt).
+  // EMAGLS_RENDER_FUSED=0 selects the cuFFT route, =1 the shared-memory radix-4 kernel of round 1, =3 the variant of
+  // the default that only pulls the next group's samples into L2 during the accumulation (8.9 ms).
+  const int fused_mode = env_int("EMAGLS_RENDER_FUSED", 2);
   if ((fused_mode == 2 || fused_mode == 3) && N == 2 * FR_M && (num_samples % 2 == 0) && (ov % 2 == 0) &&
       (reinterpret_cast<uintptr_t>(in) % 16 == 0)) {
     cplx* TW = ar.get<cplx>((size_t)FR_TW);
@@ -705,7 +708,7 @@ void binaural_decode_dev(emagls_ctx* h, const double* in, long long num_samples,
     h->launches += 3;
     return;
   }
-  if (env_int("EMAGLS_RENDER_FUSED", 0) != 0 && N <= 4096 && N >= 8 && (num_samples % 2 == 0) && (ov % 2 == 0) &&
+  if (fused_mode == 1 && N <= 4096 && N >= 8 && (num_samples % 2 == 0) && (ov % 2 == 0) &&
       (reinterpret_cast<uintptr_t>(in) % 16 == 0)) {
     const int M2 = N / 2;
     int logM = 0;
