@@ -282,9 +282,9 @@ def main():
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(nsteps):
-            designer.step()
-            designer.wait()          # the host has its shard (and rank 0 the gathered device bank)
-        torch.cuda.synchronize()
+            designer.step()          # returns when the design is enqueued; the D2H + gather of this step run on the
+        designer.wait()              # transfer stream while the next step is designed into the other bank buffer
+        torch.cuda.synchronize()     # every host shard (and rank 0's gathered device banks) is complete here
         return emdist.max_over_ranks(time.perf_counter() - t0, dev)
 
     e2e_steps = max(5, min(args.steps, 10))
@@ -648,7 +648,9 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                         "steps": e2e_steps, "includes_nccl_gather": world > 1,
                         "path": "emagls_b200.dist.ShardedDesigner: pinned host inputs -> H2D -> emagls_design_emagls2_dev "
-                                "-> NCCL send/recv of the shards into rank 0's device bank -> D2H of every shard (pinned)",
+                                "-> D2H of every shard (pinned) and NCCL send/recv of the shards into rank 0's device bank on a "
+                                "transfer stream, double-buffered banks: the transfers of step i overlap the design of step "
+                                "i + 1; the timed region ends when the last step's transfers have finished",
                         "max_rel_diff_vs_device_resident_banks": e2e_same, "host_api_call": host_api},
                 "strong_scaling": strong, "parity_spot_check": spot, "config3": config3,
                 "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline,

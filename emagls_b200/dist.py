@@ -90,10 +90,15 @@ def gather_into(local: torch.Tensor, total: torch.Tensor | None, n_total: int, d
 class ShardedDesigner:
     """End-to-end eMagLS2 design of one orientation batch sharded over the ranks: host inputs
     in pinned memory -> H2D -> `emagls_design_emagls2_dev` on this rank's contiguous block of orientations ->
-    NCCL gather of the banks into rank 0's device bank -> D2H of this rank's shard into pinned host memory.
-    No data-path collective; the gather is the only exchange.  All buffers are allocated once."""
+    D2H of this rank's shard into pinned host memory and NCCL gather of the banks into rank 0's device bank.
+    No data-path collective; the gather is the only exchange.  All buffers are allocated once.
 
-    def __init__(self, handle, hL, hR, az, ze, mic_radius, maz, mze, order, fs, length, rotations_total, config=None):
+    The banks are double buffered: the transfers of step i (D2H + gather) run on a second stream while step i + 1
+    is designed into the other buffer, so in steady state the exchange costs nothing but its bandwidth.  `step()`
+    returns once the design has been enqueued; `wait()` returns when every transfer issued so far has finished."""
+
+    def __init__(self, handle, hL, hR, az, ze, mic_radius, maz, mze, order, fs, length, rotations_total, config=None,
+                 buffers: int = 2):
         import ctypes as C
         import numpy as np
         self.C, self.np, self.h = C, np, handle
@@ -102,6 +107,7 @@ class ShardedDesigner:
         self.dev = torch.device("cuda", handle.device if hasattr(handle, "device") else local_rank)
         self.cfg = config if config is not None else handle.default_config()
         self.stream = torch.cuda.ExternalStream(handle.stream, device=self.dev)
+        self.xfer = torch.cuda.Stream(device=self.dev)
         R = np.ascontiguousarray(np.asarray(rotations_total, dtype=np.float64).reshape(-1, 9))
         self.n_total = R.shape[0]
         self.lo, self.hi = shard_range(self.n_total, rank, world)
@@ -117,20 +123,46 @@ class ShardedDesigner:
                         pin(R[self.lo:self.hi])]
         self.h2d_bytes = sum(h.numel() * 8 for h, _ in self.host_in)
         shape = (max(self.n_local, 1), self.M, self.len)       # [len, M, B] column-major
-        # rank 0 designs straight into its slice of the total bank [2 ears][n_total]
-        self.total = (torch.empty((2, self.n_total, self.M, self.len), dtype=torch.float64, device=self.dev)
-                      if rank == 0 else None)
-        if rank == 0:
-            self.bank = [self.total[e, self.lo:self.hi] for e in range(2)]
-        else:
-            self.bank = [torch.empty(shape, dtype=torch.float64, device=self.dev)[: self.n_local] for _ in range(2)]
-        self.host_out = [torch.empty((self.n_local, self.M, self.len), dtype=torch.float64).pin_memory()
-                         for _ in range(2)]
+        self.nbuf = max(1, int(buffers))
+        self.totals, self.banks, self.host_outs = [], [], []
+        for _ in range(self.nbuf):
+            # rank 0 designs straight into its slice of the total bank [2 ears][n_total]
+            total = (torch.empty((2, self.n_total, self.M, self.len), dtype=torch.float64, device=self.dev)
+                     if rank == 0 else None)
+            if rank == 0:
+                bank = [total[e, self.lo:self.hi] for e in range(2)]
+            else:
+                bank = [torch.empty(shape, dtype=torch.float64, device=self.dev)[: self.n_local] for _ in range(2)]
+            self.totals.append(total)
+            self.banks.append(bank)
+            self.host_outs.append([torch.empty((self.n_local, self.M, self.len), dtype=torch.float64).pin_memory()
+                                   for _ in range(2)])
+        self.designed = [torch.cuda.Event() for _ in range(self.nbuf)]
+        self.moved = [None] * self.nbuf          # event: the transfers out of buffer b have finished
+        self.cur = 0                             # buffer the next step designs into
+        self.last = 0                            # buffer of the latest step
         self.d2h_bytes = 2 * self.n_local * self.M * self.len * 8
+
+    # the buffers of the latest step (device bank of this rank, gathered bank on rank 0, pinned host shard)
+    @property
+    def bank(self):
+        return self.banks[self.last]
+
+    @property
+    def total(self):
+        return self.totals[self.last]
+
+    @property
+    def host_out(self):
+        return self.host_outs[self.last]
 
     def step(self, gather: bool = True):
         C, h = self.C, self.h
+        b = self.cur
+        bank, total = self.banks[b], self.totals[b]
         with torch.cuda.stream(self.stream):
+            if self.moved[b] is not None:
+                self.stream.wait_event(self.moved[b])       # the previous contents of this buffer have left
             for hbuf, dbuf in self.host_in:
                 dbuf.copy_(hbuf, non_blocking=True)
             d = [db for _, db in self.host_in]
@@ -138,17 +170,26 @@ class ShardedDesigner:
                 rc = h.lib.emagls_design_emagls2_dev(
                     h.ptr, C.byref(self.cfg), d[0].data_ptr(), d[1].data_ptr(), self.T, self.D, d[2].data_ptr(),
                     d[3].data_ptr(), self.r, d[4].data_ptr(), d[5].data_ptr(), self.M, self.order, self.fs, self.len,
-                    1, self.n_local, d[6].data_ptr(), self.bank[0].data_ptr(), self.bank[1].data_ptr(), None)
+                    1, self.n_local, d[6].data_ptr(), bank[0].data_ptr(), bank[1].data_ptr(), None)
                 h.check(rc)
+            self.designed[b].record(self.stream)
+        with torch.cuda.stream(self.xfer):
+            self.xfer.wait_event(self.designed[b])
             for e in range(2):
-                self.host_out[e].copy_(self.bank[e], non_blocking=True)
+                self.host_outs[b][e].copy_(bank[e], non_blocking=True)
             if gather and self.world > 1:
                 for e in range(2):
-                    gather_into(self.bank[e], self.total[e] if self.total is not None else None, self.n_total, 0)
-        return self.total
+                    gather_into(bank[e], total[e] if total is not None else None, self.n_total, 0)
+            ev = torch.cuda.Event()
+            ev.record(self.xfer)
+            self.moved[b] = ev
+        self.last = b
+        self.cur = (b + 1) % self.nbuf
+        return total
 
     def wait(self):
         self.stream.synchronize()
+        self.xfer.synchronize()
 
 
 def render_shard(n_frames: int, taps: int, rank: int, world: int) -> tuple[int, int, int]:
