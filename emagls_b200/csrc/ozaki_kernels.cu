@@ -280,11 +280,11 @@ template <int T, class Epi, class Cfg = oz::TileDefault>
 static cudaError_t oz_fwd_t(cudaStream_t st, const OzFwdArgs& a) {
   CUtensorMap tmA, tmB, tmC;
   if (!oz::make_operand_map(&tmA, a.YhA_q, a.D, a.KpS, T, oz::TILE_M) ||
-      !oz::make_operand_map(&tmB, a.Cv_q, a.rows, a.KpS, T, oz::TILE_N))
+      !oz::make_operand_map(&tmB, a.Cv_q, a.rows, a.KpS, T, Cfg::NT))
     return cudaErrorInvalidValue;
   const bool tma_out = oz::epi_tma_stage<Epi>::value != 0;
   if (tma_out && !oz::make_output_map(&tmC, a.Tt_q, a.rows, a.D, a.KpD, T, oz::TILE_N)) return cudaErrorInvalidValue;
-  oz::GemmArgs g{a.D, a.rows, a.KpS, a.sYhA, a.sCv, oz_fwd_debug, 0, oz::TILE_N};   // m fastest: the 42 MB of Cv digits are the shared operand
+  oz::GemmArgs g{a.D, a.rows, a.KpS, a.sYhA, a.sCv, oz_fwd_debug, 0, Cfg::NT};   // m fastest: the 42 MB of Cv digits are the shared operand
   Epi epi{a.Tt_q, (long long)a.rows * a.KpD, a.KpD, a.sT, a.absH, a.abs_set_stride, a.abs_ear_stride,
           a.up, a.sc, a.scale_stride, a.orient_per_set, a.nyquist};
   if constexpr (oz::epi_raw<Epi>::value) epi.sB = a.sCv;
@@ -327,12 +327,25 @@ cudaError_t launch_oz_fwd(cudaStream_t st, const OzFwdArgs& a) {
 
 cudaError_t launch_oz_bwd(cudaStream_t st, const int8_t* Tt_q, const double* sT, int rows, const int8_t* B_q,
                           const double* sB, int S, int KpD, int T, double* tq) {
-  // 80-column tiles when they leave fewer padded columns than 64-column tiles (S = 400: 5 x 80 against 7 x 64)
-  const bool wide = ((S + 79) / 80) * 80 < ((S + 63) / 64) * 64 && !getenv("EMAGLS_OZ_NARROW");
-  if (wide)
-    return oz::launch_ozaki_gemm<oz::EpiStoreF64, oz::TileWide>(st, Tt_q, sT, B_q, sB, rows, S, KpD, T,
-                                                                oz::EpiStoreF64{tq, (long long)S}, sm_count());
-  return oz::launch_ozaki_gemm(st, Tt_q, sT, B_q, sB, rows, S, KpD, T, oz::EpiStoreF64{tq, (long long)S}, sm_count());
+  // Tile width by shape: a k-step costs (128 + NT) operand bytes per slice (TMA traffic and the shared-memory reads of
+  // the MMAs), and the launch takes ceil(tiles / SMs) rounds of tiles.  80 columns for the 3600-orientation batch
+  // (S = 400 = 5 x 80: no padded columns, the A operand passes through L2 5 instead of 7 times); 48 columns when that
+  // brings an otherwise half-empty grid to one full round (450 orientations per GPU: 135 tiles instead of 75).
+  const int sms = sm_count();
+  const int m_tiles = (rows + oz::TILE_M - 1) / oz::TILE_M;
+  auto cost = [&](int nt) {
+    const long long tiles = (long long)m_tiles * ((S + nt - 1) / nt);
+    return ((tiles + sms - 1) / sms) * (long long)(128 + nt);
+  };
+  int nt = 64;
+  if (!getenv("EMAGLS_OZ_NARROW")) {
+    if (cost(80) <= cost(nt)) nt = 80;
+    if (cost(48) < cost(nt)) nt = 48;
+  }
+  const oz::EpiStoreF64 epi{tq, (long long)S};
+  if (nt == 80) return oz::launch_ozaki_gemm<oz::EpiStoreF64, oz::TileWide>(st, Tt_q, sT, B_q, sB, rows, S, KpD, T, epi, sms);
+  if (nt == 48) return oz::launch_ozaki_gemm<oz::EpiStoreF64, oz::TileCfg<48, 3>>(st, Tt_q, sT, B_q, sB, rows, S, KpD, T, epi, sms);
+  return oz::launch_ozaki_gemm(st, Tt_q, sT, B_q, sB, rows, S, KpD, T, epi, sms);
 }
 
 }  // namespace emagls

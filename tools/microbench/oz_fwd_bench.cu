@@ -54,13 +54,17 @@ int main(int argc, char** argv) {
     if (T == 6) {
       if (mode == 0) return oz_fwd_t<6, EpiPhaseSlice<6>>(0, fa);
       if (mode == 1) return oz_fwd_t<6, EpiPhaseSliceRaw<6>>(0, fa);
+      if (mode == 3) return oz_fwd_t<6, EpiPhaseSliceRaw<6>, oz::TileWide>(0, fa);
+      if (mode == 4) return oz_fwd_t<6, EpiPhaseSliceRaw<6>, oz::TileCfg<48, 3>>(0, fa);
       return oz_fwd_t<6, EpiPhaseSliceTma<6>, Ring2>(0, fa);
     }
     if (mode == 0) return oz_fwd_t<4, EpiPhaseSlice<4>>(0, fa);
     if (mode == 1) return oz_fwd_t<4, EpiPhaseSliceRaw<4>>(0, fa);
+    if (mode == 3) return oz_fwd_t<4, EpiPhaseSliceRaw<4>, oz::TileWide>(0, fa);
+    if (mode == 4) return oz_fwd_t<4, EpiPhaseSliceRaw<4>, oz::TileCfg<48, 3>>(0, fa);
     return oz_fwd_t<4, EpiPhaseSliceTma<4>, Ring2>(0, fa);
   };
-  const char* names[3] = {"scaled", "raw", "tma"};
+  const char* names[5] = {"scaled", "raw", "tma", "raw80", "raw48"};
   const size_t nq = (size_t)T * rows * KpD;
   std::vector<int8_t> ref(nq), got(nq);
   std::vector<double> sref(rows), sgot(rows);
@@ -78,7 +82,7 @@ int main(int argc, char** argv) {
     printf("long run %s: %.4f ms per launch after 12000 launches\n", names[long_mode], msl / 2000);
     return 0;
   }
-  for (int mode = 0; mode < 3; ++mode) {
+  for (int mode = 0; mode < 5; ++mode) {
     CK(cudaMemset(qT, 0, nq));
     CK(cudaMemset(sT, 0, (size_t)rows * 8));
     CK(run(mode));
