@@ -33,7 +33,7 @@ BlockPlan make_block_plan(int S, int Mc) {
 }
 
 size_t factor_smem_bytes(const BlockPlan& bp) {
-  return (size_t)bp.MC * (bp.MC + bp.RB) * sizeof(cplx) + (size_t)(2 * bp.MC + 72) * sizeof(cplx) + 256;
+  return (size_t)bp.MC * (bp.MC + bp.RB + 1) * sizeof(cplx) + (size_t)(2 * bp.MC + 72) * sizeof(cplx) + 256;
 }
 
 template <int GW>
@@ -151,7 +151,9 @@ __device__ void qr_block(cplx* Wk, int LD, int Mc, bool first, int hi, cplx* tau
 template <int MC, int RB>
 __global__ void __launch_bounds__(FT, (MC == 32) ? (RB <= 64 ? 4 : 3) : 1)
 factor_kernel(BlockPlan bp, RowSource src, OperatorSet ops, int kbase, int G, double regul, int try_fast) {
-  constexpr int LD = MC + RB;
+  // one element of padding per column: with LD = MC + RB the column stride is a multiple of 128 bytes and the
+  // block loads / flushes below (consecutive threads -> consecutive columns) hit one bank group (ncu, round 1: 4.3-way)
+  constexpr int LD = MC + RB + 1;
   extern __shared__ __align__(16) unsigned char fsm_raw[];
   cplx* Wk = reinterpret_cast<cplx*>(fsm_raw);
   cplx* tau_s = Wk + (size_t)MC * LD;
