@@ -3,10 +3,12 @@
  * comes from (a loop of 3600 single calls pays the per-call setup 3600 times).
  *
  * [wMlsL, wMlsR] = getEMagLs2FiltersBatch(hL, hR, hrirGridAziRad, hrirGridZenRad, micRadius, ...
- *                       micGridAziRad, micGridZenRad, order, fs, len, rotations)
+ *                       micGridAziRad, micGridZenRad, order, fs, len, rotations, applyDiffusenessConst)
  *   hL, hR     [numSamples x numDirections x numSets]
  *   rotations  [3 x 3 x B]: head orientation b sees HRIR-grid direction u at R(:,:,b) * u, i.e. page b equals one
  *              reference call with hrirGridAziRad/ZenRad rotated by R(:,:,b)  (lib/getEMagLs2Filters.m:1-2)
+ *   applyDiffusenessConst  optional, default false: the diffuse-field covariance constraint of earlier reference
+ *              versions (CHANGELOG.md:10-18), an extension of this library (emagls_config.diffuseness_const)
  *   wMlsL/R    [len x numMics x (numSets * B)], set index slowest
  * Binds emagls_design_emagls2() with num_sets / num_orient / rotations (include/emagls_cuda.h).
  * Build where MATLAB exists:  mex -R2018a -I../include getEMagLs2FiltersBatch.c -L../emagls_b200/lib -lemagls_cuda
@@ -18,6 +20,7 @@
 void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   if (nrhs < 11) mexErrMsgIdAndTxt("eMagLS:nargin", "getEMagLs2FiltersBatch needs 11 arguments");
   emagls_config cfg; emagls_config_default(&cfg);
+  if (nrhs > 11 && !mxIsEmpty(prhs[11]) && mxGetScalar(prhs[11]) != 0.0) cfg.diffuseness_const = 1;
   const mwSize* hd = mxGetDimensions(prhs[0]);
   const int T = (int)hd[0], D = (int)hd[1];
   const int sets = mxGetNumberOfDimensions(prhs[0]) > 2 ? (int)hd[2] : 1;

@@ -88,3 +88,23 @@ def test_constraint_is_off_by_default_and_rejects_the_complex_basis(em, case):
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     with pytest.raises(NotImplementedError):
         em.getEMagLsFilters(case["hL"], case["hR"], *case["args"], "complex", handle=h, applyDiffusenessConst=True)
+
+
+def test_constraint_in_an_orientation_batch(em, case):
+    """Batched call with the constraint: page b equals the oracle on the HRIR grid rotated by R_b (as for the plain
+    designer, tests/test_gpu_design.py), two HRTF sets sharing the orientation-dependent Gram matrices."""
+    h = em.Handle(0)
+    az, ze, r, maz, mze, order, fs, length = case["args"]
+    Rm = np.stack([np.eye(3), synth.rotation_yaw_pitch(50.0, -20.0)])
+    hL2 = np.stack([case["hL"], 0.7 * case["hR"]], 2)
+    hR2 = np.stack([case["hR"], 1.3 * case["hL"]], 2)
+    wL, wR = em.getEMagLs2Filters(hL2, hR2, *case["args"], rotations=Rm, handle=h, applyDiffusenessConst=True)
+    assert wL.shape == (length, 32, 4)                                  # [len, M, sets * B], set index slowest
+    for s in range(2):
+        for b in range(2):
+            raz, rze = synth.rotate_grid(az, ze, Rm[b])
+            oL, oR = oracle.getEMagLs2Filters(hL2[:, :, s], hR2[:, :, s], raz, rze, r, maz, mze, order, fs, length,
+                                              applyDiffusenessConst=True)
+            page = s * 2 + b
+            assert np.abs(wL[:, :, page] - oL).max() <= 5e-8 * np.abs(oL).max(), (s, b)
+            assert np.abs(wR[:, :, page] - oR).max() <= 5e-8 * np.abs(oR).max(), (s, b)

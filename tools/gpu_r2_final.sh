@@ -16,27 +16,24 @@ python tools/bench_digest.py gpurun_out/${TAG}_bench.json || tail -c 2000 gpurun
 timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err
 tail -c 600 gpurun_out/${TAG}_bench_ref.json
 [ "$2" = "nocap" ] && exit 0
-# launch list: warm-up + one timed step of a short run (cold-cache, serialised: shares, not absolutes)
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv -k regex:emagls\|oz -c 12000 \
-    --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --no-render --no-cpu-baseline --no-spot-check \
-    > gpurun_out/${TAG}_bench_under_ncu.json 2>&1
+# launch list of one 3600-orientation design (cold-cache, serialised: shares, not absolutes)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv \
+    python tools/gpu_ncu_factor.py 3600 > gpurun_out/${TAG}_launches.log 2>&1
 python tools/ncu_launch_summary.py gpurun_out/${TAG}_launches.csv > gpurun_out/${TAG}_launches.summary.txt 2>&1
 head -24 gpurun_out/${TAG}_launches.summary.txt
 rm -f gpurun_out/${TAG}_launches.csv.gz; gzip -f gpurun_out/${TAG}_launches.csv
 cap() { # name regex skip count
-  timeout 400 ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c $4 -f -o gpurun_out/$1 \
+  timeout 400 ncu --set full --clock-control none --import-source on -k "regex:$2" -s $3 -c $4 -f -o gpurun_out/$1 \
       python tools/gpu_ncu_factor.py 3600 > gpurun_out/$1.log 2>&1
   ncu -i gpurun_out/$1.ncu-rep --page details > gpurun_out/$1.details.txt 2>/dev/null
   ncu -i gpurun_out/$1.ncu-rep --page raw --csv > gpurun_out/$1.raw.csv 2>/dev/null
-  ncu -i gpurun_out/$1.ncu-rep --page source --csv > gpurun_out/$1.source.csv 2>/dev/null
   echo "== $1"; grep -E "^  [a-z].*\(|Duration|Registers Per|Achieved Occ|Executed Ipc Active|No Eligible|Mem Busy|Max Bandwidth|DRAM Throughput" gpurun_out/$1.details.txt | head -40
-  sz=$(stat -c %s gpurun_out/$1.ncu-rep 2>/dev/null || echo 0)
-  if [ "$sz" -gt 9000000 ]; then rm -f gpurun_out/$1.ncu-rep; fi
+  rm -f gpurun_out/$1.ncu-rep
 }
 cap ${TAG}_oz "ozaki_gemm_kernel" 40 2
 cap ${TAG}_tsqr "tsqr_sep_kernel" 1 1
 cap ${TAG}_svdclip "svdclip_kernel" 1 1
-cap ${TAG}_bwd "bwd_small_kernel\|chain_bwd_sep_kernel" 3 2
-cap ${TAG}_gram "gram_sweep_kernel\|gemm_f64_kernel" 6 2
-python tools/ncu_traffic.py gpurun_out/${TAG}_oz.raw.csv gpurun_out/${TAG}_oz_traffic.json "ncu --set full --clock-control none, ozaki_gemm_kernel<6> launches 41-42 of a 3600-orientation design; tools/gpu_r2_final.sh ${TAG}" > /dev/null 2>&1
+cap ${TAG}_bwd "bwd_fused_kernel|chain_bwd_sep_kernel" 3 2
+cap ${TAG}_gram "gram_sweep_kernel" 1 1
+python tools/ncu_traffic.py gpurun_out/${TAG}_oz.raw.csv gpurun_out/${TAG}_oz_traffic.json "ncu --set full --clock-control none, ozaki_gemm_kernel<6> launches 41-42 of a 3600-orientation design (forward EpiPhaseSliceRaw 128x64 tiles, backward EpiStoreF64 128x80 tiles); tools/gpu_r2_final.sh ${TAG}" > /dev/null 2>&1
 ls -la gpurun_out/ | grep ${TAG} | awk '{print $5, $9}'
