@@ -548,34 +548,20 @@ fused_render16_kernel(const double* __restrict__ in, long long num_samples, int 
     const int nc = min(4, num_ch - cg);
     if (PRE) {
       if (more) fr_load_first(v, in, num_samples, cg + 4 + g4, cg + 4 + g4 < num_ch, s_first, t);
-      // bins k and M - k together: with E = (z_k + conj z_{M-k}) / 2 and O = -(i/2) (z_k - conj z_{M-k}) the two
-      // spectrum values are X_k = E + W_k O and X_{M-k} = conj(E - W_k O) (W_{M-k} = -conj W_k), so one pair of
-      // shared-memory loads and one twiddle product serve both.  Pairs p = tid, tid + 512 (p < M/2) and p = M/2
-      // (its own partner) for thread 0.
-      for (int j = 0; j < 3; ++j) {
+      for (int j = 0; j < 5; ++j) {
         const int k = tid + FR_T * j;
-        if (k > M / 2) break;
-        const int k2 = M - k;
-        const bool self = (k == k2);
+        if (k > M) break;                              // bin M (Nyquist) belongs to thread 0
         const cplx wn = WN[k];
-        const cplx wh = mk(0.5 * wn.y, -0.5 * wn.x);   // -(i/2) W_k
-        cplx aL = accL[k], aR = accR[k], bL = accL[k2], bR = accR[k2];
-        const int ik = fr_pad(k), im = fr_pad(k2 & (M - 1));
+        cplx aL = accL[k], aR = accR[k];
+        const int ik = fr_pad(k & (M - 1)), im = fr_pad((M - k) & (M - 1));
         for (int c = 0; c < nc; ++c) {
           const cplx zk = Zb[c * FR_LD + ik], zm = cconj(Zb[c * FR_LD + im]);
-          const cplx E = mk(0.5 * (zk.x + zm.x), 0.5 * (zk.y + zm.y));
-          const cplx wo = cmul(wh, csub(zk, zm));
-          const cplx X1 = cadd(E, wo), X2 = mk(E.x - wo.x, wo.y - E.y);          // conj(E - W O)
-          const long long hl = (long long)(cg + c) * F, hr = ((long long)num_ch + cg + c) * F;
-          cfma(aL, X1, Hw[hl + k]);
-          cfma(aR, X1, Hw[hr + k]);
-          if (!self) {
-            cfma(bL, X2, Hw[hl + k2]);
-            cfma(bR, X2, Hw[hr + k2]);
-          }
+          const cplx sm_ = cadd(zk, zm), df = cmul(wn, csub(zk, zm));
+          const cplx X = mk(0.5 * (sm_.x + df.y), 0.5 * (sm_.y - df.x));     // sm/2 - (i/2) df
+          cfma(aL, X, Hw[(long long)(cg + c) * F + k]);
+          cfma(aR, X, Hw[((long long)num_ch + cg + c) * F + k]);
         }
         accL[k] = aL; accR[k] = aR;
-        if (!self) { accL[k2] = bL; accR[k2] = bR; }
       }
     } else {
       if (more) fr_prefetch_first(in, num_samples, cg + 4 + g4, cg + 4 + g4 < num_ch, s_first, t);
