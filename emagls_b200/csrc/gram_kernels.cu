@@ -267,22 +267,25 @@ gram_sweep_kernel(const double* __restrict__ Gre, const double* __restrict__ Gim
       if (!(d > 0.0) || !(d < 1e300)) {
         ok = false;
       } else {
-        const double inv = 1.0 / d;
+        const double inv = __drcp_rn(d);
+        // One update for every lane: rows i != k take a_ij -= f_i conj(A_jk) with f_i = a_ik / d; the pivot row itself
+        // becomes a_kj / d = conj(A_jk) / d (Hermitian), i.e. the same update from a zeroed row with f_k = -1/d,
+        // and the pivot column ends as f for all of them (no divergent second path).
+        cplx f = mk(a[k].x * inv, a[k].y * inv);
         if (lane == k) {
+          f = mk(-inv, 0.0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) a[j] = (j == k) ? mk(-inv, 0.0) : mk(a[j].x * inv, a[j].y * inv);
-        } else {
-          const cplx f = mk(a[k].x * inv, a[k].y * inv);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (j == k) continue;
-            const cplx cj = col[j];                // broadcast
-            // a_ij -= f * conj(A_jk)
-            a[j].x = fma(-f.x, cj.x, a[j].x); a[j].x = fma(-f.y, cj.y, a[j].x);
-            a[j].y = fma(-f.y, cj.x, a[j].y); a[j].y = fma(f.x, cj.y, a[j].y);
-          }
-          a[k] = f;
+          for (int j = 0; j < 32; ++j) a[j] = mk(0.0, 0.0);
         }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j == k) continue;
+          const cplx cj = col[j];                  // broadcast
+          // a_ij -= f * conj(A_jk)
+          a[j].x = fma(-f.x, cj.x, a[j].x); a[j].x = fma(-f.y, cj.y, a[j].x);
+          a[j].y = fma(-f.y, cj.x, a[j].y); a[j].y = fma(f.x, cj.y, a[j].y);
+        }
+        a[k] = f;
       }
       __syncwarp();
     }
