@@ -20,6 +20,40 @@ __global__ void unused_fnv_kernel(const uint8_t* p, size_t n, unsigned long long
   atomicAdd(out, acc);
 }
 
+
+// ---- synthetic epilogue functors (interference study): the accumulators are drained as usual, then each epilogue
+// thread runs one kind of work only, sized like the real functor (about 1.3 us per 8-column chunk when run alone)
+template <int KIND>
+struct EpiSynthetic {
+  static constexpr bool raw = true;
+  int8_t* Tq; long long slice_stride; int Kpad; double* sink; const double* src; int iters;
+  struct TileState { int dummy; };
+  __device__ __forceinline__ TileState begin_tile(int, int, int, int) const { return TileState{0}; }
+  __device__ __forceinline__ void apply(TileState&, int m, int n0, const double (&v)[8], int M, int N) const {
+    if (KIND == 0) {            // integer ALU chain
+      unsigned x = (unsigned)__double2loint(v[0]) | 1u;
+      for (int i = 0; i < iters; ++i) x = x * 1664525u + 1013904223u;
+      if (x == 0x12345678u) sink[m] = 1.0;
+    } else if (KIND == 1) {     // FP64 chain (4 independent)
+      double a = v[0], b = v[1], c = v[2], d = v[3];
+      for (int i = 0; i < iters; ++i) { a = fma(a, 1.0000001, 1e-9); b = fma(b, 0.9999999, 1e-9); c = fma(c, 1.0000002, 1e-9); d = fma(d, 0.9999998, 1e-9); }
+      if (a + b + c + d == 12345.678) sink[m] = a;
+    } else if (KIND == 2) {     // byte stores like the digit stores: 8 columns x 6 planes x 2 (re / im)
+      int8_t* p = Tq + (long long)n0 * Kpad + m;
+      const int q = __double2loint(v[0]);
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int s_ = 0; s_ < 6; ++s_) p[(long long)s_ * slice_stride + (long long)c * Kpad] = (int8_t)(q + c + s_);
+    } else {                    // dependent global loads (L2 hits)
+      const double* p = src + (m & 1023);
+      double acc = 0.0;
+      for (int i = 0; i < iters; ++i) acc += p[(long long)((i * 977 + n0) & 4095) * 1024];
+      if (acc == 12345.678) sink[m] = acc;
+    }
+  }
+};
+
 int main(int argc, char** argv) {
   const int P = argc > 1 ? atoi(argv[1]) : 3600, sets = argc > 2 ? atoi(argv[2]) : 1, reps = argc > 3 ? atoi(argv[3]) : 20;
   const int long_mode = argc > 5 ? atoi(argv[5]) : -1;   // >= 0: run this variant for about five seconds (clock sampling)
@@ -131,6 +165,34 @@ int main(int argc, char** argv) {
     const double ops = 2.0 * D * (double)rows * KpS * (T * (T + 1) / 2);
     printf("oz_fwd %-6s P=%d sets=%d T=%d: %.4f ms per launch, %.0f int8 TOP/s; vs scaled: %zu of %zu values differ (max %.3g in units of the leading digit), %zu scales differ\n",
            names[mode], P, sets, T, ms / reps, ops / (ms / reps * 1e-3) / 1e12, bad, (size_t)rows * KpD, maxdiff, bad_s);
+  }
+
+  {
+    double *sink, *srcb;
+    CK(cudaMalloc(&sink, 1 << 20)); CK(cudaMalloc(&srcb, (size_t)4096 * 1024 * 8 + 8192)); CK(cudaMemset(srcb, 0, (size_t)4096 * 1024 * 8 + 8192));
+    CUtensorMap tmA, tmB;
+    if (!oz::make_operand_map(&tmA, qY, D, KpS, T, oz::TILE_M) || !oz::make_operand_map(&tmB, qC, rows, KpS, T, oz::TILE_N)) return 3;
+    auto run_syn = [&](int kind, int iters, int dbg) -> cudaError_t {
+      oz::GemmArgs g{D, rows, KpS, sY, sC, dbg, 0, oz::TILE_N};
+      if (kind == 0) return oz::launch_ozaki_gemm_t<6, EpiSynthetic<0>>(0, tmA, tmB, g, EpiSynthetic<0>{qT, (long long)rows * KpD, KpD, sink, srcb, iters}, 148);
+      if (kind == 1) return oz::launch_ozaki_gemm_t<6, EpiSynthetic<1>>(0, tmA, tmB, g, EpiSynthetic<1>{qT, (long long)rows * KpD, KpD, sink, srcb, iters}, 148);
+      if (kind == 2) return oz::launch_ozaki_gemm_t<6, EpiSynthetic<2>>(0, tmA, tmB, g, EpiSynthetic<2>{qT, (long long)rows * KpD, KpD, sink, srcb, iters}, 148);
+      return oz::launch_ozaki_gemm_t<6, EpiSynthetic<3>>(0, tmA, tmB, g, EpiSynthetic<3>{qT, (long long)rows * KpD, KpD, sink, srcb, iters}, 148);
+    };
+    const char* kn[4] = {"int-alu", "fp64", "byte-stores", "global-loads"};
+    const int its[4] = {600, 150, 1, 4};
+    if (T == 6)
+      for (int kind = 0; kind < 4; ++kind)
+        for (int dbg : {0, 2}) {
+          CK(run_syn(kind, its[kind], dbg));
+          CK(cudaEventRecord(e0));
+          for (int i = 0; i < reps; ++i) CK(run_syn(kind, its[kind], dbg));
+          CK(cudaEventRecord(e1));
+          CK(cudaDeviceSynchronize());
+          float msd = 0;
+          CK(cudaEventElapsedTime(&msd, e0, e1));
+          printf("synthetic functor %-12s %s: %.4f ms\n", kn[kind], dbg == 2 ? "without MMAs" : "with MMAs   ", msd / reps);
+        }
   }
   return 0;
 }
