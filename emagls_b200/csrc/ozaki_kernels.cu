@@ -7,6 +7,7 @@
 #include <string>
 #include "kernels.h"
 #include "ozaki.cuh"
+#include "phase_fixed.cuh"
 
 namespace emagls {
 
@@ -134,6 +135,66 @@ struct EpiPhaseSliceRaw {
   __device__ __forceinline__ void apply(TileState& ts, int m, int n0, const double (&v)[8], int M, int N) const {
     int8_t* p = Tq + (long long)n0 * Kpad + m;
     phase_slice(ts, m, n0, v, N, [&](int q, uint32_t zl, uint32_t zh) { put_digits(p + (long long)q * Kpad, slice_stride, zl, zh); });
+  }
+};
+// The same epilogue without FP64 instructions in the functor (phase_fixed.cuh): FP64 work does not overlap with the
+// tcgen05 MMAs of the next tile on this part, integer work does.  The drained values are taken apart as bit patterns,
+// |y|^-1 comes from a 22-bit MUFU seed and one third-order correction in 64-bit fixed point, and the digits are those
+// of rn(t 2^24) formed in integer arithmetic.  Against EpiPhaseSliceRaw the last digit may differ by one unit
+// (|Z - exact| <= 0.6 instead of <= 0.53; tests/test_phase_fixed.py).
+template <int T>
+struct EpiPhaseSliceFix {
+  static constexpr bool raw = true;
+  int8_t* Tq; long long slice_stride; int Kpad;   // [T][rows][Kpad], element (n, m) at n * Kpad + m
+  double* sT;                                     // [rows] scale of row n (written by the m == 0 lanes)
+  const double* absH; long long abs_set_stride, abs_ear_stride;   // this bin: [set][ear][dir]
+  const double* up; const double* sc; int scale_stride;           // 2^(6-e), 2^(e-6) at [(set*2+ear)*scale_stride]
+  int orient_per_set; int nyquist;
+  const double* sB;                               // [rows] scales of the rows of c (the B operand)
+  struct TileState { uint64_t mu[2]; int set; };
+  __device__ __forceinline__ void load_set(TileState& ts, int set, int m) const {
+    ts.set = set;
+#pragma unroll
+    for (int ear = 0; ear < 2; ++ear)
+      ts.mu[ear] = pfx::magnitude_fixed<T>(absH[(long long)set * abs_set_stride + (long long)ear * abs_ear_stride + m],
+                                           up[(set * 2 + ear) * scale_stride]);
+  }
+  __device__ __forceinline__ TileState begin_tile(int m, int n, int M, int N) const {
+    TileState ts;
+    load_set(ts, (min(n, N - 1) >> 2) / orient_per_set, m);   // a chunk past the last column is never applied
+    return ts;
+  }
+  __device__ __forceinline__ void apply(TileState& ts, int m, int n0, const double (&v)[8], int M, int N) const {
+    const int prob = n0 >> 2;
+    int set = prob / orient_per_set;
+    int left = (set + 1) * orient_per_set - prob;     // problems left in this set, >= 1
+    if (m == 0) {                                     // scale of the output rows (one writer per row)
+      int s2 = set, l2 = left;
+      for (int q = 0; q < 8 && n0 + q < N; q += 2) {
+        const int e = (q >> 1) & 1;
+        const double s_ = sc[(s2 * 2 + e) * scale_stride];
+        sT[n0 + q] = s_; sT[n0 + q + 1] = s_;
+        if (e == 1 && --l2 == 0) { ++s2; l2 = orient_per_set; }
+      }
+    }
+    int8_t* p = Tq + (long long)n0 * Kpad + m;
+#pragma unroll
+    for (int q = 0; q < 8; q += 2) {
+      if (n0 + q >= N) break;
+      const int e = (q >> 1) & 1;
+      if (set != ts.set) load_set(ts, set, m);        // warp-uniform: a tile rarely straddles two HRTF sets
+      const int4 sb = *reinterpret_cast<const int4*>(sB + n0 + q);   // warp-uniform: two powers of two
+      const int dexp = ((sb.y >> 20) & 0x7FF) - ((sb.w >> 20) & 0x7FF);
+      int64_t Zr, Zi;
+      pfx::phase_fixed(v[q], v[q + 1], dexp, ts.mu[e], Zr, Zi);
+      if (nyquist) Zi = 0;
+      uint32_t zl, zh;
+      pfx::split_words<T>(Zr, zl, zh);
+      EpiPhaseSliceRaw<T>::put_digits(p + (long long)q * Kpad, slice_stride, zl, zh);
+      pfx::split_words<T>(Zi, zl, zh);
+      EpiPhaseSliceRaw<T>::put_digits(p + (long long)(q + 1) * Kpad, slice_stride, zl, zh);
+      if (e == 1 && --left == 0) { ++set; left = orient_per_set; }   // next pair belongs to the next problem
+    }
   }
 };
 // ... with the digits staged in shared memory and stored by TMA (oz::epi_tma_stage): the byte stores go to
@@ -305,16 +366,33 @@ cudaError_t launch_oz_fwd(cudaStream_t st, const OzFwdArgs& a) {
       default: return cudaErrorInvalidValue;
     }
   }
-  // A/B switches: EMAGLS_OZ_FWD=scaled is the epilogue of round 1 on the scaled FP64 values (F2I / I2F slicing),
-  // =tma the integer epilogue with the digits staged in shared memory and stored by TMA (two-stage operand ring to
-  // make room; 0.44 against 0.425 ms per launch, profiles/r02_v16_fwd_microbench.txt); default: the integer epilogue
-  // with byte stores to global memory.  All three produce the same bytes.
+  // Default for six digits: the FP64-free functor (EpiPhaseSliceFix: its integer work overlaps with the MMAs of the
+  // next tile, FP64 work does not; 0.34 against 0.425 ms per launch, profiles/r02_v40_fwd_fix.txt) on 128 x 80 tiles
+  // when that takes fewer rounds of tiles.  With four digits the MMAs of a tile are too short to hide the longer
+  // integer functor, so the FP64 functor on the raw accumulators stays (0.076 against 0.078 ms).
+  // A/B switches: EMAGLS_OZ_FWD=raw is that FP64 functor for every digit count (bitwise the digits of round 1),
+  // =fix the integer functor for every digit count, =scaled the epilogue of round 1 on the scaled FP64 values
+  // (F2I / I2F slicing), =tma the raw functor with the digits staged in shared memory and stored by TMA (two-stage
+  // operand ring to make room; 0.44 against 0.425 ms per launch, profiles/r02_v16_fwd_microbench.txt).  raw, scaled and
+  // tma write the same bytes; fix may differ from them by one unit of the last digit (phase_fixed.cuh).
   static const int mode = [] {
     const char* e = getenv("EMAGLS_OZ_FWD");
-    return !e ? 1 : (std::string(e) == "scaled" ? 2 : (std::string(e) == "tma" ? 0 : 1));
+    if (!e) return 4;
+    const std::string v(e);
+    return v == "scaled" ? 2 : (v == "tma" ? 0 : (v == "fix" ? 3 : (v == "raw" ? 1 : 4)));
   }();
   using Ring2 = oz::TileCfg<oz::TILE_N, 2>;
-  switch (a.T * 4 + mode) {
+  const bool fix = mode == 3 || (mode == 4 && a.T == 6);
+  if (fix) {
+    const int sms = sm_count();
+    const long long m_tiles = (a.D + oz::TILE_M - 1) / oz::TILE_M;
+    auto cost = [&](int nt) { return ((m_tiles * ((a.rows + nt - 1) / nt) + sms - 1) / sms) * (long long)(128 + nt); };
+    const bool wide = cost(oz::TileWide::NT) < cost(oz::TILE_N);
+    if (a.T == 6) return wide ? oz_fwd_t<6, EpiPhaseSliceFix<6>, oz::TileWide>(st, a) : oz_fwd_t<6, EpiPhaseSliceFix<6>>(st, a);
+    if (a.T == 4) return wide ? oz_fwd_t<4, EpiPhaseSliceFix<4>, oz::TileWide>(st, a) : oz_fwd_t<4, EpiPhaseSliceFix<4>>(st, a);
+    return cudaErrorInvalidValue;
+  }
+  switch (a.T * 4 + (mode == 4 ? 1 : mode)) {
     case 4 * 4 + 0: return oz_fwd_t<4, EpiPhaseSliceTma<4>, Ring2>(st, a);
     case 6 * 4 + 0: return oz_fwd_t<6, EpiPhaseSliceTma<6>, Ring2>(st, a);
     case 4 * 4 + 1: return oz_fwd_t<4, EpiPhaseSliceRaw<4>>(st, a);

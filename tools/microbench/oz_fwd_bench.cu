@@ -90,15 +90,20 @@ int main(int argc, char** argv) {
       if (mode == 1) return oz_fwd_t<6, EpiPhaseSliceRaw<6>>(0, fa);
       if (mode == 3) return oz_fwd_t<6, EpiPhaseSliceRaw<6>, oz::TileWide>(0, fa);
       if (mode == 4) return oz_fwd_t<6, EpiPhaseSliceRaw<6>, oz::TileCfg<48, 3>>(0, fa);
+      if (mode == 5) return oz_fwd_t<6, EpiPhaseSliceFix<6>>(0, fa);
+      if (mode == 6) return oz_fwd_t<6, EpiPhaseSliceFix<6>, oz::TileWide>(0, fa);
       return oz_fwd_t<6, EpiPhaseSliceTma<6>, Ring2>(0, fa);
     }
     if (mode == 0) return oz_fwd_t<4, EpiPhaseSlice<4>>(0, fa);
     if (mode == 1) return oz_fwd_t<4, EpiPhaseSliceRaw<4>>(0, fa);
     if (mode == 3) return oz_fwd_t<4, EpiPhaseSliceRaw<4>, oz::TileWide>(0, fa);
     if (mode == 4) return oz_fwd_t<4, EpiPhaseSliceRaw<4>, oz::TileCfg<48, 3>>(0, fa);
+    if (mode == 5) return oz_fwd_t<4, EpiPhaseSliceFix<4>>(0, fa);
+    if (mode == 6) return oz_fwd_t<4, EpiPhaseSliceFix<4>, oz::TileWide>(0, fa);
     return oz_fwd_t<4, EpiPhaseSliceTma<4>, Ring2>(0, fa);
   };
-  const char* names[5] = {"scaled", "raw", "tma", "raw80", "raw48"};
+  const char* names[7] = {"scaled", "raw", "tma", "raw80", "raw48", "fix", "fix80"};
+  const int mode_list[4] = {0, 1, 5, 6};
   const size_t nq = (size_t)T * rows * KpD;
   std::vector<int8_t> ref(nq), got(nq);
   std::vector<double> sref(rows), sgot(rows);
@@ -116,7 +121,7 @@ int main(int argc, char** argv) {
     printf("long run %s: %.4f ms per launch after 12000 launches\n", names[long_mode], msl / 2000);
     return 0;
   }
-  for (int mode = 0; mode < 5; ++mode) {
+  for (int mode : mode_list) {
     CK(cudaMemset(qT, 0, nq));
     CK(cudaMemset(sT, 0, (size_t)rows * 8));
     CK(run(mode));
@@ -143,7 +148,7 @@ int main(int argc, char** argv) {
         }
       }
     }
-    for (int dbg : {1, 2, 3, 4, 6}) {   // decomposition: 1 no epilogue, 2 no MMAs, 3 operand ring only, 4 drain only, 6 drain only without MMAs
+    for (int dbg : {1, 4}) {   // decomposition: 1 no epilogue, 2 no MMAs, 3 operand ring only, 4 drain only, 6 drain only without MMAs
       oz_fwd_debug = dbg;
       CK(run(mode));
       CK(cudaEventRecord(e0));
