@@ -51,8 +51,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// EMAGLS_OZ_WAIT_HINT (ns) > 0: try_wait carries a suspend-time hint, so a waiting thread sleeps in hardware until the
+// phase completes (or the hint expires) instead of polling: the TMA and MMA warps share their schedulers with epilogue
+// warps, and every polling iteration (try_wait + clock + compare + branch) is an issue slot those warps do not get
+#ifndef EMAGLS_OZ_WAIT_HINT
+#define EMAGLS_OZ_WAIT_HINT 0
+#endif
 __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if EMAGLS_OZ_WAIT_HINT > 0
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)EMAGLS_OZ_WAIT_HINT)
+      : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -60,6 +75,7 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 // bounded wait: a protocol error becomes a trap (launch failure) instead of a hung GPU
@@ -504,7 +520,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int ci = 0; ci < CH_PER_WARP; ++ci) {
             const int c0 = chunk0 + ci * chunk_step;
-            if (c0 < n_lim && m < g.M) epi.apply(ts, m, n0 + c0, v[ci], g.M, g.N);
+            if (c0 < n_lim && (epi_all_lanes<Epi>::value || m < g.M)) epi.apply(ts, m, n0 + c0, v[ci], g.M, g.N);   // all_lanes: warp-uniform entry
           }
         }
       } else {

@@ -142,9 +142,14 @@ struct EpiPhaseSliceRaw {
 // |y|^-1 comes from a 22-bit MUFU seed and one third-order correction in 64-bit fixed point, and the digits are those
 // of rn(t 2^24) formed in integer arithmetic.  Against EpiPhaseSliceRaw the last digit may differ by one unit
 // (|Z - exact| <= 0.6 instead of <= 0.53; tests/test_phase_fixed.py).
-template <int T>
+// WORDS: the digit bytes of four columns are packed per plane, transposed across groups of four lanes (two shuffles
+// and two byte permutes per word) and leave as 4-byte stores: lane l writes rows l & ~3 .. (l & ~3) + 3 of column
+// l & 3.  A quarter of the store instructions and of their address arithmetic; the whole warp enters apply() (lanes
+// past the last row contribute zero bytes, which land in the row padding), so N must be a multiple of 4.
+template <int T, bool WORDS = false>
 struct EpiPhaseSliceFix {
   static constexpr bool raw = true;
+  static constexpr bool all_lanes = WORDS;
   int8_t* Tq; long long slice_stride; int Kpad;   // [T][rows][Kpad], element (n, m) at n * Kpad + m
   double* sT;                                     // [rows] scale of row n (written by the m == 0 lanes)
   const double* absH; long long abs_set_stride, abs_ear_stride;   // this bin: [set][ear][dir]
@@ -159,41 +164,99 @@ struct EpiPhaseSliceFix {
       ts.mu[ear] = pfx::magnitude_fixed<T>(absH[(long long)set * abs_set_stride + (long long)ear * abs_ear_stride + m],
                                            up[(set * 2 + ear) * scale_stride]);
   }
+  // the same out of line: a tile rarely straddles two HRTF sets, and twelve inlined copies of the conversion made the
+  // epilogue's straight-line code a third longer (instruction-cache footprint)
+  static __device__ __noinline__ uint64_t mu_cold(const double* x, const double* u) { return pfx::magnitude_fixed<T>(*x, *u); }
+  __device__ __forceinline__ void load_set_cold(TileState& ts, int set, int m) const {
+    ts.set = set;
+#pragma unroll
+    for (int ear = 0; ear < 2; ++ear)
+      ts.mu[ear] = mu_cold(absH + ((long long)set * abs_set_stride + (long long)ear * abs_ear_stride + m),
+                           up + (set * 2 + ear) * scale_stride);
+  }
   __device__ __forceinline__ TileState begin_tile(int m, int n, int M, int N) const {
     TileState ts;
     load_set(ts, (min(n, N - 1) >> 2) / orient_per_set, m);   // a chunk past the last column is never applied
     return ts;
   }
+  // digit j of a column goes to plane T-1-j (j < 3: bytes of zl; j >= 3: bytes of zh): one 64-bit pointer per plane,
+  // formed once per chunk, plus a 32-bit column offset
+  static __device__ __forceinline__ void put_digits_at(int8_t* const (&pl)[T], uint32_t off, uint32_t zl, uint32_t zh) {
+    pl[T - 1][off] = (int8_t)zl;
+    pl[T - 2][off] = (int8_t)(zl >> 8);
+    pl[T - 3][off] = (int8_t)(zl >> 16);
+    pl[T - 4][off] = (int8_t)zh;
+    if (T >= 5) pl[T >= 5 ? T - 5 : 0][off] = (int8_t)(zh >> 8);
+    if (T >= 6) pl[T >= 6 ? T - 6 : 0][off] = (int8_t)(zh >> 16);
+  }
+  // scale of the output rows n0 .. n0+7 (one writer per row: the m == 0 lane)
+  __device__ __forceinline__ void put_scales(int n0, int N, int set, int left) const {
+    for (int q = 0; q < 8 && n0 + q < N; q += 2) {
+      const int e = (q >> 1) & 1;
+      const double s_ = sc[(set * 2 + e) * scale_stride];
+      sT[n0 + q] = s_; sT[n0 + q + 1] = s_;
+      if (e == 1 && --left == 0) { ++set; left = orient_per_set; }
+    }
+  }
+  // digit words (zl, zh) of the (re, im) columns n0 + q, n0 + q + 1
+  __device__ __forceinline__ void pair_digits(const TileState& ts, int n0, int q, double vr, double vi, uint32_t& rl,
+                                              uint32_t& rh, uint32_t& il, uint32_t& ih) const {
+    const int4 sb = *reinterpret_cast<const int4*>(sB + n0 + q);   // warp-uniform: two powers of two
+    const int dexp = ((sb.y >> 20) & 0x7FF) - ((sb.w >> 20) & 0x7FF);
+    int64_t Zr, Zi;
+    pfx::phase_fixed(vr, vi, dexp, ts.mu[(q >> 1) & 1], Zr, Zi);
+    if (nyquist) Zi = 0;
+    pfx::split_words<T>(Zr, rl, rh);
+    pfx::split_words<T>(Zi, il, ih);
+  }
   __device__ __forceinline__ void apply(TileState& ts, int m, int n0, const double (&v)[8], int M, int N) const {
     const int prob = n0 >> 2;
     int set = prob / orient_per_set;
     int left = (set + 1) * orient_per_set - prob;     // problems left in this set, >= 1
-    if (m == 0) {                                     // scale of the output rows (one writer per row)
-      int s2 = set, l2 = left;
-      for (int q = 0; q < 8 && n0 + q < N; q += 2) {
-        const int e = (q >> 1) & 1;
-        const double s_ = sc[(s2 * 2 + e) * scale_stride];
-        sT[n0 + q] = s_; sT[n0 + q + 1] = s_;
-        if (e == 1 && --l2 == 0) { ++s2; l2 = orient_per_set; }
-      }
-    }
-    int8_t* p = Tq + (long long)n0 * Kpad + m;
+    if (m == 0) put_scales(n0, N, set, left);
+    if constexpr (!WORDS) {
+      int8_t* pl[T];
 #pragma unroll
-    for (int q = 0; q < 8; q += 2) {
-      if (n0 + q >= N) break;
-      const int e = (q >> 1) & 1;
-      if (set != ts.set) load_set(ts, set, m);        // warp-uniform: a tile rarely straddles two HRTF sets
-      const int4 sb = *reinterpret_cast<const int4*>(sB + n0 + q);   // warp-uniform: two powers of two
-      const int dexp = ((sb.y >> 20) & 0x7FF) - ((sb.w >> 20) & 0x7FF);
-      int64_t Zr, Zi;
-      pfx::phase_fixed(v[q], v[q + 1], dexp, ts.mu[e], Zr, Zi);
-      if (nyquist) Zi = 0;
-      uint32_t zl, zh;
-      pfx::split_words<T>(Zr, zl, zh);
-      EpiPhaseSliceRaw<T>::put_digits(p + (long long)q * Kpad, slice_stride, zl, zh);
-      pfx::split_words<T>(Zi, zl, zh);
-      EpiPhaseSliceRaw<T>::put_digits(p + (long long)(q + 1) * Kpad, slice_stride, zl, zh);
-      if (e == 1 && --left == 0) { ++set; left = orient_per_set; }   // next pair belongs to the next problem
+      for (int s_ = 0; s_ < T; ++s_) pl[s_] = Tq + ((long long)s_ * slice_stride + (long long)n0 * Kpad + m);
+      const uint32_t col = (uint32_t)Kpad;
+#pragma unroll
+      for (int q = 0; q < 8; q += 2) {
+        if (n0 + q >= N) break;
+        if (set != ts.set) load_set_cold(ts, set, m);   // warp-uniform: a tile rarely straddles two HRTF sets
+        uint32_t rl, rh, il, ih;
+        pair_digits(ts, n0, q, v[q], v[q + 1], rl, rh, il, ih);
+        put_digits_at(pl, (uint32_t)q * col, rl, rh);
+        put_digits_at(pl, (uint32_t)(q + 1) * col, il, ih);
+        if ((q & 2) && --left == 0) { ++set; left = orient_per_set; }   // next pair belongs to the next problem
+      }
+    } else {
+      const int lane = threadIdx.x & 31, g = lane & 3;
+      const uint32_t selA = (lane & 2) ? 0x3276u : 0x5410u, selB = (lane & 1) ? 0x3715u : 0x6240u;
+      const uint32_t keep = m < M ? 0xFFFFFFFFu : 0u;
+      const bool writer = m - g < M;                  // the group's first row exists (then all four lie below Kpad)
+      const int mc = min(m, M - 1);
+      // this lane's word: column n0 + g (+ 4), rows m - g .. m - g + 3; the plane / column-group offsets are uniform
+      int8_t* const pw = Tq + ((long long)(n0 + g) * Kpad + (m - g));
+      const long long col4 = 4ll * Kpad;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {                   // four columns = both ears of one problem
+        if (n0 + 4 * h >= N) break;
+        if (set != ts.set) load_set_cold(ts, set, mc);
+        uint32_t zl[4], zh[4];
+        pair_digits(ts, n0, 4 * h, v[4 * h], v[4 * h + 1], zl[0], zh[0], zl[1], zh[1]);
+        pair_digits(ts, n0, 4 * h + 2, v[4 * h + 2], v[4 * h + 3], zl[2], zh[2], zl[3], zh[3]);
+        if (--left == 0) { ++set; left = orient_per_set; }
+        uint32_t w[6];                                // w[j]: digit T-1-j of the four columns
+        oz::transpose4x3(zl[0], zl[1], zl[2], zl[3], w[0], w[1], w[2]);
+        oz::transpose4x3(zh[0], zh[1], zh[2], zh[3], w[3], w[4], w[5]);
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+          uint32_t x = w[j] & keep;
+          x = __byte_perm(x, __shfl_xor_sync(0xffffffffu, x, 2), selA);
+          x = __byte_perm(x, __shfl_xor_sync(0xffffffffu, x, 1), selB);
+          if (writer) *reinterpret_cast<uint32_t*>(pw + ((long long)(T - 1 - j) * slice_stride + h * col4)) = x;
+        }
+      }
     }
   }
 };
@@ -388,8 +451,15 @@ cudaError_t launch_oz_fwd(cudaStream_t st, const OzFwdArgs& a) {
     const long long m_tiles = (a.D + oz::TILE_M - 1) / oz::TILE_M;
     auto cost = [&](int nt) { return ((m_tiles * ((a.rows + nt - 1) / nt) + sms - 1) / sms) * (long long)(128 + nt); };
     const bool wide = cost(oz::TileWide::NT) < cost(oz::TILE_N);
-    if (a.T == 6) return wide ? oz_fwd_t<6, EpiPhaseSliceFix<6>, oz::TileWide>(st, a) : oz_fwd_t<6, EpiPhaseSliceFix<6>>(st, a);
-    if (a.T == 4) return wide ? oz_fwd_t<4, EpiPhaseSliceFix<4>, oz::TileWide>(st, a) : oz_fwd_t<4, EpiPhaseSliceFix<4>>(st, a);
+    // 4-byte digit stores (lane-transposed) unless EMAGLS_OZ_FWD_BYTES is set or the row count is not a multiple of 4
+    static const bool bytes = getenv("EMAGLS_OZ_FWD_BYTES") != nullptr;
+    if (bytes || (a.rows & 3)) {
+      if (a.T == 6) return wide ? oz_fwd_t<6, EpiPhaseSliceFix<6>, oz::TileWide>(st, a) : oz_fwd_t<6, EpiPhaseSliceFix<6>>(st, a);
+      if (a.T == 4) return wide ? oz_fwd_t<4, EpiPhaseSliceFix<4>, oz::TileWide>(st, a) : oz_fwd_t<4, EpiPhaseSliceFix<4>>(st, a);
+      return cudaErrorInvalidValue;
+    }
+    if (a.T == 6) return wide ? oz_fwd_t<6, EpiPhaseSliceFix<6, true>, oz::TileWide>(st, a) : oz_fwd_t<6, EpiPhaseSliceFix<6, true>>(st, a);
+    if (a.T == 4) return wide ? oz_fwd_t<4, EpiPhaseSliceFix<4, true>, oz::TileWide>(st, a) : oz_fwd_t<4, EpiPhaseSliceFix<4, true>>(st, a);
     return cudaErrorInvalidValue;
   }
   switch (a.T * 4 + (mode == 4 ? 1 : mode)) {

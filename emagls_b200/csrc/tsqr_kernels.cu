@@ -24,6 +24,7 @@
 // Reflector storage ("sep" block plan): V [S][32] row-major (a block of 32 rows is one contiguous 16 KB
 // tile; entry (r, c) is the tail of reflector c of block r/32, scaled so that v = [1; tail] with the 1
 // at R-space row c), tau [nblk][32].
+#include <algorithm>
 #include <cstdlib>
 #include "kernels.h"
 #include "reflect.cuh"
@@ -401,7 +402,8 @@ __device__ __forceinline__ void rot_phase(cplx (&xa)[2], cplx (&xb)[2], cplx (&j
 
 template <int OCC>
 __global__ void __launch_bounds__(SV_T, OCC)
-svdclip_kernel(int Mc, const cplx* __restrict__ Rin, OperatorSet ops, int G, double regul, int try_fast, int warm) {
+svdclip_kernel(int Mc, const cplx* __restrict__ Rin, OperatorSet ops, int G, double regul, int try_fast, int warm,
+               int split_from, int pieces) {
   extern __shared__ __align__(16) unsigned char sv_raw[];
   cplx* Xs = reinterpret_cast<cplx*>(sv_raw);           // column-major: X(i, c) = Xs[c*32 + i]
   cplx* Js = Xs + 1024;                                 // column-major
@@ -411,10 +413,18 @@ svdclip_kernel(int Mc, const cplx* __restrict__ Rin, OperatorSet ops, int G, dou
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int hw = tid >> 4, hl = tid & 15;
   const bool hi8 = (hl & 8) != 0;
-  const int prob = blockIdx.x;
+  // CTAs below split_from take all G bins of one orientation; the orientations from split_from on (the remainder of
+  // the last full round of CTAs) are cut into `pieces` bin ranges each, so the last round is short (launch_svdclip)
+  int prob = blockIdx.x, slot_lo = 0, slot_hi = G;
+  if (prob >= split_from) {
+    const int r = prob - split_from, piece = r % pieces;
+    prob = split_from + r / pieces;
+    slot_lo = (int)((long long)piece * G / pieces);
+    slot_hi = (int)((long long)(piece + 1) * G / pieces);
+  }
   bool have_j = false;                      // Js holds the converged J of the previous bin
 
-  for (int slot = 0; slot < G; ++slot) {
+  for (int slot = slot_lo; slot < slot_hi; ++slot) {
     const long long oidx = (long long)prob * G + slot;
     const cplx* Rg = Rin + oidx * 1024;     // R_C row-major: R(j, i) = Rg[j*32 + i]
     cplx* Pg = ops.Pb + oidx * ops.pb_stride;
@@ -703,14 +713,37 @@ cudaError_t launch_tsqr_sep(cudaStream_t st, const BlockPlan& bp, const RowSourc
   return cudaGetLastError();
 }
 
+static int sv_sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
 cudaError_t launch_svdclip(cudaStream_t st, int Mc, const cplx* Rin, const OperatorSet& ops, int num_prob, int G,
                            double regul, int try_fast, int warm) {
   if (Mc > 32) return cudaErrorInvalidValue;
   const size_t smem = (size_t)2 * 1024 * sizeof(cplx) + (size_t)(32 + 32 + 20) * sizeof(double);
   // EMAGLS_JACOBI_OCC=5: five CTAs per SM under a 102-register cap (A/B switch; default four CTAs, 128 registers)
   static const int occ = [] { const char* e = getenv("EMAGLS_JACOBI_OCC"); return (e && atoi(e) == 5) ? 5 : 4; }();
-  if (occ == 5) svdclip_kernel<5><<<num_prob, SV_T, smem, st>>>(Mc, Rin, ops, G, regul, try_fast, warm);
-  else svdclip_kernel<4><<<num_prob, SV_T, smem, st>>>(Mc, Rin, ops, G, regul, try_fast, warm);
+  // Tail of the grid: CTAs take about equally long, so with `resident` CTAs in flight a launch lasts
+  // ceil(num_prob / resident) rounds and the last round may be almost empty (3600 orientations on 592 places: 6.08
+  // -> 7 rounds).  The orientations of that remainder are cut into bin ranges, as many as fit into one round, so
+  // the last round lasts 1 / pieces of a full one (plus one cold Jacobi start per piece).  EMAGLS_JACOBI_NO_SPLIT=1: off.
+  static const bool no_split = getenv("EMAGLS_JACOBI_NO_SPLIT") != nullptr;
+  const int resident = occ * sv_sm_count();
+  int split_from = num_prob, pieces = 1;
+  const int rem = num_prob % resident;
+  if (!no_split && num_prob > resident && rem > 0 && G > 1) {
+    pieces = std::min(G, resident / rem);
+    if (pieces > 1) split_from = num_prob - rem; else pieces = 1;
+  }
+  const int grid = split_from + (num_prob - split_from) * pieces;
+  if (occ == 5) svdclip_kernel<5><<<grid, SV_T, smem, st>>>(Mc, Rin, ops, G, regul, try_fast, warm, split_from, pieces);
+  else svdclip_kernel<4><<<grid, SV_T, smem, st>>>(Mc, Rin, ops, G, regul, try_fast, warm, split_from, pieces);
   return cudaGetLastError();
 }
 

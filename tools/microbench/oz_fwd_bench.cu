@@ -92,6 +92,8 @@ int main(int argc, char** argv) {
       if (mode == 4) return oz_fwd_t<6, EpiPhaseSliceRaw<6>, oz::TileCfg<48, 3>>(0, fa);
       if (mode == 5) return oz_fwd_t<6, EpiPhaseSliceFix<6>>(0, fa);
       if (mode == 6) return oz_fwd_t<6, EpiPhaseSliceFix<6>, oz::TileWide>(0, fa);
+      if (mode == 7) return oz_fwd_t<6, EpiPhaseSliceFix<6, true>>(0, fa);
+      if (mode == 8) return oz_fwd_t<6, EpiPhaseSliceFix<6, true>, oz::TileWide>(0, fa);
       return oz_fwd_t<6, EpiPhaseSliceTma<6>, Ring2>(0, fa);
     }
     if (mode == 0) return oz_fwd_t<4, EpiPhaseSlice<4>>(0, fa);
@@ -100,10 +102,13 @@ int main(int argc, char** argv) {
     if (mode == 4) return oz_fwd_t<4, EpiPhaseSliceRaw<4>, oz::TileCfg<48, 3>>(0, fa);
     if (mode == 5) return oz_fwd_t<4, EpiPhaseSliceFix<4>>(0, fa);
     if (mode == 6) return oz_fwd_t<4, EpiPhaseSliceFix<4>, oz::TileWide>(0, fa);
+    if (mode == 7) return oz_fwd_t<4, EpiPhaseSliceFix<4, true>>(0, fa);
+    if (mode == 8) return oz_fwd_t<4, EpiPhaseSliceFix<4, true>, oz::TileWide>(0, fa);
     return oz_fwd_t<4, EpiPhaseSliceTma<4>, Ring2>(0, fa);
   };
-  const char* names[7] = {"scaled", "raw", "tma", "raw80", "raw48", "fix", "fix80"};
-  const int mode_list[4] = {0, 1, 5, 6};
+  const char* names[9] = {"scaled", "raw", "tma", "raw80", "raw48", "fix", "fix80", "fixw", "fixw80"};
+  const int mode_list[6] = {0, 1, 5, 6, 7, 8};   // fix*: FP64-free functor (byte stores), fixw*: the same with 4-byte stores
+  std::vector<int8_t> fixref;
   const size_t nq = (size_t)T * rows * KpD;
   std::vector<int8_t> ref(nq), got(nq);
   std::vector<double> sref(rows), sgot(rows);
@@ -130,6 +135,12 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(sgot.data(), sT, (size_t)rows * 8, cudaMemcpyDeviceToHost));
     size_t bad = 0, bad_s = 0, shown = 0;
     double maxdiff = 0.0;
+    if (mode == 5) fixref = got;
+    if (mode > 5 && !fixref.empty()) {              // every variant of the integer functor writes the same bytes
+      size_t nb = 0;
+      for (size_t i = 0; i < nq; ++i) nb += (got[i] != fixref[i]);
+      printf("   %-6s vs fix: %zu of %zu bytes differ\n", names[mode], nb, nq);
+    }
     if (mode == 0) { ref = got; sref = sgot; }
     else {
       for (int r = 0; r < rows; ++r) {
@@ -143,7 +154,7 @@ int main(int argc, char** argv) {
           }
           if (neq) {
             ++bad; maxdiff = std::max(maxdiff, std::fabs(va - vb));
-            if (shown < 6) { printf("   mismatch row %d col %d: ref %.17g got %.17g\n", r, m, va, vb); ++shown; }
+            if (shown < 2) { printf("   mismatch row %d col %d: ref %.17g got %.17g\n", r, m, va, vb); ++shown; }
           }
         }
       }
