@@ -18,6 +18,7 @@
 // issuer (one elected thread), warps 2..17: epilogue (TMEM -> registers -> FP64, accumulators released,
 // then the functor).
 #pragma once
+#include <algorithm>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -25,19 +26,28 @@
 namespace emagls {
 namespace oz {
 
+#ifndef EMAGLS_OZ_EPI_WARPS
+#define EMAGLS_OZ_EPI_WARPS 16
+#endif
 constexpr int TILE_M = 128, TILE_N = 64, TILE_K = 64, STAGES = 3, MAX_SLICES = 6;
 // Tile width / ring depth per use: 64 x 3 stages by default; 80 x 2 stages for the backward product
 // (N = 400 = 5 x 80: no padded columns, the 235 MB A operand streams through L2 5 instead of 7 times;
 // 6 x 80 = 480 TMEM columns).
-template <int NT_, int ST_> struct TileCfg { static constexpr int NT = NT_, ST = ST_; };
+// EW: epilogue warps (a multiple of 4: EW / 4 per TMEM lane group, each taking every (EW / 4)-th 8-column chunk).
+// 16 warps on an 80-column tile leave ten chunks to four warps per lane group (3 + 3 + 2 + 2); 20 warps take two each.
+// SH: thread-block cluster of two CTAs that share one operand tile (TMA multicast: the CTA of rank 0 fetches the tile
+// once from L2 into the shared memory of both).  1 = the pair works on two neighbouring column tiles of the same row
+// tile (A shared), 2 = on two neighbouring row tiles of the same column tile (B shared).  The operand ring runs at the
+// L2 -> SMEM limit of the part (12.8 TB/s, section 5 of DESIGN.md), so the shared tile is traffic taken off that path.
+template <int NT_, int ST_, int EW_ = EMAGLS_OZ_EPI_WARPS, int SH_ = 0> struct TileCfg {
+  static constexpr int NT = NT_, ST = ST_, EW = EW_, THREADS = 64 + 32 * EW_, SHARE = SH_;
+  static_assert(EW_ % 4 == 0 && EW_ >= 4 && 64 + 32 * EW_ <= 1024, "epilogue warps: whole lane groups");
+  static_assert(SH_ >= 0 && SH_ <= 2, "share: none, A, B");
+};
 using TileDefault = TileCfg<TILE_N, STAGES>;
 using TileWide = TileCfg<80, 2>;
 constexpr int A_SLICE_BYTES = TILE_M * TILE_K;   // 8 KB
-#ifndef EMAGLS_OZ_EPI_WARPS
-#define EMAGLS_OZ_EPI_WARPS 16
-#endif
-constexpr int EPI_WARPS = EMAGLS_OZ_EPI_WARPS;  // EPI_WARPS / 4 warps per TMEM lane group, interleaved 8-column chunks
-constexpr int THREADS = 64 + 32 * EPI_WARPS;
+constexpr int EPI_WARPS = EMAGLS_OZ_EPI_WARPS;  // default of TileCfg::EW
 
 // ------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -100,6 +110,23 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, ui
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// the same tile delivered to the same shared-memory offset (and signalled on the same barrier offset) of every CTA in mask
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {   // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // shared-memory tile -> global tensor (bulk async group of the issuing thread)
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -135,6 +162,11 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
 // arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// ... on the barrier at the same offset in every CTA of mask
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 // 32 lanes x 8 consecutive 32-bit columns: thread i of the warp receives lane (base lane + i)
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t (&v)[8]) {
@@ -273,6 +305,26 @@ __device__ __forceinline__ void tile_origin(const GemmArgs& g, int tile, int m_t
   else { m0 = (tile % m_tiles) * TILE_M; n0 = (tile / m_tiles) * g.tile_n; }
 }
 
+// Work item of a cluster pair (share != 0): item -> the tile of the CTA of this rank; false if the pair's second
+// tile lies past the edge (odd tile count: that CTA only keeps the barrier protocol going)
+__device__ __forceinline__ bool pair_tile_origin(const GemmArgs& g, int share, int item, int rank, int m_tiles, int n_tiles,
+                                                 int& m0, int& n0) {
+  int mi, ni;
+  if (share == 1) {            // two column tiles of one row tile
+    const int n_pairs = (n_tiles + 1) >> 1;
+    int np;
+    if (g.n_fastest) { np = item % n_pairs; mi = item / n_pairs; } else { mi = item % m_tiles; np = item / m_tiles; }
+    ni = 2 * np + rank;
+  } else {                     // two row tiles of one column tile
+    const int m_pairs = (m_tiles + 1) >> 1;
+    int mp;
+    if (g.n_fastest) { ni = item % n_tiles; mp = item / n_tiles; } else { mp = item % m_pairs; ni = item / m_pairs; }
+    mi = 2 * mp + rank;
+  }
+  m0 = mi * TILE_M; n0 = ni * g.tile_n;
+  return mi < m_tiles && ni < n_tiles;
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -361,13 +413,13 @@ struct EpiStoreF64 {
 };
 
 template <int T, class Epi, class Cfg = TileDefault>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
 ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, GemmArgs g, Epi epi) {
   extern __shared__ uint8_t oz_smem_raw[];
   // 1024-byte aligned carve-up: [stage][A slices | B slices]
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr int NT = Cfg::NT, ST = Cfg::ST, B_SLICE_BYTES = NT * TILE_K;
+  constexpr int NT = Cfg::NT, ST = Cfg::ST, EPI_WARPS = Cfg::EW, B_SLICE_BYTES = NT * TILE_K;
   constexpr int stage_bytes = T * (A_SLICE_BYTES + B_SLICE_BYTES);
   uint8_t* epi_stage_area = base + (size_t)ST * stage_bytes;   // only for staged functors (see launch: extra smem)
   __shared__ __align__(8) uint64_t full_bar[ST], empty_bar[ST], tmem_full_bar, tmem_empty_bar;
@@ -375,7 +427,17 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (g.M + TILE_M - 1) / TILE_M, n_tiles = (g.N + NT - 1) / NT;
-  const int num_tiles = m_tiles * n_tiles;
+  // work items: tiles, or (share != 0) pairs of tiles taken by the two CTAs of a cluster in lockstep
+  constexpr int SHARE = Cfg::SHARE;
+  constexpr uint16_t PAIR_MASK = 3;
+  const int rank = SHARE ? (int)cluster_rank() : 0;
+  const int num_tiles = SHARE == 1 ? m_tiles * ((n_tiles + 1) >> 1) : (SHARE == 2 ? ((m_tiles + 1) >> 1) * n_tiles : m_tiles * n_tiles);
+  const int item0 = SHARE ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, item_step = SHARE ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto origin = [&](int item, int& m0, int& n0) -> bool {
+    if (SHARE) return pair_tile_origin(g, SHARE, item, rank, m_tiles, n_tiles, m0, n0);
+    tile_origin(g, item, m_tiles, n_tiles, m0, n0);
+    return true;
+  };
   const int ksteps_total = g.Kpad / 32;
   const int num_kt = (g.Kpad + TILE_K - 1) / TILE_K;
   constexpr uint32_t tmem_cols = (T * NT <= 256) ? 256u : 512u;
@@ -384,7 +446,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (epi_tma_stage<Epi>::value) tma_prefetch_desc(&tmC);
-    for (int s = 0; s < ST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < ST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], SHARE ? 2 : 1); }   // pair: both MMA warps release a stage
     mbar_init(&tmem_full_bar, 1);
     mbar_init(&tmem_empty_bar, EPI_WARPS);   // one arrival per epilogue warp
     fence_barrier_init();
@@ -392,6 +454,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) tmem_alloc(&tmem_base_s, tmem_cols);
   tc_fence_before();
   __syncthreads();
+  if (SHARE) cluster_sync_all();   // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
@@ -399,16 +462,31 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ================================================================= TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = item0; tile < num_tiles; tile += item_step) {
         int m0, n0;
-        tile_origin(g, tile, m_tiles, n_tiles, m0, n0);
+        const bool valid = origin(tile, m0, n0);
         for (int kt = 0; kt < num_kt; ++kt) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = base + (size_t)stage * stage_bytes;
           uint8_t* sb = sa + (size_t)T * A_SLICE_BYTES;
-          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-          tma_load_3d(sa, &tmA, &full_bar[stage], kt * TILE_K, m0, 0);
-          tma_load_3d(sb, &tmB, &full_bar[stage], kt * TILE_K, n0, 0);
+          if (SHARE == 0) {
+            mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+            tma_load_3d(sa, &tmA, &full_bar[stage], kt * TILE_K, m0, 0);
+            tma_load_3d(sb, &tmB, &full_bar[stage], kt * TILE_K, n0, 0);
+          } else {
+            // the shared tile arrives from the CTA of rank 0 (multicast), the other one from this CTA; a CTA without
+            // a tile of its own only receives the shared one
+            constexpr uint32_t a_bytes = (uint32_t)(T * A_SLICE_BYTES), b_bytes = (uint32_t)(T * B_SLICE_BYTES);
+            const uint32_t shared_bytes = SHARE == 1 ? a_bytes : b_bytes, own_bytes = SHARE == 1 ? b_bytes : a_bytes;
+            mbar_expect_tx(&full_bar[stage], shared_bytes + (valid ? own_bytes : 0u));
+            if (SHARE == 1) {
+              if (rank == 0) tma_load_3d_mc(sa, &tmA, &full_bar[stage], kt * TILE_K, m0, 0, PAIR_MASK);
+              if (valid) tma_load_3d(sb, &tmB, &full_bar[stage], kt * TILE_K, n0, 0);
+            } else {
+              if (valid) tma_load_3d(sa, &tmA, &full_bar[stage], kt * TILE_K, m0, 0);
+              if (rank == 0) tma_load_3d_mc(sb, &tmB, &full_bar[stage], kt * TILE_K, n0, 0, PAIR_MASK);
+            }
+          }
           if (++stage == ST) { stage = 0; phase ^= 1; }
         }
       }
@@ -421,9 +499,18 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // 128 x 64 x 32 MMA occupies the tensor pipe.
     int stage = 0; uint32_t phase = 0, acc_phase = 0;
     const bool leader = elect_one();
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = item0; tile < num_tiles; tile += item_step) {
       int m0, n0;
-      tile_origin(g, tile, m_tiles, n_tiles, m0, n0);
+      const bool valid = origin(tile, m0, n0);
+      if (!valid) {   // no tile of its own: consume the stages so that the peer's ring keeps moving
+        for (int kt = 0; kt < num_kt; ++kt) {
+          mbar_wait(&full_bar[stage], phase);
+          if (leader) umma_commit_mc(&empty_bar[stage], PAIR_MASK);
+          __syncwarp();
+          if (++stage == ST) { stage = 0; phase ^= 1; }
+        }
+        continue;
+      }
       const int n_mma = min(NT, ((g.N - n0) + 15) & ~15);
       const uint32_t idesc = instr_desc_i8(TILE_M, n_mma);
       mbar_wait(&tmem_empty_bar, acc_phase ^ 1);   // epilogue has drained the accumulators
@@ -453,7 +540,8 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
             }
           }
-          umma_commit(&empty_bar[stage]);            // smem slot reusable once these MMAs retire
+          if (SHARE) umma_commit_mc(&empty_bar[stage], PAIR_MASK);   // both producers write into this CTA's slot
+          else umma_commit(&empty_bar[stage]);       // smem slot reusable once these MMAs retire
           if (kt == num_kt - 1) umma_commit(&tmem_full_bar);   // accumulators complete
         }
         __syncwarp();
@@ -468,9 +556,9 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     constexpr int chunk_step = 8 * (EPI_WARPS / 4);
     constexpr int CH_PER_WARP = (NT + chunk_step - 1) / chunk_step;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = item0; tile < num_tiles; tile += item_step) {
       int m0, n0;
-      tile_origin(g, tile, m_tiles, n_tiles, m0, n0);
+      if (!origin(tile, m0, n0)) continue;
       const int n_mma = min(NT, ((g.N - n0) + 15) & ~15);
       const int m = m0 + lg * 32 + lane;
       const int n_lim = (g.dbg & 1) ? 0 : n_mma;
@@ -569,6 +657,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (SHARE) cluster_sync_all();   // the peer may still arrive on this CTA's barriers until it is done, too
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
@@ -638,9 +727,24 @@ cudaError_t launch_ozaki_gemm_t(cudaStream_t st, const CUtensorMap& tmA, const C
   cudaError_t e = cudaFuncSetAttribute(ozaki_gemm_kernel<T, Epi, Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   g.tile_n = Cfg::NT;
-  const int tiles = ((g.M + TILE_M - 1) / TILE_M) * ((g.N + Cfg::NT - 1) / Cfg::NT);
-  ozaki_gemm_kernel<T, Epi, Cfg><<<tiles < num_sms ? tiles : num_sms, THREADS, smem, st>>>(tmA, tmB, tmC ? *tmC : tmA, g, epi);
-  return cudaGetLastError();
+  const int m_tiles = (g.M + TILE_M - 1) / TILE_M, n_tiles = (g.N + Cfg::NT - 1) / Cfg::NT;
+  if (Cfg::SHARE == 0) {
+    const int tiles = m_tiles * n_tiles;
+    ozaki_gemm_kernel<T, Epi, Cfg><<<tiles < num_sms ? tiles : num_sms, Cfg::THREADS, smem, st>>>(tmA, tmB, tmC ? *tmC : tmA, g, epi);
+    return cudaGetLastError();
+  }
+  static_assert(Cfg::SHARE == 0 || (epi_tma_stage<Epi>::value == 0 && !epi_staged<Epi>::value), "cluster pairs: plain functors");
+  const int pairs = Cfg::SHARE == 1 ? m_tiles * ((n_tiles + 1) / 2) : ((m_tiles + 1) / 2) * n_tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * std::min(pairs, num_sms / 2)));
+  cfg.blockDim = dim3((unsigned)Cfg::THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, ozaki_gemm_kernel<T, Epi, Cfg>, tmA, tmB, tmC ? *tmC : tmA, g, epi);
 }
 
 // C = A * B^T from sliced operands Aq [T][M][Kpad], Bq [T][N][Kpad]

@@ -458,8 +458,11 @@ cudaError_t launch_oz_fwd(cudaStream_t st, const OzFwdArgs& a) {
       if (a.T == 4) return wide ? oz_fwd_t<4, EpiPhaseSliceFix<4>, oz::TileWide>(st, a) : oz_fwd_t<4, EpiPhaseSliceFix<4>>(st, a);
       return cudaErrorInvalidValue;
     }
-    if (a.T == 6) return wide ? oz_fwd_t<6, EpiPhaseSliceFix<6, true>, oz::TileWide>(st, a) : oz_fwd_t<6, EpiPhaseSliceFix<6, true>>(st, a);
-    if (a.T == 4) return wide ? oz_fwd_t<4, EpiPhaseSliceFix<4, true>, oz::TileWide>(st, a) : oz_fwd_t<4, EpiPhaseSliceFix<4, true>>(st, a);
+    // 80 columns = ten chunks per lane group: 20 epilogue warps take two each (16 leave 3 + 3 + 2 + 2; 0.321 against
+    // 0.334 ms per launch, profiles/r02_v46_cluster.txt)
+    using Wide20 = oz::TileCfg<80, 2, 20>;
+    if (a.T == 6) return wide ? oz_fwd_t<6, EpiPhaseSliceFix<6, true>, Wide20>(st, a) : oz_fwd_t<6, EpiPhaseSliceFix<6, true>>(st, a);
+    if (a.T == 4) return wide ? oz_fwd_t<4, EpiPhaseSliceFix<4, true>, Wide20>(st, a) : oz_fwd_t<4, EpiPhaseSliceFix<4, true>>(st, a);
     return cudaErrorInvalidValue;
   }
   switch (a.T * 4 + (mode == 4 ? 1 : mode)) {

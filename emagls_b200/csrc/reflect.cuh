@@ -11,6 +11,28 @@ __device__ __forceinline__ double wsum(double v) {
 }
 
 __device__ __forceinline__ cplx wsumc(cplx v) { v.x = wsum(v.x); v.y = wsum(v.y); return v; }
+// Warp sums of two complex values at once: reduce-scatter over the first two butterfly stages (a lane keeps one of
+// the four scalars, chosen by lane bits 4 and 3), three stages on that scalar, all-gather back: 18 shuffles instead of
+// the 40 of two wsumc() calls (the applied-reflector chains are bound by the shuffle pipe: one warp instruction per
+// clock and SM).  Every lane ends up with the same bits (the butterfly additions commute).
+__device__ __forceinline__ void wsum2c(cplx& a, cplx& b, int lane) {
+  const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+  cplx keep = hi16 ? b : a;
+  const cplx send = hi16 ? a : b;
+  keep.x += __shfl_xor_sync(0xffffffffu, send.x, 16);
+  keep.y += __shfl_xor_sync(0xffffffffu, send.y, 16);
+  double k = hi8 ? keep.y : keep.x;
+  k += __shfl_xor_sync(0xffffffffu, hi8 ? keep.x : keep.y, 8);
+  k += __shfl_xor_sync(0xffffffffu, k, 4);
+  k += __shfl_xor_sync(0xffffffffu, k, 2);
+  k += __shfl_xor_sync(0xffffffffu, k, 1);
+  const double o = __shfl_xor_sync(0xffffffffu, k, 8);       // the other component of the same value
+  cplx c, d;
+  c.x = hi8 ? o : k; c.y = hi8 ? k : o;                      // the complete sum of (hi16 ? b : a)
+  d.x = __shfl_xor_sync(0xffffffffu, c.x, 16);
+  d.y = __shfl_xor_sync(0xffffffffu, c.y, 16);
+  a = hi16 ? d : c; b = hi16 ? c : d;
+}
 
 // apply Q_C (forward = false: Q_C * x, blocks/reflectors in reverse order with tau) or
 // Q_C^H (forward = true: blocks/reflectors in order with conj(tau)) to x0, x1 (length S).
@@ -66,7 +88,7 @@ __device__ inline void apply_qc(const BlockPlan& bp, const cplx* __restrict__ V,
         const int i = cur.lo + lane + 32 * u;
         if (i < cur.r1) { cfmac(w0, vc[u], x0[i]); cfmac(w1, vc[u], x1[i]); }
       }
-      w0 = wsumc(w0); w1 = wsumc(w1);
+      wsum2c(w0, w1, lane);
       const cplx f0 = cmul(ta, w0), f1 = cmul(ta, w1);
       if (lane == 0) { x0[j] = csub(x0[j], f0); x1[j] = csub(x1[j], f1); }
 #pragma unroll

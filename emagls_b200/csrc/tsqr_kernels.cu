@@ -599,17 +599,17 @@ __device__ __forceinline__ void load_half(const cplx* __restrict__ row, bool ok,
 }
 
 // reflectors j0 .. j0+15 of one block (Q_C^H: in order, conj(tau))
-__device__ __forceinline__ void apply_half(const cplx (&v)[16], int j0, const cplx tau_l, cplx& xb0, cplx& xb1,
-                                           cplx& xr0, cplx& xr1, int lane) {
+// tau_blk: the 32 scalars of this block (read with a warp-uniform address: one load instead of four shuffles)
+__device__ __forceinline__ void apply_half(const cplx (&v)[16], int j0, const cplx* __restrict__ tau_blk, cplx& xb0,
+                                           cplx& xb1, cplx& xr0, cplx& xr1, int lane) {
 #pragma unroll
   for (int jj = 0; jj < 16; ++jj) {
     const int j = j0 + jj;
-    cplx ta;
-    ta.x = __shfl_sync(0xffffffffu, tau_l.x, j);
-    ta.y = -__shfl_sync(0xffffffffu, tau_l.y, j);
+    const double2 tj = __ldg(reinterpret_cast<const double2*>(tau_blk + j));
+    const cplx ta = mk(tj.x, -tj.y);
     cplx w0 = cmulc(xb0, v[jj]), w1 = cmulc(xb1, v[jj]);   // x * conj(v)
     if (lane == j) { w0 = cadd(w0, xr0); w1 = cadd(w1, xr1); }
-    w0 = wsumc(w0); w1 = wsumc(w1);
+    wsum2c(w0, w1, lane);
     const cplx f0 = cmul(ta, w0), f1 = cmul(ta, w1);
     if (lane == j) { xr0 = csub(xr0, f0); xr1 = csub(xr1, f1); }
     cfms(xb0, f0, v[jj]); cfms(xb1, f1, v[jj]);
@@ -656,15 +656,14 @@ chain_bwd_sep_kernel(BlockPlan bp, OperatorSet ops, int slot, int G, const doubl
   for (int t = 0; t < nblk; ++t) {
     const int r = t * 32 + lane;
     load_half(V + (long long)r * 32 + 16, r < S, vb);
-    const double2 tl = __ldg(reinterpret_cast<const double2*>(tau + t * 32 + lane));
-    const cplx tau_l = mk(tl.x, tl.y);
-    apply_half(va, 0, tau_l, xb0, xb1, xr0, xr1, lane);
+    const cplx* tau_blk = tau + t * 32;
+    apply_half(va, 0, tau_blk, xb0, xb1, xr0, xr1, lane);
     cplx nx0 = mk(0.0, 0.0), nx1 = mk(0.0, 0.0);
     if (t + 1 < nblk) {
       load_half(V + (long long)(r + 32) * 32, r + 32 < S, va);
       load_rhs(t0, t1, S, r + 32, nsplit, split_stride, nx0, nx1);
     }
-    apply_half(vb, 16, tau_l, xb0, xb1, xr0, xr1, lane);
+    apply_half(vb, 16, tau_blk, xb0, xb1, xr0, xr1, lane);
     xb0 = nx0; xb1 = nx1;
   }
   // W(m) = sum_i z(i) Pb(i, m)

@@ -239,3 +239,41 @@ def test_optional_fp32_contraction_path(em, h, c1, oracle_c1):
     w64, _ = em.getEMagLs2Filters(c1["hL"], c1["hR"], *args, handle=h)
     d = rel(wL, w64)
     assert 0 < d < 1e-5, d
+
+
+_FWD_VARIANT_SNIPPET = r"""
+import sys, numpy as np
+sys.path.insert(0, {root!r})
+import emagls_b200 as em
+from emagls_b200 import synth
+g = synth.load_grids()
+az, ze = g["hrirGridAziRad"][::3], g["hrirGridZenRad"][::3]
+hL, hR = synth.synth_hrirs(az, ze, taps=64, delay=20)
+R = np.stack([np.eye(3), synth.rotation_yaw_pitch(40.0, 10.0), synth.rotation_yaw_pitch(-75.0, -20.0)])
+wL, wR = em.getEMagLs2Filters(hL, hR, az, ze, g["micRadius"], g["micGridAziRad"], g["micGridZenRad"], 4, g["fs"], 128,
+                              rotations=R, handle=em.Handle(0))
+np.savez({out!r}, wL=wL, wR=wR)
+"""
+
+
+def test_forward_functor_variants_agree(tmp_path):
+    """The forward tensor-core product has three epilogue functors that must give the same filters
+    (lib/getEMagLs2Filters.m:95-103, t = |H_k| y / |y|): the FP64-free one with 4-byte stores (default for six
+    digits), the same with byte stores (EMAGLS_OZ_FWD_BYTES: identical bytes, so identical filters) and the FP64 one
+    (EMAGLS_OZ_FWD=raw: may differ by one unit of the last base-256 digit, 2^-46 of a row maximum).  The switches are
+    read once per process, hence the subprocesses."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for name, env in (("default", {}), ("bytes", {"EMAGLS_OZ_FWD_BYTES": "1"}), ("raw", {"EMAGLS_OZ_FWD": "raw"})):
+        out = str(tmp_path / f"{name}.npz")
+        e = dict(os.environ)
+        e.update(env)
+        subprocess.run([sys.executable, "-c", _FWD_VARIANT_SNIPPET.format(root=root, out=out)], check=True, env=e,
+                       timeout=600)
+        res[name] = np.load(out)
+    for k in ("wL", "wR"):
+        assert np.array_equal(res["default"][k], res["bytes"][k]), k
+        assert rel(res["default"][k], res["raw"][k]) <= 2e-10, (k, rel(res["default"][k], res["raw"][k]))

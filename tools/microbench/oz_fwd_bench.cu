@@ -94,6 +94,11 @@ int main(int argc, char** argv) {
       if (mode == 6) return oz_fwd_t<6, EpiPhaseSliceFix<6>, oz::TileWide>(0, fa);
       if (mode == 7) return oz_fwd_t<6, EpiPhaseSliceFix<6, true>>(0, fa);
       if (mode == 8) return oz_fwd_t<6, EpiPhaseSliceFix<6, true>, oz::TileWide>(0, fa);
+      if (mode == 9) return oz_fwd_t<6, EpiPhaseSliceFix<6>, oz::TileCfg<80, 2, 20>>(0, fa);
+      if (mode == 10) return oz_fwd_t<6, EpiPhaseSliceFix<6, true>, oz::TileCfg<80, 2, 20>>(0, fa);
+      if (mode == 11) return oz_fwd_t<6, EpiPhaseSliceFix<6, true>, oz::TileCfg<80, 2, 24>>(0, fa);
+      if (mode == 12) return oz_fwd_t<6, EpiPhaseSliceFix<6, true>, oz::TileCfg<80, 2, 20, 1>>(0, fa);
+      if (mode == 13) return oz_fwd_t<6, EpiPhaseSliceFix<6, true>, oz::TileCfg<80, 2, 20, 2>>(0, fa);
       return oz_fwd_t<6, EpiPhaseSliceTma<6>, Ring2>(0, fa);
     }
     if (mode == 0) return oz_fwd_t<4, EpiPhaseSlice<4>>(0, fa);
@@ -104,10 +109,15 @@ int main(int argc, char** argv) {
     if (mode == 6) return oz_fwd_t<4, EpiPhaseSliceFix<4>, oz::TileWide>(0, fa);
     if (mode == 7) return oz_fwd_t<4, EpiPhaseSliceFix<4, true>>(0, fa);
     if (mode == 8) return oz_fwd_t<4, EpiPhaseSliceFix<4, true>, oz::TileWide>(0, fa);
+    if (mode == 9) return oz_fwd_t<4, EpiPhaseSliceFix<4>, oz::TileCfg<80, 2, 20>>(0, fa);
+    if (mode == 10) return oz_fwd_t<4, EpiPhaseSliceFix<4, true>, oz::TileCfg<80, 2, 20>>(0, fa);
+    if (mode == 11) return oz_fwd_t<4, EpiPhaseSliceFix<4, true>, oz::TileCfg<80, 2, 24>>(0, fa);
+    if (mode == 12) return oz_fwd_t<4, EpiPhaseSliceFix<4, true>, oz::TileCfg<80, 2, 20, 1>>(0, fa);
+    if (mode == 13) return oz_fwd_t<4, EpiPhaseSliceFix<4, true>, oz::TileCfg<80, 2, 20, 2>>(0, fa);
     return oz_fwd_t<4, EpiPhaseSliceTma<4>, Ring2>(0, fa);
   };
-  const char* names[9] = {"scaled", "raw", "tma", "raw80", "raw48", "fix", "fix80", "fixw", "fixw80"};
-  const int mode_list[6] = {0, 1, 5, 6, 7, 8};   // fix*: FP64-free functor (byte stores), fixw*: the same with 4-byte stores
+  const char* names[14] = {"scaled", "raw", "tma", "raw80", "raw48", "fix", "fix80", "fixw", "fixw80", "fix80e20", "fixw80e20", "fixw80e24", "fixw80e20A", "fixw80e20B"};
+  const int mode_list[6] = {0, 1, 5, 10, 12, 13};   // ...A / ...B: cluster pairs with the A / B tile multicast   // fix*: FP64-free functor (byte stores), fixw*: the same with 4-byte stores
   std::vector<int8_t> fixref;
   const size_t nq = (size_t)T * rows * KpD;
   std::vector<int8_t> ref(nq), got(nq);
@@ -139,7 +149,7 @@ int main(int argc, char** argv) {
     if (mode > 5 && !fixref.empty()) {              // every variant of the integer functor writes the same bytes
       size_t nb = 0;
       for (size_t i = 0; i < nq; ++i) nb += (got[i] != fixref[i]);
-      printf("   %-6s vs fix: %zu of %zu bytes differ\n", names[mode], nb, nq);
+      printf("   %-9s vs fix: %zu of %zu bytes differ\n", names[mode], nb, nq);
     }
     if (mode == 0) { ref = got; sref = sgot; }
     else {
@@ -168,7 +178,7 @@ int main(int argc, char** argv) {
       CK(cudaDeviceSynchronize());
       float msd = 0;
       CK(cudaEventElapsedTime(&msd, e0, e1));
-      printf("   %-6s dbg=%d: %.4f ms\n", names[mode], dbg, msd / reps);
+      printf("   %-9s dbg=%d: %.4f ms\n", names[mode], dbg, msd / reps);
     }
     oz_fwd_debug = 0;
     for (int i = 0; i < 3; ++i) CK(run(mode));
@@ -179,7 +189,7 @@ int main(int argc, char** argv) {
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     const double ops = 2.0 * D * (double)rows * KpS * (T * (T + 1) / 2);
-    printf("oz_fwd %-6s P=%d sets=%d T=%d: %.4f ms per launch, %.0f int8 TOP/s; vs scaled: %zu of %zu values differ (max %.3g in units of the leading digit), %zu scales differ\n",
+    printf("oz_fwd %-9s P=%d sets=%d T=%d: %.4f ms per launch, %.0f int8 TOP/s; vs scaled: %zu of %zu values differ (max %.3g in units of the leading digit), %zu scales differ\n",
            names[mode], P, sets, T, ms / reps, ops / (ms / reps * 1e-3) / 1e12, bad, (size_t)rows * KpD, maxdiff, bad_s);
   }
 

@@ -112,6 +112,25 @@ int main(int argc, char** argv) {
   fails += run_cfg<TileWide>(1000, 400, 2702, 6, 0, 0, 0);
   for (int dbg = 0; dbg < 4; ++dbg) fails += run_cfg<TileWide>(14400, 400, 2702, 6, 10, 0, dbg);
   fails += run_cfg<TileWide>(2702, 14400, 400, 6, 10, 0, 0);
+  fails += run_cfg<TileCfg<80, 2, 20>>(1000, 400, 2702, 6, 0, 0, 0);     // 20 epilogue warps: two chunks per warp
+  fails += run_cfg<TileCfg<80, 2, 20>>(14400, 400, 2702, 6, 10, 0, 0);
+  fails += run_cfg<TileCfg<80, 2, 20>>(1800, 400, 2702, 6, 10, 0, 0);
+  fails += run_cfg<TileWide>(1800, 400, 2702, 6, 10, 0, 0);
+  fails += run_cfg<TileCfg<48, 3>>(1800, 400, 2702, 6, 10, 0, 0);
+  fails += run_cfg<TileCfg<48, 3, 12>>(1800, 400, 2702, 6, 10, 0, 0);    // six chunks: 12 warps take two each
+  // cluster pairs with a multicast operand: B shared (two row tiles), A shared (two column tiles); odd tile counts
+  fails += run_cfg<TileCfg<80, 2, 16, 2>>(1100, 400, 2702, 6, 0, 0, 0);
+  fails += run_cfg<TileCfg<80, 2, 16, 1>>(1100, 400, 2702, 6, 0, 0, 0);
+  fails += run_cfg<TileCfg<64, 3, 16, 1>>(300, 200, 400, 6, 0, 4, 0);
+  fails += run_cfg<TileCfg<64, 3, 16, 2>>(300, 200, 400, 6, 0, 4, 0);
+  for (int dbg = 0; dbg < 4; ++dbg) fails += run_cfg<TileCfg<80, 2, 16, 2>>(14400, 400, 2702, 6, 10, 0, dbg);
+  fails += run_cfg<TileCfg<80, 2, 20, 2>>(14400, 400, 2702, 6, 10, 0, 0);
+  fails += run_cfg<TileCfg<80, 2, 16, 1>>(14400, 400, 2702, 6, 10, 0, 0);
+  fails += run_cfg<TileCfg<80, 2, 16, 2>>(1800, 400, 2702, 6, 10, 0, 0);
+  fails += run_cfg<TileCfg<48, 3, 16, 2>>(1800, 400, 2702, 6, 10, 0, 0);
+  for (int dbg = 0; dbg < 4; dbg += 1) fails += run_cfg<TileCfg<80, 2, 16, 1>>(2702, 14400, 400, 6, 10, 0, dbg);
+  fails += run_cfg<TileCfg<64, 3, 16, 1>>(2702, 14400, 400, 6, 10, 0, 0);
+  fails += run_cfg<TileCfg<80, 3, 16, 1>>(2702, 14400, 400, 4, 10, 0, 0);
   fails += run(2702, 14400, 400, 4, 10, 0);
   fails += run_cfg<TileWide>(14400, 400, 2702, 4, 10, 0, 0);
   printf("%s (%d failing)\n", fails ? "FAIL" : "PASS", fails);
