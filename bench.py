@@ -266,6 +266,21 @@ def main():
     stats = h.stats_read()
     launches = h.launches - launches0
     value = world * B * args.steps / (ms * 1e-3)
+    # secondary: what the profiler's event pairs (about two timing events per launch on the stream, inside the timed
+    # region above) cost: the same step alternately without and with them, each timed on its own
+    evp = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(2 * args.steps)]
+    torch.cuda.synchronize()
+    for i in range(2 * args.steps):
+        h.profile(bool(i & 1))
+        l2_flush()
+        evp[i][0].record(stream)
+        step_dev()
+        evp[i][1].record(stream)
+    torch.cuda.synchronize()
+    h.profile_read()
+    h.profile(False)
+    ms_unprofiled = sum(evp[i][0].elapsed_time(evp[i][1]) for i in range(0, 2 * args.steps, 2)) / args.steps
+    ms_reprofiled = sum(evp[i][0].elapsed_time(evp[i][1]) for i in range(1, 2 * args.steps, 2)) / args.steps
 
     # ---------------- end to end (pinned host buffers -> H2D -> design -> NCCL gather of the banks into rank 0's
     # device bank -> D2H of every rank's shard), through the package's sharded designer (emagls_b200/dist.py).
@@ -501,6 +516,9 @@ def main():
     roofline["tensor_gemm"] = gemm_roof
     roofline["algorithmic_tflops_whole_job"] = value / world * ALGO_GFLOP_PER_SET / 1e3
     roofline["jacobi_mean_sweeps"] = (jac_sw / jac_p) if jac_p else None
+    roofline["profiler_cost_check"] = {"ms_per_step_without_events": round(ms_unprofiled, 3),
+                                       "ms_per_step_with_events": round(ms_reprofiled, 3),
+                                       "note": "alternating steps after the timed region, each timed on its own"}
 
     # ---------------- render (secondary metric: Msamples/s of the 32 -> 2 channel, 512-tap FIR)
     render = None

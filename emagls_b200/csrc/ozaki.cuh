@@ -19,6 +19,7 @@
 // then the functor).
 #pragma once
 #include <algorithm>
+#include <type_traits>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -219,6 +220,22 @@ __device__ __forceinline__ double combine_diagonals(const int32_t (&a)[MAX_SLICE
     if (d < T) L = fma(L, 256.0, i2d_exact(a[d][q]));
   return fma(H, (double)(1 << (8 * (T - 3))), L);
 }
+// The same integer, exact, in 64-bit integer arithmetic (|v| < 2^63): multiply-adds with 64-bit accumulators (IMAD.WIDE)
+// instead of 11 FP64 instructions per element -- the drain is the one phase of the epilogue that cannot overlap with
+// MMAs, and FP64 is the slowest pipe it could use.  For functors that declare `int64_values`.
+template <int T>
+__device__ __forceinline__ long long combine_diagonals_i64(const int32_t (&a)[MAX_SLICES][8], int q) {
+  long long H = (long long)a[0][q];
+#pragma unroll
+  for (int d = 1; d < 3; ++d)
+    if (d < T) H = H * 256 + (long long)a[d][q];
+  if (T <= 3) return H;
+  long long L = (long long)a[3][q];
+#pragma unroll
+  for (int d = 4; d < MAX_SLICES; ++d)
+    if (d < T) L = L * 256 + (long long)a[d][q];
+  return H * (long long)(1 << (8 * (T - 3))) + L;
+}
 // weight of the integer above: C = sA sB 256^-(T-1) v
 template <int T> __device__ __forceinline__ double diagonal_weight() { return 1.0 / (double)(1ull << (8 * (T - 1))); }
 
@@ -357,6 +374,8 @@ template <class E> struct epi_raw<E, decltype((void)E::raw)> { static constexpr 
 // are written), so apply_staged() is also entered for rows m >= M and must stage zeros there).
 template <class E, class = void> struct epi_tma_stage { static constexpr int value = 0; };
 template <class E> struct epi_tma_stage<E, decltype((void)E::tma_stage_bytes)> { static constexpr int value = E::tma_stage_bytes; };
+template <class E, class = void> struct epi_i64 { static constexpr bool value = false; };
+template <class E> struct epi_i64<E, decltype((void)E::int64_values)> { static constexpr bool value = E::int64_values; };
 template <class E, class = void> struct epi_all_lanes { static constexpr bool value = false; };
 template <class E> struct epi_all_lanes<E, decltype((void)E::all_lanes)> { static constexpr bool value = E::all_lanes; };
 
@@ -565,7 +584,8 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // Phase 1 (drain): this warp's chunks go TMEM -> registers -> FP64 (exact integers, one rounding); the
       // accumulators are then handed back, so the MMA warp starts the next tile while phase 2 (the functor:
       // phase continuation, slicing, global stores) runs from registers.
-      double v[CH_PER_WARP][8];
+      using Val = typename std::conditional<epi_raw<Epi>::value && epi_i64<Epi>::value, long long, double>::type;
+      Val v[CH_PER_WARP][8];
       auto drain = [&]() {
 #pragma unroll
         for (int ci = 0; ci < CH_PER_WARP; ++ci) {
@@ -577,7 +597,10 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (d < T) tmem_ld8(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(d * NT + c0), a[d]);
             tmem_ld_wait();
 #pragma unroll
-            for (int q = 0; q < 8; ++q) v[ci][q] = combine_diagonals<T>(a, q);
+            for (int q = 0; q < 8; ++q) {
+              if constexpr (std::is_same<Val, long long>::value) v[ci][q] = combine_diagonals_i64<T>(a, q);
+              else v[ci][q] = combine_diagonals<T>(a, q);
+            }
           }
         }
         tc_fence_before();

@@ -150,6 +150,7 @@ template <int T, bool WORDS = false>
 struct EpiPhaseSliceFix {
   static constexpr bool raw = true;
   static constexpr bool all_lanes = WORDS;
+  static constexpr bool int64_values = true;      // the drain hands over exact 64-bit integers (no FP64 at all)
   int8_t* Tq; long long slice_stride; int Kpad;   // [T][rows][Kpad], element (n, m) at n * Kpad + m
   double* sT;                                     // [rows] scale of row n (written by the m == 0 lanes)
   const double* absH; long long abs_set_stride, abs_ear_stride;   // this bin: [set][ear][dir]
@@ -199,17 +200,17 @@ struct EpiPhaseSliceFix {
     }
   }
   // digit words (zl, zh) of the (re, im) columns n0 + q, n0 + q + 1
-  __device__ __forceinline__ void pair_digits(const TileState& ts, int n0, int q, double vr, double vi, uint32_t& rl,
+  __device__ __forceinline__ void pair_digits(const TileState& ts, int n0, int q, long long vr, long long vi, uint32_t& rl,
                                               uint32_t& rh, uint32_t& il, uint32_t& ih) const {
     const int4 sb = *reinterpret_cast<const int4*>(sB + n0 + q);   // warp-uniform: two powers of two
     const int dexp = ((sb.y >> 20) & 0x7FF) - ((sb.w >> 20) & 0x7FF);
     int64_t Zr, Zi;
-    pfx::phase_fixed(vr, vi, dexp, ts.mu[(q >> 1) & 1], Zr, Zi);
+    pfx::phase_fixed_i64(vr, vi, dexp, ts.mu[(q >> 1) & 1], Zr, Zi);
     if (nyquist) Zi = 0;
     pfx::split_words<T>(Zr, rl, rh);
     pfx::split_words<T>(Zi, il, ih);
   }
-  __device__ __forceinline__ void apply(TileState& ts, int m, int n0, const double (&v)[8], int M, int N) const {
+  __device__ __forceinline__ void apply(TileState& ts, int m, int n0, const long long (&v)[8], int M, int N) const {
     const int prob = n0 >> 2;
     int set = prob / orient_per_set;
     int left = (set + 1) * orient_per_set - prob;     // problems left in this set, >= 1

@@ -116,6 +116,9 @@ EM_PFX_HD uint64_t mul_hi_approx(uint32_t Mh, uint32_t Ml, uint64_t U) {   // fl
   return mul_wide(Mh, Uh) + (mul_wide(Mh, Ul) >> 32) + (mul_wide(Ml, Uh) >> 32);
 }
 
+// the normalisation on aligned magnitudes A, B (the larger one in [2^61, 2^62)) and the signs of re / im
+EM_PFX_HD void phase_from_aligned(uint64_t A, uint64_t B, bool neg_r, bool neg_i, uint64_t mu_fix, int64_t& Zr, int64_t& Zi);
+
 EM_PFX_HD void phase_fixed(double vr, double vi, int dexp, uint64_t mu_fix, int64_t& Zr, int64_t& Zi) {
   uint32_t rh, rl, ih, il;
   dbits(vr, rh, rl);
@@ -131,6 +134,34 @@ EM_PFX_HD void phase_fixed(double vr, double vi, int dexp, uint64_t mu_fix, int6
   const int E = ear > eai ? ear : eai;
   const int sa = E - ear, sb = E - eai;                              // one of them is 0
   const uint64_t A = (Mr << 9) >> (sa > 63 ? 63 : sa), B = (Mi << 9) >> (sb > 63 ? 63 : sb);   // < 2^62
+  phase_from_aligned(A, B, (rh >> 31) != 0, (ih >> 31) != 0, mu_fix, Zr, Zi);
+}
+
+// The same from the exact 64-bit integers (|v| < 2^63) the accumulator drain can deliver without FP64 instructions:
+// no rounding to 53 bits in between.
+EM_PFX_HD int clz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __clzll((long long)x);
+#else
+  return x ? __builtin_clzll(x) : 64;
+#endif
+}
+EM_PFX_HD void phase_fixed_i64(int64_t vr, int64_t vi, int dexp, uint64_t mu_fix, int64_t& Zr, int64_t& Zi) {
+  if ((vr | vi) == 0) {                                              // angle(0) = 0
+    Zr = (int64_t)((mu_fix + 0x8000ull) >> 16);
+    Zi = 0;
+    return;
+  }
+  const uint64_t ur = (uint64_t)(vr < 0 ? -vr : vr), ui = (uint64_t)(vi < 0 ? -vi : vi);
+  const int nr = vr ? clz64(ur) : 0, ni = vi ? clz64(ui) : 0;        // >= 1 for nonzero values
+  const int ear = vr ? dexp - nr : -(1 << 20), eai = vi ? -ni : -(1 << 20);   // exponent of the leading bit, minus 63
+  const int E = ear > eai ? ear : eai;
+  const int sa = E - ear, sb = E - eai;                              // one of them is 0
+  const uint64_t A = ((ur << nr) >> 2) >> (sa > 63 ? 63 : sa), B = ((ui << ni) >> 2) >> (sb > 63 ? 63 : sb);   // < 2^62
+  phase_from_aligned(A, B, vr < 0, vi < 0, mu_fix, Zr, Zi);
+}
+
+EM_PFX_HD void phase_from_aligned(uint64_t A, uint64_t B, bool neg_r, bool neg_i, uint64_t mu_fix, int64_t& Zr, int64_t& Zi) {
   const uint32_t R0 = seed_r0((uint32_t)(A >> 38), (uint32_t)(B >> 38));
   const uint64_t P = mul_wide((uint32_t)(A >> 32), R0) + (mul_wide((uint32_t)A, R0) >> 32);
   const uint64_t Q = mul_wide((uint32_t)(B >> 32), R0) + (mul_wide((uint32_t)B, R0) >> 32);
@@ -139,8 +170,8 @@ EM_PFX_HD void phase_fixed(double vr, double vi, int dexp, uint64_t mu_fix, int6
   const uint32_t Mh = (uint32_t)(mu_fix >> 32), Ml = (uint32_t)mu_fix;
   const int64_t zr = (int64_t)((mul_hi_approx(Mh, Ml, U) + 2048ull) >> 12);
   const int64_t zi = (int64_t)((mul_hi_approx(Mh, Ml, W) + 2048ull) >> 12);
-  Zr = (rh >> 31) ? -zr : zr;
-  Zi = (ih >> 31) ? -zi : zi;
+  Zr = neg_r ? -zr : zr;
+  Zi = neg_i ? -zi : zi;
 }
 
 // Balanced base-256 digits of Z = a 2^24 256^(T-4), |a| <= 64, as two words: byte j of zl is digit T-1-j (j < 3),

@@ -47,6 +47,13 @@ static int run(long long n, unsigned seed, double& worst) {
     }
     const double dr = (double)fabsq((__float128)Zr - er), di = (double)fabsq((__float128)Zi - ei);
     worst = std::fmax(worst, std::fmax(dr, di));
+    if (std::fabs(vr) < 9.2e18 && std::fabs(vi) < 9.2e18) {         // the entry on exact 64-bit integers
+      int64_t Yr, Yi;
+      phase_fixed_i64((int64_t)vr, (int64_t)vi, dexp, mu_fix, Yr, Yi);
+      const double d2 = std::fmax((double)fabsq((__float128)Yr - er), (double)fabsq((__float128)Yi - ei));
+      worst = std::fmax(worst, d2);
+      if (std::llabs(Yr - Zr) > 1 || std::llabs(Yi - Zi) > 1) { if (bad < 5) printf("i64 / f64 entry disagree: %lld %lld vs %lld %lld\n", (long long)Yr, (long long)Yi, (long long)Zr, (long long)Zi); ++bad; }
+    }
     for (int c = 0; c < 2; ++c) {
       const int64_t Z = c ? Zi : Zr;
       uint32_t zl, zh;
