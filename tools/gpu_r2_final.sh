@@ -35,5 +35,5 @@ cap ${TAG}_tsqr "tsqr_sep_kernel" 1 1
 cap ${TAG}_svdclip "svdclip_kernel" 1 1
 cap ${TAG}_bwd "bwd_fused_kernel|chain_bwd_sep_kernel" 3 2
 cap ${TAG}_gram "gram_sweep_kernel" 1 1
-python tools/ncu_traffic.py gpurun_out/${TAG}_oz.raw.csv gpurun_out/${TAG}_oz_traffic.json "ncu --set full --clock-control none, ozaki_gemm_kernel<6> launches 41-42 of a 3600-orientation design (forward EpiPhaseSliceFix (integer functor, 4-byte stores) 128x80 tiles with 20 epilogue warps, backward EpiStoreF64 128x80 tiles); tools/gpu_r2_final.sh ${TAG}" > /dev/null 2>&1
+python tools/ncu_traffic.py gpurun_out/${TAG}_oz.raw.csv gpurun_out/${TAG}_oz_traffic.json "ncu --set full --clock-control none, ozaki_gemm_kernel<6> launches 41-42 of a 3600-orientation design (forward EpiPhaseSliceFix (integer drain + integer functor, no FP64 instruction, 4-byte stores) 128x80 tiles with 20 epilogue warps, backward EpiStoreF64 128x80 tiles); tools/gpu_r2_final.sh ${TAG}" > /dev/null 2>&1
 ls -la gpurun_out/ | grep ${TAG} | awk '{print $5, $9}'
