@@ -336,7 +336,7 @@ def main():
                   "includes": "H2D of the inputs, design, NCCL gather into rank 0's bank, D2H of every shard"}
         del ss
 
-    # ---------------- parity spot check of the timed batch (outside the timed regions): three orientations of the
+    # ---------------- parity spot check of the timed batch (outside the timed regions): three random orientations and the last one of the
     # bank the device-resident steps produced against the oracle (NumPy restatement of the reference), rank 0
     spot = None
     if rank == 0 and not args.no_spot_check:
@@ -345,6 +345,8 @@ def main():
         from emagls_b200 import synth
         rng = np.random.default_rng(12345)
         idx = sorted(int(i) for i in rng.choice(B, size=min(3, B), replace=False))
+        if B - 1 not in idx:
+            idx.append(B - 1)   # the end of the batch: the part the Jacobi launch cuts into bin ranges (launch_svdclip)
 
         def ref(i):
             raz, rze = synth.rotate_grid(pr["az"], pr["ze"], pr["R"][i])

@@ -123,6 +123,24 @@ def test_emagls2_orientation_batch_full_size_properties(em, h, c1):
     assert rel(wL[:, :, -2], sL) < 5e-9 and rel(wL[:, :, -1], sL) < 5e-9
 
 
+def test_last_partial_round_of_the_jacobi_launch_matches_a_small_batch(em, h, c1):
+    """A batch larger than the number of resident Jacobi CTAs (4 per SM: 592 on a B200): the orientations of the
+    last partial round are cut into bin ranges (launch_svdclip, tsqr_kernels.cu).  Their filters must equal those
+    of the same orientations designed as a small batch of their own (no split there); the only difference allowed
+    is the rounding of cold against warm Jacobi starts (lib/getEMagLs2Filters.m:86-89 is the same SVD either way)."""
+    Rall = synth.orientation_grid()
+    R = Rall[np.arange(603) * 5 % Rall.shape[0]]      # 603 orientations: 11 of them in the last round of 592
+    args = (c1["az"], c1["ze"], c1["r"], c1["maz"], c1["mze"], 4, c1["fs"], 512)
+    wL, wR = em.getEMagLs2Filters(c1["hL"], c1["hR"], *args, rotations=R, handle=h)
+    tail = slice(603 - 12, 603)                        # the split orientations and one before them
+    sL, sR = em.getEMagLs2Filters(c1["hL"], c1["hR"], *args, rotations=R[tail], handle=h)
+    assert np.all(np.isfinite(wL)) and np.all(np.isfinite(wR))
+    assert rel(wL[:, :, tail], sL) < 5e-9 and rel(wR[:, :, tail], sR) < 5e-9
+    head = slice(0, 4)
+    s2L, _ = em.getEMagLs2Filters(c1["hL"], c1["hR"], *args, rotations=R[head], handle=h)
+    assert rel(wL[:, :, head], s2L) < 5e-9
+
+
 def test_emagls2_through_cabi_matches_reference_golden_conventions(em, h, goldens):
     """Golden pin (3) through the CUDA path: order-4 surrogate HRIRs from the LS golden reproduce the
     eMagLS2 golden's low bins to a few percent (any convention error gives O(1))."""
