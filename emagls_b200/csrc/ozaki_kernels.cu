@@ -138,9 +138,10 @@ struct EpiPhaseSliceRaw {
   }
 };
 // The same epilogue without FP64 instructions in the functor (phase_fixed.cuh): FP64 work does not overlap with the
-// tcgen05 MMAs of the next tile on this part, integer work does.  The drained values are taken apart as bit patterns,
-// |y|^-1 comes from a 22-bit MUFU seed and one third-order correction in 64-bit fixed point, and the digits are those
-// of rn(t 2^24) formed in integer arithmetic.  Against EpiPhaseSliceRaw the last digit may differ by one unit
+// tcgen05 MMAs of the next tile on this part, integer work does.  The drain hands over the exact 64-bit integers
+// (int64_values: the kernel instance then contains no FP64 instruction at all), they are normalised by
+// count-leading-zeros and shifts, |y|^-1 comes from a 22-bit MUFU seed and one third-order correction in 64-bit
+// fixed point, and the digits are those of rn(t 2^24) formed in integer arithmetic.  Against EpiPhaseSliceRaw the last digit may differ by one unit
 // (|Z - exact| <= 0.6 instead of <= 0.53; tests/test_phase_fixed.py).
 // WORDS: the digit bytes of four columns are packed per plane, transposed across groups of four lanes (two shuffles
 // and two byte permutes per word) and leave as 4-byte stores: lane l writes rows l & ~3 .. (l & ~3) + 3 of column

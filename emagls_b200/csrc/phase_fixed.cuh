@@ -6,7 +6,8 @@
 // tile).  Everything below runs on the integer pipes; the only floating-point instructions are one FP32 FMA / MUL
 // pair and MUFU.RSQ for a 22-bit seed of 1 / |y|.
 //
-//   inputs   vr, vi     the exact integer results of the re / im column (FP64 bit patterns from the drain),
+//   inputs   vr, vi     the exact integer results of the re / im column (phase_fixed_i64: the 64-bit integers of the
+//                       integer drain; phase_fixed: FP64 bit patterns of the FP64 drain, rounded to 53 bits),
 //            dexp       exponent(scale of the re row of c) - exponent(scale of the im row) (both powers of two),
 //            mu_fix     |H_k| 2^(6 - e_H) 256^(T-4) 2^40 as an integer (< 2^62)
 //   outputs  Zr, Zi  =  rn(t 2^24) with t = mu y / |y|,  |Z| <= 2^46: the integer whose balanced base-256 digits
